@@ -1,0 +1,197 @@
+// dsp.cuh — device-side DSP primitives shared by the voice and effect kernels.
+//
+// Formulas are the ones written down in docs/ORACLE_SPEC.md.  Quantities that
+// decide a discontinuity (oscillator phase, pulse duty, envelope stage, sample
+// index) are integers so that the closed-form / scanned evaluation here is
+// bit-identical to a frame-by-frame accumulation; smooth quantities are f64.
+#pragma once
+
+#include <cstdint>
+#include <cuda_runtime.h>
+
+namespace gbk {
+
+typedef unsigned long long u64;
+typedef long long i64;
+
+constexpr i64 kHeld = 1ll << 60;
+constexpr i64 kNever = -(1ll << 60);
+constexpr double kTwo64 = 18446744073709551616.0;
+constexpr double kLog2_800 = 9.6438561897747243;
+constexpr double kPi = 3.141592653589793238462643383279;
+
+// ---- waveforms (gb_waveform) ----
+enum { W_NONE = 0, W_SINE, W_SQUARE, W_PULSE, W_TRIANGLE, W_SAW, W_NOISE, W_DZERO, W_DMAX, W_DMIN };
+enum { LFO_NONE = 0, LFO_AMPLITUDE, LFO_PITCH, LFO_PULSE_WIDTH, LFO_FILTER_CUTOFF };
+
+__host__ __device__ __forceinline__ u64 splitmix64(u64 x) {
+  x += 0x9E3779B97F4A7C15ull;
+  x = (x ^ (x >> 30)) * 0xBF58476D1CE4E5B9ull;
+  x = (x ^ (x >> 27)) * 0x94D049BB133111EBull;
+  return x ^ (x >> 31);
+}
+
+// fractional cycles -> 2^64-scaled phase increment
+__device__ __forceinline__ u64 cycles_to_q(double c) {
+  c -= floor(c);
+  double r = c * kTwo64;
+  if (!(r < kTwo64)) return 0ull;
+  return __double2ull_rz(r);
+}
+__device__ __forceinline__ double pos_of(u64 q) {
+  return __ull2double_rn(q >> 11) * (1.0 / 9007199254740992.0);
+}
+
+// Oscillator output for phase q.  `wf` is warp-uniform.
+__device__ __forceinline__ double wave_value(int wf, u64 q, u64 duty_q, u64 seed, i64 frame) {
+  const u64 half = 1ull << 63;
+  switch (wf) {
+    case W_SINE: return sinpi(2.0 * pos_of(q));
+    case W_SQUARE: return q < half ? 1.0 : -1.0;
+    case W_PULSE: return q < duty_q ? 1.0 : -1.0;
+    case W_TRIANGLE: {
+      double p = pos_of(q);
+      return q < half ? 4.0 * p - 1.0 : 3.0 - 4.0 * p;
+    }
+    case W_SAW: {
+      double p = pos_of(q);
+      return q < half ? 2.0 * p : 2.0 * p - 2.0;
+    }
+    case W_NOISE:
+      return __ull2double_rn(splitmix64(seed + (u64)frame) >> 11) * (1.0 / 4503599627370496.0) - 1.0;
+    case W_DMAX: return 1.0;
+    case W_DMIN: return -1.0;
+    default: return 0.0;
+  }
+}
+
+// ---- ADSR over integer frame counts ----
+struct EnvShape {
+  i64 na, nd, nr;
+  double sustain;
+  double inv_na, inv_nd, inv_nr;
+};
+
+__device__ __forceinline__ double env_pre(const EnvShape& s, i64 n_on, double l_on, i64 n) {
+  i64 k = n - n_on;
+  if (k < s.na) {
+    double t = (double)k * s.inv_na;
+    return l_on + (1.0 - l_on) * (t * (2.0 - t));
+  }
+  i64 k2 = k - s.na;
+  if (k2 < s.nd) {
+    double u = 1.0 - (double)k2 * s.inv_nd;
+    return s.sustain + (1.0 - s.sustain) * (u * u);
+  }
+  return s.sustain;
+}
+__device__ __forceinline__ double env_level(const EnvShape& s, i64 n_on, i64 n_off, double l_on, double l_off,
+                                            i64 n) {
+  if (n < n_on) return 0.0;
+  if (n < n_off) return env_pre(s, n_on, l_on, n);
+  i64 k = n - n_off;
+  if (k < s.nr) {
+    double u = 1.0 - (double)k * s.inv_nr;
+    return l_off * (u * u);
+  }
+  return 0.0;
+}
+
+// ---- 24 dB low-pass: two transposed-DF2 sections; only b0,a1,a2 are free (b1=2*b0, b2=b0) ----
+struct Lp24Ripple {
+  double c0, c2, c1k, c3k;
+};
+struct SecCoef {
+  double b0, a1, a2;
+};
+// k = tan(pi*fc/sr)
+__device__ __forceinline__ void lp24_from_k(const Lp24Ripple& rp, double k, SecCoef& s1, SecCoef& s2) {
+  double kk = k * k;
+  double c1 = k * rp.c1k, c3 = k * rp.c3k;
+  double a0 = 1.0 / (c1 + kk + rp.c0);
+  s1.a1 = 2.0 * (rp.c0 - kk) * a0;
+  s1.a2 = (c1 - kk - rp.c0) * a0;
+  s1.b0 = a0 * kk;
+  a0 = 1.0 / (c3 + kk + rp.c2);
+  s2.a1 = 2.0 * (rp.c2 - kk) * a0;
+  s2.a2 = (c3 - kk - rp.c2) * a0;
+  s2.b0 = a0 * kk;
+}
+
+// ---- 2x2 affine maps (state-space recurrences) and their warp scan ----
+// s' = M s + v ;  M = [m00 m01; m10 m11]
+struct Affine2 {
+  double m00, m01, m10, m11, v0, v1;
+};
+__device__ __forceinline__ Affine2 affine_identity() {
+  Affine2 a;
+  a.m00 = 1.0; a.m01 = 0.0; a.m10 = 0.0; a.m11 = 1.0; a.v0 = 0.0; a.v1 = 0.0;
+  return a;
+}
+// apply `later` after `earlier`
+__device__ __forceinline__ Affine2 affine_compose(const Affine2& earlier, const Affine2& later) {
+  Affine2 r;
+  r.m00 = later.m00 * earlier.m00 + later.m01 * earlier.m10;
+  r.m01 = later.m00 * earlier.m01 + later.m01 * earlier.m11;
+  r.m10 = later.m10 * earlier.m00 + later.m11 * earlier.m10;
+  r.m11 = later.m10 * earlier.m01 + later.m11 * earlier.m11;
+  r.v0 = later.m00 * earlier.v0 + later.m01 * earlier.v1 + later.v0;
+  r.v1 = later.m10 * earlier.v0 + later.m11 * earlier.v1 + later.v1;
+  return r;
+}
+__device__ __forceinline__ Affine2 affine_shfl_up(const Affine2& a, int delta) {
+  Affine2 r;
+  r.m00 = __shfl_up_sync(0xffffffffu, a.m00, delta);
+  r.m01 = __shfl_up_sync(0xffffffffu, a.m01, delta);
+  r.m10 = __shfl_up_sync(0xffffffffu, a.m10, delta);
+  r.m11 = __shfl_up_sync(0xffffffffu, a.m11, delta);
+  r.v0 = __shfl_up_sync(0xffffffffu, a.v0, delta);
+  r.v1 = __shfl_up_sync(0xffffffffu, a.v1, delta);
+  return r;
+}
+// Inclusive Kogge-Stone scan over the 32 lanes (lane order = time order).
+__device__ __forceinline__ Affine2 affine_warp_scan(Affine2 a, int lane) {
+#pragma unroll
+  for (int d = 1; d < 32; d <<= 1) {
+    Affine2 prev = affine_shfl_up(a, d);
+    if (lane >= d) a = affine_compose(prev, a);
+  }
+  return a;
+}
+// Given the inclusive scan and the state at the start of the warp's span, return the state at the
+// start of this lane's chunk, and (in *span_end) the state after the whole 32-lane span.
+__device__ __forceinline__ void affine_lane_entry(const Affine2& incl, int lane, double s0, double s1, double& e0,
+                                                  double& e1, double& end0, double& end1) {
+  Affine2 ex = affine_shfl_up(incl, 1);
+  if (lane == 0) ex = affine_identity();
+  e0 = ex.m00 * s0 + ex.m01 * s1 + ex.v0;
+  e1 = ex.m10 * s0 + ex.m11 * s1 + ex.v1;
+  double t0 = incl.m00 * s0 + incl.m01 * s1 + incl.v0;
+  double t1 = incl.m10 * s0 + incl.m11 * s1 + incl.v1;
+  end0 = __shfl_sync(0xffffffffu, t0, 31);
+  end1 = __shfl_sync(0xffffffffu, t1, 31);
+}
+
+// Segmented u64 sum scan (phase accumulators with resets).
+struct SegSum {
+  u64 sum;
+  int reset;  // 1 if a reset happened inside the span; sum then counts from the last reset
+};
+__device__ __forceinline__ SegSum segsum_compose(const SegSum& earlier, const SegSum& later) {
+  SegSum r;
+  r.reset = earlier.reset | later.reset;
+  r.sum = later.reset ? later.sum : earlier.sum + later.sum;
+  return r;
+}
+__device__ __forceinline__ SegSum segsum_warp_scan(SegSum a, int lane) {
+#pragma unroll
+  for (int d = 1; d < 32; d <<= 1) {
+    SegSum prev;
+    prev.sum = __shfl_up_sync(0xffffffffu, a.sum, d);
+    prev.reset = __shfl_up_sync(0xffffffffu, a.reset, d);
+    if (lane >= d) a = segsum_compose(prev, a);
+  }
+  return a;
+}
+
+}  // namespace gbk

@@ -1,0 +1,1509 @@
+// engine.cu — host-side block scheduler + C ABI (include/groove_b200.h) of the B200 renderer.
+//
+// What the reference does per FRAME (Orchestrator::tick -> handle_work + gather_audio,
+// orchestration/src/orchestrator.rs:856-877,367-470) this engine does per CHUNK of up to
+// `max_block` frames:
+//   1. gb_finalize() snapshots the patch graph once into a topologically sorted plan — the
+//      reference author's own TODO (orchestrator.rs:357-359);
+//   2. note events are resolved on the host into per-voice event lists (voice allocation only
+//      needs integer frame arithmetic), control events into per-effect parameter segments;
+//   3. all voices of one instrument type render in ONE kernel launch (voice_kernels.cuh), each
+//      instrument into its node buffer; effects run in plan order (fx_kernels.cuh);
+//   4. the main mixer's buffer is the result (f64 stereo in HBM), copied to the caller.
+// There is no CPU fallback: every DSP operation happens in a CUDA kernel of this library.
+
+#include <algorithm>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <map>
+#include <memory>
+#include <string>
+#include <vector>
+
+#include <cuda_runtime.h>
+
+#include "../../include/groove_b200.h"
+#include "fx_kernels.cuh"
+#include "voice_kernels.cuh"
+
+using namespace gbk;
+
+namespace {
+
+constexpr int kVoiceWarps = 8;  // warps per voice CTA
+constexpr uint32_t kDefaultMaxBlock = 1u << 16;
+
+std::string g_create_err;
+
+template <typename T>
+struct DevBuf {  // growable device array with a pinned host mirror for uploads
+  T* d = nullptr;
+  T* h = nullptr;
+  size_t cap = 0;
+  ~DevBuf() { release(); }
+  void release() {
+    if (d) cudaFree(d);
+    if (h) cudaFreeHost(h);
+    d = nullptr; h = nullptr; cap = 0;
+  }
+  bool reserve(size_t n) {
+    if (n <= cap) return true;
+    size_t ncap = std::max<size_t>(n, cap * 2 + 16);
+    T* nd = nullptr; T* nh = nullptr;
+    if (cudaMalloc(&nd, ncap * sizeof(T)) != cudaSuccess) return false;
+    if (cudaMallocHost(&nh, ncap * sizeof(T)) != cudaSuccess) { cudaFree(nd); return false; }
+    if (d) cudaFree(d);
+    if (h) cudaFreeHost(h);
+    d = nd; h = nh; cap = ncap;
+    return true;
+  }
+};
+
+inline uint64_t h_cycles_to_q(double c) {
+  c -= std::floor(c);
+  double r = c * 18446744073709551616.0;
+  if (!(r < 18446744073709551616.0)) return 0;
+  return (uint64_t)r;
+}
+inline int64_t frames_of(double seconds, double sr) {
+  if (!(seconds > 0.0)) return 0;
+  return (int64_t)std::llround(seconds * sr);
+}
+inline double note_hz(int key) { return 440.0 * std::exp2(((double)key - 69.0) / 12.0); }
+inline double pct_to_hz(double pct) { return 25.0 * std::exp2(pct * 9.6438561897747243); }
+inline double clamp01(double v) { return v < 0.0 ? 0.0 : (v > 1.0 ? 1.0 : v); }
+inline double denormalize_q(double v) { return v * v * 10.0 + 0.707; }
+inline void dca_gains(double gain, double pan, double* gl, double* gr) {
+  double a = 0.5 * (pan + 1.0), b = 0.5 * (pan - 1.0);
+  *gl = gain * (1.0 - a * a);
+  *gr = gain * (1.0 - b * b);
+}
+inline EnvShape make_shape(const gb_envelope_params& p, double sr) {
+  EnvShape s;
+  s.na = frames_of(p.attack, sr);
+  s.nd = frames_of(p.decay, sr);
+  s.nr = frames_of(p.release, sr);
+  s.sustain = clamp01(p.sustain);
+  s.inv_na = s.na > 0 ? 1.0 / (double)s.na : 0.0;
+  s.inv_nd = s.nd > 0 ? 1.0 / (double)s.nd : 0.0;
+  s.inv_nr = s.nr > 0 ? 1.0 / (double)s.nr : 0.0;
+  return s;
+}
+inline Lp24Ripple make_ripple(double ripple) {
+  Lp24Ripple r;
+  double sg = std::sinh(ripple);
+  double cg = std::cosh(ripple);
+  cg *= cg;
+  r.c0 = 1.0 / (cg - 0.85355339059327376220);
+  r.c2 = 1.0 / (cg - 0.14644660940672623780);
+  r.c1k = r.c0 * sg * 1.84775906502257351225;
+  r.c3k = r.c2 * sg * 0.76536686473017954345;
+  return r;
+}
+inline void host_lp24(const Lp24Ripple& rp, double cutoff, double sr, SecCoef* s1, SecCoef* s2) {
+  double fc = cutoff;
+  if (fc > 0.49 * sr) fc = 0.49 * sr;
+  if (fc < 1.0) fc = 1.0;
+  double k = std::tan(3.141592653589793238462643383279 * fc / sr);
+  double kk = k * k;
+  double c1 = k * rp.c1k, c3 = k * rp.c3k;
+  double a0 = 1.0 / (c1 + kk + rp.c0);
+  s1->a1 = 2.0 * (rp.c0 - kk) * a0;
+  s1->a2 = (c1 - kk - rp.c0) * a0;
+  s1->b0 = a0 * kk;
+  a0 = 1.0 / (c3 + kk + rp.c2);
+  s2->a1 = 2.0 * (rp.c2 - kk) * a0;
+  s2->a2 = (c3 - kk - rp.c2) * a0;
+  s2->b0 = a0 * kk;
+}
+// RBJ cookbook (doc/Audio-EQ-Cookbook.txt:74-198), a0-normalised.
+BiquadCoefs host_rbj(int kind, double cutoff, double p2, double sr) {
+  const double kTwoPi = 6.283185307179586476925286766559;
+  double fc = cutoff;
+  if (fc > 0.49 * sr) fc = 0.49 * sr;
+  if (fc < 1e-3) fc = 1e-3;
+  double w0 = kTwoPi * fc / sr;
+  double cs = std::cos(w0), sn = std::sin(w0);
+  double b0, b1, b2, a0, a1, a2;
+  switch (kind) {
+    case GB_FX_LOW_PASS_12DB: {
+      double q = p2 > 1e-6 ? p2 : 1e-6;
+      double alpha = sn / (2.0 * q);
+      b0 = (1.0 - cs) / 2.0; b1 = 1.0 - cs; b2 = (1.0 - cs) / 2.0;
+      a0 = 1.0 + alpha; a1 = -2.0 * cs; a2 = 1.0 - alpha;
+    } break;
+    case GB_FX_HIGH_PASS_12DB: {
+      double q = p2 > 1e-6 ? p2 : 1e-6;
+      double alpha = sn / (2.0 * q);
+      b0 = (1.0 + cs) / 2.0; b1 = -(1.0 + cs); b2 = (1.0 + cs) / 2.0;
+      a0 = 1.0 + alpha; a1 = -2.0 * cs; a2 = 1.0 - alpha;
+    } break;
+    case GB_FX_BAND_PASS_12DB: {
+      double bw = p2 > 1e-6 ? p2 : 1e-6;
+      double alpha = sn * std::sinh(0.34657359027997264 * bw * w0 / sn);
+      b0 = alpha; b1 = 0.0; b2 = -alpha;
+      a0 = 1.0 + alpha; a1 = -2.0 * cs; a2 = 1.0 - alpha;
+    } break;
+    case GB_FX_BAND_STOP_12DB: {
+      double bw = p2 > 1e-6 ? p2 : 1e-6;
+      double alpha = sn * std::sinh(0.34657359027997264 * bw * w0 / sn);
+      b0 = 1.0; b1 = -2.0 * cs; b2 = 1.0;
+      a0 = 1.0 + alpha; a1 = -2.0 * cs; a2 = 1.0 - alpha;
+    } break;
+    case GB_FX_ALL_PASS_12DB: {
+      double q = p2 > 1e-6 ? p2 : 1e-6;
+      double alpha = sn / (2.0 * q);
+      b0 = 1.0 - alpha; b1 = -2.0 * cs; b2 = 1.0 + alpha;
+      a0 = 1.0 + alpha; a1 = -2.0 * cs; a2 = 1.0 - alpha;
+    } break;
+    case GB_FX_PEAKING_EQ_12DB: {
+      double A = std::pow(10.0, p2 / 40.0);
+      double alpha = sn / (2.0 * 0.70710678118654752440);
+      b0 = 1.0 + alpha * A; b1 = -2.0 * cs; b2 = 1.0 - alpha * A;
+      a0 = 1.0 + alpha / A; a1 = -2.0 * cs; a2 = 1.0 - alpha / A;
+    } break;
+    case GB_FX_LOW_SHELF_12DB: {
+      double A = std::pow(10.0, p2 / 40.0);
+      double alpha = sn / 2.0 * 1.41421356237309504880;
+      double t = 2.0 * std::sqrt(A) * alpha;
+      b0 = A * ((A + 1.0) - (A - 1.0) * cs + t);
+      b1 = 2.0 * A * ((A - 1.0) - (A + 1.0) * cs);
+      b2 = A * ((A + 1.0) - (A - 1.0) * cs - t);
+      a0 = (A + 1.0) + (A - 1.0) * cs + t;
+      a1 = -2.0 * ((A - 1.0) + (A + 1.0) * cs);
+      a2 = (A + 1.0) + (A - 1.0) * cs - t;
+    } break;
+    default: {
+      double A = std::pow(10.0, p2 / 40.0);
+      double alpha = sn / 2.0 * 1.41421356237309504880;
+      double t = 2.0 * std::sqrt(A) * alpha;
+      b0 = A * ((A + 1.0) + (A - 1.0) * cs + t);
+      b1 = -2.0 * A * ((A - 1.0) + (A + 1.0) * cs);
+      b2 = A * ((A + 1.0) + (A - 1.0) * cs - t);
+      a0 = (A + 1.0) - (A - 1.0) * cs + t;
+      a1 = 2.0 * ((A - 1.0) - (A + 1.0) * cs);
+      a2 = (A + 1.0) - (A - 1.0) * cs - t;
+    } break;
+  }
+  BiquadCoefs c;
+  c.b0 = b0 / a0; c.b1 = b1 / a0; c.b2 = b2 / a0; c.a1 = a1 / a0; c.a2 = a2 / a0;
+  return c;
+}
+inline uint64_t step_to_q32(double step) {
+  double r = step * 4294967296.0;
+  if (!(r >= 1.0)) return 1;
+  if (r > 1.8e19) r = 1.8e19;
+  return (uint64_t)r;
+}
+inline int64_t frames_until_end(size_t len, uint64_t step_q) {
+  unsigned __int128 target = (unsigned __int128)len << 32;
+  unsigned __int128 k = (target + step_q - 1) / step_q;
+  if (k > (unsigned __int128)kHeld) return kHeld;
+  return (int64_t)k;
+}
+
+// ---- host-side voice allocation (integer frames only) -------------------------------------
+struct Slot {
+  int key = -1;
+  int64_t on_frame = kNever;
+  int64_t idle_at = kNever;
+  bool held = false;
+};
+struct SlotStore {
+  std::vector<Slot> slots;
+  int note_on(int64_t f, int key) {
+    int pick = -1;
+    for (size_t i = 0; i < slots.size(); ++i)
+      if (slots[i].key == key && f < slots[i].idle_at) { pick = (int)i; break; }
+    if (pick < 0)
+      for (size_t i = 0; i < slots.size(); ++i)
+        if (f >= slots[i].idle_at) { pick = (int)i; break; }
+    if (pick < 0) {
+      pick = 0;
+      for (size_t i = 1; i < slots.size(); ++i)
+        if (slots[i].on_frame < slots[pick].on_frame) pick = (int)i;
+    }
+    slots[pick].key = key;
+    slots[pick].on_frame = f;
+    slots[pick].idle_at = kHeld;
+    slots[pick].held = true;
+    return pick;
+  }
+};
+
+struct SampleDev {
+  double* d = nullptr;
+  size_t n = 0;
+  int channels = 1;
+  double sr = 44100.0, root_hz = 0.0;
+};
+struct SampleVoiceHost {
+  int64_t n_on = kNever, n_end = kNever;
+  uint64_t step_q = 0;
+  int sample = -1;
+};
+
+struct Node {
+  uint32_t uid = 0;
+  int kind = 0;
+  bool is_inst = false;
+  std::vector<uint32_t> sources;  // uids, patch order
+  int order = -1;                 // position in the plan (-1 = unreachable)
+  double2* buf = nullptr;         // chunk output (max_block frames)
+  double2* scratch = nullptr;     // pre-reduction when > kMaxSources inputs / partial sums
+  // --- instruments ---
+  gb_welsh_params wp;
+  gb_fm_params fp;
+  gb_sampler_params sp;
+  gb_toy_source_params tp;
+  int table_index = -1;  // index in the welsh/fm instrument table
+  int voice0 = 0, nvoices = 0;
+  int64_t release_frames = 0;
+  SlotStore store;
+  std::vector<SampleDev> samples;
+  std::vector<SampleVoiceHost> svoices;
+  int key_to_voice[128];
+  // --- effects ---
+  double p[4] = {0, 0, 0, 0};  // raw parameters in control-index order
+  BiquadState* d_bq = nullptr;
+  Lp24State* d_lp = nullptr;
+  int delay_frames = 0;
+  double2* hist[2] = {nullptr, nullptr};
+  int hist_cur = 0;
+  ChorusTaps taps;
+  ReverbDesc rv;
+  double* rv_comb_out = nullptr;  // [2][4][max_block]
+  double* rv_ap_out[2] = {nullptr, nullptr};  // [2][max_block] each
+};
+
+}  // namespace
+
+struct gb_engine {
+  int device = 0;
+  double sr = 44100.0;
+  uint32_t max_block = kDefaultMaxBlock;
+  cudaStream_t stream = nullptr;
+  bool finalized = false;
+  int64_t pos = 0;
+  uint32_t next_uid = 2;
+  int num_sms = 148;
+  std::map<uint32_t, std::unique_ptr<Node>> nodes;
+  std::vector<Node*> plan;  // reachable nodes, sources before consumers
+  std::vector<gb_event> events;
+  std::string err;
+
+  // voice tables
+  std::vector<WelshInst> h_winst;
+  std::vector<FmInst> h_finst;
+  WelshInst* d_winst = nullptr;
+  FmInst* d_finst = nullptr;
+  WelshVoice* d_wvoice = nullptr;
+  FmVoice* d_fvoice = nullptr;
+  int n_wvoice = 0, n_fvoice = 0;
+  bool winst_dirty = true, finst_dirty = true;
+  DevBuf<CtaWork> wwork, fwork;
+  int n_wwork = 0, n_fwork = 0;
+  DevBuf<VoiceEvent> wev, fev;
+  DevBuf<int> wev_off, fev_off;
+  DevBuf<SamplePlay> plays;
+  std::vector<void*> allocations;  // everything cudaMalloc'ed at finalize/load time
+
+  double2* last_out = nullptr;  // main mixer buffer of the last chunk
+  size_t last_frames = 0;
+  double2* d_full = nullptr;    // whole-call result (render_device / read_last), grown on demand
+  size_t full_cap = 0;
+  size_t full_frames = 0;       // frames of d_full that hold the last device-resident render
+  short2* d_pcm = nullptr;
+  size_t pcm_cap = 0;
+
+  // stats
+  gb_stats stats;
+  bool timing = false;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+};
+
+namespace {
+
+int fail(gb_engine* e, int code, const char* fmt, ...) {
+  char buf[512];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof buf, fmt, ap);
+  va_end(ap);
+  if (e) e->err = buf;
+  else g_create_err = buf;
+  return code;
+}
+#define CUDA_TRY(e, expr)                                                                        \
+  do {                                                                                           \
+    cudaError_t _rc = (expr);                                                                    \
+    if (_rc != cudaSuccess)                                                                      \
+      return fail(e, GB_ECUDA, "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_rc), __FILE__, __LINE__); \
+  } while (0)
+
+template <typename T>
+int dev_alloc(gb_engine* e, T** out, size_t count, bool zero = true) {
+  void* p = nullptr;
+  size_t bytes = std::max<size_t>(count, 1) * sizeof(T);
+  CUDA_TRY(e, cudaMalloc(&p, bytes));
+  if (zero) CUDA_TRY(e, cudaMemsetAsync(p, 0, bytes, e->stream));
+  e->allocations.push_back(p);
+  *out = (T*)p;
+  return 0;
+}
+
+Node* find(gb_engine* e, uint32_t uid) {
+  auto it = e->nodes.find(uid);
+  return it == e->nodes.end() ? nullptr : it->second.get();
+}
+
+void welsh_inst_from_params(const Node& n, double sr, WelshInst* I) {
+  const gb_welsh_params& p = n.wp;
+  const double top = 1.0 - 1.0 / 9007199254740992.0;
+  memset(I, 0, sizeof *I);
+  I->amp = make_shape(p.amp_envelope, sr);
+  I->filt = make_shape(p.filter_envelope, sr);
+  I->w1 = p.oscillator_1.waveform;
+  I->w2 = p.oscillator_2.waveform;
+  I->wl = p.lfo.waveform;
+  I->sync = p.oscillator_2_sync ? 1 : 0;
+  I->routing = p.lfo_routing;
+  I->uid = (int)n.uid;
+  I->voice0 = n.voice0;
+  I->duty1_q = h_cycles_to_q(std::min(clamp01(p.oscillator_1.pulse_width), top));
+  I->duty2_q = h_cycles_to_q(std::min(clamp01(p.oscillator_2.pulse_width), top));
+  I->dutyl_q = h_cycles_to_q(std::min(clamp01(p.lfo.pulse_width), top));
+  I->lfo_dq = h_cycles_to_q(p.lfo.frequency / sr);
+  I->duty1 = p.oscillator_1.pulse_width;
+  I->duty2 = p.oscillator_2.pulse_width;
+  I->mix = p.oscillator_mix;
+  I->depth = p.lfo_depth;
+  if (p.filter_cutoff_end != 0.0) {
+    I->filter_mode = FILTER_ENVELOPE;
+    I->cut_a = p.filter_cutoff_start;
+    I->cut_b = (1.0 - p.filter_cutoff_start) * p.filter_cutoff_end;
+  } else if (p.lfo_routing == GB_LFO_FILTER_CUTOFF) {
+    I->filter_mode = FILTER_LFO;
+    I->cut_a = p.filter_cutoff_start;
+    I->cut_b = 0.0;
+  } else {
+    I->filter_mode = FILTER_FIXED;
+  }
+  I->rp = make_ripple(p.filter_passband_ripple);
+  host_lp24(I->rp, p.filter_cutoff_hz, sr, &I->fixed1, &I->fixed2);
+  double pan = p.voice_dca.pan + p.dca.pan;
+  pan = pan < -1.0 ? -1.0 : (pan > 1.0 ? 1.0 : pan);
+  dca_gains(p.voice_dca.gain * p.dca.gain, pan, &I->gl, &I->gr);
+  I->pi_over_sr = 3.141592653589793238462643383279 / sr;
+  I->sr = sr;
+}
+void fm_inst_from_params(const Node& n, double sr, FmInst* I) {
+  memset(I, 0, sizeof *I);
+  I->car = make_shape(n.fp.carrier_envelope, sr);
+  I->mod = make_shape(n.fp.modulator_envelope, sr);
+  I->depth = n.fp.depth;
+  I->beta = n.fp.beta;
+  dca_gains(n.fp.dca.gain, n.fp.dca.pan, &I->gl, &I->gr);
+  I->uid = (int)n.uid;
+  I->voice0 = n.voice0;
+}
+
+struct Launch {  // per-launch accounting (+ optional CUDA-event timing on the engine's stream)
+  gb_engine* e;
+  bool voice;
+  Launch(gb_engine* e_, bool voice_) : e(e_), voice(voice_) {
+    if (e->timing) cudaEventRecord(e->ev0, e->stream);
+  }
+  ~Launch() {
+    e->stats.kernel_launches++;
+    if (voice) e->stats.voice_kernel_launches++;
+    if (e->timing) {
+      cudaEventRecord(e->ev1, e->stream);
+      cudaEventSynchronize(e->ev1);
+      float ms = 0.f;
+      cudaEventElapsedTime(&ms, e->ev0, e->ev1);
+      if (voice) e->stats.voice_kernel_ms += ms;
+      else e->stats.fx_kernel_ms += ms;
+    }
+  }
+};
+
+inline int cdiv(int a, int b) { return (a + b - 1) / b; }
+
+// Sum a node's inputs.  Up to kMaxSources go straight into the consuming kernel; more are
+// pre-reduced left to right into the node's scratch buffer.
+int gather_sources(gb_engine* e, Node* n, int frames, SourceList* out) {
+  std::vector<const double2*> ptrs;
+  for (uint32_t s : n->sources) {
+    Node* sn = find(e, s);
+    if (sn && sn->order >= 0 && sn->buf) ptrs.push_back(sn->buf);
+  }
+  memset(out, 0, sizeof *out);
+  if ((int)ptrs.size() <= kMaxSources) {
+    out->n = (int)ptrs.size();
+    for (int i = 0; i < out->n; ++i) out->p[i] = ptrs[i];
+    return 0;
+  }
+  size_t i = 0;
+  bool first = true;
+  while (i < ptrs.size()) {
+    SourceList sl;
+    memset(&sl, 0, sizeof sl);
+    if (!first) sl.p[sl.n++] = n->scratch;
+    while (i < ptrs.size() && sl.n < kMaxSources) sl.p[sl.n++] = ptrs[i++];
+    Launch l(e, false);
+    pointwise_kernel<<<cdiv(frames, 256), 256, 0, e->stream>>>(sl, n->scratch, 0, frames, OP_SUM, 0.0, 0.0);
+    first = false;
+  }
+  out->n = 1;
+  out->p[0] = n->scratch;
+  return 0;
+}
+
+void effect_apply_param(gb_engine* e, Node* n, int index, double raw) {
+  if (index < 0 || index >= 4) return;
+  n->p[index] = raw;
+  (void)e;
+}
+// ControlValue (0..1) -> raw parameter, per effect kind (mirrors set_<field>(value.into()),
+// proc-macros/src/control.rs:159-161).
+double control_to_raw(const Node* n, int index, double v) {
+  switch (n->kind) {
+    case GB_FX_BITCRUSHER: return std::floor(v * 16.0);
+    case GB_FX_LOW_PASS_24DB:
+      return index == GB_CTL_FILTER_CUTOFF ? pct_to_hz(clamp01(v)) : denormalize_q(v);
+    case GB_FX_LOW_PASS_12DB: case GB_FX_HIGH_PASS_12DB: case GB_FX_ALL_PASS_12DB:
+      return index == GB_CTL_FILTER_CUTOFF ? pct_to_hz(clamp01(v)) : denormalize_q(v);
+    case GB_FX_BAND_PASS_12DB: case GB_FX_BAND_STOP_12DB:
+      return index == GB_CTL_FILTER_CUTOFF ? pct_to_hz(clamp01(v)) : v * 4.0;
+    case GB_FX_PEAKING_EQ_12DB: case GB_FX_LOW_SHELF_12DB: case GB_FX_HIGH_SHELF_12DB:
+      return index == GB_CTL_FILTER_CUTOFF ? pct_to_hz(clamp01(v)) : (2.0 * v - 1.0) * 24.0;
+    case GB_INST_WELSH: case GB_INST_FM:
+      return index == GB_CTL_INST_DCA_PAN ? 2.0 * v - 1.0 : v;
+    default: return v;
+  }
+}
+bool effect_accepts(const Node* n, int index) {
+  switch (n->kind) {
+    case GB_FX_GAIN: case GB_FX_BITCRUSHER: case GB_FX_REVERB: return index == 0;
+    case GB_FX_LIMITER: case GB_FX_COMPRESSOR: return index == 0 || index == 1;
+    case GB_FX_CHORUS: return index == GB_CTL_CHORUS_WET_DRY_MIX;
+    case GB_FX_LOW_PASS_24DB: return index == 0 || index == 1;
+    case GB_INST_WELSH: case GB_INST_FM: return index == 0 || index == 1;
+    default:
+      if (n->kind >= GB_FX_LOW_PASS_12DB && n->kind <= GB_FX_HIGH_SHELF_12DB) return index == 0 || index == 1;
+      return false;
+  }
+}
+
+// Run one effect node over chunk frames [t0,t1) with its current parameters.
+int run_effect_segment(gb_engine* e, Node* n, const SourceList& src, int frames, int t0, int t1, int64_t chunk_pos) {
+  if (t1 <= t0) return 0;
+  const int nseg = t1 - t0;
+  switch (n->kind) {
+    case GB_FX_MIXER: {
+      Launch l(e, false);
+      pointwise_kernel<<<cdiv(nseg, 256), 256, 0, e->stream>>>(src, n->buf, t0, t1, OP_SUM, 0.0, 0.0);
+    } break;
+    case GB_FX_GAIN: {
+      Launch l(e, false);
+      pointwise_kernel<<<cdiv(nseg, 256), 256, 0, e->stream>>>(src, n->buf, t0, t1, OP_GAIN, n->p[0], 0.0);
+    } break;
+    case GB_FX_LIMITER: {
+      Launch l(e, false);
+      pointwise_kernel<<<cdiv(nseg, 256), 256, 0, e->stream>>>(src, n->buf, t0, t1, OP_LIMITER, n->p[0], n->p[1]);
+    } break;
+    case GB_FX_BITCRUSHER: {
+      Launch l(e, false);
+      pointwise_kernel<<<cdiv(nseg, 256), 256, 0, e->stream>>>(src, n->buf, t0, t1, OP_BITCRUSHER,
+                                                                std::exp2(std::floor(n->p[0])), 0.0);
+    } break;
+    case GB_FX_COMPRESSOR: {
+      Launch l(e, false);
+      pointwise_kernel<<<cdiv(nseg, 256), 256, 0, e->stream>>>(src, n->buf, t0, t1, OP_COMPRESSOR, n->p[0], n->p[1]);
+    } break;
+    case GB_FX_LOW_PASS_24DB: {
+      Lp24Coefs c;
+      Lp24Ripple rp = make_ripple(n->p[1]);
+      host_lp24(rp, n->p[0], e->sr, &c.s1, &c.s2);
+      Launch l(e, false);
+      lp24_kernel<<<1, 32 * kFxWarps, 0, e->stream>>>(src, n->buf, t0, t1, c, n->d_lp);
+    } break;
+    case GB_FX_CHORUS: {
+      Launch l(e, false);
+      chorus_kernel<<<cdiv(nseg, 256), 256, 0, e->stream>>>(src, n->hist[n->hist_cur], std::max(n->delay_frames, 1),
+                                                             n->taps, n->p[GB_CTL_CHORUS_WET_DRY_MIX], n->buf, t0, t1);
+    } break;
+    case GB_FX_REVERB: {
+      int maxd = 0;
+      for (int i = 0; i < 4; ++i) maxd = std::max(maxd, n->rv.comb_d[i]);
+      {
+        Launch l(e, false);
+        dim3 grid(cdiv(maxd, 256), 8);
+        reverb_comb_kernel<<<grid, 256, 0, e->stream>>>(src, n->rv, n->p[0], n->rv_comb_out, frames, chunk_pos, t0, t1);
+      }
+      for (int stage = 0; stage < 2; ++stage) {
+        Launch l(e, false);
+        dim3 grid(cdiv(n->rv.ap_d[stage], 256), 2);
+        reverb_allpass_kernel<<<grid, 256, 0, e->stream>>>(stage == 0 ? n->rv_comb_out : n->rv_ap_out[0],
+                                                            stage == 0 ? 4 : 1, (size_t)frames, n->rv, stage,
+                                                            n->rv_ap_out[stage], frames, chunk_pos, t0, t1);
+      }
+      {
+        Launch l(e, false);
+        interleave_kernel<<<cdiv(nseg, 256), 256, 0, e->stream>>>(n->rv_ap_out[1], n->buf, frames, t0, t1);
+      }
+    } break;
+    default:
+      if (n->kind >= GB_FX_LOW_PASS_12DB && n->kind <= GB_FX_HIGH_SHELF_12DB) {
+        BiquadCoefs c = host_rbj(n->kind, n->p[0], n->p[1], e->sr);
+        Launch l(e, false);
+        biquad_df1_kernel<<<1, 32 * kFxWarps, 0, e->stream>>>(src, n->buf, t0, t1, c, n->d_bq);
+      }
+      break;
+  }
+  return 0;
+}
+
+}  // namespace
+
+// ===================================================================== C ABI ===
+extern "C" {
+
+int gb_create(const gb_config* cfg, gb_engine** out) {
+  if (!cfg || !out) return fail(nullptr, GB_EINVAL, "null argument");
+  if (cfg->abi_version != GB_ABI_VERSION) return fail(nullptr, GB_EINVAL, "ABI version mismatch");
+  if (!(cfg->sample_rate > 0.0)) return fail(nullptr, GB_EINVAL, "sample_rate must be positive");
+  int count = 0;
+  cudaError_t rc = cudaGetDeviceCount(&count);
+  if (rc != cudaSuccess || count == 0)
+    return fail(nullptr, GB_ENODEV, "no CUDA device available (%s); this library has no CPU fallback",
+                rc == cudaSuccess ? "device count is 0" : cudaGetErrorString(rc));
+  if (cfg->device < 0 || cfg->device >= count) return fail(nullptr, GB_ENODEV, "device ordinal out of range");
+  if (cudaSetDevice(cfg->device) != cudaSuccess) return fail(nullptr, GB_ENODEV, "cudaSetDevice failed");
+  std::unique_ptr<gb_engine> e(new gb_engine());
+  e->device = cfg->device;
+  e->sr = cfg->sample_rate;
+  e->max_block = cfg->max_block ? cfg->max_block : kDefaultMaxBlock;
+  memset(&e->stats, 0, sizeof e->stats);
+  cudaDeviceProp prop;
+  if (cudaGetDeviceProperties(&prop, e->device) == cudaSuccess) e->num_sms = prop.multiProcessorCount;
+  if (cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking) != cudaSuccess)
+    return fail(nullptr, GB_ECUDA, "cudaStreamCreate failed");
+  cudaEventCreate(&e->ev0);
+  cudaEventCreate(&e->ev1);
+  auto mixer = std::make_unique<Node>();
+  mixer->uid = GB_MAIN_MIXER;
+  mixer->kind = GB_FX_MIXER;
+  e->nodes[GB_MAIN_MIXER] = std::move(mixer);
+  *out = e.release();
+  return 0;
+}
+
+void gb_destroy(gb_engine* e) {
+  if (!e) return;
+  cudaSetDevice(e->device);
+  if (e->stream) cudaStreamSynchronize(e->stream);
+  for (void* p : e->allocations) cudaFree(p);
+  if (e->d_full) cudaFree(e->d_full);
+  if (e->d_pcm) cudaFree(e->d_pcm);
+  if (e->ev0) cudaEventDestroy(e->ev0);
+  if (e->ev1) cudaEventDestroy(e->ev1);
+  if (e->stream) cudaStreamDestroy(e->stream);
+  delete e;
+}
+
+const char* gb_last_error(const gb_engine* e) { return e ? e->err.c_str() : g_create_err.c_str(); }
+
+int gb_add_instrument(gb_engine* e, int32_t kind, const void* params, size_t size, uint32_t* uid) {
+  if (!e || !uid) return GB_EINVAL;
+  if (e->finalized) return fail(e, GB_ESTATE, "engine is finalized");
+  auto n = std::make_unique<Node>();
+  n->uid = e->next_uid;
+  n->kind = kind;
+  n->is_inst = true;
+  for (int& k : n->key_to_voice) k = -1;
+  switch (kind) {
+    case GB_INST_WELSH:
+      if (!params || size != sizeof(gb_welsh_params)) return fail(e, GB_EINVAL, "bad welsh params size");
+      n->wp = *(const gb_welsh_params*)params;
+      n->nvoices = n->wp.voices ? (int)n->wp.voices : 8;
+      n->release_frames = frames_of(n->wp.amp_envelope.release, e->sr);
+      n->store.slots.resize(n->nvoices);
+      break;
+    case GB_INST_FM:
+      if (!params || size != sizeof(gb_fm_params)) return fail(e, GB_EINVAL, "bad fm params size");
+      n->fp = *(const gb_fm_params*)params;
+      n->nvoices = n->fp.voices ? (int)n->fp.voices : 8;
+      n->release_frames = frames_of(n->fp.carrier_envelope.release, e->sr);
+      n->store.slots.resize(n->nvoices);
+      break;
+    case GB_INST_SAMPLER:
+      if (!params || size != sizeof(gb_sampler_params)) return fail(e, GB_EINVAL, "bad sampler params size");
+      n->sp = *(const gb_sampler_params*)params;
+      n->nvoices = n->sp.voices ? (int)n->sp.voices : 8;
+      n->store.slots.resize(n->nvoices);
+      n->svoices.resize(n->nvoices);
+      break;
+    case GB_INST_DRUMKIT:
+      break;
+    case GB_INST_TOY_SOURCE:
+      if (!params || size != sizeof(gb_toy_source_params)) return fail(e, GB_EINVAL, "bad toy params size");
+      n->tp = *(const gb_toy_source_params*)params;
+      break;
+    default:
+      return fail(e, GB_EINVAL, "unknown instrument kind %d", kind);
+  }
+  *uid = n->uid;
+  e->nodes[n->uid] = std::move(n);
+  e->next_uid++;
+  return 0;
+}
+
+int gb_add_effect(gb_engine* e, int32_t kind, const void* params, size_t size, uint32_t* uid) {
+  if (!e || !uid) return GB_EINVAL;
+  if (e->finalized) return fail(e, GB_ESTATE, "engine is finalized");
+  auto n = std::make_unique<Node>();
+  n->uid = e->next_uid;
+  n->kind = kind;
+#define NEED(T) if (!params || size != sizeof(T)) return fail(e, GB_EINVAL, "bad effect params size for kind %d", kind)
+  switch (kind) {
+    case GB_FX_MIXER: break;
+    case GB_FX_GAIN: NEED(gb_gain_params); n->p[0] = ((const gb_gain_params*)params)->ceiling; break;
+    case GB_FX_LIMITER:
+      NEED(gb_limiter_params);
+      n->p[0] = ((const gb_limiter_params*)params)->min;
+      n->p[1] = ((const gb_limiter_params*)params)->max;
+      break;
+    case GB_FX_BITCRUSHER: NEED(gb_bitcrusher_params); n->p[0] = ((const gb_bitcrusher_params*)params)->bits; break;
+    case GB_FX_COMPRESSOR:
+      NEED(gb_compressor_params);
+      n->p[0] = ((const gb_compressor_params*)params)->threshold;
+      n->p[1] = ((const gb_compressor_params*)params)->ratio;
+      break;
+    case GB_FX_DELAY:
+      NEED(gb_delay_params);
+      n->delay_frames = (int)frames_of(((const gb_delay_params*)params)->seconds, e->sr);
+      break;
+    case GB_FX_CHORUS: {
+      NEED(gb_chorus_params);
+      const gb_chorus_params* c = (const gb_chorus_params*)params;
+      int nv = (int)c->voices;
+      nv = nv < 1 ? 1 : (nv > 64 ? 64 : nv);
+      int64_t d = frames_of(c->delay_seconds, e->sr);
+      n->delay_frames = (int)d;
+      n->taps.nv = nv;
+      for (int i = 0; i < nv; ++i) n->taps.tap[i] = (int)(d * (i + 1) / nv);
+      n->p[GB_CTL_CHORUS_WET_DRY_MIX] = c->wet_dry_mix;
+    } break;
+    case GB_FX_REVERB: {
+      NEED(gb_reverb_params);
+      const gb_reverb_params* r = (const gb_reverb_params*)params;
+      static const double comb_s[4] = {0.0297, 0.0371, 0.0411, 0.0437};
+      static const double ap_delay[2] = {0.0050, 0.0017};
+      static const double ap_decay[2] = {0.09683, 0.03292};
+      double seconds = r->seconds > 1e-6 ? r->seconds : 1e-6;
+      memset(&n->rv, 0, sizeof n->rv);
+      for (int i = 0; i < 4; ++i) {
+        n->rv.comb_d[i] = (int)std::max<int64_t>(frames_of(comb_s[i], e->sr), 1);
+        n->rv.comb_g[i] = std::pow(0.001, comb_s[i] / seconds);
+      }
+      for (int i = 0; i < 2; ++i) {
+        n->rv.ap_d[i] = (int)std::max<int64_t>(frames_of(ap_delay[i], e->sr), 1);
+        n->rv.ap_g[i] = std::pow(0.001, ap_delay[i] / ap_decay[i]);
+      }
+      n->p[0] = r->attenuation;
+    } break;
+    case GB_FX_LOW_PASS_24DB:
+      NEED(gb_lowpass24_params);
+      n->p[0] = ((const gb_lowpass24_params*)params)->cutoff;
+      n->p[1] = ((const gb_lowpass24_params*)params)->passband_ripple;
+      break;
+    default:
+      if (kind >= GB_FX_LOW_PASS_12DB && kind <= GB_FX_HIGH_SHELF_12DB) {
+        NEED(gb_biquad_params);
+        n->p[0] = ((const gb_biquad_params*)params)->cutoff;
+        n->p[1] = ((const gb_biquad_params*)params)->param2;
+      } else {
+        return fail(e, GB_EINVAL, "unknown effect kind %d", kind);
+      }
+  }
+#undef NEED
+  *uid = n->uid;
+  e->nodes[n->uid] = std::move(n);
+  e->next_uid++;
+  return 0;
+}
+
+int gb_load_sample(gb_engine* e, uint32_t uid, uint8_t key, const double* frames, size_t n_frames, int32_t channels,
+                   double sample_rate, double root_hz) {
+  if (!e) return GB_EINVAL;
+  if (!frames || n_frames == 0 || (channels != 1 && channels != 2)) return fail(e, GB_EINVAL, "bad sample");
+  Node* n = find(e, uid);
+  if (!n) return fail(e, GB_ENOENT, "unknown uid %u", uid);
+  if (n->kind != GB_INST_SAMPLER && n->kind != GB_INST_DRUMKIT) return fail(e, GB_EINVAL, "entity does not take samples");
+  cudaSetDevice(e->device);
+  SampleDev s;
+  s.n = n_frames;
+  s.channels = channels;
+  s.sr = sample_rate;
+  size_t bytes = n_frames * (size_t)channels * sizeof(double);
+  CUDA_TRY(e, cudaMalloc(&s.d, bytes));
+  e->allocations.push_back(s.d);
+  CUDA_TRY(e, cudaMemcpy(s.d, frames, bytes, cudaMemcpyHostToDevice));
+  e->stats.h2d_bytes += bytes;
+  if (n->kind == GB_INST_SAMPLER) {
+    s.root_hz = root_hz > 0.0 ? root_hz : (n->sp.root_hz > 0.0 ? n->sp.root_hz : 440.0);
+    n->samples.clear();
+    n->samples.push_back(s);
+  } else {
+    if (key >= 128) return fail(e, GB_EINVAL, "bad key");
+    if (n->key_to_voice[key] < 0) {
+      n->key_to_voice[key] = (int)n->svoices.size();
+      n->samples.push_back(s);
+      SampleVoiceHost v;
+      v.sample = (int)n->samples.size() - 1;
+      n->svoices.push_back(v);
+    } else {
+      n->samples[n->svoices[n->key_to_voice[key]].sample] = s;
+    }
+  }
+  return 0;
+}
+
+int gb_patch(gb_engine* e, uint32_t src, uint32_t dst) {
+  if (!e) return GB_EINVAL;
+  if (e->finalized) return fail(e, GB_ESTATE, "engine is finalized");
+  Node* s = find(e, src);
+  Node* d = find(e, dst);
+  if (!s || !d) return fail(e, GB_ENOENT, "unknown uid");
+  if (d->is_inst) return fail(e, GB_EGRAPH, "input device is not an effect");
+  if (src == dst) return fail(e, GB_EGRAPH, "cannot patch a device to itself");
+  if (std::find(d->sources.begin(), d->sources.end(), src) == d->sources.end()) d->sources.push_back(src);
+  return 0;
+}
+
+int gb_finalize(gb_engine* e) {
+  if (!e) return GB_EINVAL;
+  if (e->finalized) return fail(e, GB_ESTATE, "engine is already finalized");
+  cudaSetDevice(e->device);
+  // post-order DFS from the main mixer: sources before consumers; detects cycles.
+  std::map<uint32_t, int> color;
+  std::vector<std::pair<Node*, size_t>> st;
+  Node* root = find(e, GB_MAIN_MIXER);
+  st.push_back({root, 0});
+  color[root->uid] = 1;
+  e->plan.clear();
+  while (!st.empty()) {
+    auto& top = st.back();
+    if (top.second >= top.first->sources.size()) {
+      color[top.first->uid] = 2;
+      top.first->order = (int)e->plan.size();
+      e->plan.push_back(top.first);
+      st.pop_back();
+      continue;
+    }
+    uint32_t cu = top.first->sources[top.second++];
+    Node* c = find(e, cu);
+    if (!c) continue;
+    if (color[cu] == 1) return fail(e, GB_EGRAPH, "patch graph has a cycle");
+    if (color[cu] == 0) {
+      color[cu] = 1;
+      st.push_back({c, 0});
+    }
+  }
+  const size_t mb = e->max_block;
+  int wv = 0, fv = 0;
+  for (Node* n : e->plan) {
+    int rc = dev_alloc(e, &n->buf, mb);
+    if (rc) return rc;
+    if (n->kind == GB_INST_WELSH) {
+      n->table_index = (int)e->h_winst.size();
+      n->voice0 = wv;
+      wv += n->nvoices;
+      e->h_winst.emplace_back();
+    } else if (n->kind == GB_INST_FM) {
+      n->table_index = (int)e->h_finst.size();
+      n->voice0 = fv;
+      fv += n->nvoices;
+      e->h_finst.emplace_back();
+    }
+    if (!n->is_inst) {
+      if ((int)n->sources.size() > kMaxSources && (rc = dev_alloc(e, &n->scratch, mb))) return rc;
+      if (n->kind >= GB_FX_LOW_PASS_12DB && n->kind <= GB_FX_HIGH_SHELF_12DB && (rc = dev_alloc(e, &n->d_bq, 1))) return rc;
+      if (n->kind == GB_FX_LOW_PASS_24DB && (rc = dev_alloc(e, &n->d_lp, 1))) return rc;
+      if (n->kind == GB_FX_DELAY || n->kind == GB_FX_CHORUS) {
+        size_t len = (size_t)std::max(n->delay_frames, 1);
+        if ((rc = dev_alloc(e, &n->hist[0], len)) || (rc = dev_alloc(e, &n->hist[1], len))) return rc;
+      }
+      if (n->kind == GB_FX_REVERB) {
+        for (int ch = 0; ch < 2; ++ch) {
+          for (int i = 0; i < 4; ++i)
+            if ((rc = dev_alloc(e, &n->rv.comb_ring[ch][i], (size_t)n->rv.comb_d[i]))) return rc;
+          for (int i = 0; i < 2; ++i)
+            if ((rc = dev_alloc(e, &n->rv.ap_ring[ch][i], (size_t)n->rv.ap_d[i]))) return rc;
+        }
+        if ((rc = dev_alloc(e, &n->rv_comb_out, 8 * mb)) || (rc = dev_alloc(e, &n->rv_ap_out[0], 2 * mb)) ||
+            (rc = dev_alloc(e, &n->rv_ap_out[1], 2 * mb)))
+          return rc;
+      }
+    }
+  }
+  // voice state: every voice starts idle
+  e->n_wvoice = wv;
+  e->n_fvoice = fv;
+  if (wv) {
+    int rc = dev_alloc(e, &e->d_wvoice, (size_t)wv, false);
+    if (rc) return rc;
+    if ((rc = dev_alloc(e, &e->d_winst, e->h_winst.size()))) return rc;
+    std::vector<WelshVoice> init((size_t)wv);
+    memset(init.data(), 0, init.size() * sizeof(WelshVoice));
+    for (auto& v : init) { v.n_on = kNever; v.n_off = kNever; v.anchor = 0; }
+    CUDA_TRY(e, cudaMemcpy(e->d_wvoice, init.data(), init.size() * sizeof(WelshVoice), cudaMemcpyHostToDevice));
+  }
+  if (fv) {
+    int rc = dev_alloc(e, &e->d_fvoice, (size_t)fv, false);
+    if (rc) return rc;
+    if ((rc = dev_alloc(e, &e->d_finst, e->h_finst.size()))) return rc;
+    std::vector<FmVoice> init((size_t)fv);
+    memset(init.data(), 0, init.size() * sizeof(FmVoice));
+    for (auto& v : init) { v.n_on = kNever; v.n_off = kNever; v.anchor = 0; }
+    CUDA_TRY(e, cudaMemcpy(e->d_fvoice, init.data(), init.size() * sizeof(FmVoice), cudaMemcpyHostToDevice));
+  }
+  // CTA work lists.  vpc: aim for about two CTAs per SM across all voices of a type.
+  auto plan_work = [&](int kind, int total_voices, DevBuf<CtaWork>& buf, int* count) -> int {
+    std::vector<CtaWork> work;
+    if (total_voices == 0) { *count = 0; return 0; }
+    int target = std::max(1, e->num_sms);
+    int vpc = std::max(kVoiceWarps, cdiv(total_voices, target));
+    vpc = cdiv(vpc, kVoiceWarps) * kVoiceWarps;
+    for (Node* n : e->plan) {
+      if (n->kind != kind) continue;
+      int ncta = cdiv(n->nvoices, vpc);
+      if (ncta > 1) {
+        int rc = dev_alloc(e, &n->scratch, (size_t)ncta * mb);
+        if (rc) return rc;
+      }
+      int per = cdiv(cdiv(n->nvoices, ncta), 1);
+      int v = 0;
+      for (int c = 0; c < ncta; ++c) {
+        CtaWork w;
+        w.inst = n->table_index;
+        w.voice0 = n->voice0 + v;
+        w.nvoices = std::min(per, n->nvoices - v);
+        w.pad = ncta;
+        w.out = ncta == 1 ? n->buf : n->scratch + (size_t)c * mb;
+        work.push_back(w);
+        v += w.nvoices;
+      }
+    }
+    if (!buf.reserve(work.size())) return fail(e, GB_ENOMEM, "out of memory");
+    memcpy(buf.h, work.data(), work.size() * sizeof(CtaWork));
+    CUDA_TRY(e, cudaMemcpy(buf.d, buf.h, work.size() * sizeof(CtaWork), cudaMemcpyHostToDevice));
+    *count = (int)work.size();
+    return 0;
+  };
+  int rc;
+  if ((rc = plan_work(GB_INST_WELSH, wv, e->wwork, &e->n_wwork))) return rc;
+  if ((rc = plan_work(GB_INST_FM, fv, e->fwork, &e->n_fwork))) return rc;
+  CUDA_TRY(e, cudaFuncSetAttribute(welsh_kernel<kVoiceWarps>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                   (int)(kVoiceWarps * kTileStride * sizeof(double2))));
+  CUDA_TRY(e, cudaFuncSetAttribute(fm_kernel<kVoiceWarps>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                   (int)(kVoiceWarps * kTileStride * sizeof(double2))));
+  CUDA_TRY(e, cudaStreamSynchronize(e->stream));
+  e->finalized = true;
+  e->winst_dirty = e->finst_dirty = true;
+  return 0;
+}
+
+int gb_push_events(gb_engine* e, const gb_event* ev, size_t n) {
+  if (!e || (!ev && n)) return GB_EINVAL;
+  for (size_t i = 0; i < n; ++i) {
+    if (ev[i].frame < e->pos) return fail(e, GB_EINVAL, "event frame %lld is in the past (position %lld)",
+                                          (long long)ev[i].frame, (long long)e->pos);
+    if (!find(e, ev[i].uid)) return fail(e, GB_ENOENT, "event targets unknown uid %u", ev[i].uid);
+  }
+  e->events.insert(e->events.end(), ev, ev + n);
+  std::stable_sort(e->events.begin(), e->events.end(),
+                   [](const gb_event& a, const gb_event& b) { return a.frame < b.frame; });
+  return 0;
+}
+
+}  // extern "C"
+
+namespace {
+
+struct ControlPoint {
+  int t;  // chunk-relative frame
+  int index;
+  double raw;
+};
+
+// Render one chunk of `frames` (<= max_block) frames starting at e->pos.  Events for the chunk are
+// e->events[0 .. n_ev).
+int render_chunk(gb_engine* e, int frames, size_t n_ev) {
+  const int64_t f0 = e->pos;
+  // ---- 1. resolve events ----
+  std::vector<std::vector<VoiceEvent>> wlists((size_t)e->n_wvoice), flists((size_t)e->n_fvoice);
+  std::map<Node*, std::vector<ControlPoint>> controls;
+  bool any_w = false, any_f = false;
+  for (size_t i = 0; i < n_ev; ++i) {
+    const gb_event& ev = e->events[i];
+    Node* n = find(e, ev.uid);
+    if (!n || n->order < 0) continue;  // unpatched entities never render (orchestrator.rs:378-430)
+    const int64_t f = std::max(ev.frame, f0);
+    if (ev.type == GB_EV_NOTE_ON || ev.type == GB_EV_NOTE_OFF) {
+      const bool on = ev.type == GB_EV_NOTE_ON;
+      const int key = ev.a;
+      if (n->kind == GB_INST_WELSH || n->kind == GB_INST_FM) {
+        auto& lists = n->kind == GB_INST_WELSH ? wlists : flists;
+        (n->kind == GB_INST_WELSH ? any_w : any_f) = true;
+        if (on) {
+          int v = n->store.note_on(f, key);
+          VoiceEvent ve;
+          ve.frame = f; ve.type = VEV_NOTE_ON; ve.pad = 0;
+          if (n->kind == GB_INST_WELSH) {
+            const gb_oscillator_params& o1 = n->wp.oscillator_1;
+            const gb_oscillator_params& o2 = n->wp.oscillator_2;
+            ve.cyc1 = (o1.fixed_frequency > 0.0 ? o1.fixed_frequency : note_hz(key) * o1.frequency_tune) / e->sr;
+            ve.cyc2 = (o2.fixed_frequency > 0.0 ? o2.fixed_frequency : note_hz(key) * o2.frequency_tune) / e->sr;
+          } else {
+            ve.cyc1 = note_hz(key) / e->sr;
+            ve.cyc2 = ve.cyc1 * n->fp.ratio;
+          }
+          lists[(size_t)(n->voice0 + v)].push_back(ve);
+        } else {
+          for (size_t s = 0; s < n->store.slots.size(); ++s) {
+            Slot& sl = n->store.slots[s];
+            if (sl.key == key && sl.held) {
+              sl.held = false;
+              sl.idle_at = f + n->release_frames;
+              VoiceEvent ve;
+              ve.frame = f; ve.type = VEV_NOTE_OFF; ve.pad = 0; ve.cyc1 = 0.0; ve.cyc2 = 0.0;
+              lists[(size_t)n->voice0 + s].push_back(ve);
+            }
+          }
+        }
+      } else if (n->kind == GB_INST_SAMPLER) {
+        if (n->samples.empty()) continue;
+        if (on) {
+          int v = n->store.note_on(f, key);
+          const SampleDev& s = n->samples[0];
+          SampleVoiceHost& sv = n->svoices[(size_t)v];
+          // a retriggered voice's previous play ends here: record it if it overlaps this chunk
+          sv.sample = 0;
+          sv.step_q = step_to_q32(note_hz(key) / s.root_hz * (s.sr / e->sr));
+          sv.n_on = f;
+          sv.n_end = f + frames_until_end(s.n, sv.step_q);
+          n->store.slots[(size_t)v].idle_at = sv.n_end;
+        } else {
+          for (size_t s = 0; s < n->store.slots.size(); ++s) {
+            Slot& sl = n->store.slots[s];
+            if (sl.key == key && sl.held) {
+              sl.held = false;
+              sl.idle_at = f;
+              if (f < n->svoices[s].n_end) n->svoices[s].n_end = f;
+            }
+          }
+        }
+      } else if (n->kind == GB_INST_DRUMKIT) {
+        if (!on || key < 0 || key >= 128 || n->key_to_voice[key] < 0) continue;
+        SampleVoiceHost& sv = n->svoices[(size_t)n->key_to_voice[key]];
+        const SampleDev& s = n->samples[(size_t)sv.sample];
+        sv.step_q = step_to_q32(s.sr / e->sr);
+        sv.n_on = f;
+        sv.n_end = f + frames_until_end(s.n, sv.step_q);
+      }
+    } else if (ev.type == GB_EV_CONTROL || ev.type == GB_EV_SET_PARAM) {
+      if (!effect_accepts(n, ev.a)) continue;
+      ControlPoint cp;
+      cp.t = (int)(f - f0);
+      cp.index = ev.a;
+      cp.raw = ev.type == GB_EV_CONTROL ? control_to_raw(n, ev.a, ev.value) : ev.value;
+      controls[n].push_back(cp);
+    }
+  }
+  e->events.erase(e->events.begin(), e->events.begin() + (long)n_ev);
+
+  // NOTE on sampler retriggers inside a chunk: a voice restarted twice in one chunk keeps only the
+  // latest play above.  Plays are therefore snapshotted per event below via `pending_plays`.
+  // (handled by render splitting chunks at sampler note-ons; see split_points in gb_render.)
+
+  // ---- 2. instrument parameter changes (DCA) apply at the chunk start (chunks are split there) ----
+  for (auto& kv : controls) {
+    Node* n = kv.first;
+    if (!n->is_inst) continue;
+    for (const ControlPoint& cp : kv.second) {
+      if (n->kind == GB_INST_WELSH) {
+        if (cp.index == GB_CTL_INST_DCA_GAIN) n->wp.dca.gain = cp.raw; else n->wp.dca.pan = cp.raw;
+        e->winst_dirty = true;
+      } else if (n->kind == GB_INST_FM) {
+        if (cp.index == GB_CTL_INST_DCA_GAIN) n->fp.dca.gain = cp.raw; else n->fp.dca.pan = cp.raw;
+        e->finst_dirty = true;
+      }
+    }
+  }
+
+  // ---- 3. voices ----
+  auto upload_events = [&](std::vector<std::vector<VoiceEvent>>& lists, DevBuf<VoiceEvent>& evb, DevBuf<int>& offb,
+                           bool any) -> int {
+    size_t nv = lists.size(), total = 0;
+    if (!offb.reserve(nv + 1)) return fail(e, GB_ENOMEM, "out of memory");
+    if (any)
+      for (auto& l : lists) total += l.size();
+    if (!evb.reserve(total + 1)) return fail(e, GB_ENOMEM, "out of memory");
+    size_t k = 0;
+    for (size_t v = 0; v < nv; ++v) {
+      offb.h[v] = (int)k;
+      if (any)
+        for (auto& x : lists[v]) evb.h[k++] = x;
+    }
+    offb.h[nv] = (int)k;
+    CUDA_TRY(e, cudaMemcpyAsync(offb.d, offb.h, (nv + 1) * sizeof(int), cudaMemcpyHostToDevice, e->stream));
+    e->stats.h2d_bytes += (nv + 1) * sizeof(int);
+    if (k) {
+      CUDA_TRY(e, cudaMemcpyAsync(evb.d, evb.h, k * sizeof(VoiceEvent), cudaMemcpyHostToDevice, e->stream));
+      e->stats.h2d_bytes += k * sizeof(VoiceEvent);
+    }
+    return 0;
+  };
+  const size_t tile_bytes = (size_t)kVoiceWarps * kTileStride * sizeof(double2);
+  if (e->n_wvoice) {
+    if (e->winst_dirty) {
+      for (Node* n : e->plan)
+        if (n->kind == GB_INST_WELSH) welsh_inst_from_params(*n, e->sr, &e->h_winst[(size_t)n->table_index]);
+      CUDA_TRY(e, cudaMemcpyAsync(e->d_winst, e->h_winst.data(), e->h_winst.size() * sizeof(WelshInst),
+                                  cudaMemcpyHostToDevice, e->stream));
+      CUDA_TRY(e, cudaStreamSynchronize(e->stream));  // h_winst is pageable
+      e->stats.h2d_bytes += e->h_winst.size() * sizeof(WelshInst);
+      e->winst_dirty = false;
+    }
+    int rc = upload_events(wlists, e->wev, e->wev_off, any_w);
+    if (rc) return rc;
+    {
+      Launch l(e, true);
+      welsh_kernel<kVoiceWarps><<<e->n_wwork, 32 * kVoiceWarps, tile_bytes, e->stream>>>(
+          e->d_winst, e->d_wvoice, e->wwork.d, e->wev.d, e->wev_off.d, f0, frames);
+    }
+    e->stats.voice_samples += (uint64_t)e->n_wvoice * (uint64_t)frames;
+  }
+  if (e->n_fvoice) {
+    if (e->finst_dirty) {
+      for (Node* n : e->plan)
+        if (n->kind == GB_INST_FM) fm_inst_from_params(*n, e->sr, &e->h_finst[(size_t)n->table_index]);
+      CUDA_TRY(e, cudaMemcpyAsync(e->d_finst, e->h_finst.data(), e->h_finst.size() * sizeof(FmInst),
+                                  cudaMemcpyHostToDevice, e->stream));
+      CUDA_TRY(e, cudaStreamSynchronize(e->stream));
+      e->stats.h2d_bytes += e->h_finst.size() * sizeof(FmInst);
+      e->finst_dirty = false;
+    }
+    int rc = upload_events(flists, e->fev, e->fev_off, any_f);
+    if (rc) return rc;
+    {
+      Launch l(e, true);
+      fm_kernel<kVoiceWarps><<<e->n_fwork, 32 * kVoiceWarps, tile_bytes, e->stream>>>(
+          e->d_finst, e->d_fvoice, e->fwork.d, e->fev.d, e->fev_off.d, f0, frames);
+    }
+    e->stats.voice_samples += (uint64_t)e->n_fvoice * (uint64_t)frames;
+  }
+  // samplers / drumkits / toy sources: one launch per instrument
+  {
+    size_t total = 0;
+    for (Node* n : e->plan)
+      if (n->kind == GB_INST_SAMPLER || n->kind == GB_INST_DRUMKIT) total += n->svoices.size();
+    if (!e->plays.reserve(total + 1)) return fail(e, GB_ENOMEM, "out of memory");
+    size_t k = 0;
+    std::vector<std::pair<Node*, std::pair<size_t, int>>> launches;
+    for (Node* n : e->plan) {
+      if (n->kind != GB_INST_SAMPLER && n->kind != GB_INST_DRUMKIT) continue;
+      size_t k0 = k;
+      for (const SampleVoiceHost& sv : n->svoices) {
+        if (sv.sample < 0 || sv.n_end <= f0 || sv.n_on >= f0 + frames) continue;
+        const SampleDev& s = n->samples[(size_t)sv.sample];
+        SamplePlay pl;
+        pl.n_on = sv.n_on; pl.n_end = sv.n_end; pl.step_q = sv.step_q;
+        pl.data = s.d; pl.len = s.n; pl.channels = s.channels; pl.pad = 0;
+        e->plays.h[k++] = pl;
+      }
+      launches.push_back({n, {k0, (int)(k - k0)}});
+    }
+    if (k) {
+      CUDA_TRY(e, cudaMemcpyAsync(e->plays.d, e->plays.h, k * sizeof(SamplePlay), cudaMemcpyHostToDevice, e->stream));
+      e->stats.h2d_bytes += k * sizeof(SamplePlay);
+    }
+    for (auto& L : launches) {
+      Launch l(e, true);
+      sampler_kernel<<<cdiv(frames, 256), 256, 0, e->stream>>>(e->plays.d + L.second.first, L.second.second,
+                                                                L.first->buf, f0, frames);
+      e->stats.voice_samples += (uint64_t)L.first->svoices.size() * (uint64_t)frames;
+    }
+  }
+  // ---- 4. plan walk: partial sums of split instruments, toy sources, effects ----
+  for (Node* n : e->plan) {
+    if (n->is_inst) {
+      if (n->kind == GB_INST_TOY_SOURCE) {
+        Launch l(e, false);
+        fill_kernel<<<cdiv(frames, 256), 256, 0, e->stream>>>(n->buf, frames, n->tp.level_left, n->tp.level_right);
+      } else if ((n->kind == GB_INST_WELSH || n->kind == GB_INST_FM) && n->scratch) {
+        // instrument split over several CTAs: sum its partials (left to right)
+        const CtaWork* wk = n->kind == GB_INST_WELSH ? e->wwork.h : e->fwork.h;
+        int cnt = n->kind == GB_INST_WELSH ? e->n_wwork : e->n_fwork;
+        std::vector<const double2*> parts;
+        for (int i = 0; i < cnt; ++i)
+          if (wk[i].inst == n->table_index) parts.push_back(wk[i].out);
+        size_t i = 0;
+        bool first = true;
+        while (i < parts.size()) {
+          SourceList sl;
+          memset(&sl, 0, sizeof sl);
+          if (!first) sl.p[sl.n++] = n->buf;
+          while (i < parts.size() && sl.n < kMaxSources) sl.p[sl.n++] = parts[i++];
+          Launch l(e, false);
+          pointwise_kernel<<<cdiv(frames, 256), 256, 0, e->stream>>>(sl, n->buf, 0, frames, OP_SUM, 0.0, 0.0);
+          first = false;
+        }
+      }
+      continue;
+    }
+    SourceList src;
+    int rc = gather_sources(e, n, frames, &src);
+    if (rc) return rc;
+    if (n->kind == GB_FX_DELAY) {
+      {
+        Launch l(e, false);
+        delay_kernel<<<cdiv(frames, 256), 256, 0, e->stream>>>(src, n->hist[n->hist_cur], std::max(n->delay_frames, 1),
+                                                                n->delay_frames, n->buf, frames);
+      }
+      if (n->delay_frames > 0) {
+        Launch l(e, false);
+        history_update_kernel<<<cdiv(n->delay_frames, 256), 256, 0, e->stream>>>(
+            src, n->hist[n->hist_cur], n->hist[n->hist_cur ^ 1], n->delay_frames, frames);
+        n->hist_cur ^= 1;
+      }
+      continue;
+    }
+    // parameter segments
+    std::vector<ControlPoint> cps;
+    auto it = controls.find(n);
+    if (it != controls.end()) cps = it->second;
+    std::stable_sort(cps.begin(), cps.end(), [](const ControlPoint& a, const ControlPoint& b) { return a.t < b.t; });
+    int t = 0;
+    size_t ci = 0;
+    while (t < frames) {
+      while (ci < cps.size() && cps[ci].t <= t) {
+        effect_apply_param(e, n, cps[ci].index, cps[ci].raw);
+        ++ci;
+      }
+      int t1 = ci < cps.size() ? std::min(cps[ci].t, frames) : frames;
+      rc = run_effect_segment(e, n, src, frames, t, t1, f0);
+      if (rc) return rc;
+      t = t1;
+    }
+    if (n->kind == GB_FX_CHORUS && n->delay_frames > 0) {
+      Launch l(e, false);
+      history_update_kernel<<<cdiv(n->delay_frames, 256), 256, 0, e->stream>>>(
+          src, n->hist[n->hist_cur], n->hist[n->hist_cur ^ 1], n->delay_frames, frames);
+      n->hist_cur ^= 1;
+    }
+  }
+  CUDA_TRY(e, cudaGetLastError());
+  Node* root = find(e, GB_MAIN_MIXER);
+  e->last_out = root->buf;
+  e->last_frames = (size_t)frames;
+  e->pos += frames;
+  return 0;
+}
+
+enum OutMode { OUT_F64, OUT_PCM16, OUT_DEVICE };
+
+// Split the request into chunks: at most max_block frames, and never across an event that the
+// chunk kernels take as constant (instrument DCA changes, sampler/drumkit note-ons after the first
+// at a given voice).
+int render_impl(gb_engine* e, void* out, size_t frames, size_t* done, OutMode mode) {
+  if (!e) return GB_EINVAL;
+  if (!e->finalized) return fail(e, GB_ESTATE, "engine is not finalized");
+  if (frames && !out && mode != OUT_DEVICE) return fail(e, GB_EINVAL, "null output buffer");
+  cudaSetDevice(e->device);
+  if (mode == OUT_DEVICE || mode == OUT_PCM16) {
+    if (frames > e->full_cap) {
+      if (e->d_full) cudaFree(e->d_full);
+      e->d_full = nullptr;
+      e->full_cap = 0;
+      CUDA_TRY(e, cudaMalloc(&e->d_full, std::max<size_t>(frames, 1) * sizeof(double2)));
+      e->full_cap = frames;
+    }
+  }
+  size_t produced = 0;
+  while (produced < frames) {
+    const int64_t f0 = e->pos;
+    int64_t limit = (int64_t)std::min<size_t>(frames - produced, e->max_block);
+    // find the split point, then take every event strictly before the chunk end
+    for (size_t i = 0; i < e->events.size() && e->events[i].frame < f0 + limit; ++i) {
+      const gb_event& ev = e->events[i];
+      if (ev.frame <= f0) continue;
+      Node* n = find(e, ev.uid);
+      if (!n || n->order < 0) continue;
+      bool split = false;
+      if (n->is_inst && (ev.type == GB_EV_CONTROL || ev.type == GB_EV_SET_PARAM)) split = true;
+      if ((n->kind == GB_INST_SAMPLER || n->kind == GB_INST_DRUMKIT) &&
+          (ev.type == GB_EV_NOTE_ON || ev.type == GB_EV_NOTE_OFF))
+        split = true;  // sampler plays are constant per chunk: a (re)trigger starts a new chunk
+      if (split) {
+        limit = ev.frame - f0;
+        break;
+      }
+    }
+    size_t n_ev = 0;
+    while (n_ev < e->events.size() && e->events[n_ev].frame < f0 + limit) ++n_ev;
+    int rc = render_chunk(e, (int)limit, n_ev);
+    if (rc) return rc;
+    const size_t n = (size_t)limit;
+    if (mode == OUT_F64) {
+      CUDA_TRY(e, cudaMemcpyAsync((double*)out + 2 * produced, e->last_out, n * sizeof(double2), cudaMemcpyDeviceToHost,
+                                  e->stream));
+      CUDA_TRY(e, cudaStreamSynchronize(e->stream));
+      e->stats.d2h_bytes += n * sizeof(double2);
+    } else {
+      CUDA_TRY(e, cudaMemcpyAsync(e->d_full + produced, e->last_out, n * sizeof(double2), cudaMemcpyDeviceToDevice,
+                                  e->stream));
+      CUDA_TRY(e, cudaStreamSynchronize(e->stream));
+    }
+    produced += n;
+  }
+  if (mode == OUT_PCM16 && frames) {
+    if (frames > e->pcm_cap) {
+      if (e->d_pcm) cudaFree(e->d_pcm);
+      e->d_pcm = nullptr;
+      e->pcm_cap = 0;
+      CUDA_TRY(e, cudaMalloc(&e->d_pcm, frames * sizeof(short2)));
+      e->pcm_cap = frames;
+    }
+    {
+      Launch l(e, false);
+      pcm16_kernel<<<cdiv((int)frames, 256), 256, 0, e->stream>>>(e->d_full, e->d_pcm, (int)frames);
+    }
+    CUDA_TRY(e, cudaMemcpyAsync(out, e->d_pcm, frames * sizeof(short2), cudaMemcpyDeviceToHost, e->stream));
+    CUDA_TRY(e, cudaStreamSynchronize(e->stream));
+    e->stats.d2h_bytes += frames * sizeof(short2);
+  }
+  e->full_frames = mode != OUT_F64 ? frames : 0;
+  if (done) *done = produced;
+  return 0;
+}
+
+}  // namespace
+
+extern "C" {
+
+int gb_render_block(gb_engine* e, double* out, size_t frames, size_t* done) {
+  return render_impl(e, out, frames, done, OUT_F64);
+}
+int gb_render_pcm16(gb_engine* e, int16_t* out, size_t frames, size_t* done) {
+  return render_impl(e, out, frames, done, OUT_PCM16);
+}
+int gb_render_device(gb_engine* e, size_t frames, size_t* done) {
+  return render_impl(e, nullptr, frames, done, OUT_DEVICE);
+}
+int gb_read_last(gb_engine* e, double* out, size_t frames) {
+  if (!e || !out) return GB_EINVAL;
+  if (!e->d_full || frames > e->full_frames) return fail(e, GB_ESTATE, "no device-resident render of that size");
+  cudaSetDevice(e->device);
+  CUDA_TRY(e, cudaMemcpy(out, e->d_full, frames * sizeof(double2), cudaMemcpyDeviceToHost));
+  e->stats.d2h_bytes += frames * sizeof(double2);
+  return 0;
+}
+int64_t gb_position(const gb_engine* e) { return e ? e->pos : -1; }
+
+// ---- state save / restore -------------------------------------------------------------------
+// Layout: header {magic, pos, n_wvoice, n_fvoice, n_nodes} then device voice tables, then per plan
+// node its host allocation state and device effect state.  Only valid for an engine built by the
+// same sequence of add/patch/finalize calls.
+}  // extern "C"
+namespace {
+struct Blob {
+  std::vector<uint8_t> data;
+  template <typename T>
+  void put(const T& v) {
+    const uint8_t* p = (const uint8_t*)&v;
+    data.insert(data.end(), p, p + sizeof(T));
+  }
+  void put_bytes(const void* p, size_t n) { data.insert(data.end(), (const uint8_t*)p, (const uint8_t*)p + n); }
+};
+struct Reader {
+  const uint8_t* p;
+  size_t left;
+  bool ok = true;
+  template <typename T>
+  void get(T* v) { get_bytes(v, sizeof(T)); }
+  void get_bytes(void* dst, size_t n) {
+    if (n > left) { ok = false; return; }
+    memcpy(dst, p, n);
+    p += n; left -= n;
+  }
+};
+int dev_to_blob(gb_engine* e, Blob& b, const void* d, size_t bytes) {
+  std::vector<uint8_t> tmp(bytes);
+  if (bytes) CUDA_TRY(e, cudaMemcpy(tmp.data(), d, bytes, cudaMemcpyDeviceToHost));
+  b.put_bytes(tmp.data(), bytes);
+  return 0;
+}
+int blob_to_dev(gb_engine* e, Reader& r, void* d, size_t bytes) {
+  std::vector<uint8_t> tmp(bytes);
+  r.get_bytes(tmp.data(), bytes);
+  if (!r.ok) return fail(e, GB_EINVAL, "state blob truncated");
+  if (bytes) CUDA_TRY(e, cudaMemcpy(d, tmp.data(), bytes, cudaMemcpyHostToDevice));
+  return 0;
+}
+template <typename F>
+int for_each_state_region(gb_engine* e, F&& fn) {
+  int rc;
+  if (e->n_wvoice && (rc = fn(e->d_wvoice, (size_t)e->n_wvoice * sizeof(WelshVoice)))) return rc;
+  if (e->n_fvoice && (rc = fn(e->d_fvoice, (size_t)e->n_fvoice * sizeof(FmVoice)))) return rc;
+  for (Node* n : e->plan) {
+    if (n->d_bq && (rc = fn(n->d_bq, sizeof(BiquadState)))) return rc;
+    if (n->d_lp && (rc = fn(n->d_lp, sizeof(Lp24State)))) return rc;
+    if (n->hist[0]) {
+      size_t len = (size_t)std::max(n->delay_frames, 1) * sizeof(double2);
+      if ((rc = fn(n->hist[n->hist_cur], len))) return rc;
+    }
+    if (n->kind == GB_FX_REVERB) {
+      for (int ch = 0; ch < 2; ++ch) {
+        for (int i = 0; i < 4; ++i)
+          if ((rc = fn(n->rv.comb_ring[ch][i], (size_t)n->rv.comb_d[i] * sizeof(double)))) return rc;
+        for (int i = 0; i < 2; ++i)
+          if ((rc = fn(n->rv.ap_ring[ch][i], (size_t)n->rv.ap_d[i] * sizeof(double)))) return rc;
+      }
+    }
+  }
+  return 0;
+}
+}  // namespace
+extern "C" {
+
+int gb_save_state(gb_engine* e, void* buf, size_t* size) {
+  if (!e || !size) return GB_EINVAL;
+  if (!e->finalized) return fail(e, GB_ESTATE, "engine is not finalized");
+  cudaSetDevice(e->device);
+  CUDA_TRY(e, cudaStreamSynchronize(e->stream));
+  Blob b;
+  uint64_t magic = 0x31305453424700ull;  // "GBST01"
+  b.put(magic);
+  b.put(e->pos);
+  b.put(e->n_wvoice);
+  b.put(e->n_fvoice);
+  uint32_t nplan = (uint32_t)e->plan.size();
+  b.put(nplan);
+  for (Node* n : e->plan) {
+    b.put(n->uid);
+    b.put(n->p);
+    b.put(n->wp.dca);
+    b.put(n->fp.dca);
+    uint32_t ns = (uint32_t)n->store.slots.size();
+    b.put(ns);
+    for (auto& s : n->store.slots) b.put(s);
+    uint32_t nsv = (uint32_t)n->svoices.size();
+    b.put(nsv);
+    for (auto& s : n->svoices) b.put(s);
+  }
+  uint64_t nev = e->events.size();
+  b.put(nev);
+  for (auto& ev : e->events) b.put(ev);
+  int rc = for_each_state_region(e, [&](void* d, size_t bytes) { return dev_to_blob(e, b, d, bytes); });
+  if (rc) return rc;
+  if (!buf) {
+    *size = b.data.size();
+    return 0;
+  }
+  if (*size < b.data.size()) return fail(e, GB_EINVAL, "state buffer too small");
+  memcpy(buf, b.data.data(), b.data.size());
+  *size = b.data.size();
+  return 0;
+}
+
+int gb_restore_state(gb_engine* e, const void* buf, size_t size) {
+  if (!e || !buf) return GB_EINVAL;
+  if (!e->finalized) return fail(e, GB_ESTATE, "engine is not finalized");
+  cudaSetDevice(e->device);
+  CUDA_TRY(e, cudaStreamSynchronize(e->stream));
+  Reader r{(const uint8_t*)buf, size};
+  uint64_t magic = 0;
+  int nw = 0, nf = 0;
+  uint32_t nplan = 0;
+  int64_t pos = 0;
+  r.get(&magic); r.get(&pos); r.get(&nw); r.get(&nf); r.get(&nplan);
+  if (!r.ok || magic != 0x31305453424700ull || nw != e->n_wvoice || nf != e->n_fvoice || nplan != e->plan.size())
+    return fail(e, GB_EINVAL, "state blob does not match this engine");
+  for (Node* n : e->plan) {
+    uint32_t uid = 0, ns = 0, nsv = 0;
+    r.get(&uid);
+    if (!r.ok || uid != n->uid) return fail(e, GB_EINVAL, "state blob does not match this engine's plan");
+    r.get(&n->p);
+    r.get(&n->wp.dca);
+    r.get(&n->fp.dca);
+    r.get(&ns);
+    if (ns != n->store.slots.size()) return fail(e, GB_EINVAL, "state blob voice-store mismatch");
+    for (auto& s : n->store.slots) r.get(&s);
+    r.get(&nsv);
+    if (nsv != n->svoices.size()) return fail(e, GB_EINVAL, "state blob sample-voice mismatch");
+    for (auto& s : n->svoices) r.get(&s);
+  }
+  uint64_t nev = 0;
+  r.get(&nev);
+  if (!r.ok || nev > r.left / sizeof(gb_event)) return fail(e, GB_EINVAL, "state blob truncated");
+  e->events.resize((size_t)nev);
+  for (auto& ev : e->events) r.get(&ev);
+  int rc = for_each_state_region(e, [&](void* d, size_t bytes) { return blob_to_dev(e, r, d, bytes); });
+  if (rc) return rc;
+  e->pos = pos;
+  e->winst_dirty = e->finst_dirty = true;
+  return 0;
+}
+
+// ---- measurement ------------------------------------------------------------------------------
+int gb_get_stats(gb_engine* e, gb_stats* out) {
+  if (!e || !out) return GB_EINVAL;
+  *out = e->stats;
+  return 0;
+}
+int gb_reset_stats(gb_engine* e) {
+  if (!e) return GB_EINVAL;
+  memset(&e->stats, 0, sizeof e->stats);
+  return 0;
+}
+int gb_set_timing(gb_engine* e, int32_t enabled) {
+  if (!e) return GB_EINVAL;
+  e->timing = enabled != 0;
+  return 0;
+}
+int gb_measure_fma_peak(gb_engine* e, int32_t fp64, double* tflops) {
+  if (!e || !tflops) return GB_EINVAL;
+  cudaSetDevice(e->device);
+  const int blocks = e->num_sms * 16, threads = 256, iters = 1 << 14;
+  void* d = nullptr;
+  CUDA_TRY(e, cudaMalloc(&d, (size_t)blocks * threads * sizeof(double)));
+  cudaEvent_t a, b;
+  cudaEventCreate(&a);
+  cudaEventCreate(&b);
+  float best = 1e30f;
+  for (int rep = 0; rep < 5; ++rep) {
+    cudaEventRecord(a, e->stream);
+    if (fp64) fma_peak_kernel<double><<<blocks, threads, 0, e->stream>>>((double*)d, iters);
+    else fma_peak_kernel<float><<<blocks, threads, 0, e->stream>>>((float*)d, iters);
+    cudaEventRecord(b, e->stream);
+    cudaEventSynchronize(b);
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, a, b);
+    if (rep > 0 && ms < best) best = ms;
+  }
+  cudaEventDestroy(a);
+  cudaEventDestroy(b);
+  cudaFree(d);
+  CUDA_TRY(e, cudaGetLastError());
+  double flops = (double)blocks * threads * (double)iters * 8.0 * 2.0;
+  *tflops = flops / ((double)best * 1e-3) / 1e12;
+  return 0;
+}
+
+}  // extern "C"

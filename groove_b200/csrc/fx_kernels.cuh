@@ -1,0 +1,380 @@
+// fx_kernels.cuh — stream effects over stereo f64 chunks (double2 = one StereoSample).
+//
+// Each kernel replaces `transform_audio(StereoSample)` called once per frame
+// (orchestration/src/orchestrator.rs:446-456) by one pass over the whole chunk:
+//   * memoryless effects (mixer/gain/limiter/bitcrusher/compressor) are fused with the summation
+//     of their inputs: 16 B read per source + 16 B write per frame;
+//   * IIR filters are 2x2 affine recurrences scanned across a CTA (lane chunk -> warp shuffle
+//     scan -> cross-warp combine through shared memory);
+//   * delay-line effects are evaluated polyphase: a recirculating line of D frames is D
+//     independent first-order recurrences, one thread each, with no scan at all.
+#pragma once
+
+#include "dsp.cuh"
+
+namespace gbk {
+
+constexpr int kMaxSources = 8;
+struct SourceList {
+  const double2* p[kMaxSources];
+  int n;
+};
+
+__device__ __forceinline__ double2 sum_sources(const SourceList& s, int t) {
+  double l = 0.0, r = 0.0;
+#pragma unroll
+  for (int k = 0; k < kMaxSources; ++k) {
+    if (k < s.n) {
+      double2 v = s.p[k][t];
+      l += v.x; r += v.y;
+    }
+  }
+  return make_double2(l, r);
+}
+
+enum { OP_SUM = 0, OP_GAIN, OP_LIMITER, OP_BITCRUSHER, OP_COMPRESSOR };
+
+__device__ __forceinline__ double op_apply(int op, double x, double a, double b) {
+  switch (op) {
+    case OP_GAIN: return x * a;
+    case OP_LIMITER: {
+      double m = fabs(x);
+      m = m < a ? a : (m > b ? b : m);
+      return copysign(m, x);
+    }
+    case OP_BITCRUSHER: {
+      // a = 2^bits
+      double m = __ddiv_rn(__dmul_rn(floor(__ddiv_rn(__dmul_rn(fabs(x), 32767.0), a)), a), 32767.0);
+      return copysign(m, x);
+    }
+    case OP_COMPRESSOR: {
+      double m = fabs(x);
+      if (m > a) m = a + (m - a) * b;
+      return copysign(m, x);
+    }
+    default: return x;
+  }
+}
+
+// out[t] = op(sum of sources[t]) for t in [t0, t1)
+__global__ void __launch_bounds__(256) pointwise_kernel(SourceList src, double2* __restrict__ out, int t0, int t1,
+                                                         int op, double a, double b) {
+  int t = t0 + blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= t1) return;
+  double2 v = sum_sources(src, t);
+  out[t] = make_double2(op_apply(op, v.x, a, b), op_apply(op, v.y, a, b));
+}
+
+__global__ void __launch_bounds__(256) fill_kernel(double2* __restrict__ out, int n, double l, double r) {
+  int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t < n) out[t] = make_double2(l, r);
+}
+
+// f64 stereo -> 16-bit PCM: (x * 32767.0) as i16 — truncate toward zero, saturate, NaN -> 0
+// (orchestration/src/helpers.rs:78,90-91).
+__device__ __forceinline__ short pcm16_of(double x) {
+  double v = x * 32767.0;
+  if (v != v) return 0;
+  if (v >= 32767.0) return 32767;
+  if (v <= -32768.0) return -32768;
+  return (short)__double2int_rz(v);
+}
+__global__ void __launch_bounds__(256) pcm16_kernel(const double2* __restrict__ in, short2* __restrict__ out, int n) {
+  int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t < n) {
+    double2 v = in[t];
+    out[t] = make_short2(pcm16_of(v.x), pcm16_of(v.y));
+  }
+}
+
+// ---------------------------------------------------------------- IIR sections ---
+constexpr int kFxT = 8;
+constexpr int kFxWarps = 8;
+constexpr int kFxRound = kFxWarps * 32 * kFxT;  // frames per CTA round
+
+struct BiquadCoefs {  // a0-normalised RBJ coefficients, Direct Form 1
+  double b0, b1, b2, a1, a2;
+};
+struct BiquadState {  // per channel: x[n-1], x[n-2], y[n-1], y[n-2]
+  double x1[2], x2[2], y1[2], y2[2];
+};
+
+// Cross-warp exclusive combine: every warp publishes its aggregate; warp w composes 0..w-1.
+__device__ __forceinline__ void cta_entry_state(const Affine2& warp_total, Affine2* sh, int warp, int lane, double s0,
+                                                double s1, double& w0, double& w1, double& end0, double& end1) {
+  if (lane == 31) sh[warp] = warp_total;
+  __syncthreads();
+  double a = s0, b = s1;
+  for (int w = 0; w < kFxWarps; ++w) {
+    if (w == warp) { w0 = a; w1 = b; }
+    Affine2 m = sh[w];
+    double na = m.m00 * a + m.m01 * b + m.v0;
+    double nb = m.m10 * a + m.m11 * b + m.v1;
+    a = na; b = nb;
+  }
+  end0 = a; end1 = b;
+  __syncthreads();
+}
+
+// One launch = one biquad effect over frames [t0,t1) of the chunk with constant coefficients.
+// One CTA of kFxWarps warps; both channels per thread.
+__global__ void __launch_bounds__(32 * kFxWarps) biquad_df1_kernel(SourceList src, double2* __restrict__ out,
+                                                                    int t0, int t1, BiquadCoefs c,
+                                                                    BiquadState* __restrict__ state) {
+  __shared__ Affine2 sh[2][kFxWarps];
+  __shared__ double2 sx[kFxRound + 2];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  BiquadState st = *state;
+  for (int r0 = t0; r0 < t1; r0 += kFxRound) {
+    // stage the round's input (coalesced), with the two history frames in front
+    for (int i = threadIdx.x; i < kFxRound; i += blockDim.x) {
+      int t = r0 + i;
+      sx[i + 2] = t < t1 ? sum_sources(src, t) : make_double2(0.0, 0.0);
+    }
+    if (threadIdx.x == 0) {
+      sx[0] = make_double2(st.x2[0], st.x2[1]);
+      sx[1] = make_double2(st.x1[0], st.x1[1]);
+    }
+    __syncthreads();
+    const int base = (warp * 32 + lane) * kFxT;  // round-relative first frame of this lane
+    double yp[2][kFxT], g0[kFxT], g1[kFxT];
+    double p0[2] = {0.0, 0.0}, p1[2] = {0.0, 0.0};
+    double h00 = 1.0, h01 = 0.0, h10 = 0.0, h11 = 1.0;
+    int nvalid = t1 - (r0 + base);
+#pragma unroll
+    for (int j = 0; j < kFxT; ++j) {
+      if (j < nvalid) {
+        double2 x0 = sx[base + j + 2], xm1 = sx[base + j + 1], xm2 = sx[base + j];
+        double v[2] = {c.b0 * x0.x + c.b1 * xm1.x + c.b2 * xm2.x, c.b0 * x0.y + c.b1 * xm1.y + c.b2 * xm2.y};
+#pragma unroll
+        for (int ch = 0; ch < 2; ++ch) {
+          double y = v[ch] - c.a1 * p0[ch] - c.a2 * p1[ch];
+          yp[ch][j] = y;
+          p1[ch] = p0[ch];
+          p0[ch] = y;
+        }
+        // homogeneous: contribution of the entry state (y1,y2) to y[n] is row 0 of A^(j+1)
+        double t00 = -c.a1 * h00 - c.a2 * h10, t01 = -c.a1 * h01 - c.a2 * h11;
+        h10 = h00; h11 = h01;
+        h00 = t00; h01 = t01;
+        g0[j] = h00; g1[j] = h01;
+      } else {
+        yp[0][j] = 0.0; yp[1][j] = 0.0; g0[j] = 0.0; g1[j] = 0.0;
+      }
+    }
+    double e0[2], e1[2], endv0[2], endv1[2];
+#pragma unroll
+    for (int ch = 0; ch < 2; ++ch) {
+      Affine2 a;
+      a.m00 = h00; a.m01 = h01; a.m10 = h10; a.m11 = h11; a.v0 = p0[ch]; a.v1 = p1[ch];
+      Affine2 inc = affine_warp_scan(a, lane);
+      double w0, w1, ce0, ce1;
+      Affine2 tot = inc;  // lane 31 holds the warp total
+      cta_entry_state(tot, sh[ch], warp, lane, st.y1[ch], st.y2[ch], w0, w1, ce0, ce1);
+      double d0, d1;
+      affine_lane_entry(inc, lane, w0, w1, e0[ch], e1[ch], d0, d1);
+      endv0[ch] = ce0; endv1[ch] = ce1;
+    }
+#pragma unroll
+    for (int j = 0; j < kFxT; ++j) {
+      if (j < nvalid) {
+        double l = yp[0][j] + g0[j] * e0[0] + g1[j] * e1[0];
+        double r = yp[1][j] + g0[j] * e0[1] + g1[j] * e1[1];
+        out[r0 + base + j] = make_double2(l, r);
+      }
+    }
+    // carry state to the next round
+    int last = min(kFxRound, t1 - r0);  // frames in this round
+    double2 xl1 = sx[last + 1], xl2 = sx[last];
+    __syncthreads();
+    st.x1[0] = xl1.x; st.x1[1] = xl1.y;
+    st.x2[0] = xl2.x; st.x2[1] = xl2.y;
+    st.y1[0] = endv0[0]; st.y1[1] = endv0[1];
+    st.y2[0] = endv1[0]; st.y2[1] = endv1[1];
+  }
+  if (threadIdx.x == 0) *state = st;
+}
+
+// 24 dB low-pass effect: two transposed-DF2 sections with constant coefficients.
+struct Lp24Coefs {
+  SecCoef s1, s2;
+};
+struct Lp24State {
+  double s[2][4];
+};
+__global__ void __launch_bounds__(32 * kFxWarps) lp24_kernel(SourceList src, double2* __restrict__ out, int t0,
+                                                              int t1, Lp24Coefs c, Lp24State* __restrict__ state) {
+  __shared__ Affine2 sh[2][kFxWarps];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  Lp24State st = *state;
+  for (int r0 = t0; r0 < t1; r0 += kFxRound) {
+    const int base = r0 + (warp * 32 + lane) * kFxT;
+    int nvalid = t1 - base;
+    double sig[2][kFxT];
+#pragma unroll
+    for (int j = 0; j < kFxT; ++j) {
+      double2 v = j < nvalid ? sum_sources(src, base + j) : make_double2(0.0, 0.0);
+      sig[0][j] = v.x; sig[1][j] = v.y;
+    }
+#pragma unroll
+    for (int sec = 0; sec < 2; ++sec) {
+      const SecCoef k = sec == 0 ? c.s1 : c.s2;
+      double g0[kFxT], g1[kFxT];
+      double p0[2] = {0.0, 0.0}, p1[2] = {0.0, 0.0};
+      double h00 = 1.0, h01 = 0.0, h10 = 0.0, h11 = 1.0;
+#pragma unroll
+      for (int j = 0; j < kFxT; ++j) {
+        g0[j] = 0.0; g1[j] = 0.0;
+        if (j < nvalid) {
+#pragma unroll
+          for (int ch = 0; ch < 2; ++ch) {
+            double bx = k.b0 * sig[ch][j];
+            double y = bx + p0[ch];
+            sig[ch][j] = y;
+            double n0 = 2.0 * bx + k.a1 * y + p1[ch];
+            p1[ch] = bx + k.a2 * y;
+            p0[ch] = n0;
+          }
+          g0[j] = h00; g1[j] = h01;
+          double t00 = k.a1 * h00 + h10, t01 = k.a1 * h01 + h11;
+          h10 = k.a2 * h00; h11 = k.a2 * h01;
+          h00 = t00; h01 = t01;
+        }
+      }
+#pragma unroll
+      for (int ch = 0; ch < 2; ++ch) {
+        Affine2 a;
+        a.m00 = h00; a.m01 = h01; a.m10 = h10; a.m11 = h11; a.v0 = p0[ch]; a.v1 = p1[ch];
+        Affine2 inc = affine_warp_scan(a, lane);
+        double w0, w1, ce0, ce1, e0, e1, d0, d1;
+        cta_entry_state(inc, sh[ch], warp, lane, st.s[ch][2 * sec], st.s[ch][2 * sec + 1], w0, w1, ce0, ce1);
+        affine_lane_entry(inc, lane, w0, w1, e0, e1, d0, d1);
+        st.s[ch][2 * sec] = ce0; st.s[ch][2 * sec + 1] = ce1;
+#pragma unroll
+        for (int j = 0; j < kFxT; ++j) sig[ch][j] += g0[j] * e0 + g1[j] * e1;
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < kFxT; ++j)
+      if (j < nvalid) out[base + j] = make_double2(sig[0][j], sig[1][j]);
+  }
+  if (threadIdx.x == 0) *state = st;
+}
+
+// ------------------------------------------------------------- delay-line effects ---
+// `hist` holds the last `len` input frames before the chunk: hist[len-1] = x[chunk_start-1].
+__device__ __forceinline__ double2 delayed_input(const SourceList& src, const double2* hist, int len, int t, int d) {
+  int s = t - d;
+  if (s >= 0) return sum_sources(src, s);
+  return hist[len + s];
+}
+// Delay: y[n] = x[n-D]
+__global__ void __launch_bounds__(256) delay_kernel(SourceList src, const double2* __restrict__ hist, int len, int d,
+                                                     double2* __restrict__ out, int n) {
+  int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t < n) out[t] = d == 0 ? sum_sources(src, t) : delayed_input(src, hist, len, t, d);
+}
+// Chorus: y[n] = (1-w) x[n] + w * mean_i x[n - taps[i]]
+struct ChorusTaps {
+  int tap[64];
+  int nv;
+};
+__global__ void __launch_bounds__(256) chorus_kernel(SourceList src, const double2* __restrict__ hist, int len,
+                                                      ChorusTaps taps, double wet, double2* __restrict__ out, int t0,
+                                                      int t1) {
+  int t = t0 + blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= t1) return;
+  double2 x = sum_sources(src, t);
+  double al = 0.0, ar = 0.0;
+  for (int i = 0; i < taps.nv; ++i) {
+    double2 v = taps.tap[i] == 0 ? x : delayed_input(src, hist, len, t, taps.tap[i]);
+    al += v.x; ar += v.y;
+  }
+  double inv = (double)taps.nv;
+  out[t] = make_double2(__dadd_rn(__dmul_rn(1.0 - wet, x.x), __dmul_rn(wet, __ddiv_rn(al, inv))),
+                        __dadd_rn(__dmul_rn(1.0 - wet, x.y), __dmul_rn(wet, __ddiv_rn(ar, inv))));
+}
+// new_hist = last `len` frames of (hist ++ chunk input); written to a second buffer (ping-pong).
+__global__ void __launch_bounds__(256) history_update_kernel(SourceList src, const double2* __restrict__ hist,
+                                                              double2* __restrict__ new_hist, int len, int n) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= len) return;
+  int s = n - len + i;  // chunk-relative frame that lands in slot i
+  new_hist[i] = s >= 0 ? sum_sources(src, s) : hist[i + n];
+}
+
+// Reverb.  Recirculating comb:  y[n] = w[n-D],  w[n] = a*x[n] + g*w[n-D]   (ring[n mod D] holds w)
+// One thread per (channel, comb, residue); writes its comb's output into its own plane.
+struct ReverbDesc {
+  int comb_d[4];
+  double comb_g[4];
+  int ap_d[2];
+  double ap_g[2];
+  double* comb_ring[2][4];  // per channel, per comb: D doubles
+  double* ap_ring[2][2];
+};
+__global__ void __launch_bounds__(256) reverb_comb_kernel(SourceList src, ReverbDesc d, double attenuation,
+                                                           double* __restrict__ comb_out /* [2][4][n] */, int n,
+                                                           long long pos0, int t0, int t1) {
+  int comb = blockIdx.y & 3, ch = blockIdx.y >> 2;
+  int D = d.comb_d[comb];
+  int r = blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= D) return;
+  double g = d.comb_g[comb];
+  double* ring = d.comb_ring[ch][comb];
+  double* o = comb_out + ((size_t)(ch * 4 + comb)) * (size_t)n;
+  // first frame >= t0 whose ring slot ((pos0 + t) mod D) is r
+  int first = (int)((r - ((pos0 + t0) % D) + D) % D) + t0;
+  double w = ring[r];
+  for (int t = first; t < t1; t += D) {
+    double2 x = sum_sources(src, t);
+    double xa = (ch == 0 ? x.x : x.y) * attenuation;
+    o[t] = w;
+    w = __dadd_rn(xa, __dmul_rn(g, w));
+  }
+  ring[r] = w;
+}
+// All-pass:  y[n] = -g*x[n] + w[n-D],  w[n] = x[n] + g*y[n].  Stage 0 reads the 4 comb planes.
+__global__ void __launch_bounds__(256) reverb_allpass_kernel(const double* __restrict__ in /* planes */, int nplanes,
+                                                              size_t plane_stride, ReverbDesc d, int stage,
+                                                              double* __restrict__ out /* [2][n] */, int n,
+                                                              long long pos0, int t0, int t1) {
+  int ch = blockIdx.y;
+  int D = d.ap_d[stage];
+  int r = blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= D) return;
+  double g = d.ap_g[stage];
+  double* ring = d.ap_ring[ch][stage];
+  const double* ip = in + (size_t)ch * (size_t)nplanes * plane_stride;
+  double* o = out + (size_t)ch * (size_t)n;
+  int first = (int)((r - ((pos0 + t0) % D) + D) % D) + t0;
+  double w = ring[r];
+  for (int t = first; t < t1; t += D) {
+    double x = 0.0;
+    for (int p = 0; p < nplanes; ++p) x += ip[(size_t)p * plane_stride + t];
+    double y = __dadd_rn(__dmul_rn(-g, x), w);
+    o[t] = y;
+    w = __dadd_rn(x, __dmul_rn(g, y));
+  }
+  ring[r] = w;
+}
+__global__ void __launch_bounds__(256) interleave_kernel(const double* __restrict__ planes /* [2][n] */,
+                                                          double2* __restrict__ out, int n, int t0, int t1) {
+  int t = t0 + blockIdx.x * blockDim.x + threadIdx.x;
+  if (t < t1) out[t] = make_double2(planes[t], planes[(size_t)n + t]);
+}
+
+// ---------------------------------------------------------------- microbenchmark ---
+template <typename T>
+__global__ void __launch_bounds__(256) fma_peak_kernel(T* out, int iters) {
+  T a0 = (T)threadIdx.x * (T)1e-3, a1 = a0 + (T)1, a2 = a0 + (T)2, a3 = a0 + (T)3;
+  T a4 = a0 + (T)4, a5 = a0 + (T)5, a6 = a0 + (T)6, a7 = a0 + (T)7;
+  const T m = (T)0.999999, c = (T)1e-6;
+  for (int i = 0; i < iters; ++i) {
+    a0 = a0 * m + c; a1 = a1 * m + c; a2 = a2 * m + c; a3 = a3 * m + c;
+    a4 = a4 * m + c; a5 = a5 * m + c; a6 = a6 * m + c; a7 = a7 * m + c;
+  }
+  out[blockIdx.x * blockDim.x + threadIdx.x] = a0 + a1 + a2 + a3 + a4 + a5 + a6 + a7;
+}
+
+}  // namespace gbk

@@ -1,0 +1,653 @@
+// voice_kernels.cuh — instrument voices: Welsh subtractive synth, FM operator pair, sampler/drumkit.
+//
+// Work decomposition (replaces the reference's per-frame `tick(1)` + `value()` walk,
+// orchestration/src/orchestrator.rs:401-410):
+//   * one WARP per voice, marching over the render chunk in blocks of 32 lanes x T frames;
+//     lane l owns T consecutive frames, so lane order == time order.
+//   * everything that has a closed form per frame (oscillator phase, LFO, both ADSRs, the
+//     per-frame 24 dB coefficient set) is evaluated independently per frame;
+//   * the filter feedback is a time-varying 2x2 linear recurrence per section.  Each lane runs
+//     its T frames from a zero state while tracking the homogeneous response, the 32 lane
+//     aggregates are combined with a warp-shuffle scan of affine maps, and each lane then fixes
+//     its T outputs up with 2 FMAs per frame;
+//   * frequency-modulated phases (pitch LFO, FM carrier) are 64-bit integer prefix sums, scanned
+//     the same way (exact, so the result does not depend on the association order);
+//   * the W voices of a CTA are summed through shared memory, so per-voice audio never goes to
+//     HBM: one 16-byte store per frame per CTA.
+#pragma once
+
+#include "dsp.cuh"
+
+namespace gbk {
+
+constexpr int kT = 8;                 // frames per lane
+constexpr int kBlockFrames = 32 * kT; // frames per warp step
+constexpr int kTileStride = kBlockFrames + kBlockFrames / 8;  // padded (16-byte units)
+
+enum { VEV_NOTE_ON = 1, VEV_NOTE_OFF = 2 };
+
+struct VoiceEvent {
+  i64 frame;
+  int type;
+  int pad;
+  double cyc1, cyc2;  // base cycles per frame of oscillator 1 / 2 (FM: carrier / unused)
+};
+
+// ------------------------------------------------------------------------ Welsh ---
+struct WelshInst {
+  EnvShape amp, filt;
+  int w1, w2, wl, sync, routing, filter_mode, uid, voice0;
+  u64 duty1_q, duty2_q, dutyl_q, lfo_dq;
+  double duty1, duty2;
+  double mix, depth;
+  double cut_a, cut_b;
+  Lp24Ripple rp;
+  SecCoef fixed1, fixed2;
+  double gl, gr;
+  double pi_over_sr, sr;
+};
+enum { FILTER_FIXED = 0, FILTER_ENVELOPE = 1, FILTER_LFO = 2 };
+
+struct WelshVoice {
+  i64 n_on, n_off;
+  double la_on, la_off, lf_on, lf_off;
+  i64 anchor;       // frame at which p1/p2/pl are valid (closed-form path); LFO anchor always
+  u64 p1, p2, pl;   // PITCH path: p1/p2 are the phases at (chunk position - 1)
+  u64 d1, d2;
+  double cyc1, cyc2;
+  double s[4];
+};
+
+struct CtaWork {
+  int inst;       // index into the instrument table
+  int voice0;     // first voice (global index) handled by this CTA
+  int nvoices;    // any count; processed in rounds of W (warps per CTA)
+  int pad;
+  double2* out;   // chunk-relative output buffer (node buffer or a partial)
+};
+
+struct Phases {
+  u64 p1, p2, pl;
+};
+
+// Phases at frame m (m >= anchor-1) of an unmodulated voice, closed form.
+__device__ __forceinline__ Phases welsh_phases_at(const WelshVoice& st, const WelshInst& I, i64 m) {
+  Phases ph;
+  i64 k = m - st.anchor;
+  u64 uk = (u64)k;
+  ph.pl = st.pl + uk * I.lfo_dq;
+  ph.p1 = st.p1 + uk * st.d1;
+  ph.p2 = st.p2 + uk * st.d2;
+  if (I.sync && k > 0 && st.d1 != 0) {
+    // frames since oscillator 1 last wrapped; if that is after the anchor, oscillator 2 restarted there
+    u64 j = ph.p1 / st.d1;
+    if (j < uk) ph.p2 = j * st.d2;
+  }
+  return ph;
+}
+
+template <bool PITCH>
+__device__ __noinline__ WelshVoice welsh_fold(WelshVoice st, const WelshInst* Ip, VoiceEvent ev, bool* restart) {
+  // by value + noinline: note events are rare, so the call sites stay small and the caller's
+  // copy of the state stays in registers.  *restart = the oscillators restart (note-on of an idle voice)
+  const WelshInst& I = *Ip;
+  i64 f = ev.frame;
+  *restart = false;
+  if (ev.type == VEV_NOTE_ON) {
+    bool was = f >= st.n_on && f < st.n_off + I.amp.nr;
+    double la = 0.0, lf = 0.0;
+    if (was) {
+      la = env_level(I.amp, st.n_on, st.n_off, st.la_on, st.la_off, f);
+      lf = env_level(I.filt, st.n_on, st.n_off, st.lf_on, st.lf_off, f);
+      if (PITCH) {
+        st.pl += (u64)(f - 1 - st.anchor) * I.lfo_dq;
+      } else {
+        Phases ph = welsh_phases_at(st, I, f - 1);
+        st.p1 = ph.p1; st.p2 = ph.p2; st.pl = ph.pl;
+      }
+      st.anchor = f - 1;
+    } else {
+      st.pl = 0;
+      if (!PITCH) { st.p1 = 0; st.p2 = 0; }
+      st.anchor = f;
+    }
+    st.la_on = la; st.lf_on = lf;
+    st.n_on = f; st.n_off = kHeld;
+    st.cyc1 = ev.cyc1; st.cyc2 = ev.cyc2;
+    st.d1 = cycles_to_q(ev.cyc1); st.d2 = cycles_to_q(ev.cyc2);
+    *restart = !was;
+  } else {
+    st.la_off = env_pre(I.amp, st.n_on, st.la_on, f);
+    st.lf_off = env_pre(I.filt, st.n_on, st.lf_on, f);
+    st.n_off = f;
+  }
+  return st;
+}
+
+// One warp step: kBlockFrames frames of one voice starting at frame fb (absolute), valid frames < f_end.
+// `st` is the warp-uniform voice state at fb; on return it is the state at fb + kBlockFrames.
+// EV (warp-uniform) = this voice has note events inside the block; the EV=false instantiation is
+// the hot path and contains no event handling at all.
+template <bool PITCH, bool EV>
+__device__ __forceinline__ void welsh_block(WelshVoice& st, const WelshInst& I, const VoiceEvent* __restrict__ ev,
+                                            int& ei, int e_end, i64 fb, i64 f_end, int lane, u64 seed1, u64 seed2,
+                                            u64 seedl, double2* tile_row, bool accumulate) {
+  const i64 c0 = fb + (i64)lane * kT;
+  const i64 blk_end = fb + kBlockFrames;
+
+  // ---- lane-local note state: fold the events that precede this lane's chunk ----
+  WelshVoice ls = st;
+  int li = ei;
+  i64 next_ev = kHeld;
+  bool rs_dummy;
+  if (EV) {
+    while (li < e_end && ev[li].frame < c0) {
+      ls = welsh_fold<PITCH>(ls, &I, ev[li], &rs_dummy);
+      ++li;
+    }
+    next_ev = li < e_end ? ev[li].frame : kHeld;
+  }
+
+  double yp[kT], g0[kT], g1[kT], sb0[kT], sa1[kT], sa2[kT], ampf[kT];
+  unsigned play_bits = 0;
+
+  // ---- PITCH: pre-passes for the modulated phase increments and their (segmented) scans ----
+  double pf[PITCH ? kT : 1];
+  unsigned reset_bits = 0;  // bit j = oscillators restart at frame c0+j
+  u64 ent1 = 0, ent2 = 0;   // phases at c0-1
+  if (PITCH) {
+    WelshVoice ps = ls;
+    int pi = li;
+    i64 pnext = next_ev;
+    SegSum a1; a1.sum = 0; a1.reset = 0;
+    unsigned pplay = 0;
+#pragma unroll
+    for (int j = 0; j < kT; ++j) {
+      i64 n = c0 + j;
+      if (EV) {
+        while (n == pnext) {
+          bool rs;
+          ps = welsh_fold<true>(ps, &I, ev[pi], &rs);
+          if (rs) reset_bits |= 1u << j;
+          ++pi;
+          pnext = pi < e_end ? ev[pi].frame : kHeld;
+        }
+      }
+      bool play = n >= ps.n_on && n < ps.n_off + I.amp.nr && n < f_end;
+      double f = 1.0;
+      if (play) {
+        pplay |= 1u << j;
+        u64 pl = ps.pl + (u64)(n - ps.anchor) * I.lfo_dq;
+        double l = wave_value(I.wl, pl, I.dutyl_q, seedl, n);
+        f = exp2(l * I.depth);
+        if (reset_bits & (1u << j)) { a1.sum = 0; a1.reset = 1; }
+        else a1.sum += cycles_to_q(ps.cyc1 * f);
+      }
+      pf[j] = f;
+    }
+    SegSum inc1 = segsum_warp_scan(a1, lane);
+    SegSum ex1;
+    ex1.sum = __shfl_up_sync(0xffffffffu, inc1.sum, 1);
+    ex1.reset = __shfl_up_sync(0xffffffffu, inc1.reset, 1);
+    if (lane == 0) { ex1.sum = 0; ex1.reset = 0; }
+    ent1 = ex1.reset ? ex1.sum : st.p1 + ex1.sum;
+    u64 tot1 = inc1.reset ? inc1.sum : st.p1 + inc1.sum;
+    tot1 = __shfl_sync(0xffffffffu, tot1, 31);
+    // oscillator 2: restarts on note restarts and (hard sync) on oscillator-1 wraps
+    SegSum a2; a2.sum = 0; a2.reset = 0;
+    {
+      WelshVoice qs = ls;
+      int qi = li;
+      i64 qnext = next_ev;
+      u64 p1 = ent1;
+#pragma unroll
+      for (int j = 0; j < kT; ++j) {
+        i64 n = c0 + j;
+        if (EV) {
+          while (n == qnext) {
+            bool rs;
+            qs = welsh_fold<true>(qs, &I, ev[qi], &rs);
+            ++qi;
+            qnext = qi < e_end ? ev[qi].frame : kHeld;
+          }
+        }
+        if (pplay & (1u << j)) {
+          bool rs = (reset_bits >> j) & 1u;
+          u64 d1 = cycles_to_q(qs.cyc1 * pf[j]);
+          bool wrapped;
+          if (rs) { p1 = 0; wrapped = false; }
+          else { p1 += d1; wrapped = p1 < d1; }
+          if (rs || (I.sync && wrapped)) { a2.sum = 0; a2.reset = 1; }
+          else a2.sum += cycles_to_q(qs.cyc2 * pf[j]);
+        }
+      }
+    }
+    SegSum inc2 = segsum_warp_scan(a2, lane);
+    SegSum ex2;
+    ex2.sum = __shfl_up_sync(0xffffffffu, inc2.sum, 1);
+    ex2.reset = __shfl_up_sync(0xffffffffu, inc2.reset, 1);
+    if (lane == 0) { ex2.sum = 0; ex2.reset = 0; }
+    ent2 = ex2.reset ? ex2.sum : st.p2 + ex2.sum;
+    u64 tot2 = inc2.reset ? inc2.sum : st.p2 + inc2.sum;
+    tot2 = __shfl_sync(0xffffffffu, tot2, 31);
+    st.p1 = tot1;  // running phases at blk_end-1 (note folds do not touch p1/p2 on this path)
+    st.p2 = tot2;
+  }
+
+  // ---- pass 1: per-frame closed forms + section-1 response from a zero state ----
+  Phases ph;
+  if (PITCH) { ph.p1 = ent1; ph.p2 = ent2; ph.pl = 0; }
+  else ph = welsh_phases_at(ls, I, c0 - 1);
+  double ps0 = 0.0, ps1 = 0.0, h00 = 1.0, h01 = 0.0, h10 = 0.0, h11 = 1.0;
+#pragma unroll
+  for (int j = 0; j < kT; ++j) {
+    i64 n = c0 + j;
+    bool restart = false;
+    if (EV) {
+      while (n == next_ev) {
+        bool rs;
+        ls = welsh_fold<PITCH>(ls, &I, ev[li], &rs);
+        restart |= rs;
+        ++li;
+        next_ev = li < e_end ? ev[li].frame : kHeld;
+        if (!PITCH) ph = welsh_phases_at(ls, I, n - 1);
+      }
+    }
+    bool play = n >= ls.n_on && n < ls.n_off + I.amp.nr && n < f_end;
+    yp[j] = 0.0; g0[j] = 0.0; g1[j] = 0.0; ampf[j] = 0.0;
+    sb0[j] = 0.0; sa1[j] = 0.0; sa2[j] = 0.0;
+    if (play) {
+      play_bits |= 1u << j;
+      // LFO
+      double ld = 0.0;
+      if (I.routing != LFO_NONE) {
+        u64 pl;
+        if (PITCH) pl = ls.pl + (u64)(n - ls.anchor) * I.lfo_dq;
+        else { ph.pl += I.lfo_dq; pl = ph.pl; }
+        ld = wave_value(I.wl, pl, I.dutyl_q, seedl, n) * I.depth;
+      }
+      // oscillators
+      if (PITCH) {
+        if (restart) { ph.p1 = 0; ph.p2 = 0; }
+        else {
+          u64 d1 = cycles_to_q(ls.cyc1 * pf[j]);
+          ph.p1 += d1;
+          bool wrapped = ph.p1 < d1;
+          if (I.sync && wrapped) ph.p2 = 0;
+          else ph.p2 += cycles_to_q(ls.cyc2 * pf[j]);
+        }
+      } else {
+        ph.p1 += ls.d1;
+        bool wrapped = ph.p1 < ls.d1;
+        if (I.sync && wrapped) ph.p2 = 0;
+        else ph.p2 += ls.d2;
+      }
+      u64 du1 = I.duty1_q, du2 = I.duty2_q;
+      if (I.routing == LFO_PULSE_WIDTH) {
+        const double top = 1.0 - 1.0 / 9007199254740992.0;
+        double a = __dadd_rn(I.duty1, __dmul_rn(0.5, ld));
+        double b = __dadd_rn(I.duty2, __dmul_rn(0.5, ld));
+        a = a < 0.0 ? 0.0 : (a > top ? top : a);
+        b = b < 0.0 ? 0.0 : (b > top ? top : b);
+        du1 = cycles_to_q(a);
+        du2 = cycles_to_q(b);
+      }
+      double o1 = wave_value(I.w1, ph.p1, du1, seed1, n);
+      double o2 = wave_value(I.w2, ph.p2, du2, seed2, n);
+      double x = o1 * I.mix + o2 * (1.0 - I.mix);
+      // filter coefficients
+      SecCoef c1 = I.fixed1, c2 = I.fixed2;
+      if (I.filter_mode != FILTER_FIXED) {
+        double pct;
+        if (I.filter_mode == FILTER_ENVELOPE) {
+          double fe = env_level(I.filt, ls.n_on, ls.n_off, ls.lf_on, ls.lf_off, n);
+          pct = I.cut_a + I.cut_b * fe;
+        } else {
+          pct = I.cut_a * (1.0 + ld);
+        }
+        pct = pct < 0.0 ? 0.0 : (pct > 1.0 ? 1.0 : pct);
+        double fc = 25.0 * exp2(pct * kLog2_800);
+        double fmax = 0.49 * I.sr;
+        fc = fc > fmax ? fmax : fc;
+        fc = fc < 1.0 ? 1.0 : fc;
+        lp24_from_k(I.rp, tan(fc * I.pi_over_sr), c1, c2);
+      }
+      sb0[j] = c2.b0; sa1[j] = c2.a1; sa2[j] = c2.a2;
+      // amplitude
+      double ae = env_level(I.amp, ls.n_on, ls.n_off, ls.la_on, ls.la_off, n);
+      ampf[j] = ae * (I.routing == LFO_AMPLITUDE ? 0.5 * (1.0 + ld) : 0.5);
+      // section 1 from zero state, plus homogeneous response
+      double bx = c1.b0 * x;
+      double y = bx + ps0;
+      yp[j] = y; g0[j] = h00; g1[j] = h01;
+      double n0 = 2.0 * bx + c1.a1 * y + ps1;
+      ps1 = bx + c1.a2 * y;
+      ps0 = n0;
+      double t00 = c1.a1 * h00 + h10, t01 = c1.a1 * h01 + h11;
+      h10 = c1.a2 * h00; h11 = c1.a2 * h01;
+      h00 = t00; h01 = t01;
+    }
+  }
+  // ---- scan section 1, fix up, run section 2 from zero state ----
+  double e0, e1, end0, end1;
+  {
+    Affine2 a;
+    a.m00 = h00; a.m01 = h01; a.m10 = h10; a.m11 = h11; a.v0 = ps0; a.v1 = ps1;
+    Affine2 inc = affine_warp_scan(a, lane);
+    affine_lane_entry(inc, lane, st.s[0], st.s[1], e0, e1, end0, end1);
+    st.s[0] = end0; st.s[1] = end1;
+  }
+  ps0 = 0.0; ps1 = 0.0; h00 = 1.0; h01 = 0.0; h10 = 0.0; h11 = 1.0;
+#pragma unroll
+  for (int j = 0; j < kT; ++j) {
+    if (play_bits & (1u << j)) {
+      double x = yp[j] + g0[j] * e0 + g1[j] * e1;  // true section-1 output
+      double bx = sb0[j] * x;
+      double y = bx + ps0;
+      yp[j] = y; g0[j] = h00; g1[j] = h01;
+      double n0 = 2.0 * bx + sa1[j] * y + ps1;
+      ps1 = bx + sa2[j] * y;
+      ps0 = n0;
+      double t00 = sa1[j] * h00 + h10, t01 = sa1[j] * h01 + h11;
+      h10 = sa2[j] * h00; h11 = sa2[j] * h01;
+      h00 = t00; h01 = t01;
+    }
+  }
+  {
+    Affine2 a;
+    a.m00 = h00; a.m01 = h01; a.m10 = h10; a.m11 = h11; a.v0 = ps0; a.v1 = ps1;
+    Affine2 inc = affine_warp_scan(a, lane);
+    affine_lane_entry(inc, lane, st.s[2], st.s[3], e0, e1, end0, end1);
+    st.s[2] = end0; st.s[3] = end1;
+  }
+  // ---- amplitude, DCA, into the CTA tile ----
+#pragma unroll
+  for (int j = 0; j < kT; ++j) {
+    double m = (yp[j] + g0[j] * e0 + g1[j] * e1) * ampf[j];
+    int t = lane * kT + j;
+    double2 o = make_double2(m * I.gl, m * I.gr);
+    if (accumulate) {
+      double2 p = tile_row[t + (t >> 3)];
+      o.x += p.x; o.y += p.y;
+    }
+    tile_row[t + (t >> 3)] = o;
+  }
+  // ---- advance the warp-uniform note state over this block's events ----
+  if (EV) {
+    while (ei < e_end && ev[ei].frame < blk_end) {
+      st = welsh_fold<PITCH>(st, &I, ev[ei], &rs_dummy);
+      ++ei;
+    }
+  }
+}
+
+// Sum the W per-voice tiles of one block and store 16 bytes per frame.
+template <int W>
+__device__ __forceinline__ void cta_reduce_store(const double2* tiles, const int* s_active, double2* out, i64 fb,
+                                                 i64 f0, i64 f_end) {
+  for (int t = threadIdx.x; t < kBlockFrames; t += 32 * W) {
+    i64 n = fb + t;
+    if (n < f_end) {
+      double l = 0.0, r = 0.0;
+      int u = t + (t >> 3);
+#pragma unroll
+      for (int w = 0; w < W; ++w) {
+        if (s_active[w]) {
+          double2 v = tiles[w * kTileStride + u];
+          l += v.x; r += v.y;
+        }
+      }
+      out[n - f0] = make_double2(l, r);
+    }
+  }
+}
+
+// grid = number of CtaWork items; block = 32 * W threads; dynamic smem = W * kTileStride double2.
+template <int W>
+__global__ void __launch_bounds__(32 * W) welsh_kernel(const WelshInst* __restrict__ insts,
+                                                        WelshVoice* __restrict__ voices,
+                                                        const CtaWork* __restrict__ work,
+                                                        const VoiceEvent* __restrict__ events,
+                                                        const int* __restrict__ ev_off, i64 f0, int nframes) {
+  extern __shared__ double2 smem_tiles[];
+  __shared__ int s_active[W];
+  const CtaWork wk = work[blockIdx.x];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const WelshInst& I = insts[wk.inst];
+  double2* tile_row = smem_tiles + warp * kTileStride;
+  const i64 f_end = f0 + nframes;
+  const bool pitch = I.routing == LFO_PITCH;
+  for (i64 fb = f0; fb < f_end; fb += kBlockFrames) {
+    bool any = false;
+    for (int g = warp; g < wk.nvoices; g += W) {
+      const int vi = wk.voice0 + g;
+      WelshVoice st = voices[vi];
+      int ei = ev_off[vi];
+      const int e_end = ev_off[vi + 1];
+      while (ei < e_end && events[ei].frame < fb) ++ei;  // already folded into st by earlier blocks
+      bool idle = fb >= st.n_off + I.amp.nr;
+      bool ev_here = ei < e_end && events[ei].frame < fb + kBlockFrames;
+      if (idle && !ev_here) continue;
+      const int local = vi - I.voice0;
+      const u64 seed1 = splitmix64(((u64)(unsigned)I.uid << 32) ^ (u64)(2 * local));
+      const u64 seed2 = splitmix64(((u64)(unsigned)I.uid << 32) ^ (u64)(2 * local + 1));
+      const u64 seedl = splitmix64(((u64)(unsigned)I.uid << 32) ^ 0x4C464F00ull ^ (u64)local);
+      if (pitch) {
+        if (ev_here) welsh_block<true, true>(st, I, events, ei, e_end, fb, f_end, lane, seed1, seed2, seedl, tile_row, any);
+        else welsh_block<true, false>(st, I, events, ei, e_end, fb, f_end, lane, seed1, seed2, seedl, tile_row, any);
+      } else {
+        if (ev_here) welsh_block<false, true>(st, I, events, ei, e_end, fb, f_end, lane, seed1, seed2, seedl, tile_row, any);
+        else welsh_block<false, false>(st, I, events, ei, e_end, fb, f_end, lane, seed1, seed2, seedl, tile_row, any);
+      }
+      any = true;
+      __syncwarp();
+      if (lane == 0) voices[vi] = st;
+      __syncwarp();
+    }
+    if (lane == 0) s_active[warp] = any ? 1 : 0;
+    __syncthreads();
+    cta_reduce_store<W>(smem_tiles, s_active, wk.out, fb, f0, f_end);
+    __syncthreads();
+  }
+}
+
+// --------------------------------------------------------------------------- FM ---
+struct FmInst {
+  EnvShape car, mod;
+  double depth, beta;
+  double gl, gr;
+  int uid, voice0;
+};
+struct FmVoice {
+  i64 n_on, n_off;
+  double lc_on, lc_off, lm_on, lm_off;
+  i64 anchor;   // modulator phase anchor
+  u64 pm, dm;   // modulator phase at anchor, increment
+  u64 pc;       // carrier phase at (chunk position - 1)
+  double cyc_c; // carrier base cycles per frame
+  double pad;
+};
+
+__device__ __noinline__ FmVoice fm_fold(FmVoice st, const FmInst* Ip, VoiceEvent ev, bool* restart) {
+  const FmInst& I = *Ip;
+  i64 f = ev.frame;
+  *restart = false;
+  if (ev.type == VEV_NOTE_ON) {
+    bool was = f >= st.n_on && f < st.n_off + I.car.nr;
+    double lc = 0.0, lm = 0.0;
+    if (was) {
+      lc = env_level(I.car, st.n_on, st.n_off, st.lc_on, st.lc_off, f);
+      lm = env_level(I.mod, st.n_on, st.n_off, st.lm_on, st.lm_off, f);
+      st.pm += (u64)(f - 1 - st.anchor) * st.dm;
+      st.anchor = f - 1;
+    } else {
+      st.pm = 0;
+      st.anchor = f;
+    }
+    st.lc_on = lc; st.lm_on = lm;
+    st.n_on = f; st.n_off = kHeld;
+    st.cyc_c = ev.cyc1;
+    st.dm = cycles_to_q(ev.cyc2);
+    *restart = !was;
+  } else {
+    st.lc_off = env_pre(I.car, st.n_on, st.lc_on, f);
+    st.lm_off = env_pre(I.mod, st.n_on, st.lm_on, f);
+    st.n_off = f;
+  }
+  return st;
+}
+
+template <bool EV>
+__device__ __forceinline__ void fm_block(FmVoice& st, const FmInst& I, const VoiceEvent* __restrict__ ev, int& ei,
+                                         int e_end, i64 fb, i64 f_end, int lane, double2* tile_row,
+                                         bool accumulate) {
+  const i64 c0 = fb + (i64)lane * kT;
+  const i64 blk_end = fb + kBlockFrames;
+  FmVoice ls = st;
+  int li = ei;
+  i64 next_ev = kHeld;
+  bool rs_dummy;
+  if (EV) {
+    while (li < e_end && ev[li].frame < c0) {
+      ls = fm_fold(ls, &I, ev[li], &rs_dummy);
+      ++li;
+    }
+    next_ev = li < e_end ? ev[li].frame : kHeld;
+  }
+  u64 dc[kT];
+  double cenv[kT];
+  unsigned play_bits = 0, reset_bits = 0;
+  SegSum a; a.sum = 0; a.reset = 0;
+#pragma unroll
+  for (int j = 0; j < kT; ++j) {
+    i64 n = c0 + j;
+    if (EV) {
+      while (n == next_ev) {
+        bool rs;
+        ls = fm_fold(ls, &I, ev[li], &rs);
+        if (rs) reset_bits |= 1u << j;
+        ++li;
+        next_ev = li < e_end ? ev[li].frame : kHeld;
+      }
+    }
+    bool play = n >= ls.n_on && n < ls.n_off + I.car.nr && n < f_end;
+    dc[j] = 0; cenv[j] = 0.0;
+    if (play) {
+      play_bits |= 1u << j;
+      u64 pm = ls.pm + (u64)(n - ls.anchor) * ls.dm;
+      double mval = sinpi(2.0 * pos_of(pm));
+      double menv = env_level(I.mod, ls.n_on, ls.n_off, ls.lm_on, ls.lm_off, n);
+      double x = __dmul_rn(__dmul_rn(__dmul_rn(mval, menv), I.depth), I.beta);
+      dc[j] = cycles_to_q(__dmul_rn(ls.cyc_c, __dadd_rn(1.0, x)));
+      cenv[j] = env_level(I.car, ls.n_on, ls.n_off, ls.lc_on, ls.lc_off, n);
+      if (reset_bits & (1u << j)) { a.sum = 0; a.reset = 1; }
+      else a.sum += dc[j];
+    }
+  }
+  SegSum inc = segsum_warp_scan(a, lane);
+  SegSum ex;
+  ex.sum = __shfl_up_sync(0xffffffffu, inc.sum, 1);
+  ex.reset = __shfl_up_sync(0xffffffffu, inc.reset, 1);
+  if (lane == 0) { ex.sum = 0; ex.reset = 0; }
+  u64 pc = ex.reset ? ex.sum : st.pc + ex.sum;
+  u64 tot = inc.reset ? inc.sum : st.pc + inc.sum;
+  st.pc = __shfl_sync(0xffffffffu, tot, 31);
+#pragma unroll
+  for (int j = 0; j < kT; ++j) {
+    double m = 0.0;
+    if (play_bits & (1u << j)) {
+      if (reset_bits & (1u << j)) pc = 0;
+      else pc += dc[j];
+      m = sinpi(2.0 * pos_of(pc)) * cenv[j];
+    }
+    int t = lane * kT + j;
+    double2 o = make_double2(m * I.gl, m * I.gr);
+    if (accumulate) {
+      double2 p = tile_row[t + (t >> 3)];
+      o.x += p.x; o.y += p.y;
+    }
+    tile_row[t + (t >> 3)] = o;
+  }
+  if (EV) {
+    while (ei < e_end && ev[ei].frame < blk_end) {
+      st = fm_fold(st, &I, ev[ei], &rs_dummy);
+      ++ei;
+    }
+  }
+}
+
+template <int W>
+__global__ void __launch_bounds__(32 * W) fm_kernel(const FmInst* __restrict__ insts, FmVoice* __restrict__ voices,
+                                                     const CtaWork* __restrict__ work,
+                                                     const VoiceEvent* __restrict__ events,
+                                                     const int* __restrict__ ev_off, i64 f0, int nframes) {
+  extern __shared__ double2 smem_tiles[];
+  __shared__ int s_active[W];
+  const CtaWork wk = work[blockIdx.x];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const FmInst& I = insts[wk.inst];
+  double2* tile_row = smem_tiles + warp * kTileStride;
+  const i64 f_end = f0 + nframes;
+  for (i64 fb = f0; fb < f_end; fb += kBlockFrames) {
+    bool any = false;
+    for (int g = warp; g < wk.nvoices; g += W) {
+      const int vi = wk.voice0 + g;
+      FmVoice st = voices[vi];
+      int ei = ev_off[vi];
+      const int e_end = ev_off[vi + 1];
+      while (ei < e_end && events[ei].frame < fb) ++ei;
+      bool idle = fb >= st.n_off + I.car.nr;
+      bool ev_here = ei < e_end && events[ei].frame < fb + kBlockFrames;
+      if (idle && !ev_here) continue;
+      if (ev_here) fm_block<true>(st, I, events, ei, e_end, fb, f_end, lane, tile_row, any);
+      else fm_block<false>(st, I, events, ei, e_end, fb, f_end, lane, tile_row, any);
+      any = true;
+      __syncwarp();
+      if (lane == 0) voices[vi] = st;
+      __syncwarp();
+    }
+    if (lane == 0) s_active[warp] = any ? 1 : 0;
+    __syncthreads();
+    cta_reduce_store<W>(smem_tiles, s_active, wk.out, fb, f0, f_end);
+    __syncthreads();
+  }
+}
+
+// ------------------------------------------------------------ sampler / drumkit ---
+// The host tracks every "play" (a voice sounding one sample from n_on until n_end) with integer
+// frame arithmetic, so the device needs no persistent state: one thread per output frame sums the
+// plays that cover it, in voice order.
+struct SamplePlay {
+  i64 n_on, n_end;
+  u64 step_q;       // 32.32 sample frames per output frame
+  const double* data;
+  u64 len;          // frames
+  int channels;
+  int pad;
+};
+
+__global__ void __launch_bounds__(256) sampler_kernel(const SamplePlay* __restrict__ plays, int nplays,
+                                                       double2* __restrict__ out, i64 f0, int nframes) {
+  int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= nframes) return;
+  i64 n = f0 + t;
+  double l = 0.0, r = 0.0;
+  for (int p = 0; p < nplays; ++p) {
+    SamplePlay pl = plays[p];
+    if (n >= pl.n_on && n < pl.n_end) {
+      u64 idx = ((u64)(n - pl.n_on) * pl.step_q) >> 32;
+      if (idx < pl.len) {
+        if (pl.channels == 2) {
+          double2 v = reinterpret_cast<const double2*>(pl.data)[idx];
+          l += v.x; r += v.y;
+        } else {
+          double v = __ldg(pl.data + idx);
+          l += v; r += v;
+        }
+      }
+    }
+  }
+  out[t] = make_double2(l, r);
+}
+
+}  // namespace gbk
