@@ -1,0 +1,336 @@
+#!/usr/bin/env python
+"""bench.py — voice-samples/s of the Groove synthesis hot path on B200 (BASELINE.json metric).
+
+    python bench.py --gpus N --steps K --warmup W            # this repo's CUDA path
+    python bench.py --impl reference --gpus N ...            # the CPU implementation (oracle) on host cores
+
+A *step* is one full render of BASELINE config 4 — 4096 Welsh `cello` voices, 60 s at 48 kHz stereo
+= 1.17965e10 voice-samples — through the engine.  At N > 1 every rank renders its own 4096-voice
+shard (weak scaling) and the stereo buses are summed onto rank 0 with one NCCL f64 reduce.
+
+Printed JSON (one line, rank 0):
+  value      whole-job voice-samples/s, device-timed (CUDA events on the engine's stream around
+             each render call), inputs resident in HBM, result left in HBM;
+  e2e        the same metric through the C ABI with host buffers: events pushed from host memory
+             and the f64 stereo result copied back to a host buffer inside the timed region;
+  roofline   dominant kernel (welsh_kernel) against the FP64 vector pipe, which is what binds this
+             path: achieved = 150 FLOP x voice-samples per launch / CUDA-event
+             launch time; peak = FP64 FMA microbenchmark measured live on the same GPU;
+  cpu_baseline  the CPU oracle (reference-structured restatement) on a bounded sample, 1 core.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import multiprocessing as mp
+import os
+import subprocess
+import sys
+import tempfile
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+
+METRIC = "voice_samples_per_sec"
+UNIT = "voice-samples/s"
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--voices", type=int, default=4096, help="voices per GPU (config 4: 4096)")
+    ap.add_argument("--seconds", type=float, default=60.0, help="audio seconds per step (config 4: 60)")
+    ap.add_argument("--max-block", type=int, default=1 << 16)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--cpu-sample-voices", type=int, default=256)
+    ap.add_argument("--cpu-sample-seconds", type=float, default=4.0)
+    return ap.parse_args()
+
+
+# --------------------------------------------------------------------------- CPU legs ---
+def _oracle_render_slice(args):
+    """Worker: render `voices` voices x `frames` frames of config 4 on the CPU oracle; returns seconds."""
+    voices, frames, voice_offset = args
+    from groove_b200 import workloads
+    from tests.oracle_binding import OracleEngine
+    o = OracleEngine(48000.0)
+    n = workloads.build_cfg4(o, workloads.cfg4_slice(voices, frames, voice_offset))
+    t = time.perf_counter()
+    done = 0
+    out = np.empty((4800, 2))
+    while done < n:                       # 64-frame-multiple buffers like the reference CLI loop
+        k = min(4800, n - done)
+        o.render(k, out)
+        done += k
+    return time.perf_counter() - t
+
+
+def cpu_baseline_single(voices: int, seconds: float) -> dict:
+    frames = int(seconds * 48000)
+    dt = _oracle_render_slice((voices, frames, 0))
+    return {
+        "value": voices * frames / dt, "unit": UNIT, "cores": 1, "kind": "port",
+        "sample": f"config-4 voices 0..{voices - 1}, first {seconds:g} s ({voices * frames:.3e} voice-samples), "
+                  f"oracle/groove_oracle.cpp per-frame graph walk, {dt:.2f} s wall",
+    }
+
+
+def run_reference_arm(a) -> None:
+    """--impl reference: the CPU implementation of the path on all host cores.
+
+    The reference itself cannot be built (no Rust toolchain, DSP source absent: SURVEY.md §0), so this
+    arm times the oracle port.  Each step = `cores` independent renders in parallel processes, each a
+    bounded slice of config 4 (distinct voices).
+    """
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    cores = os.cpu_count() or 1
+    voices_each, seconds = 32, 3.0
+    frames = int(seconds * 48000)
+    jobs = [(voices_each, frames, i * voices_each) for i in range(cores)]
+    ctx = mp.get_context("spawn")
+    with ctx.Pool(cores) as pool:
+        for _ in range(a.warmup):
+            pool.map(_oracle_render_slice, jobs)
+        t0 = time.perf_counter()
+        for _ in range(a.steps):
+            pool.map(_oracle_render_slice, jobs)
+        dt = time.perf_counter() - t0
+    total = cores * voices_each * frames * a.steps
+    value = total / dt
+    sample = (f"{cores} parallel processes x ({voices_each} config-4 voices x {seconds:g} s) per step; "
+              "oracle port (reference is not buildable here)")
+    print(json.dumps({
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": a.gpus, "steps": a.steps,
+        "warmup": a.warmup, "ms_per_step": dt / a.steps * 1e3, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": "config-4: 4096-voice Welsh cello subtractive synth, 48 kHz stereo (bounded sample per step)",
+                   "sample": sample},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "realtime_factor": value / (4096 * 48000.0),
+    }), flush=True)
+
+
+# ------------------------------------------------------------------------------ GPU leg ---
+class ClockSampler:
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        self.tmp = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
+        self.proc = None
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100", "-i", str(gpu_index)],
+                stdout=self.tmp, stderr=subprocess.DEVNULL)
+        except OSError:
+            self.proc = None
+
+    def stop(self) -> dict:
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        self.tmp.flush()
+        self.tmp.seek(0)
+        sm, mx, power = [], [], []
+        reasons = set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for line in self.tmp.read().splitlines():
+            f = [x.strip() for x in line.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1])); mx.append(float(f[2])); power.append(float(f[3]))
+            except ValueError:
+                continue
+            for nm, v in zip(names, f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(nm)
+        os.unlink(self.tmp.name)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
+        busy = [s for s, p in zip(sm, power) if p > 0.5 * max(power)] or sm
+        return {"sm_mhz": float(np.median(busy)), "sm_max_mhz": float(max(mx)), "power_w_max": float(max(power)),
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def run_ours(a) -> None:
+    import torch
+    import torch.distributed as dist
+
+    from groove_b200 import Engine, workloads
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; this repo has no CPU fallback for the product path")
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    frames = int(round(a.seconds * 48000))
+    cfg = workloads.Cfg4(total_voices=a.voices, frames=frames,
+                         note_off_base=int(frames * 2_400_000 / 2_880_000),
+                         groups=min(128, a.voices), voice_offset=rank * a.voices)
+
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
+    host_out = np.empty((frames, 2), dtype=np.float64)
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    def bus_reduce(eng):
+        """Sum the per-rank stereo buses onto rank 0: one NCCL f64 reduce over NVLink."""
+        if world == 1:
+            return None
+        ptr, n = eng.last_device_buffer()
+
+        class _Wrap:
+            __cuda_array_interface__ = {"shape": (n, 2), "typestr": "<f8", "data": (ptr, False), "version": 2}
+        t = torch.as_tensor(_Wrap(), device=torch.device("cuda", local))
+        dist.reduce(t, dst=0, op=dist.ReduceOp.SUM)
+        return t
+
+    def one_step(mode: str):
+        """Build config 4 and render it.  Engine construction (allocation, plan) is setup, not the
+        hot path: it stays outside the timed spans; events are pushed inside the e2e span."""
+        eng = Engine(48000.0, device=local, max_block=a.max_block)
+        eng.set_timing(True)
+        workloads.build_cfg4(eng, cfg)
+        flush.zero_()
+        barrier()
+        t0 = time.perf_counter()
+        if mode == "device":
+            eng.render_device(frames)
+            bus_reduce(eng)
+            torch.cuda.synchronize()
+        else:
+            if world == 1:
+                eng.render(frames, host_out)
+            else:
+                eng.render_device(frames)
+                t = bus_reduce(eng)
+                if rank == 0:
+                    host_out[:] = t.cpu().numpy()
+                torch.cuda.synchronize()
+        wall = time.perf_counter() - t0
+        st = eng.stats()
+        eng.close()
+        return wall, st
+
+    # warm-up (both modes), then the timed steps
+    for _ in range(max(a.warmup, 1)):
+        one_step("device")
+    one_step("e2e")
+    barrier()
+    sampler = ClockSampler(local) if rank == 0 else None
+    dev_ms, kern_ms, launches, vlaunches, wall_dev = 0.0, 0.0, 0, 0, 0.0
+    t_region = time.perf_counter()
+    for _ in range(a.steps):
+        wall, st = one_step("device")
+        dev_ms += st.render_ms
+        kern_ms += st.voice_kernel_ms
+        launches += st.kernel_launches
+        vlaunches += st.voice_kernel_launches
+        wall_dev += wall
+    barrier()
+    region_s = time.perf_counter() - t_region
+    e2e_wall, h2d, d2h = 0.0, 0, 0
+    for _ in range(a.steps):
+        wall, st = one_step("e2e")
+        e2e_wall += wall
+        h2d += st.h2d_bytes
+        d2h += st.d2h_bytes if world == 1 else (frames * 16 if rank == 0 else 0)
+    barrier()
+    clocks = sampler.stop() if sampler else None
+
+    # max over ranks
+    vals = torch.tensor([dev_ms, wall_dev, e2e_wall, kern_ms], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(vals, op=dist.ReduceOp.MAX)
+    dev_ms, wall_dev, e2e_wall, kern_ms = [float(x) for x in vals.tolist()]
+    # N > 1: the reduce is outside the engine's events, so the step time is the synchronized wall time
+    step_s = (dev_ms * 1e-3 if world == 1 else wall_dev) / a.steps
+    total_vs = cfg.voice_samples * world
+    value = total_vs / step_s
+    e2e_value = total_vs / (e2e_wall / a.steps)
+
+    if rank == 0:
+        eng = Engine(48000.0, device=local)
+        fp64_peak = eng.measure_fma_peak(True)
+        fp32_peak = eng.measure_fma_peak(False)
+        eng.close()
+        peaks = {}
+        try:
+            with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+                peaks = json.load(f)
+        except OSError:
+            pass
+        hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
+        vs_per_launch = cfg.voice_samples * a.steps / max(vlaunches, 1)
+        launch_s = kern_ms * 1e-3 / max(vlaunches, 1)
+        achieved_tflops = workloads.W_VOICE_FLOP * vs_per_launch / launch_s / 1e12
+        # algorithmic HBM bytes: 16 B stereo f64 out per frame per CTA partial + voice state in/out
+        out = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": a.steps, "warmup": max(a.warmup, 1),
+            "ms_per_step": step_s * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f64", "data": "synthetic",
+            "config": {
+                "workload": "config-4: 4096-voice Welsh-cookbook cello subtractive synth (dual osc + LFO + 2 ADSR + "
+                            "per-frame 24 dB LPF), 60 s at 48 kHz stereo" if (a.voices, a.seconds) == (4096, 60.0)
+                            else f"config-4 recipe scaled: {a.voices} voices x {a.seconds:g} s at 48 kHz stereo",
+                "voices_per_gpu": a.voices, "frames": frames, "voice_samples_per_step": total_vs,
+                "max_block": a.max_block, "parallelism": f"voices sharded over {world} GPU(s); one NCCL f64 bus reduce",
+                "l2": "256 MiB device memset between steps (L2 flush); fresh engine per step",
+            },
+            "realtime_factor": value / (a.voices * world * 48000.0),
+            "gpu_launches": int(launches // a.steps),
+            "e2e": {"value": e2e_value, "unit": UNIT, "ms_per_step": e2e_wall / a.steps * 1e3,
+                    "h2d_bytes_per_step": int(h2d // a.steps), "d2h_bytes_per_step": int(d2h // a.steps)},
+            "roofline": {
+                "bound": "fp64", "kernel": "welsh_kernel<8>", "achieved": achieved_tflops, "peak": fp64_peak,
+                "unit": "TFLOP/s", "frac": achieved_tflops / fp64_peak, "traffic": None,
+                "peak_source": "FP64 FMA microbenchmark measured live on this GPU (gb_measure_fma_peak); "
+                               "MEASURED_PEAKS.json has no FP64 entry",
+                "algorithmic_flop_per_voice_sample": workloads.W_VOICE_FLOP,
+                "voice_samples_per_launch": vs_per_launch, "launch_ms": launch_s * 1e3,
+                "kernel_share_of_step": kern_ms * 1e-3 / a.steps / step_s if world == 1 else None,
+                "fp32_peak_tflops": fp32_peak,
+                "hbm": {"peak_gbs": hbm_peak, "peak_source": "MEASURED_PEAKS.json" if peaks else "fallback 6650"},
+            },
+            "clocks": clocks,
+            "timed_region_s": region_s,
+        }
+        if not a.no_cpu_baseline:
+            out["cpu_baseline"] = cpu_baseline_single(a.cpu_sample_voices, a.cpu_sample_seconds)
+        print(json.dumps(out), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    a = parse_args()
+    if a.impl == "reference":
+        run_reference_arm(a)
+    else:
+        run_ours(a)
+
+
+if __name__ == "__main__":
+    main()

@@ -129,14 +129,15 @@ class Config(C.Structure):
 
 class Stats(C.Structure):
     _fields_ = [("kernel_launches", C.c_uint64), ("voice_kernel_launches", C.c_uint64),
-                ("voice_kernel_ms", C.c_double), ("fx_kernel_ms", C.c_double),
+                ("voice_kernel_ms", C.c_double), ("fx_kernel_ms", C.c_double), ("render_ms", C.c_double),
                 ("voice_samples", C.c_uint64), ("h2d_bytes", C.c_uint64), ("d2h_bytes", C.c_uint64)]
 
 
 # every symbol include/groove_b200.h declares (suffix after the prefix)
 ABI_SYMBOLS = (
     "create", "destroy", "last_error", "add_instrument", "add_effect", "load_sample", "patch", "finalize",
-    "push_events", "render_block", "render_pcm16", "render_device", "read_last", "position", "save_state",
+    "push_events", "render_block", "render_pcm16", "render_device", "last_device_buffer", "read_last", "position",
+    "save_state",
     "restore_state", "get_stats", "reset_stats", "set_timing", "measure_fma_peak",
 )
 
@@ -191,6 +192,7 @@ class Renderer:
             "render_pcm16": (C.c_int, [vp, vp, C.c_size_t, C.POINTER(C.c_size_t)]),
             "render_device": (C.c_int, [vp, C.c_size_t, C.POINTER(C.c_size_t)]),
             "read_last": (C.c_int, [vp, vp, C.c_size_t]),
+            "last_device_buffer": (C.c_int, [vp, C.POINTER(vp), C.POINTER(C.c_size_t)]),
             "position": (C.c_int64, [vp]),
             "save_state": (C.c_int, [vp, vp, C.POINTER(C.c_size_t)]),
             "restore_state": (C.c_int, [vp, vp, C.c_size_t]),
@@ -309,6 +311,13 @@ class Renderer:
         out = np.empty((frames, 2), dtype=np.float64)
         self._check(self._f("read_last")(self._h, out.ctypes.data, frames))
         return out
+
+    def last_device_buffer(self):
+        """(device pointer, frames) of the last ``render_device`` result (f64 L,R interleaved in HBM)."""
+        ptr = C.c_void_p()
+        n = C.c_size_t()
+        self._check(self._f("last_device_buffer")(self._h, C.byref(ptr), C.byref(n)))
+        return ptr.value, n.value
 
     @property
     def position(self) -> int:

@@ -321,7 +321,11 @@ struct gb_engine {
   // stats
   gb_stats stats;
   bool timing = false;
-  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  // CUDA-event pairs recorded around launches / render calls on the engine stream; resolved
+  // lazily (gb_get_stats) so that timing never serialises the stream.
+  struct TimedSpan { cudaEvent_t a, b; int what; };  // what: 0 = fx kernel, 1 = voice kernel, 2 = render call
+  std::vector<TimedSpan> spans;
+  std::vector<std::pair<cudaEvent_t, cudaEvent_t>> event_pool;
 };
 
 namespace {
@@ -410,23 +414,45 @@ void fm_inst_from_params(const Node& n, double sr, FmInst* I) {
   I->voice0 = n.voice0;
 }
 
+bool span_begin(gb_engine* e, int what) {
+  if (!e->timing) return false;
+  std::pair<cudaEvent_t, cudaEvent_t> ev;
+  if (!e->event_pool.empty()) {
+    ev = e->event_pool.back();
+    e->event_pool.pop_back();
+  } else {
+    if (cudaEventCreate(&ev.first) != cudaSuccess || cudaEventCreate(&ev.second) != cudaSuccess) return false;
+  }
+  cudaEventRecord(ev.first, e->stream);
+  e->spans.push_back({ev.first, ev.second, what});
+  return true;
+}
+void span_end(gb_engine* e, size_t index) { cudaEventRecord(e->spans[index].b, e->stream); }
+void resolve_spans(gb_engine* e) {
+  for (auto& sp : e->spans) {
+    cudaEventSynchronize(sp.b);
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, sp.a, sp.b);
+    if (sp.what == 1) e->stats.voice_kernel_ms += ms;
+    else if (sp.what == 0) e->stats.fx_kernel_ms += ms;
+    else e->stats.render_ms += ms;
+    e->event_pool.push_back({sp.a, sp.b});
+  }
+  e->spans.clear();
+}
+
 struct Launch {  // per-launch accounting (+ optional CUDA-event timing on the engine's stream)
   gb_engine* e;
-  bool voice;
-  Launch(gb_engine* e_, bool voice_) : e(e_), voice(voice_) {
-    if (e->timing) cudaEventRecord(e->ev0, e->stream);
-  }
-  ~Launch() {
+  bool timed;
+  size_t index;
+  Launch(gb_engine* e_, bool voice) : e(e_) {
     e->stats.kernel_launches++;
     if (voice) e->stats.voice_kernel_launches++;
-    if (e->timing) {
-      cudaEventRecord(e->ev1, e->stream);
-      cudaEventSynchronize(e->ev1);
-      float ms = 0.f;
-      cudaEventElapsedTime(&ms, e->ev0, e->ev1);
-      if (voice) e->stats.voice_kernel_ms += ms;
-      else e->stats.fx_kernel_ms += ms;
-    }
+    timed = span_begin(e, voice ? 1 : 0);
+    index = e->spans.size() - 1;
+  }
+  ~Launch() {
+    if (timed) span_end(e, index);
   }
 };
 
@@ -592,8 +618,6 @@ int gb_create(const gb_config* cfg, gb_engine** out) {
   if (cudaGetDeviceProperties(&prop, e->device) == cudaSuccess) e->num_sms = prop.multiProcessorCount;
   if (cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking) != cudaSuccess)
     return fail(nullptr, GB_ECUDA, "cudaStreamCreate failed");
-  cudaEventCreate(&e->ev0);
-  cudaEventCreate(&e->ev1);
   auto mixer = std::make_unique<Node>();
   mixer->uid = GB_MAIN_MIXER;
   mixer->kind = GB_FX_MIXER;
@@ -609,8 +633,8 @@ void gb_destroy(gb_engine* e) {
   for (void* p : e->allocations) cudaFree(p);
   if (e->d_full) cudaFree(e->d_full);
   if (e->d_pcm) cudaFree(e->d_pcm);
-  if (e->ev0) cudaEventDestroy(e->ev0);
-  if (e->ev1) cudaEventDestroy(e->ev1);
+  resolve_spans(e);
+  for (auto& ev : e->event_pool) { cudaEventDestroy(ev.first); cudaEventDestroy(ev.second); }
   if (e->stream) cudaStreamDestroy(e->stream);
   delete e;
 }
@@ -1236,6 +1260,8 @@ int render_impl(gb_engine* e, void* out, size_t frames, size_t* done, OutMode mo
     }
   }
   size_t produced = 0;
+  const bool call_timed = span_begin(e, 2);
+  const size_t call_span = e->spans.size() - 1;
   while (produced < frames) {
     const int64_t f0 = e->pos;
     int64_t limit = (int64_t)std::min<size_t>(frames - produced, e->max_block);
@@ -1288,6 +1314,7 @@ int render_impl(gb_engine* e, void* out, size_t frames, size_t* done, OutMode mo
     CUDA_TRY(e, cudaStreamSynchronize(e->stream));
     e->stats.d2h_bytes += frames * sizeof(short2);
   }
+  if (call_timed) span_end(e, call_span);
   e->full_frames = mode != OUT_F64 ? frames : 0;
   if (done) *done = produced;
   return 0;
@@ -1312,6 +1339,13 @@ int gb_read_last(gb_engine* e, double* out, size_t frames) {
   cudaSetDevice(e->device);
   CUDA_TRY(e, cudaMemcpy(out, e->d_full, frames * sizeof(double2), cudaMemcpyDeviceToHost));
   e->stats.d2h_bytes += frames * sizeof(double2);
+  return 0;
+}
+int gb_last_device_buffer(gb_engine* e, void** device_ptr, size_t* frames) {
+  if (!e || !device_ptr || !frames) return GB_EINVAL;
+  if (!e->d_full || e->full_frames == 0) return fail(e, GB_ESTATE, "no device-resident render");
+  *device_ptr = e->d_full;
+  *frames = e->full_frames;
   return 0;
 }
 int64_t gb_position(const gb_engine* e) { return e ? e->pos : -1; }
@@ -1464,11 +1498,15 @@ int gb_restore_state(gb_engine* e, const void* buf, size_t size) {
 // ---- measurement ------------------------------------------------------------------------------
 int gb_get_stats(gb_engine* e, gb_stats* out) {
   if (!e || !out) return GB_EINVAL;
+  cudaSetDevice(e->device);
+  resolve_spans(e);
   *out = e->stats;
   return 0;
 }
 int gb_reset_stats(gb_engine* e) {
   if (!e) return GB_EINVAL;
+  cudaSetDevice(e->device);
+  resolve_spans(e);
   memset(&e->stats, 0, sizeof e->stats);
   return 0;
 }

@@ -244,6 +244,9 @@ int gb_render_block(gb_engine* e, double* out_interleaved_lr, size_t frames, siz
 int gb_render_pcm16(gb_engine* e, int16_t* out_interleaved_lr, size_t frames, size_t* frames_done);
 /* Render without any host copy (result stays in HBM); used to time the device path alone. */
 int gb_render_device(gb_engine* e, size_t frames, size_t* frames_done);
+/* Device address (double2[frames], L,R interleaved f64) of the most recent gb_render_device result; for
+   in-HBM consumers such as a multi-GPU bus reduction.  Valid until the next render call. */
+int gb_last_device_buffer(gb_engine* e, void** device_ptr, size_t* frames);
 /* Copy the most recent device-resident render (<= frames of it) to the host. */
 int gb_read_last(gb_engine* e, double* out_interleaved_lr, size_t frames);
 int64_t gb_position(const gb_engine* e);         /* frames rendered so far */
@@ -257,6 +260,7 @@ typedef struct {
   uint64_t voice_kernel_launches;
   double voice_kernel_ms;        /* CUDA-event time of the voice kernels since the last reset */
   double fx_kernel_ms;           /* ... of the effect / mix kernels */
+  double render_ms;              /* CUDA-event time of whole render calls (first op to last op on the stream) */
   uint64_t voice_samples;        /* voice x frame units the voice kernels covered */
   uint64_t h2d_bytes;
   uint64_t d2h_bytes;

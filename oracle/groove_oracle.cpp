@@ -33,6 +33,7 @@
 #include <algorithm>
 #include <cmath>
 #include <cstdint>
+#include <climits>
 #include <cstdio>
 #include <cstring>
 #include <map>
@@ -254,6 +255,11 @@ struct VoiceStore {
 struct Entity {
   uint32_t uid = 0;
   int kind = 0;
+  // Fan-out memo: a node reachable over several patch paths is evaluated ONCE per frame and its
+  // output shared.  (The reference's walk would re-tick it once per path, orchestrator.rs:401-410 —
+  // a DFS artifact that transposes the instrument; none of its 95 project fixtures has fan-out.)
+  int64_t memo_frame = INT64_MIN;
+  Stereo memo;
   virtual ~Entity() {}
   virtual bool is_instrument() const { return false; }
   // instruments
@@ -1228,9 +1234,14 @@ static Stereo gather_frame(go_engine* e, int64_t frame) {
     if (it == e->store.end()) continue;
     Entity* ent = it->second.get();
     if (!en.collect) {
-      if (ent->is_instrument()) {
+      if (ent->memo_frame == frame) {
+        sum.l += ent->memo.l;
+        sum.r += ent->memo.r;
+      } else if (ent->is_instrument()) {
         ent->tick(frame);
         Stereo v = ent->value();
+        ent->memo_frame = frame;
+        ent->memo = v;
         sum.l += v.l;
         sum.r += v.r;
       } else {
@@ -1242,6 +1253,8 @@ static Stereo gather_frame(go_engine* e, int64_t frame) {
       }
     } else {
       Stereo v = ent->transform_audio(sum);
+      ent->memo_frame = frame;
+      ent->memo = v;
       sum.l = en.acc.l + v.l;
       sum.r = en.acc.r + v.r;
     }
