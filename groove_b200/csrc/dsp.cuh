@@ -38,8 +38,10 @@ __device__ __forceinline__ u64 cycles_to_q(double c) {
   if (!(r < kTwo64)) return 0ull;
   return __double2ull_rz(r);
 }
+// phase -> position in [0,1): the top 52 bits, exactly (q >> 12) * 2^-52.  Built by placing them in
+// the mantissa of a double in [1,2) — integer ops plus one DADD instead of a 64-bit I2F on the XU pipe.
 __device__ __forceinline__ double pos_of(u64 q) {
-  return __ull2double_rn(q >> 11) * (1.0 / 9007199254740992.0);
+  return __longlong_as_double((long long)(0x3FF0000000000000ull | (q >> 12))) - 1.0;
 }
 
 // Oscillator output for phase q.  `wf` is warp-uniform.

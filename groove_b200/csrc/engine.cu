@@ -289,6 +289,8 @@ struct gb_engine {
   int64_t pos = 0;
   uint32_t next_uid = 2;
   int num_sms = 148;
+  int welsh_occ = 2;        // resident CTAs per SM the Welsh kernel is compiled for (GB_WELSH_OCC=1|2)
+  int cta_target_mult = 1;  // CTAs per SM the voice work lists aim for (GB_CTA_MULT)
   std::map<uint32_t, std::unique_ptr<Node>> nodes;
   std::vector<Node*> plan;  // reachable nodes, sources before consumers
   std::vector<gb_event> events;
@@ -402,6 +404,33 @@ void welsh_inst_from_params(const Node& n, double sr, WelshInst* I) {
   dca_gains(p.voice_dca.gain * p.dca.gain, pan, &I->gl, &I->gr);
   I->pi_over_sr = 3.141592653589793238462643383279 / sr;
   I->sr = sr;
+  auto shape = [](int wf, uint64_t duty_q, OscShape* o) {
+    memset(o, 0, sizeof *o);
+    o->thresh = 1ull << 63;
+    switch (wf) {
+      case GB_WAVE_SINE: o->kind = 1; break;
+      case GB_WAVE_NOISE: o->kind = 2; break;
+      case GB_WAVE_SQUARE: o->b_lo = 1.0; o->b_hi = -1.0; break;
+      case GB_WAVE_PULSE_WIDTH: o->thresh = duty_q; o->b_lo = 1.0; o->b_hi = -1.0; break;
+      case GB_WAVE_TRIANGLE: o->a_lo = 4.0; o->b_lo = -1.0; o->a_hi = -4.0; o->b_hi = 3.0; break;
+      case GB_WAVE_SAWTOOTH: o->a_lo = 2.0; o->b_lo = 0.0; o->a_hi = 2.0; o->b_hi = -2.0; break;
+      case GB_WAVE_DEBUG_MAX: o->b_lo = 1.0; o->b_hi = 1.0; break;
+      case GB_WAVE_DEBUG_MIN: o->b_lo = -1.0; o->b_hi = -1.0; break;
+      default: break;  // none / debug-zero: 0
+    }
+  };
+  shape(I->w1, I->duty1_q, &I->s1);
+  shape(I->w2, I->duty2_q, &I->s2);
+  shape(I->wl, I->dutyl_q, &I->sl);
+  I->log2_25_over_sr = std::log2(25.0 / sr);
+  I->u_min = 1.0 / sr;
+  I->u_max = 0.49;
+  for (int j = 0; j < kT; ++j) {
+    uint64_t q = (uint64_t)j * I->lfo_dq;  // mod 2^64
+    double ang = 6.283185307179586476925286766559 * ((double)q / 18446744073709551616.0);
+    I->lfo_cos[j] = std::cos(ang);
+    I->lfo_sin[j] = std::sin(ang);
+  }
 }
 void fm_inst_from_params(const Node& n, double sr, FmInst* I) {
   memset(I, 0, sizeof *I);
@@ -616,6 +645,8 @@ int gb_create(const gb_config* cfg, gb_engine** out) {
   memset(&e->stats, 0, sizeof e->stats);
   cudaDeviceProp prop;
   if (cudaGetDeviceProperties(&prop, e->device) == cudaSuccess) e->num_sms = prop.multiProcessorCount;
+  if (const char* v = getenv("GB_WELSH_OCC")) e->welsh_occ = atoi(v) == 1 ? 1 : 2;
+  if (const char* v = getenv("GB_CTA_MULT")) e->cta_target_mult = std::max(1, atoi(v));
   if (cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking) != cudaSuccess)
     return fail(nullptr, GB_ECUDA, "cudaStreamCreate failed");
   auto mixer = std::make_unique<Node>();
@@ -900,7 +931,7 @@ int gb_finalize(gb_engine* e) {
   auto plan_work = [&](int kind, int total_voices, DevBuf<CtaWork>& buf, int* count) -> int {
     std::vector<CtaWork> work;
     if (total_voices == 0) { *count = 0; return 0; }
-    int target = std::max(1, e->num_sms);
+    int target = std::max(1, e->num_sms * e->cta_target_mult);
     int vpc = std::max(kVoiceWarps, cdiv(total_voices, target));
     vpc = cdiv(vpc, kVoiceWarps) * kVoiceWarps;
     for (Node* n : e->plan) {
@@ -932,7 +963,9 @@ int gb_finalize(gb_engine* e) {
   int rc;
   if ((rc = plan_work(GB_INST_WELSH, wv, e->wwork, &e->n_wwork))) return rc;
   if ((rc = plan_work(GB_INST_FM, fv, e->fwork, &e->n_fwork))) return rc;
-  CUDA_TRY(e, cudaFuncSetAttribute(welsh_kernel<kVoiceWarps>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+  CUDA_TRY(e, cudaFuncSetAttribute(welsh_kernel<kVoiceWarps, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                   (int)(kVoiceWarps * kTileStride * sizeof(double2))));
+  CUDA_TRY(e, cudaFuncSetAttribute(welsh_kernel<kVoiceWarps, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                    (int)(kVoiceWarps * kTileStride * sizeof(double2))));
   CUDA_TRY(e, cudaFuncSetAttribute(fm_kernel<kVoiceWarps>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                    (int)(kVoiceWarps * kTileStride * sizeof(double2))));
@@ -1108,8 +1141,12 @@ int render_chunk(gb_engine* e, int frames, size_t n_ev) {
     if (rc) return rc;
     {
       Launch l(e, true);
-      welsh_kernel<kVoiceWarps><<<e->n_wwork, 32 * kVoiceWarps, tile_bytes, e->stream>>>(
-          e->d_winst, e->d_wvoice, e->wwork.d, e->wev.d, e->wev_off.d, f0, frames);
+      if (e->welsh_occ == 1)
+        welsh_kernel<kVoiceWarps, 1><<<e->n_wwork, 32 * kVoiceWarps, tile_bytes, e->stream>>>(
+            e->d_winst, e->d_wvoice, e->wwork.d, e->wev.d, e->wev_off.d, f0, frames);
+      else
+        welsh_kernel<kVoiceWarps, 2><<<e->n_wwork, 32 * kVoiceWarps, tile_bytes, e->stream>>>(
+            e->d_winst, e->d_wvoice, e->wwork.d, e->wev.d, e->wev_off.d, f0, frames);
     }
     e->stats.voice_samples += (uint64_t)e->n_wvoice * (uint64_t)frames;
   }

@@ -34,6 +34,43 @@ struct VoiceEvent {
 };
 
 // ------------------------------------------------------------------------ Welsh ---
+// Every piecewise-linear waveform is  value = a*p + b  with (a,b) picked by one phase compare:
+//   square  q<half ? +1 : -1      pulse  q<duty ? +1 : -1
+//   triangle q<half ? 4p-1 : 3-4p  saw    q<half ? 2p : 2p-2      constants: a = 0
+// which evaluates without a branch.  kind: 0 = affine, 1 = sine, 2 = noise.
+struct OscShape {
+  int kind, pad;
+  u64 thresh;
+  double a_lo, b_lo, a_hi, b_hi;
+};
+__device__ __forceinline__ double osc_eval(const OscShape& o, u64 q, u64 thresh, u64 seed, i64 frame) {
+  if (o.kind == 0) {
+    const bool lo = q < thresh;
+    return fma(lo ? o.a_lo : o.a_hi, pos_of(q), lo ? o.b_lo : o.b_hi);
+  }
+  if (o.kind == 1) return sinpi(2.0 * pos_of(q));
+  return __ull2double_rn(splitmix64(seed + (u64)frame) >> 11) * (1.0 / 4503599627370496.0) - 1.0;
+}
+
+// Both sections' coefficients from u = fc/sr with ONE division: with s = sin(pi u), c = cos(pi u)
+// and k = s/c, multiplying numerator and denominator of the k-form (dsp.cuh lp24_from_k) by c^2 gives
+//   b0 = s^2/D, a1 = 2(c0 c^2 - s^2)/D, a2 = (c1k s c - s^2 - c0 c^2)/D, D = c1k s c + s^2 + c0 c^2.
+__device__ __forceinline__ void lp24_from_u(const Lp24Ripple& rp, double u, SecCoef& s1, SecCoef& s2) {
+  double s, c;
+  sincospi(u, &s, &c);
+  const double ss = s * s, cc = c * c, sc = s * c;
+  const double n1 = rp.c0 * cc, n2 = rp.c2 * cc;
+  const double d1 = fma(rp.c1k, sc, ss + n1), d2 = fma(rp.c3k, sc, ss + n2);
+  const double r = 1.0 / (d1 * d2);
+  const double i1 = d2 * r, i2 = d1 * r;
+  s1.b0 = ss * i1;
+  s1.a1 = 2.0 * (n1 - ss) * i1;
+  s1.a2 = (fma(rp.c1k, sc, -ss) - n1) * i1;
+  s2.b0 = ss * i2;
+  s2.a1 = 2.0 * (n2 - ss) * i2;
+  s2.a2 = (fma(rp.c3k, sc, -ss) - n2) * i2;
+}
+
 struct WelshInst {
   EnvShape amp, filt;
   int w1, w2, wl, sync, routing, filter_mode, uid, voice0;
@@ -45,6 +82,10 @@ struct WelshInst {
   SecCoef fixed1, fixed2;
   double gl, gr;
   double pi_over_sr, sr;
+  double lfo_cos[kT], lfo_sin[kT];  // cos/sin(2*pi*j*lfo_dq/2^64): rotation table for a sine LFO
+  OscShape s1, s2, sl;              // branch-free waveform descriptions (fast path)
+  double log2_25_over_sr;           // fc/sr = exp2(pct*log2(800) + log2(25/sr))
+  double u_min, u_max;              // clamp of fc/sr: [1/sr, 0.49]
 };
 enum { FILTER_FIXED = 0, FILTER_ENVELOPE = 1, FILTER_LFO = 2 };
 
@@ -381,6 +422,178 @@ __device__ __forceinline__ void welsh_block(WelshVoice& st, const WelshInst& I, 
   }
 }
 
+// ---- fast path ---------------------------------------------------------------------------------
+// An ADSR restricted to one stage is a quadratic in the frame index: level = q0 + w*(q1 + q2*w),
+// w = w0 + j*dw.  A lane whose kT frames lie inside one stage of each envelope evaluates them with
+// 3 FMAs per frame and no integer work.
+struct EnvSeg {
+  double q0, q1, q2, w0, dw;
+};
+__device__ __forceinline__ bool env_segment(const EnvShape& s, i64 n_on, i64 n_off, double l_on, double l_off, i64 c0,
+                                            EnvSeg& g) {
+  g.q0 = 0.0; g.q1 = 0.0; g.q2 = 0.0; g.w0 = 0.0; g.dw = 0.0;
+  const i64 last = c0 + (kT - 1);
+  if (last < n_off) {
+    const i64 k = c0 - n_on;
+    if (k + (kT - 1) < s.na) {  // attack: l_on + (1-l_on) * t(2-t)
+      g.w0 = (double)k * s.inv_na; g.dw = s.inv_na;
+      g.q0 = l_on; g.q1 = 2.0 * (1.0 - l_on); g.q2 = -(1.0 - l_on);
+      return true;
+    }
+    if (k < s.na) return false;
+    const i64 k2 = k - s.na;
+    if (k2 + (kT - 1) < s.nd) {  // decay: S + (1-S) * u^2
+      g.w0 = 1.0 - (double)k2 * s.inv_nd; g.dw = -s.inv_nd;
+      g.q0 = s.sustain; g.q2 = 1.0 - s.sustain;
+      return true;
+    }
+    if (k2 < s.nd) return false;
+    g.q0 = s.sustain;
+    return true;
+  }
+  if (c0 >= n_off) {
+    const i64 k = c0 - n_off;
+    if (k + (kT - 1) < s.nr) {  // release: l_off * u^2
+      g.w0 = 1.0 - (double)k * s.inv_nr; g.dw = -s.inv_nr;
+      g.q2 = l_off;
+      return true;
+    }
+    return k >= s.nr;  // silent tail
+  }
+  return false;
+}
+__device__ __forceinline__ double env_seg_at(const EnvSeg& g, int j) {
+  double w = fma((double)j, g.dw, g.w0);
+  return fma(w, fma(g.q2, w, g.q1), g.q0);
+}
+
+// Lane classification for the fast path: 0 = needs the general path, 1 = all kT frames idle,
+// 2 = all kT frames sounding inside single envelope stages.
+__device__ __forceinline__ int welsh_lane_class(const WelshVoice& st, const WelshInst& I, i64 c0, i64 f_end,
+                                                EnvSeg& amp, EnvSeg& filt) {
+  const i64 last = c0 + (kT - 1);
+  const i64 idle_at = st.n_off + I.amp.nr;
+  if (c0 >= f_end || last < st.n_on || c0 >= idle_at) return 1;
+  if (!(c0 >= st.n_on && last < idle_at && last < f_end)) return 0;
+  if (!env_segment(I.amp, st.n_on, st.n_off, st.la_on, st.la_off, c0, amp)) return 0;
+  if (I.filter_mode == FILTER_ENVELOPE &&
+      !env_segment(I.filt, st.n_on, st.n_off, st.lf_on, st.lf_off, c0, filt))
+    return 0;
+  return 2;
+}
+
+// Same contract as welsh_block<false,false>, for blocks in which every lane is class 1 or 2.
+__device__ __forceinline__ void welsh_block_fast(WelshVoice& st, const WelshInst& I, i64 fb, int lane, int cls,
+                                                 const EnvSeg& aseg, const EnvSeg& fseg, u64 seed1, u64 seed2,
+                                                 u64 seedl, double2* tile_row, bool accumulate) {
+  const i64 c0 = fb + (i64)lane * kT;
+  double yp[kT], g0[kT], g1[kT], sb0[kT], sa1[kT], sa2[kT], ampf[kT];
+  double ps0 = 0.0, ps1 = 0.0, h00 = 1.0, h01 = 0.0, h10 = 0.0, h11 = 1.0;
+  const bool on = cls == 2;
+#pragma unroll
+  for (int j = 0; j < kT; ++j) {
+    yp[j] = 0.0; g0[j] = 0.0; g1[j] = 0.0; ampf[j] = 0.0; sb0[j] = 0.0; sa1[j] = 0.0; sa2[j] = 0.0;
+  }
+  if (on) {
+    Phases ph = welsh_phases_at(st, I, c0 - 1);
+    // sine LFO: one sincospi per lane chunk, then an angle-addition rotation per frame
+    double ls = 0.0, lc = 0.0;
+    const bool lfo_on = I.routing != LFO_NONE;
+    const bool lfo_sine = I.wl == W_SINE;
+    if (lfo_on && lfo_sine) sincospi(2.0 * pos_of(ph.pl + I.lfo_dq), &ls, &lc);
+#pragma unroll
+    for (int j = 0; j < kT; ++j) {
+      const i64 n = c0 + j;
+      double ld = 0.0;
+      if (lfo_on) {
+        ph.pl += I.lfo_dq;
+        double l = lfo_sine ? fma(ls, I.lfo_cos[j], lc * I.lfo_sin[j])
+                            : osc_eval(I.sl, ph.pl, I.sl.thresh, seedl, n);
+        ld = l * I.depth;
+      }
+      ph.p1 += st.d1;
+      const bool wrapped = ph.p1 < st.d1;
+      ph.p2 = (I.sync && wrapped) ? 0ull : ph.p2 + st.d2;
+      u64 du1 = I.s1.thresh, du2 = I.s2.thresh;
+      if (I.routing == LFO_PULSE_WIDTH) {
+        const double top = 1.0 - 1.0 / 9007199254740992.0;
+        double a = __dadd_rn(I.duty1, __dmul_rn(0.5, ld));
+        double b = __dadd_rn(I.duty2, __dmul_rn(0.5, ld));
+        a = a < 0.0 ? 0.0 : (a > top ? top : a);
+        b = b < 0.0 ? 0.0 : (b > top ? top : b);
+        if (I.w1 == W_PULSE) du1 = cycles_to_q(a);
+        if (I.w2 == W_PULSE) du2 = cycles_to_q(b);
+      }
+      const double o1 = osc_eval(I.s1, ph.p1, du1, seed1, n);
+      const double o2 = osc_eval(I.s2, ph.p2, du2, seed2, n);
+      const double x = o1 * I.mix + o2 * (1.0 - I.mix);
+      SecCoef c1 = I.fixed1, c2 = I.fixed2;
+      if (I.filter_mode != FILTER_FIXED) {
+        double pct = I.filter_mode == FILTER_ENVELOPE ? fma(I.cut_b, env_seg_at(fseg, j), I.cut_a)
+                                                      : I.cut_a * (1.0 + ld);
+        pct = pct < 0.0 ? 0.0 : (pct > 1.0 ? 1.0 : pct);
+        double u = exp2(fma(pct, kLog2_800, I.log2_25_over_sr));
+        u = u > I.u_max ? I.u_max : u;
+        u = u < I.u_min ? I.u_min : u;
+        lp24_from_u(I.rp, u, c1, c2);
+      }
+      sb0[j] = c2.b0; sa1[j] = c2.a1; sa2[j] = c2.a2;
+      ampf[j] = env_seg_at(aseg, j) * (I.routing == LFO_AMPLITUDE ? fma(0.5, ld, 0.5) : 0.5);
+      const double bx = c1.b0 * x;
+      const double y = bx + ps0;
+      yp[j] = y; g0[j] = h00; g1[j] = h01;
+      const double n0 = 2.0 * bx + c1.a1 * y + ps1;
+      ps1 = bx + c1.a2 * y;
+      ps0 = n0;
+      const double t00 = c1.a1 * h00 + h10, t01 = c1.a1 * h01 + h11;
+      h10 = c1.a2 * h00; h11 = c1.a2 * h01;
+      h00 = t00; h01 = t01;
+    }
+  }
+  double e0, e1, end0, end1;
+  {
+    Affine2 a;
+    a.m00 = h00; a.m01 = h01; a.m10 = h10; a.m11 = h11; a.v0 = ps0; a.v1 = ps1;
+    Affine2 inc = affine_warp_scan(a, lane);
+    affine_lane_entry(inc, lane, st.s[0], st.s[1], e0, e1, end0, end1);
+    st.s[0] = end0; st.s[1] = end1;
+  }
+  ps0 = 0.0; ps1 = 0.0; h00 = 1.0; h01 = 0.0; h10 = 0.0; h11 = 1.0;
+  if (on) {
+#pragma unroll
+    for (int j = 0; j < kT; ++j) {
+      const double x = yp[j] + g0[j] * e0 + g1[j] * e1;
+      const double bx = sb0[j] * x;
+      const double y = bx + ps0;
+      yp[j] = y; g0[j] = h00; g1[j] = h01;
+      const double n0 = 2.0 * bx + sa1[j] * y + ps1;
+      ps1 = bx + sa2[j] * y;
+      ps0 = n0;
+      const double t00 = sa1[j] * h00 + h10, t01 = sa1[j] * h01 + h11;
+      h10 = sa2[j] * h00; h11 = sa2[j] * h01;
+      h00 = t00; h01 = t01;
+    }
+  }
+  {
+    Affine2 a;
+    a.m00 = h00; a.m01 = h01; a.m10 = h10; a.m11 = h11; a.v0 = ps0; a.v1 = ps1;
+    Affine2 inc = affine_warp_scan(a, lane);
+    affine_lane_entry(inc, lane, st.s[2], st.s[3], e0, e1, end0, end1);
+    st.s[2] = end0; st.s[3] = end1;
+  }
+#pragma unroll
+  for (int j = 0; j < kT; ++j) {
+    const double m = (yp[j] + g0[j] * e0 + g1[j] * e1) * ampf[j];
+    const int t = lane * kT + j;
+    double2 o = make_double2(m * I.gl, m * I.gr);
+    if (accumulate) {
+      double2 p = tile_row[t + (t >> 3)];
+      o.x += p.x; o.y += p.y;
+    }
+    tile_row[t + (t >> 3)] = o;
+  }
+}
+
 // Sum the W per-voice tiles of one block and store 16 bytes per frame.
 template <int W>
 __device__ __forceinline__ void cta_reduce_store(const double2* tiles, const int* s_active, double2* out, i64 fb,
@@ -402,47 +615,83 @@ __device__ __forceinline__ void cta_reduce_store(const double2* tiles, const int
   }
 }
 
+// The general (event / pitch-LFO / stage-boundary) variants live behind one out-of-line call that
+// works on the voice record in global memory, so the kernel's register allocation is set by the
+// fast path; these variants run for a handful of blocks per note.
+__device__ __noinline__ void welsh_block_general(int variant, WelshVoice* vp, const WelshInst* Ip,
+                                                 const VoiceEvent* __restrict__ ev, int ei, int e_end, i64 fb,
+                                                 i64 f_end, int lane, u64 seed1, u64 seed2, u64 seedl,
+                                                 double2* tile_row, bool accumulate) {
+  WelshVoice st = *vp;
+  const WelshInst& I = *Ip;
+  switch (variant) {
+    case 0: welsh_block<false, false>(st, I, ev, ei, e_end, fb, f_end, lane, seed1, seed2, seedl, tile_row, accumulate); break;
+    case 1: welsh_block<false, true>(st, I, ev, ei, e_end, fb, f_end, lane, seed1, seed2, seedl, tile_row, accumulate); break;
+    case 2: welsh_block<true, false>(st, I, ev, ei, e_end, fb, f_end, lane, seed1, seed2, seedl, tile_row, accumulate); break;
+    default: welsh_block<true, true>(st, I, ev, ei, e_end, fb, f_end, lane, seed1, seed2, seedl, tile_row, accumulate); break;
+  }
+  __syncwarp();
+  if (lane == 0) *vp = st;
+  __syncwarp();
+}
+
 // grid = number of CtaWork items; block = 32 * W threads; dynamic smem = W * kTileStride double2.
-template <int W>
-__global__ void __launch_bounds__(32 * W) welsh_kernel(const WelshInst* __restrict__ insts,
-                                                        WelshVoice* __restrict__ voices,
-                                                        const CtaWork* __restrict__ work,
-                                                        const VoiceEvent* __restrict__ events,
-                                                        const int* __restrict__ ev_off, i64 f0, int nframes) {
+// __launch_bounds__(.., 2): two CTAs (16 warps) per SM, i.e. at most 128 registers per thread.
+template <int W, int MINB>
+__global__ void __launch_bounds__(32 * W, MINB) welsh_kernel(const WelshInst* __restrict__ insts,
+                                                           WelshVoice* __restrict__ voices,
+                                                           const CtaWork* __restrict__ work,
+                                                           const VoiceEvent* __restrict__ events,
+                                                           const int* __restrict__ ev_off, i64 f0, int nframes) {
   extern __shared__ double2 smem_tiles[];
   __shared__ int s_active[W];
+  __shared__ WelshInst sI;  // the CTA's instrument record: LDS instead of repeated global loads
   const CtaWork wk = work[blockIdx.x];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const WelshInst& I = insts[wk.inst];
+  {
+    const int* src = reinterpret_cast<const int*>(insts + wk.inst);
+    int* dst = reinterpret_cast<int*>(&sI);
+    for (int i = threadIdx.x; i < (int)(sizeof(WelshInst) / sizeof(int)); i += 32 * W) dst[i] = src[i];
+  }
+  __syncthreads();
+  const WelshInst& I = sI;
   double2* tile_row = smem_tiles + warp * kTileStride;
   const i64 f_end = f0 + nframes;
   const bool pitch = I.routing == LFO_PITCH;
+#pragma unroll 1
   for (i64 fb = f0; fb < f_end; fb += kBlockFrames) {
     bool any = false;
+#pragma unroll 1
     for (int g = warp; g < wk.nvoices; g += W) {
       const int vi = wk.voice0 + g;
       WelshVoice st = voices[vi];
       int ei = ev_off[vi];
       const int e_end = ev_off[vi + 1];
       while (ei < e_end && events[ei].frame < fb) ++ei;  // already folded into st by earlier blocks
-      bool idle = fb >= st.n_off + I.amp.nr;
-      bool ev_here = ei < e_end && events[ei].frame < fb + kBlockFrames;
+      const bool idle = fb >= st.n_off + I.amp.nr;
+      const bool ev_here = ei < e_end && events[ei].frame < fb + kBlockFrames;
       if (idle && !ev_here) continue;
       const int local = vi - I.voice0;
       const u64 seed1 = splitmix64(((u64)(unsigned)I.uid << 32) ^ (u64)(2 * local));
       const u64 seed2 = splitmix64(((u64)(unsigned)I.uid << 32) ^ (u64)(2 * local + 1));
       const u64 seedl = splitmix64(((u64)(unsigned)I.uid << 32) ^ 0x4C464F00ull ^ (u64)local);
-      if (pitch) {
-        if (ev_here) welsh_block<true, true>(st, I, events, ei, e_end, fb, f_end, lane, seed1, seed2, seedl, tile_row, any);
-        else welsh_block<true, false>(st, I, events, ei, e_end, fb, f_end, lane, seed1, seed2, seedl, tile_row, any);
+      bool fast = false;
+      EnvSeg aseg, fseg;
+      int cls = 0;
+      if (!pitch && !ev_here) {
+        cls = welsh_lane_class(st, I, fb + (i64)lane * kT, f_end, aseg, fseg);
+        fast = __all_sync(0xffffffffu, cls != 0);
+      }
+      if (fast) {
+        welsh_block_fast(st, I, fb, lane, cls, aseg, fseg, seed1, seed2, seedl, tile_row, any);
+        __syncwarp();
+        if (lane == 0) voices[vi] = st;
+        __syncwarp();
       } else {
-        if (ev_here) welsh_block<false, true>(st, I, events, ei, e_end, fb, f_end, lane, seed1, seed2, seedl, tile_row, any);
-        else welsh_block<false, false>(st, I, events, ei, e_end, fb, f_end, lane, seed1, seed2, seedl, tile_row, any);
+        welsh_block_general((pitch ? 2 : 0) + (ev_here ? 1 : 0), voices + vi, insts + wk.inst, events, ei, e_end, fb, f_end, lane,
+                            seed1, seed2, seedl, tile_row, any);
       }
       any = true;
-      __syncwarp();
-      if (lane == 0) voices[vi] = st;
-      __syncwarp();
     }
     if (lane == 0) s_active[warp] = any ? 1 : 0;
     __syncthreads();
@@ -588,8 +837,10 @@ __global__ void __launch_bounds__(32 * W) fm_kernel(const FmInst* __restrict__ i
   const FmInst& I = insts[wk.inst];
   double2* tile_row = smem_tiles + warp * kTileStride;
   const i64 f_end = f0 + nframes;
+#pragma unroll 1
   for (i64 fb = f0; fb < f_end; fb += kBlockFrames) {
     bool any = false;
+#pragma unroll 1
     for (int g = warp; g < wk.nvoices; g += W) {
       const int vi = wk.voice0 + g;
       FmVoice st = voices[vi];

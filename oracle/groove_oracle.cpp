@@ -63,7 +63,7 @@ inline uint64_t cycles_to_q(double c) {
   if (!(r < kTwo64)) return 0;
   return (uint64_t)r;
 }
-inline double pos_of(uint64_t q) { return (double)(q >> 11) * (1.0 / 9007199254740992.0); }
+inline double pos_of(uint64_t q) { return (double)(q >> 12) * (1.0 / 4503599627370496.0); }  // top 52 bits
 inline uint64_t splitmix64(uint64_t x) {
   x += UINT64_C(0x9E3779B97F4A7C15);
   x = (x ^ (x >> 30)) * UINT64_C(0xBF58476D1CE4E5B9);

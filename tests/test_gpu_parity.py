@@ -1,0 +1,184 @@
+"""GPU parity tests (pytest -m gpu): the CUDA path, called through the C ABI, against the CPU oracle.
+
+Tolerance (BASELINE.json north_star): per-sample absolute error <= 1e-6 of full scale and 16-bit
+PCM within +-1 LSB.  The kernels actually land around 1e-11; TIGHT is asserted too so a regression
+in numerical quality is caught long before the contractual bound.
+"""
+import numpy as np
+import pytest
+
+from groove_b200 import abi, workloads
+from tests import scenes
+from tests.oracle_binding import OracleEngine, pcm16
+
+pytestmark = pytest.mark.gpu
+
+TOL = 1e-6
+TIGHT = 1e-9
+
+
+def gpu_engine(sr=44100.0, **kw):
+    from groove_b200 import Engine
+    return Engine(sr, **kw)
+
+
+def both(scene, sr=44100.0, max_block=0, chunk=None):
+    o = OracleEngine(sr)
+    n = scene(o)
+    ref = o.render(n)
+    g = gpu_engine(sr, max_block=max_block)
+    scene(g)
+    if chunk is None:
+        out = g.render(n)
+    else:
+        parts, done = [], 0
+        while done < n:
+            k = min(chunk, n - done)
+            parts.append(g.render(k).copy())
+            done += k
+        out = np.concatenate(parts)
+    st = g.stats()
+    g.close()
+    assert st.kernel_launches > 0
+    return out, ref
+
+
+def check(out, ref, tol=TOL, tight=TIGHT):
+    err = float(np.abs(out - ref).max())
+    assert err <= tol, f"max abs error {err}"
+    assert err <= tight, f"numerical quality regressed: {err}"
+    a = pcm16(np.clip(out, -1.0, 1.0)).astype(np.int32)
+    b = pcm16(np.clip(ref, -1.0, 1.0)).astype(np.int32)
+    assert int(np.abs(a - b).max()) <= 1
+
+
+@pytest.mark.parametrize("name", list(scenes.ALL_SCENES))
+@pytest.mark.parametrize("max_block", [0, 1000, 257])
+def test_scene_parity(name, max_block):
+    out, ref = both(scenes.ALL_SCENES[name], max_block=max_block)
+    check(out, ref)
+
+
+@pytest.mark.parametrize("chunk", [17, 64, 4099])
+def test_caller_buffer_size_does_not_change_audio(chunk):
+    """orchestrator.rs:1683 uses a prime buffer (17): state must carry exactly across render calls."""
+    out, ref = both(scenes.scene_welsh_variants, chunk=chunk)
+    check(out, ref)
+    out, ref = both(scenes.scene_effects_rack, chunk=chunk)
+    check(out, ref)
+
+
+def test_graph_semantics_on_gpu():
+    """orchestrator.rs:1444-1668 restated on the GPU engine: silence, sums, gain chains, branch."""
+    g = gpu_engine()
+    g.finalize()
+    assert np.all(g.render(100) == 0.0)
+    g.close()
+    out, ref = both(scenes.scene_graph_toys)
+    assert np.allclose(out, 0.1 + 0.5 * (0.3 + 0.5), atol=1e-15)
+    assert np.array_equal(out, ref)
+
+
+def test_pcm16_output_matches_oracle_conversion():
+    g = gpu_engine()
+    n = scenes.scene_drums_and_sampler(g)
+    pcm = g.render_pcm16(n)
+    g.close()
+    o = OracleEngine()
+    scenes.scene_drums_and_sampler(o)
+    ref = pcm16(o.render(n))
+    assert pcm.dtype == np.int16 and pcm.shape == (n, 2)
+    assert int(np.abs(pcm.astype(np.int32) - ref.astype(np.int32)).max()) <= 1
+    assert np.abs(ref).max() == 32767  # the scene clips: saturation is exercised
+
+
+def test_device_resident_render_and_readback():
+    g = gpu_engine()
+    n = scenes.scene_fm(g)
+    done = g.render_device(n)
+    assert done == n
+    ptr, frames = g.last_device_buffer()
+    assert ptr and frames == n
+    out = g.read_last(n)
+    g.close()
+    o = OracleEngine()
+    scenes.scene_fm(o)
+    check(out, o.render(n))
+
+
+def test_save_restore_state_roundtrip():
+    g = gpu_engine()
+    n = scenes.scene_effects_rack(g)
+    first = g.render(5000).copy()
+    blob = g.save_state()
+    rest_a = g.render(n - 5000).copy()
+    g.restore_state(blob)
+    assert g.position == 5000
+    rest_b = g.render(n - 5000).copy()
+    g.close()
+    assert np.array_equal(rest_a, rest_b)
+    o = OracleEngine()
+    scenes.scene_effects_rack(o)
+    check(np.concatenate([first, rest_a]), o.render(n))
+
+
+def test_high_q_low_cutoff_filter_scan():
+    """SURVEY.md §7 hard part: pole radius ~0.997+ (40 Hz, high resonance) and the 0.04 Hz / Q 0.05
+    low-pass of test-data/perf-1.json; the scan must not lose precision."""
+    def scene(r):
+        p = scenes.generic_welsh(w1=abi.WAVE_SAWTOOTH, w2=abi.WAVE_SQUARE, cutoff_start=scenes.hz_to_pct(40.0),
+                                 cutoff_end=0.05, ripple=denorm(1.0), voices=2, filt=(0.0, 1.5, 0.3, 1.5))
+        u = r.add_instrument(abi.INST_WELSH, p)
+        f1 = r.add_effect(abi.FX_LOW_PASS_12DB, abi.BiquadParams(0.04, 0.05))
+        f2 = r.add_effect(abi.FX_ALL_PASS_12DB, abi.BiquadParams(40.0, 20.0))
+        r.patch_chain([u, f2, abi.MAIN_MIXER])
+        r.patch_chain([u, f1, abi.MAIN_MIXER])
+        r.finalize()
+        r.note_on(0, u, 40)
+        r.note_off(30000, u, 40)
+        return 44100
+    denorm = lambda q: q * q * 10.0 + 0.707
+    out, ref = both(scene)
+    check(out, ref)
+
+
+def test_empty_and_ragged_inputs():
+    g = gpu_engine()
+    u = g.add_instrument(abi.INST_DRUMKIT, abi.DrumkitParams())       # no samples loaded
+    s = g.add_instrument(abi.INST_SAMPLER, abi.SamplerParams(440.0, 2, 0))
+    g.patch(u, abi.MAIN_MIXER)
+    g.patch(s, abi.MAIN_MIXER)
+    g.finalize()
+    g.note_on(0, u, 35)
+    g.note_on(0, s, 60)
+    assert g.render(0).shape == (0, 2)
+    assert np.all(g.render(1) == 0.0)
+    assert np.all(g.render(1001) == 0.0)
+    g.close()
+
+
+def test_cfg4_slice_parity_and_linearity():
+    """Config 4 on a slice the oracle finishes in seconds, then a size-independent property at a
+    larger size: rendering voices A and B together equals rendering them apart and summing."""
+    cfgA = workloads.cfg4_slice(128, 20000)
+    o = OracleEngine(48000.0)
+    workloads.build_cfg4(o, cfgA)
+    ref = o.render(20000)
+    g = gpu_engine(48000.0)
+    workloads.build_cfg4(g, cfgA)
+    out = g.render(20000)
+    g.close()
+    check(out, ref)
+
+    frames = 200_000
+    def run(voices, offset):
+        e = gpu_engine(48000.0)
+        workloads.build_cfg4(e, workloads.cfg4_slice(voices, frames, offset))
+        y = e.render(frames)
+        e.close()
+        return y
+    whole = run(256, 0)
+    parts = run(128, 0) + run(128, 128)
+    # cfg4_slice(256) groups voices by i mod 128, the halves by i mod 128 as well: same voices
+    assert np.abs(whole - parts).max() < 1e-12
+    assert np.abs(whole).max() > 1e-3
