@@ -87,16 +87,18 @@ def parse_json5(text: str):
     while i < n:
         c = text[i]
         if in_str:
-            out.append(c)
             if c == "\\" and i + 1 < n:
-                out.append(text[i + 1]); i += 1
+                out.append(c)
+                out.append(text[i + 1])
+                i += 1
             elif c == q:
+                out.append('"')
                 in_str = False
+            else:
+                out.append('\\"' if c == '"' else c)
         elif c in "\"'":
             in_str, q = True, c
-            out.append('"' if c == "'" else c)
-            if c == "'":
-                q = "'"
+            out.append('"')
         elif text.startswith("//", i):
             while i < n and text[i] != "\n":
                 i += 1
