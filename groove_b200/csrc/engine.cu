@@ -253,6 +253,7 @@ struct Node {
   int order = -1;                 // position in the plan (-1 = unreachable)
   double2* buf = nullptr;         // chunk output (max_block frames)
   double2* scratch = nullptr;     // pre-reduction when > kMaxSources inputs / partial sums
+  const double2** d_src_table = nullptr;  // device table of source buffers (> kMaxSources inputs)
   // --- instruments ---
   gb_welsh_params wp;
   gb_fm_params fp;
@@ -290,7 +291,7 @@ struct gb_engine {
   uint32_t next_uid = 2;
   int num_sms = 148;
   int welsh_occ = 2;        // resident CTAs per SM the Welsh kernel is compiled for (GB_WELSH_OCC=1|2)
-  int cta_target_mult = 1;  // CTAs per SM the voice work lists aim for (GB_CTA_MULT)
+  int cta_target_mult = 2;  // CTAs per SM the voice work lists aim for (GB_CTA_MULT)
   std::map<uint32_t, std::unique_ptr<Node>> nodes;
   std::vector<Node*> plan;  // reachable nodes, sources before consumers
   std::vector<gb_event> events;
@@ -310,6 +311,8 @@ struct gb_engine {
   DevBuf<VoiceEvent> wev, fev;
   DevBuf<int> wev_off, fev_off;
   DevBuf<SamplePlay> plays;
+  DevBuf<PartialDesc> partials;  // instruments split over several CTAs (static after finalize)
+  int n_partials = 0;
   std::vector<void*> allocations;  // everything cudaMalloc'ed at finalize/load time
 
   double2* last_out = nullptr;  // main mixer buffer of the last chunk
@@ -410,10 +413,10 @@ void welsh_inst_from_params(const Node& n, double sr, WelshInst* I) {
     switch (wf) {
       case GB_WAVE_SINE: o->kind = 1; break;
       case GB_WAVE_NOISE: o->kind = 2; break;
-      case GB_WAVE_SQUARE: o->b_lo = 1.0; o->b_hi = -1.0; break;
+      case GB_WAVE_SQUARE: o->kind = 3; o->b_lo = 1.0; o->b_hi = -1.0; break;
       case GB_WAVE_PULSE_WIDTH: o->thresh = duty_q; o->b_lo = 1.0; o->b_hi = -1.0; break;
-      case GB_WAVE_TRIANGLE: o->a_lo = 4.0; o->b_lo = -1.0; o->a_hi = -4.0; o->b_hi = 3.0; break;
-      case GB_WAVE_SAWTOOTH: o->a_lo = 2.0; o->b_lo = 0.0; o->a_hi = 2.0; o->b_hi = -2.0; break;
+      case GB_WAVE_TRIANGLE: o->kind = 5; o->a_lo = 4.0; o->b_lo = -1.0; o->a_hi = -4.0; o->b_hi = 3.0; break;
+      case GB_WAVE_SAWTOOTH: o->kind = 4; o->a_lo = 2.0; o->b_lo = 0.0; o->a_hi = 2.0; o->b_hi = -2.0; break;
       case GB_WAVE_DEBUG_MAX: o->b_lo = 1.0; o->b_hi = 1.0; break;
       case GB_WAVE_DEBUG_MIN: o->b_lo = -1.0; o->b_hi = -1.0; break;
       default: break;  // none / debug-zero: 0
@@ -501,16 +504,10 @@ int gather_sources(gb_engine* e, Node* n, int frames, SourceList* out) {
     for (int i = 0; i < out->n; ++i) out->p[i] = ptrs[i];
     return 0;
   }
-  size_t i = 0;
-  bool first = true;
-  while (i < ptrs.size()) {
-    SourceList sl;
-    memset(&sl, 0, sizeof sl);
-    if (!first) sl.p[sl.n++] = n->scratch;
-    while (i < ptrs.size() && sl.n < kMaxSources) sl.p[sl.n++] = ptrs[i++];
+  {
+    // the pointer table was uploaded at finalize (sources never change afterwards)
     Launch l(e, false);
-    pointwise_kernel<<<cdiv(frames, 256), 256, 0, e->stream>>>(sl, n->scratch, 0, frames, OP_SUM, 0.0, 0.0);
-    first = false;
+    sum_table_kernel<<<cdiv(frames, 256), 256, 0, e->stream>>>(n->d_src_table, (int)ptrs.size(), n->scratch, frames);
   }
   out->n = 1;
   out->p[0] = n->scratch;
@@ -915,7 +912,7 @@ int gb_finalize(gb_engine* e) {
     if ((rc = dev_alloc(e, &e->d_winst, e->h_winst.size()))) return rc;
     std::vector<WelshVoice> init((size_t)wv);
     memset(init.data(), 0, init.size() * sizeof(WelshVoice));
-    for (auto& v : init) { v.n_on = kNever; v.n_off = kNever; v.anchor = 0; }
+    for (auto& v : init) { v.n_on = kNever; v.n_off = kNever; v.anchor = 0; v.knot_frame = kNever; }
     CUDA_TRY(e, cudaMemcpy(e->d_wvoice, init.data(), init.size() * sizeof(WelshVoice), cudaMemcpyHostToDevice));
   }
   if (fv) {
@@ -963,6 +960,36 @@ int gb_finalize(gb_engine* e) {
   int rc;
   if ((rc = plan_work(GB_INST_WELSH, wv, e->wwork, &e->n_wwork))) return rc;
   if ((rc = plan_work(GB_INST_FM, fv, e->fwork, &e->n_fwork))) return rc;
+  {
+    std::vector<PartialDesc> descs;
+    for (Node* n : e->plan) {
+      if (!(n->kind == GB_INST_WELSH || n->kind == GB_INST_FM) || !n->scratch) continue;
+      const CtaWork* wk = n->kind == GB_INST_WELSH ? e->wwork.h : e->fwork.h;
+      int cnt = n->kind == GB_INST_WELSH ? e->n_wwork : e->n_fwork;
+      PartialDesc d;
+      d.base = n->scratch; d.out = n->buf; d.stride = mb; d.count = 0; d.pad = 0;
+      for (int i = 0; i < cnt; ++i)
+        if (wk[i].inst == n->table_index) d.count++;
+      descs.push_back(d);
+    }
+    e->n_partials = (int)descs.size();
+    if (!descs.empty()) {
+      if (!e->partials.reserve(descs.size())) return fail(e, GB_ENOMEM, "out of memory");
+      memcpy(e->partials.h, descs.data(), descs.size() * sizeof(PartialDesc));
+      CUDA_TRY(e, cudaMemcpy(e->partials.d, e->partials.h, descs.size() * sizeof(PartialDesc), cudaMemcpyHostToDevice));
+    }
+    for (Node* n : e->plan) {
+      if (n->is_inst || (int)n->sources.size() <= kMaxSources) continue;
+      std::vector<const double2*> ptrs;
+      for (uint32_t su : n->sources) {
+        Node* sn = find(e, su);
+        if (sn && sn->order >= 0 && sn->buf) ptrs.push_back(sn->buf);
+      }
+      int rc2 = dev_alloc(e, &n->d_src_table, ptrs.size());
+      if (rc2) return rc2;
+      CUDA_TRY(e, cudaMemcpy((void*)n->d_src_table, ptrs.data(), ptrs.size() * sizeof(double2*), cudaMemcpyHostToDevice));
+    }
+  }
   CUDA_TRY(e, cudaFuncSetAttribute(welsh_kernel<kVoiceWarps, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                    (int)(kVoiceWarps * kTileStride * sizeof(double2))));
   CUDA_TRY(e, cudaFuncSetAttribute(welsh_kernel<kVoiceWarps, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -1201,30 +1228,18 @@ int render_chunk(gb_engine* e, int frames, size_t n_ev) {
       e->stats.voice_samples += (uint64_t)L.first->svoices.size() * (uint64_t)frames;
     }
   }
-  // ---- 4. plan walk: partial sums of split instruments, toy sources, effects ----
+  // ---- 4. partial sums of instruments split over several CTAs: one launch for all of them ----
+  if (e->n_partials) {
+    Launch l(e, false);
+    dim3 grid(cdiv(frames, 256), e->n_partials);
+    reduce_partials_kernel<<<grid, 256, 0, e->stream>>>(e->partials.d, frames);
+  }
+  // ---- 5. plan walk: toy sources, effects ----
   for (Node* n : e->plan) {
     if (n->is_inst) {
       if (n->kind == GB_INST_TOY_SOURCE) {
         Launch l(e, false);
         fill_kernel<<<cdiv(frames, 256), 256, 0, e->stream>>>(n->buf, frames, n->tp.level_left, n->tp.level_right);
-      } else if ((n->kind == GB_INST_WELSH || n->kind == GB_INST_FM) && n->scratch) {
-        // instrument split over several CTAs: sum its partials (left to right)
-        const CtaWork* wk = n->kind == GB_INST_WELSH ? e->wwork.h : e->fwork.h;
-        int cnt = n->kind == GB_INST_WELSH ? e->n_wwork : e->n_fwork;
-        std::vector<const double2*> parts;
-        for (int i = 0; i < cnt; ++i)
-          if (wk[i].inst == n->table_index) parts.push_back(wk[i].out);
-        size_t i = 0;
-        bool first = true;
-        while (i < parts.size()) {
-          SourceList sl;
-          memset(&sl, 0, sizeof sl);
-          if (!first) sl.p[sl.n++] = n->buf;
-          while (i < parts.size() && sl.n < kMaxSources) sl.p[sl.n++] = parts[i++];
-          Launch l(e, false);
-          pointwise_kernel<<<cdiv(frames, 256), 256, 0, e->stream>>>(sl, n->buf, 0, frames, OP_SUM, 0.0, 0.0);
-          first = false;
-        }
       }
       continue;
     }

@@ -65,6 +65,39 @@ __global__ void __launch_bounds__(256) pointwise_kernel(SourceList src, double2*
   out[t] = make_double2(op_apply(op, v.x, a, b), op_apply(op, v.y, a, b));
 }
 
+// out[t] = sum over a device-resident pointer table, left to right (any number of sources).
+__global__ void __launch_bounds__(256) sum_table_kernel(const double2* const* __restrict__ ptrs, int n,
+                                                         double2* __restrict__ out, int frames) {
+  int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= frames) return;
+  double l = 0.0, r = 0.0;
+  for (int k = 0; k < n; ++k) {
+    double2 v = ptrs[k][t];
+    l += v.x; r += v.y;
+  }
+  out[t] = make_double2(l, r);
+}
+// One launch for every instrument whose voices are split over several CTAs: blockIdx.y picks the
+// instrument; its partial buffers are `count` planes `stride` frames apart.
+struct PartialDesc {
+  const double2* base;
+  double2* out;
+  size_t stride;
+  int count;
+  int pad;
+};
+__global__ void __launch_bounds__(256) reduce_partials_kernel(const PartialDesc* __restrict__ descs, int frames) {
+  const PartialDesc d = descs[blockIdx.y];
+  int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= frames) return;
+  double l = 0.0, r = 0.0;
+  for (int k = 0; k < d.count; ++k) {
+    double2 v = d.base[(size_t)k * d.stride + t];
+    l += v.x; r += v.y;
+  }
+  d.out[t] = make_double2(l, r);
+}
+
 __global__ void __launch_bounds__(256) fill_kernel(double2* __restrict__ out, int n, double l, double r) {
   int t = blockIdx.x * blockDim.x + threadIdx.x;
   if (t < n) out[t] = make_double2(l, r);

@@ -43,13 +43,75 @@ struct OscShape {
   u64 thresh;
   double a_lo, b_lo, a_hi, b_hi;
 };
+// kinds 3..5 evaluate square / sawtooth / triangle without a compare: with q' = q + 2^63 (half a
+// cycle ahead, exact in fixed point) and p' = pos(q'):
+//   square = +-1 from the top phase bit;  saw = 2p' - 1;  triangle = |4p' - 2| - 1
+// which are bit-identical to the two-branch forms above (all operations exact).
 __device__ __forceinline__ double osc_eval(const OscShape& o, u64 q, u64 thresh, u64 seed, i64 frame) {
-  if (o.kind == 0) {
-    const bool lo = q < thresh;
-    return fma(lo ? o.a_lo : o.a_hi, pos_of(q), lo ? o.b_lo : o.b_hi);
+  switch (o.kind) {
+    case 0: {
+      const bool lo = q < thresh;
+      return fma(lo ? o.a_lo : o.a_hi, pos_of(q), lo ? o.b_lo : o.b_hi);
+    }
+    case 1: return sinpi(2.0 * pos_of(q));
+    case 3: return __hiloint2double((int)(0x3FF00000u | ((unsigned)(q >> 32) & 0x80000000u)), 0);
+    case 4: return fma(2.0, pos_of(q + (1ull << 63)), -1.0);
+    case 5: return fabs(fma(4.0, pos_of(q + (1ull << 63)), -2.0)) - 1.0;
+    default:
+      return __ull2double_rn(splitmix64(seed + (u64)frame) >> 11) * (1.0 / 4503599627370496.0) - 1.0;
   }
-  if (o.kind == 1) return sinpi(2.0 * pos_of(q));
-  return __ull2double_rn(splitmix64(seed + (u64)frame) >> 11) * (1.0 / 4503599627370496.0) - 1.0;
+}
+
+// ---- range-specialised elementary functions for the cutoff -> coefficient map ----------------------
+// The coefficient map only ever needs 2^y for y in [-20, 0] and sin/cos(pi u) for u in (0, 0.49].
+// On those ranges plain Taylor/Horner forms reach 1e-16 with no special cases, and with the
+// coefficients in constant memory every FMA takes its constant as a constant-bank operand (the
+// library versions re-materialise each 64-bit constant with two UMOVs when registers are short).
+__constant__ double kExp2C[13] = {  // (ln 2)^k / k!, k = 13 .. 1
+    1.3691488853904128e-12, 2.5678435993488206e-11, 4.4455382718708116e-10, 7.054911620801123e-09,
+    1.01780860092397e-07, 1.321548679014431e-06, 1.5252733804059841e-05, 0.0001540353039338161,
+    0.0013333558146428443, 0.009618129107628477, 0.05550410866482158, 0.24022650695910072, 0.6931471805599453};
+__constant__ double kSinC[9] = {  // (-1)^k / (2k+1)!, k = 8 .. 0
+    2.8114572543455206e-15, -7.6471637318198164e-13, 1.6059043836821613e-10, -2.5052108385441720e-08,
+    2.7557319223985893e-06, -1.9841269841269841e-04, 8.3333333333333332e-03, -1.6666666666666666e-01, 1.0};
+__constant__ double kCosC[9] = {  // (-1)^k / (2k)!, k = 8 .. 0
+    4.7794773323873853e-14, -1.1470745597729725e-11, 2.0876756987868100e-09, -2.7557319223985888e-07,
+    2.4801587301587302e-05, -1.3888888888888889e-03, 4.1666666666666664e-02, -0.5, 1.0};
+
+// 2^y, |y| < 1000 (no overflow/underflow handling needed by the caller's range)
+__device__ __forceinline__ double exp2_ranged(double y) {
+  const double magic = 6755399441055744.0;  // 1.5 * 2^52: rounds y to an integer in the low word
+  const double t = y + magic;
+  const int n = __double2loint(t);
+  const double f = y - (t - magic);  // [-0.5, 0.5]
+  double p = kExp2C[0];
+#pragma unroll
+  for (int k = 1; k < 13; ++k) p = fma(p, f, kExp2C[k]);
+  p = fma(p, f, 1.0);
+  return __hiloint2double(__double2hiint(p) + (n << 20), __double2loint(p));
+}
+// sin(pi u), cos(pi u) for u in [0, 0.5]
+__device__ __forceinline__ void sincospi_ranged(double u, double* s, double* c) {
+  const bool hi = u > 0.25;
+  const double t = hi ? 0.5 - u : u;  // [0, 0.25]
+  const double x = t * kPi;
+  const double z = x * x;
+  double ps = kSinC[0], pc = kCosC[0];
+#pragma unroll
+  for (int k = 1; k < 9; ++k) {
+    ps = fma(ps, z, kSinC[k]);
+    pc = fma(pc, z, kCosC[k]);
+  }
+  ps *= x;
+  *s = hi ? pc : ps;
+  *c = hi ? ps : pc;
+}
+// 1/x for normal positive x: single-precision seed + two Newton steps (relative error 1e-7 -> 1e-14 -> < 1 ulp)
+__device__ __forceinline__ double rcp_ranged(double x) {
+  double r = (double)__frcp_rn((float)x);
+  r = fma(fma(-x, r, 1.0), r, r);
+  r = fma(fma(-x, r, 1.0), r, r);
+  return r;
 }
 
 // Both sections' coefficients from u = fc/sr with ONE division: with s = sin(pi u), c = cos(pi u)
@@ -57,11 +119,11 @@ __device__ __forceinline__ double osc_eval(const OscShape& o, u64 q, u64 thresh,
 //   b0 = s^2/D, a1 = 2(c0 c^2 - s^2)/D, a2 = (c1k s c - s^2 - c0 c^2)/D, D = c1k s c + s^2 + c0 c^2.
 __device__ __forceinline__ void lp24_from_u(const Lp24Ripple& rp, double u, SecCoef& s1, SecCoef& s2) {
   double s, c;
-  sincospi(u, &s, &c);
+  sincospi_ranged(u, &s, &c);
   const double ss = s * s, cc = c * c, sc = s * c;
   const double n1 = rp.c0 * cc, n2 = rp.c2 * cc;
   const double d1 = fma(rp.c1k, sc, ss + n1), d2 = fma(rp.c3k, sc, ss + n2);
-  const double r = 1.0 / (d1 * d2);
+  const double r = rcp_ranged(d1 * d2);
   const double i1 = d2 * r, i2 = d1 * r;
   s1.b0 = ss * i1;
   s1.a1 = 2.0 * (n1 - ss) * i1;
@@ -97,6 +159,8 @@ struct WelshVoice {
   u64 d1, d2;
   double cyc1, cyc2;
   double s[4];
+  i64 knot_frame;   // frame of the carried coefficient knot (fast path, COEF_KNOTS); kNever = none
+  double knot[6];
 };
 
 struct CtaWork {
@@ -482,17 +546,81 @@ __device__ __forceinline__ int welsh_lane_class(const WelshVoice& st, const Wels
   return 2;
 }
 
-// Same contract as welsh_block<false,false>, for blocks in which every lane is class 1 or 2.
+// Exact coefficient set for cutoff fraction `pct` of the 25 Hz..20 kHz log range.
+__device__ __forceinline__ void welsh_coef_exact(const WelshInst& I, double pct, SecCoef& c1, SecCoef& c2) {
+  pct = pct < 0.0 ? 0.0 : (pct > 1.0 ? 1.0 : pct);
+  double u = exp2_ranged(fma(pct, kLog2_800, I.log2_25_over_sr));
+  u = u > I.u_max ? I.u_max : u;
+  u = u < I.u_min ? I.u_min : u;
+  lp24_from_u(I.rp, u, c1, c2);
+}
+
+// Quadratic through (0,k0), (kT/2,k4), (kT,k8) in Newton form: c(j) = k0 + j*(d1 + (j - kT/2)*d2).
+struct Quad {
+  double k0, d1, d2;
+};
+__device__ __forceinline__ Quad quad_fit(double k0, double k4, double k8) {
+  Quad q;
+  q.k0 = k0;
+  q.d1 = (k4 - k0) * (2.0 / kT);
+  q.d2 = ((k8 - k4) * (2.0 / kT) - q.d1) * (1.0 / kT);
+  return q;
+}
+__device__ __forceinline__ double quad_at(const Quad& q, int j) {
+  return fma((double)j, fma((double)(j - kT / 2), q.d2, q.d1), q.k0);
+}
+
+// Largest cutoff motion (fraction of the log range per frame) for which the per-frame coefficient
+// sets are taken from the quadratic through exact knots every kT/2 frames instead of being evaluated
+// exactly: the interpolation error grows with the cube of the rate and is <= 1e-11 absolute here
+// (docs/ORACLE_SPEC.md, "coefficient knots").
+constexpr double kKnotMaxRate = 1.0e-5;
+
+enum { COEF_FIXED = 0, COEF_EXACT = 1, COEF_KNOTS = 2 };
+
+// Fast path of the Welsh voice: same contract as welsh_block<false,false>, for blocks in which every
+// lane is class 1 (idle) or 2 (sounding inside single envelope stages).  CMODE selects how the
+// per-frame 24 dB coefficient sets are produced; COEF_KNOTS additionally needs every lane in class 2.
+template <int CMODE>
 __device__ __forceinline__ void welsh_block_fast(WelshVoice& st, const WelshInst& I, i64 fb, int lane, int cls,
                                                  const EnvSeg& aseg, const EnvSeg& fseg, u64 seed1, u64 seed2,
-                                                 u64 seedl, double2* tile_row, bool accumulate) {
+                                                 u64 seedl, double2* tile_row, bool accumulate, double* knot_out) {
   const i64 c0 = fb + (i64)lane * kT;
-  double yp[kT], g0[kT], g1[kT], sb0[kT], sa1[kT], sa2[kT], ampf[kT];
+  double yp[kT], g0[kT], g1[kT], ampf[kT];
+  double sb0[CMODE == COEF_EXACT ? kT : 1], sa1[CMODE == COEF_EXACT ? kT : 1], sa2[CMODE == COEF_EXACT ? kT : 1];
   double ps0 = 0.0, ps1 = 0.0, h00 = 1.0, h01 = 0.0, h10 = 0.0, h11 = 1.0;
   const bool on = cls == 2;
+  if (!on) {
 #pragma unroll
-  for (int j = 0; j < kT; ++j) {
-    yp[j] = 0.0; g0[j] = 0.0; g1[j] = 0.0; ampf[j] = 0.0; sb0[j] = 0.0; sa1[j] = 0.0; sa2[j] = 0.0;
+    for (int j = 0; j < kT; ++j) {
+      yp[j] = 0.0; g0[j] = 0.0; g1[j] = 0.0; ampf[j] = 0.0;
+      if (CMODE == COEF_EXACT) { sb0[j] = 0.0; sa1[j] = 0.0; sa2[j] = 0.0; }
+    }
+  }
+  // ---- coefficient knots: exact at j = kT/2 and j = kT; j = 0 comes from the previous lane ----
+  Quad qb1, qa11, qa21, qb2, qa12, qa22;
+  if (CMODE == COEF_KNOTS) {
+    SecCoef m1, m2, e1c, e2c;
+    welsh_coef_exact(I, fma(I.cut_b, env_seg_at(fseg, kT / 2), I.cut_a), m1, m2);
+    welsh_coef_exact(I, fma(I.cut_b, env_seg_at(fseg, kT), I.cut_a), e1c, e2c);
+    SecCoef s1c, s2c;
+    s1c.b0 = __shfl_up_sync(0xffffffffu, e1c.b0, 1); s1c.a1 = __shfl_up_sync(0xffffffffu, e1c.a1, 1);
+    s1c.a2 = __shfl_up_sync(0xffffffffu, e1c.a2, 1); s2c.b0 = __shfl_up_sync(0xffffffffu, e2c.b0, 1);
+    s2c.a1 = __shfl_up_sync(0xffffffffu, e2c.a1, 1); s2c.a2 = __shfl_up_sync(0xffffffffu, e2c.a2, 1);
+    if (lane == 0) {
+      if (st.knot_frame == fb) {
+        s1c.b0 = st.knot[0]; s1c.a1 = st.knot[1]; s1c.a2 = st.knot[2];
+        s2c.b0 = st.knot[3]; s2c.a1 = st.knot[4]; s2c.a2 = st.knot[5];
+      } else {
+        welsh_coef_exact(I, fma(I.cut_b, env_seg_at(fseg, 0), I.cut_a), s1c, s2c);
+      }
+    }
+    qb1 = quad_fit(s1c.b0, m1.b0, e1c.b0); qa11 = quad_fit(s1c.a1, m1.a1, e1c.a1); qa21 = quad_fit(s1c.a2, m1.a2, e1c.a2);
+    qb2 = quad_fit(s2c.b0, m2.b0, e2c.b0); qa12 = quad_fit(s2c.a1, m2.a1, e2c.a1); qa22 = quad_fit(s2c.a2, m2.a2, e2c.a2);
+    if (lane == 31) {  // the knot at fb + kBlockFrames is the next block's first knot
+      knot_out[0] = e1c.b0; knot_out[1] = e1c.a1; knot_out[2] = e1c.a2;
+      knot_out[3] = e2c.b0; knot_out[4] = e2c.a1; knot_out[5] = e2c.a2;
+    }
   }
   if (on) {
     Phases ph = welsh_phases_at(st, I, c0 - 1);
@@ -527,17 +655,16 @@ __device__ __forceinline__ void welsh_block_fast(WelshVoice& st, const WelshInst
       const double o1 = osc_eval(I.s1, ph.p1, du1, seed1, n);
       const double o2 = osc_eval(I.s2, ph.p2, du2, seed2, n);
       const double x = o1 * I.mix + o2 * (1.0 - I.mix);
-      SecCoef c1 = I.fixed1, c2 = I.fixed2;
-      if (I.filter_mode != FILTER_FIXED) {
-        double pct = I.filter_mode == FILTER_ENVELOPE ? fma(I.cut_b, env_seg_at(fseg, j), I.cut_a)
-                                                      : I.cut_a * (1.0 + ld);
-        pct = pct < 0.0 ? 0.0 : (pct > 1.0 ? 1.0 : pct);
-        double u = exp2(fma(pct, kLog2_800, I.log2_25_over_sr));
-        u = u > I.u_max ? I.u_max : u;
-        u = u < I.u_min ? I.u_min : u;
-        lp24_from_u(I.rp, u, c1, c2);
+      SecCoef c1 = I.fixed1;
+      if (CMODE == COEF_EXACT) {
+        SecCoef c2;
+        const double pct = I.filter_mode == FILTER_ENVELOPE ? fma(I.cut_b, env_seg_at(fseg, j), I.cut_a)
+                                                            : I.cut_a * (1.0 + ld);
+        welsh_coef_exact(I, pct, c1, c2);
+        sb0[j] = c2.b0; sa1[j] = c2.a1; sa2[j] = c2.a2;
+      } else if (CMODE == COEF_KNOTS) {
+        c1.b0 = quad_at(qb1, j); c1.a1 = quad_at(qa11, j); c1.a2 = quad_at(qa21, j);
       }
-      sb0[j] = c2.b0; sa1[j] = c2.a1; sa2[j] = c2.a2;
       ampf[j] = env_seg_at(aseg, j) * (I.routing == LFO_AMPLITUDE ? fma(0.5, ld, 0.5) : 0.5);
       const double bx = c1.b0 * x;
       const double y = bx + ps0;
@@ -562,15 +689,18 @@ __device__ __forceinline__ void welsh_block_fast(WelshVoice& st, const WelshInst
   if (on) {
 #pragma unroll
     for (int j = 0; j < kT; ++j) {
+      SecCoef c2 = I.fixed2;
+      if (CMODE == COEF_EXACT) { c2.b0 = sb0[j]; c2.a1 = sa1[j]; c2.a2 = sa2[j]; }
+      else if (CMODE == COEF_KNOTS) { c2.b0 = quad_at(qb2, j); c2.a1 = quad_at(qa12, j); c2.a2 = quad_at(qa22, j); }
       const double x = yp[j] + g0[j] * e0 + g1[j] * e1;
-      const double bx = sb0[j] * x;
+      const double bx = c2.b0 * x;
       const double y = bx + ps0;
       yp[j] = y; g0[j] = h00; g1[j] = h01;
-      const double n0 = 2.0 * bx + sa1[j] * y + ps1;
-      ps1 = bx + sa2[j] * y;
+      const double n0 = 2.0 * bx + c2.a1 * y + ps1;
+      ps1 = bx + c2.a2 * y;
       ps0 = n0;
-      const double t00 = sa1[j] * h00 + h10, t01 = sa1[j] * h01 + h11;
-      h10 = sa2[j] * h00; h11 = sa2[j] * h01;
+      const double t00 = c2.a1 * h00 + h10, t01 = c2.a1 * h01 + h11;
+      h10 = c2.a2 * h00; h11 = c2.a2 * h01;
       h00 = t00; h01 = t01;
     }
   }
@@ -615,6 +745,22 @@ __device__ __forceinline__ void cta_reduce_store(const double2* tiles, const int
   }
 }
 
+// Each coefficient mode of the fast path is its own out-of-line function: separate register
+// allocation and instruction footprint per mode, one call per 256-frame block.
+template <int CMODE>
+__device__ __noinline__ void welsh_fast_call(WelshVoice* vp, const WelshInst* Ip, i64 fb, int lane, int cls,
+                                             EnvSeg aseg, EnvSeg fseg, u64 seed1, u64 seed2, u64 seedl,
+                                             double2* tile_row, bool accumulate) {
+  WelshVoice st = *vp;
+  welsh_block_fast<CMODE>(st, *Ip, fb, lane, cls, aseg, fseg, seed1, seed2, seedl, tile_row, accumulate, vp->knot);
+  __syncwarp();
+  if (lane == 0) {  // everything but the knot words (lane 31 has just written those)
+    vp->s[0] = st.s[0]; vp->s[1] = st.s[1]; vp->s[2] = st.s[2]; vp->s[3] = st.s[3];
+    vp->knot_frame = CMODE == COEF_KNOTS ? fb + kBlockFrames : kNever;
+  }
+  __syncwarp();
+}
+
 // The general (event / pitch-LFO / stage-boundary) variants live behind one out-of-line call that
 // works on the voice record in global memory, so the kernel's register allocation is set by the
 // fast path; these variants run for a handful of blocks per note.
@@ -630,6 +776,7 @@ __device__ __noinline__ void welsh_block_general(int variant, WelshVoice* vp, co
     case 2: welsh_block<true, false>(st, I, ev, ei, e_end, fb, f_end, lane, seed1, seed2, seedl, tile_row, accumulate); break;
     default: welsh_block<true, true>(st, I, ev, ei, e_end, fb, f_end, lane, seed1, seed2, seedl, tile_row, accumulate); break;
   }
+  st.knot_frame = kNever;  // a carried coefficient knot is only valid between consecutive fast blocks
   __syncwarp();
   if (lane == 0) *vp = st;
   __syncwarp();
@@ -683,10 +830,24 @@ __global__ void __launch_bounds__(32 * W, MINB) welsh_kernel(const WelshInst* __
         fast = __all_sync(0xffffffffu, cls != 0);
       }
       if (fast) {
-        welsh_block_fast(st, I, fb, lane, cls, aseg, fseg, seed1, seed2, seedl, tile_row, any);
-        __syncwarp();
-        if (lane == 0) voices[vi] = st;
-        __syncwarp();
+        // the fast path changes only the filter state and the carried knot of the voice record
+        WelshVoice* vp = voices + vi;
+        const WelshInst* Ip = &I;  // shared-memory copy
+        if (I.filter_mode == FILTER_FIXED) {
+          welsh_fast_call<COEF_FIXED>(vp, Ip, fb, lane, cls, aseg, fseg, seed1, seed2, seedl, tile_row, any);
+        } else {
+          // knots need every lane sounding and the cutoff moving slowly enough over the lane's frames
+          bool smooth = false;
+          if (I.filter_mode == FILTER_ENVELOPE && cls == 2) {
+            const double w8 = fma((double)kT, fseg.dw, fseg.w0);
+            const double r0 = fabs(fma(2.0 * fseg.q2, fseg.w0, fseg.q1)), r8 = fabs(fma(2.0 * fseg.q2, w8, fseg.q1));
+            smooth = fabs(I.cut_b * fseg.dw) * fmax(r0, r8) <= kKnotMaxRate;
+          }
+          if (__all_sync(0xffffffffu, smooth))
+            welsh_fast_call<COEF_KNOTS>(vp, Ip, fb, lane, cls, aseg, fseg, seed1, seed2, seedl, tile_row, any);
+          else
+            welsh_fast_call<COEF_EXACT>(vp, Ip, fb, lane, cls, aseg, fseg, seed1, seed2, seedl, tile_row, any);
+        }
       } else {
         welsh_block_general((pitch ? 2 : 0) + (ev_here ? 1 : 0), voices + vi, insts + wk.inst, events, ei, e_end, fb, f_end, lane,
                             seed1, seed2, seedl, tile_row, any);
