@@ -171,7 +171,7 @@ def run_ours(a) -> None:
     import torch
     import torch.distributed as dist
 
-    from groove_b200 import Engine, workloads
+    from groove_b200 import Engine, parallel, workloads
 
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -182,9 +182,9 @@ def run_ours(a) -> None:
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     frames = int(round(a.seconds * 48000))
-    cfg = workloads.Cfg4(total_voices=a.voices, frames=frames,
-                         note_off_base=int(frames * 2_400_000 / 2_880_000),
-                         groups=min(128, a.voices), voice_offset=rank * a.voices)
+    cfg = parallel.shard_cfg4(
+        workloads.Cfg4(total_voices=a.voices, frames=frames, note_off_base=int(frames * 2_400_000 / 2_880_000),
+                       groups=min(128, a.voices)), rank, world, weak=True)
 
     flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
     host_out = np.empty((frames, 2), dtype=np.float64)
@@ -199,17 +199,12 @@ def run_ours(a) -> None:
         """Sum the per-rank stereo buses onto rank 0: one NCCL f64 reduce over NVLink."""
         if world == 1:
             return None
-        ptr, n = eng.last_device_buffer()
-
-        class _Wrap:
-            __cuda_array_interface__ = {"shape": (n, 2), "typestr": "<f8", "data": (ptr, False), "version": 2}
-        t = torch.as_tensor(_Wrap(), device=torch.device("cuda", local))
-        dist.reduce(t, dst=0, op=dist.ReduceOp.SUM)
-        return t
+        return parallel.reduce_bus(parallel.device_bus_tensor(eng, local), dst=0)
 
     def one_step(mode: str):
-        """Build config 4 and render it.  Engine construction (allocation, plan) is setup, not the
-        hot path: it stays outside the timed spans; events are pushed inside the e2e span."""
+        """Build config 4 and render it.  Engine construction (allocation, plan, host-side event list)
+        is setup and stays outside the timed span; the per-chunk event upload (H2D) and the result
+        download (D2H) happen inside the render call, i.e. inside the e2e span."""
         eng = Engine(48000.0, device=local, max_block=a.max_block)
         eng.set_timing(True)
         workloads.build_cfg4(eng, cfg)
