@@ -413,10 +413,10 @@ void welsh_inst_from_params(const Node& n, double sr, WelshInst* I) {
     switch (wf) {
       case GB_WAVE_SINE: o->kind = 1; break;
       case GB_WAVE_NOISE: o->kind = 2; break;
-      case GB_WAVE_SQUARE: o->kind = 3; o->b_lo = 1.0; o->b_hi = -1.0; break;
+      case GB_WAVE_SQUARE: o->b_lo = 1.0; o->b_hi = -1.0; break;
       case GB_WAVE_PULSE_WIDTH: o->thresh = duty_q; o->b_lo = 1.0; o->b_hi = -1.0; break;
-      case GB_WAVE_TRIANGLE: o->kind = 5; o->a_lo = 4.0; o->b_lo = -1.0; o->a_hi = -4.0; o->b_hi = 3.0; break;
-      case GB_WAVE_SAWTOOTH: o->kind = 4; o->a_lo = 2.0; o->b_lo = 0.0; o->a_hi = 2.0; o->b_hi = -2.0; break;
+      case GB_WAVE_TRIANGLE: o->a_lo = 4.0; o->b_lo = -1.0; o->a_hi = -4.0; o->b_hi = 3.0; break;
+      case GB_WAVE_SAWTOOTH: o->a_lo = 2.0; o->b_lo = 0.0; o->a_hi = 2.0; o->b_hi = -2.0; break;
       case GB_WAVE_DEBUG_MAX: o->b_lo = 1.0; o->b_hi = 1.0; break;
       case GB_WAVE_DEBUG_MIN: o->b_lo = -1.0; o->b_hi = -1.0; break;
       default: break;  // none / debug-zero: 0

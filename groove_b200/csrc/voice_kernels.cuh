@@ -43,23 +43,14 @@ struct OscShape {
   u64 thresh;
   double a_lo, b_lo, a_hi, b_hi;
 };
-// kinds 3..5 evaluate square / sawtooth / triangle without a compare: with q' = q + 2^63 (half a
-// cycle ahead, exact in fixed point) and p' = pos(q'):
-//   square = +-1 from the top phase bit;  saw = 2p' - 1;  triangle = |4p' - 2| - 1
-// which are bit-identical to the two-branch forms above (all operations exact).
+__device__ __forceinline__ double osc_affine(const OscShape& o, u64 q, u64 thresh) {
+  const bool lo = q < thresh;
+  return fma(lo ? o.a_lo : o.a_hi, pos_of(q), lo ? o.b_lo : o.b_hi);
+}
 __device__ __forceinline__ double osc_eval(const OscShape& o, u64 q, u64 thresh, u64 seed, i64 frame) {
-  switch (o.kind) {
-    case 0: {
-      const bool lo = q < thresh;
-      return fma(lo ? o.a_lo : o.a_hi, pos_of(q), lo ? o.b_lo : o.b_hi);
-    }
-    case 1: return sinpi(2.0 * pos_of(q));
-    case 3: return __hiloint2double((int)(0x3FF00000u | ((unsigned)(q >> 32) & 0x80000000u)), 0);
-    case 4: return fma(2.0, pos_of(q + (1ull << 63)), -1.0);
-    case 5: return fabs(fma(4.0, pos_of(q + (1ull << 63)), -2.0)) - 1.0;
-    default:
-      return __ull2double_rn(splitmix64(seed + (u64)frame) >> 11) * (1.0 / 4503599627370496.0) - 1.0;
-  }
+  if (o.kind == 0) return osc_affine(o, q, thresh);
+  if (o.kind == 1) return sinpi(2.0 * pos_of(q));
+  return __ull2double_rn(splitmix64(seed + (u64)frame) >> 11) * (1.0 / 4503599627370496.0) - 1.0;
 }
 
 // ---- range-specialised elementary functions for the cutoff -> coefficient map ----------------------
@@ -581,7 +572,7 @@ enum { COEF_FIXED = 0, COEF_EXACT = 1, COEF_KNOTS = 2 };
 // Fast path of the Welsh voice: same contract as welsh_block<false,false>, for blocks in which every
 // lane is class 1 (idle) or 2 (sounding inside single envelope stages).  CMODE selects how the
 // per-frame 24 dB coefficient sets are produced; COEF_KNOTS additionally needs every lane in class 2.
-template <int CMODE>
+template <int CMODE, bool ALL_ON>
 __device__ __forceinline__ void welsh_block_fast(WelshVoice& st, const WelshInst& I, i64 fb, int lane, int cls,
                                                  const EnvSeg& aseg, const EnvSeg& fseg, u64 seed1, u64 seed2,
                                                  u64 seedl, double2* tile_row, bool accumulate, double* knot_out) {
@@ -589,7 +580,7 @@ __device__ __forceinline__ void welsh_block_fast(WelshVoice& st, const WelshInst
   double yp[kT], g0[kT], g1[kT], ampf[kT];
   double sb0[CMODE == COEF_EXACT ? kT : 1], sa1[CMODE == COEF_EXACT ? kT : 1], sa2[CMODE == COEF_EXACT ? kT : 1];
   double ps0 = 0.0, ps1 = 0.0, h00 = 1.0, h01 = 0.0, h10 = 0.0, h11 = 1.0;
-  const bool on = cls == 2;
+  const bool on = ALL_ON || cls == 2;  // ALL_ON: every lane sounds, no divergence at all
   if (!on) {
 #pragma unroll
     for (int j = 0; j < kT; ++j) {
@@ -745,14 +736,129 @@ __device__ __forceinline__ void cta_reduce_store(const double2* tiles, const int
   }
 }
 
+// ---- the steady-state block of the common configuration --------------------------------------------
+// Preconditions (checked by the caller, all warp-uniform): both oscillators piecewise linear
+// (OscShape kind 0), no hard sync, LFO either unused or a sine routed to amplitude, cutoff driven by
+// the filter envelope and moving <= kKnotMaxRate per frame, every lane sounding inside single
+// envelope stages.  Everything the general fast path decides per frame is a compile-time constant
+// here; the arithmetic is identical to welsh_block_fast<COEF_KNOTS, true>.
+template <bool LFO_AMP>
+__device__ __noinline__ void welsh_block_simple(WelshVoice* vp, const WelshInst* Ip, i64 fb, int lane, EnvSeg aseg,
+                                                EnvSeg fseg, double2* tile_row, bool accumulate) {
+  const WelshInst& I = *Ip;
+  const i64 c0 = fb + (i64)lane * kT;
+  // ---- coefficient knots ----
+  SecCoef m1, m2, e1c, e2c, s1c, s2c;
+  welsh_coef_exact(I, fma(I.cut_b, env_seg_at(fseg, kT / 2), I.cut_a), m1, m2);
+  welsh_coef_exact(I, fma(I.cut_b, env_seg_at(fseg, kT), I.cut_a), e1c, e2c);
+  s1c.b0 = __shfl_up_sync(0xffffffffu, e1c.b0, 1); s1c.a1 = __shfl_up_sync(0xffffffffu, e1c.a1, 1);
+  s1c.a2 = __shfl_up_sync(0xffffffffu, e1c.a2, 1); s2c.b0 = __shfl_up_sync(0xffffffffu, e2c.b0, 1);
+  s2c.a1 = __shfl_up_sync(0xffffffffu, e2c.a1, 1); s2c.a2 = __shfl_up_sync(0xffffffffu, e2c.a2, 1);
+  if (lane == 0) {
+    if (vp->knot_frame == fb) {
+      s1c.b0 = vp->knot[0]; s1c.a1 = vp->knot[1]; s1c.a2 = vp->knot[2];
+      s2c.b0 = vp->knot[3]; s2c.a1 = vp->knot[4]; s2c.a2 = vp->knot[5];
+    } else {
+      welsh_coef_exact(I, fma(I.cut_b, env_seg_at(fseg, 0), I.cut_a), s1c, s2c);
+    }
+  }
+  __syncwarp();
+  if (lane == 31) {
+    vp->knot[0] = e1c.b0; vp->knot[1] = e1c.a1; vp->knot[2] = e1c.a2;
+    vp->knot[3] = e2c.b0; vp->knot[4] = e2c.a1; vp->knot[5] = e2c.a2;
+  }
+  const Quad qb1 = quad_fit(s1c.b0, m1.b0, e1c.b0), qa11 = quad_fit(s1c.a1, m1.a1, e1c.a1),
+             qa21 = quad_fit(s1c.a2, m1.a2, e1c.a2);
+  const Quad qb2 = quad_fit(s2c.b0, m2.b0, e2c.b0), qa12 = quad_fit(s2c.a1, m2.a1, e2c.a1),
+             qa22 = quad_fit(s2c.a2, m2.a2, e2c.a2);
+  // ---- phases at c0 - 1 (closed form), LFO base angle ----
+  const u64 k = (u64)(c0 - 1 - vp->anchor);
+  const u64 d1 = vp->d1, d2 = vp->d2;
+  u64 p1 = vp->p1 + k * d1, p2 = vp->p2 + k * d2;
+  double ls = 0.0, lc = 0.0;
+  if (LFO_AMP) sincospi(2.0 * pos_of(vp->pl + (k + 1) * I.lfo_dq), &ls, &lc);
+  const double mix1 = I.mix, mix2 = 1.0 - I.mix;
+  const u64 th1 = I.s1.thresh, th2 = I.s2.thresh;
+  // ---- pass 1: oscillators + section 1 from a zero state with its homogeneous response ----
+  double yp[kT], g0[kT], g1[kT];
+  double ps0 = 0.0, ps1 = 0.0, h00 = 1.0, h01 = 0.0, h10 = 0.0, h11 = 1.0;
+#pragma unroll
+  for (int j = 0; j < kT; ++j) {
+    p1 += d1;
+    p2 += d2;
+    const double x = fma(osc_affine(I.s1, p1, th1), mix1, osc_affine(I.s2, p2, th2) * mix2);
+    const double b0 = quad_at(qb1, j), a1 = quad_at(qa11, j), a2 = quad_at(qa21, j);
+    const double bx = b0 * x;
+    const double y = bx + ps0;
+    yp[j] = y; g0[j] = h00; g1[j] = h01;
+    const double n0 = fma(a1, y, fma(2.0, bx, ps1));
+    ps1 = fma(a2, y, bx);
+    ps0 = n0;
+    const double t00 = fma(a1, h00, h10), t01 = fma(a1, h01, h11);
+    h10 = a2 * h00; h11 = a2 * h01;
+    h00 = t00; h01 = t01;
+  }
+  double e0, e1, end0, end1;
+  {
+    Affine2 a;
+    a.m00 = h00; a.m01 = h01; a.m10 = h10; a.m11 = h11; a.v0 = ps0; a.v1 = ps1;
+    const Affine2 inc = affine_warp_scan(a, lane);
+    affine_lane_entry(inc, lane, vp->s[0], vp->s[1], e0, e1, end0, end1);
+  }
+  const double ns0 = end0, ns1 = end1;
+  // ---- pass 2: section 2 on the fixed-up section-1 output ----
+  ps0 = 0.0; ps1 = 0.0; h00 = 1.0; h01 = 0.0; h10 = 0.0; h11 = 1.0;
+#pragma unroll
+  for (int j = 0; j < kT; ++j) {
+    const double b0 = quad_at(qb2, j), a1 = quad_at(qa12, j), a2 = quad_at(qa22, j);
+    const double x = fma(g1[j], e1, fma(g0[j], e0, yp[j]));
+    const double bx = b0 * x;
+    const double y = bx + ps0;
+    yp[j] = y; g0[j] = h00; g1[j] = h01;
+    const double n0 = fma(a1, y, fma(2.0, bx, ps1));
+    ps1 = fma(a2, y, bx);
+    ps0 = n0;
+    const double t00 = fma(a1, h00, h10), t01 = fma(a1, h01, h11);
+    h10 = a2 * h00; h11 = a2 * h01;
+    h00 = t00; h01 = t01;
+  }
+  {
+    Affine2 a;
+    a.m00 = h00; a.m01 = h01; a.m10 = h10; a.m11 = h11; a.v0 = ps0; a.v1 = ps1;
+    const Affine2 inc = affine_warp_scan(a, lane);
+    affine_lane_entry(inc, lane, vp->s[2], vp->s[3], e0, e1, end0, end1);
+  }
+  // ---- amplitude (envelope segment x LFO), DCA, CTA tile ----
+  const double gl = I.gl, gr = I.gr;
+  double2* row = tile_row + lane * (kT + 1);
+#pragma unroll
+  for (int j = 0; j < kT; ++j) {
+    double amp = 0.5 * env_seg_at(aseg, j);
+    if (LFO_AMP) amp *= fma(fma(ls, I.lfo_cos[j], lc * I.lfo_sin[j]), I.depth, 1.0);
+    const double m = fma(g1[j], e1, fma(g0[j], e0, yp[j])) * amp;
+    double2 o = make_double2(m * gl, m * gr);
+    if (accumulate) {
+      const double2 p = row[j];
+      o.x += p.x; o.y += p.y;
+    }
+    row[j] = o;
+  }
+  __syncwarp();
+  if (lane == 0) {
+    vp->s[0] = ns0; vp->s[1] = ns1; vp->s[2] = end0; vp->s[3] = end1;
+    vp->knot_frame = fb + kBlockFrames;
+  }
+  __syncwarp();
+}
+
 // Each coefficient mode of the fast path is its own out-of-line function: separate register
 // allocation and instruction footprint per mode, one call per 256-frame block.
-template <int CMODE>
+template <int CMODE, bool ALL_ON>
 __device__ __noinline__ void welsh_fast_call(WelshVoice* vp, const WelshInst* Ip, i64 fb, int lane, int cls,
                                              EnvSeg aseg, EnvSeg fseg, u64 seed1, u64 seed2, u64 seedl,
                                              double2* tile_row, bool accumulate) {
   WelshVoice st = *vp;
-  welsh_block_fast<CMODE>(st, *Ip, fb, lane, cls, aseg, fseg, seed1, seed2, seedl, tile_row, accumulate, vp->knot);
+  welsh_block_fast<CMODE, ALL_ON>(st, *Ip, fb, lane, cls, aseg, fseg, seed1, seed2, seedl, tile_row, accumulate, vp->knot);
   __syncwarp();
   if (lane == 0) {  // everything but the knot words (lane 31 has just written those)
     vp->s[0] = st.s[0]; vp->s[1] = st.s[1]; vp->s[2] = st.s[2]; vp->s[3] = st.s[3];
@@ -805,6 +911,9 @@ __global__ void __launch_bounds__(32 * W, MINB) welsh_kernel(const WelshInst* __
   double2* tile_row = smem_tiles + warp * kTileStride;
   const i64 f_end = f0 + nframes;
   const bool pitch = I.routing == LFO_PITCH;
+  // instrument qualifies for welsh_block_simple (see its preconditions)
+  const bool simple_inst = I.s1.kind == 0 && I.s2.kind == 0 && !I.sync && I.filter_mode == FILTER_ENVELOPE &&
+                           (I.routing == LFO_NONE || (I.routing == LFO_AMPLITUDE && I.wl == W_SINE));
 #pragma unroll 1
   for (i64 fb = f0; fb < f_end; fb += kBlockFrames) {
     bool any = false;
@@ -834,7 +943,10 @@ __global__ void __launch_bounds__(32 * W, MINB) welsh_kernel(const WelshInst* __
         WelshVoice* vp = voices + vi;
         const WelshInst* Ip = &I;  // shared-memory copy
         if (I.filter_mode == FILTER_FIXED) {
-          welsh_fast_call<COEF_FIXED>(vp, Ip, fb, lane, cls, aseg, fseg, seed1, seed2, seedl, tile_row, any);
+          if (__all_sync(0xffffffffu, cls == 2))
+            welsh_fast_call<COEF_FIXED, true>(vp, Ip, fb, lane, cls, aseg, fseg, seed1, seed2, seedl, tile_row, any);
+          else
+            welsh_fast_call<COEF_FIXED, false>(vp, Ip, fb, lane, cls, aseg, fseg, seed1, seed2, seedl, tile_row, any);
         } else {
           // knots need every lane sounding and the cutoff moving slowly enough over the lane's frames
           bool smooth = false;
@@ -843,10 +955,16 @@ __global__ void __launch_bounds__(32 * W, MINB) welsh_kernel(const WelshInst* __
             const double r0 = fabs(fma(2.0 * fseg.q2, fseg.w0, fseg.q1)), r8 = fabs(fma(2.0 * fseg.q2, w8, fseg.q1));
             smooth = fabs(I.cut_b * fseg.dw) * fmax(r0, r8) <= kKnotMaxRate;
           }
-          if (__all_sync(0xffffffffu, smooth))
-            welsh_fast_call<COEF_KNOTS>(vp, Ip, fb, lane, cls, aseg, fseg, seed1, seed2, seedl, tile_row, any);
+          if (__all_sync(0xffffffffu, smooth)) {
+            if (simple_inst && I.routing == LFO_NONE)
+              welsh_block_simple<false>(vp, Ip, fb, lane, aseg, fseg, tile_row, any);
+            else if (simple_inst)
+              welsh_block_simple<true>(vp, Ip, fb, lane, aseg, fseg, tile_row, any);
+            else
+              welsh_fast_call<COEF_KNOTS, true>(vp, Ip, fb, lane, cls, aseg, fseg, seed1, seed2, seedl, tile_row, any);
+          }
           else
-            welsh_fast_call<COEF_EXACT>(vp, Ip, fb, lane, cls, aseg, fseg, seed1, seed2, seedl, tile_row, any);
+            welsh_fast_call<COEF_EXACT, false>(vp, Ip, fb, lane, cls, aseg, fseg, seed1, seed2, seedl, tile_row, any);
         }
       } else {
         welsh_block_general((pitch ? 2 : 0) + (ev_here ? 1 : 0), voices + vi, insts + wk.inst, events, ei, e_end, fb, f_end, lane,
