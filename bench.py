@@ -47,6 +47,9 @@ def parse_args():
     ap.add_argument("--voices", type=int, default=4096, help="voices per GPU (config 4: 4096)")
     ap.add_argument("--seconds", type=float, default=60.0, help="audio seconds per step (config 4: 60)")
     ap.add_argument("--max-block", type=int, default=1 << 16)
+    ap.add_argument("--workload", default="cfg4", choices=["cfg4", "cfg5"],
+                    help="cfg4 = BASELINE config 4 (headline); cfg5 = batch of one-shot patch variants")
+    ap.add_argument("--variants", type=int, default=8192, help="cfg5: variants per GPU (config 5: 65536 over 8 GPUs)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-sample-voices", type=int, default=256)
     ap.add_argument("--cpu-sample-seconds", type=float, default=4.0)
@@ -181,7 +184,10 @@ def run_ours(a) -> None:
     torch.cuda.set_device(local)
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
-    frames = int(round(a.seconds * 48000))
+    cfg5 = a.workload == "cfg5"
+    frames = workloads.CFG5_FRAMES if cfg5 else int(round(a.seconds * 48000))
+    if cfg5:
+        a.max_block = frames          # one chunk: every variant's node buffer is its full 2 s output
     cfg = parallel.shard_cfg4(
         workloads.Cfg4(total_voices=a.voices, frames=frames, note_off_base=int(frames * 2_400_000 / 2_880_000),
                        groups=min(128, a.voices)), rank, world, weak=True)
@@ -207,7 +213,10 @@ def run_ours(a) -> None:
         download (D2H) happen inside the render call, i.e. inside the e2e span."""
         eng = Engine(48000.0, device=local, max_block=a.max_block)
         eng.set_timing(True)
-        workloads.build_cfg4(eng, cfg)
+        if cfg5:
+            workloads.build_cfg5(eng, a.variants, first=rank * a.variants)
+        else:
+            workloads.build_cfg4(eng, cfg)
         flush.zero_()
         barrier()
         t0 = time.perf_counter()
@@ -262,7 +271,8 @@ def run_ours(a) -> None:
     dev_ms, wall_dev, e2e_wall, kern_ms = [float(x) for x in vals.tolist()]
     # N > 1: the reduce is outside the engine's events, so the step time is the synchronized wall time
     step_s = (dev_ms * 1e-3 if world == 1 else wall_dev) / a.steps
-    total_vs = cfg.voice_samples * world
+    per_rank_vs = a.variants * frames if cfg5 else cfg.voice_samples
+    total_vs = per_rank_vs * world
     value = total_vs / step_s
     e2e_value = total_vs / (e2e_wall / a.steps)
 
@@ -278,32 +288,35 @@ def run_ours(a) -> None:
         except OSError:
             pass
         hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
-        vs_per_launch = cfg.voice_samples * a.steps / max(vlaunches, 1)
+        vs_per_launch = per_rank_vs * a.steps / max(vlaunches, 1)
         launch_s = kern_ms * 1e-3 / max(vlaunches, 1)
-        achieved_tflops = workloads.W_VOICE_FLOP * vs_per_launch / launch_s / 1e12
+        # cfg5: half the variants are FM voices (67 FLOP), launched as a second kernel per chunk
+        flop_per_vs = 0.5 * (workloads.W_VOICE_FLOP + workloads.W_FM_FLOP) if cfg5 else workloads.W_VOICE_FLOP
+        achieved_tflops = flop_per_vs * vs_per_launch / launch_s / 1e12
         # algorithmic HBM bytes: 16 B stereo f64 out per frame per CTA partial + voice state in/out
         out = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": a.steps, "warmup": max(a.warmup, 1),
             "ms_per_step": step_s * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f64", "data": "synthetic",
             "config": {
-                "workload": "config-4: 4096-voice Welsh-cookbook cello subtractive synth (dual osc + LFO + 2 ADSR + "
+                "workload": f"config-5 recipe: {a.variants} one-shot FM/subtractive patch variants per GPU, 2 s at 48 kHz" if cfg5
+                            else "config-4: 4096-voice Welsh-cookbook cello subtractive synth (dual osc + LFO + 2 ADSR + "
                             "per-frame 24 dB LPF), 60 s at 48 kHz stereo" if (a.voices, a.seconds) == (4096, 60.0)
                             else f"config-4 recipe scaled: {a.voices} voices x {a.seconds:g} s at 48 kHz stereo",
                 "voices_per_gpu": a.voices, "frames": frames, "voice_samples_per_step": total_vs,
                 "max_block": a.max_block, "parallelism": f"voices sharded over {world} GPU(s); one NCCL f64 bus reduce",
                 "l2": "256 MiB device memset between steps (L2 flush); fresh engine per step",
             },
-            "realtime_factor": value / (a.voices * world * 48000.0),
+            "realtime_factor": value / ((a.variants if cfg5 else a.voices) * world * 48000.0),
             "gpu_launches": int(launches // a.steps),
             "e2e": {"value": e2e_value, "unit": UNIT, "ms_per_step": e2e_wall / a.steps * 1e3,
                     "h2d_bytes_per_step": int(h2d // a.steps), "d2h_bytes_per_step": int(d2h // a.steps)},
             "roofline": {
-                "bound": "fp64", "kernel": "welsh_kernel<8>", "achieved": achieved_tflops, "peak": fp64_peak,
+                "bound": "fp64", "kernel": "welsh_kernel<8,2>" + (" + fm_kernel<8>" if cfg5 else ""), "achieved": achieved_tflops, "peak": fp64_peak,
                 "unit": "TFLOP/s", "frac": achieved_tflops / fp64_peak, "traffic": None,
                 "peak_source": "FP64 FMA microbenchmark measured live on this GPU (gb_measure_fma_peak); "
                                "MEASURED_PEAKS.json has no FP64 entry",
-                "algorithmic_flop_per_voice_sample": workloads.W_VOICE_FLOP,
+                "algorithmic_flop_per_voice_sample": flop_per_vs,
                 "voice_samples_per_launch": vs_per_launch, "launch_ms": launch_s * 1e3,
                 "kernel_share_of_step": kern_ms * 1e-3 / a.steps / step_s if world == 1 else None,
                 "fp32_peak_tflops": fp32_peak,

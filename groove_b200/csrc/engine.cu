@@ -261,6 +261,7 @@ struct Node {
   gb_toy_source_params tp;
   int table_index = -1;  // index in the welsh/fm instrument table
   int voice0 = 0, nvoices = 0;
+  int partial_count = 0;  // partial output buffers in `scratch` (0 = renders straight into `buf`)
   int64_t release_frames = 0;
   SlotStore store;
   std::vector<SampleDev> samples;
@@ -307,7 +308,9 @@ struct gb_engine {
   int n_wvoice = 0, n_fvoice = 0;
   bool winst_dirty = true, finst_dirty = true;
   DevBuf<CtaWork> wwork, fwork;
+  DevBuf<WarpItem> witems, fitems;  // solo-warp work items (instruments with fewer voices than a CTA has warps)
   int n_wwork = 0, n_fwork = 0;
+  int n_wwork_grouped = 0;  // wwork[0 .. n_wwork_grouped) are grouped CTAs, the rest solo CTAs
   DevBuf<VoiceEvent> wev, fev;
   DevBuf<int> wev_off, fev_off;
   DevBuf<SamplePlay> plays;
@@ -642,7 +645,7 @@ int gb_create(const gb_config* cfg, gb_engine** out) {
   memset(&e->stats, 0, sizeof e->stats);
   cudaDeviceProp prop;
   if (cudaGetDeviceProperties(&prop, e->device) == cudaSuccess) e->num_sms = prop.multiProcessorCount;
-  if (const char* v = getenv("GB_WELSH_OCC")) e->welsh_occ = atoi(v) == 1 ? 1 : 2;
+  if (const char* v = getenv("GB_WELSH_OCC")) e->welsh_occ = atoi(v);  // 1,2: 8-warp CTAs; 4,5,6: 4-warp CTAs
   if (const char* v = getenv("GB_CTA_MULT")) e->cta_target_mult = std::max(1, atoi(v));
   if (cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking) != cudaSuccess)
     return fail(nullptr, GB_ECUDA, "cudaStreamCreate failed");
@@ -925,51 +928,82 @@ int gb_finalize(gb_engine* e) {
     CUDA_TRY(e, cudaMemcpy(e->d_fvoice, init.data(), init.size() * sizeof(FmVoice), cudaMemcpyHostToDevice));
   }
   // CTA work lists.  vpc: aim for about two CTAs per SM across all voices of a type.
-  auto plan_work = [&](int kind, int total_voices, DevBuf<CtaWork>& buf, int* count) -> int {
+  auto plan_work = [&](int kind, int total_voices, DevBuf<CtaWork>& buf, DevBuf<WarpItem>& ibuf, int* count,
+                       int* n_grouped) -> int {
     std::vector<CtaWork> work;
-    if (total_voices == 0) { *count = 0; return 0; }
+    std::vector<WarpItem> items;
+    if (total_voices == 0) { *count = 0; *n_grouped = 0; return 0; }
     int target = std::max(1, e->num_sms * e->cta_target_mult);
-    int vpc = std::max(kVoiceWarps, cdiv(total_voices, target));
-    vpc = cdiv(vpc, kVoiceWarps) * kVoiceWarps;
+    const int wpc = (kind == GB_INST_WELSH && e->welsh_occ >= 4) ? 4 : kVoiceWarps;  // warps per CTA
+    int vpc = std::max(wpc, cdiv(total_voices, target));
+    vpc = cdiv(vpc, wpc) * wpc;
     for (Node* n : e->plan) {
       if (n->kind != kind) continue;
+      if (n->nvoices < wpc) {
+        // solo warps: every voice is its own work item with its own output (partial) buffer
+        n->partial_count = n->nvoices > 1 ? n->nvoices : 0;
+        if (n->partial_count) {
+          int rc = dev_alloc(e, &n->scratch, (size_t)n->partial_count * mb);
+          if (rc) return rc;
+        }
+        for (int v = 0; v < n->nvoices; ++v) {
+          WarpItem it;
+          it.inst = n->table_index;
+          it.voice = n->voice0 + v;
+          it.out = n->partial_count ? n->scratch + (size_t)v * mb : n->buf;
+          items.push_back(it);
+        }
+        continue;
+      }
       int ncta = cdiv(n->nvoices, vpc);
+      n->partial_count = ncta > 1 ? ncta : 0;
       if (ncta > 1) {
         int rc = dev_alloc(e, &n->scratch, (size_t)ncta * mb);
         if (rc) return rc;
       }
-      int per = cdiv(cdiv(n->nvoices, ncta), 1);
+      int per = cdiv(n->nvoices, ncta);
       int v = 0;
       for (int c = 0; c < ncta; ++c) {
         CtaWork w;
         w.inst = n->table_index;
         w.voice0 = n->voice0 + v;
         w.nvoices = std::min(per, n->nvoices - v);
-        w.pad = ncta;
+        w.solo = 0;
         w.out = ncta == 1 ? n->buf : n->scratch + (size_t)c * mb;
         work.push_back(w);
         v += w.nvoices;
       }
     }
-    if (!buf.reserve(work.size())) return fail(e, GB_ENOMEM, "out of memory");
+    *n_grouped = (int)work.size();
+    for (size_t i = 0; i < items.size(); i += (size_t)wpc) {
+      CtaWork w;
+      w.inst = items[i].inst;
+      w.voice0 = (int)i;
+      w.nvoices = (int)std::min<size_t>((size_t)wpc, items.size() - i);
+      w.solo = 1;
+      w.out = nullptr;
+      work.push_back(w);
+    }
+    if (!buf.reserve(work.size()) || !ibuf.reserve(items.size() + 1)) return fail(e, GB_ENOMEM, "out of memory");
     memcpy(buf.h, work.data(), work.size() * sizeof(CtaWork));
     CUDA_TRY(e, cudaMemcpy(buf.d, buf.h, work.size() * sizeof(CtaWork), cudaMemcpyHostToDevice));
+    if (!items.empty()) {
+      memcpy(ibuf.h, items.data(), items.size() * sizeof(WarpItem));
+      CUDA_TRY(e, cudaMemcpy(ibuf.d, ibuf.h, items.size() * sizeof(WarpItem), cudaMemcpyHostToDevice));
+    }
     *count = (int)work.size();
     return 0;
   };
   int rc;
-  if ((rc = plan_work(GB_INST_WELSH, wv, e->wwork, &e->n_wwork))) return rc;
-  if ((rc = plan_work(GB_INST_FM, fv, e->fwork, &e->n_fwork))) return rc;
+  int fm_grouped = 0;
+  if ((rc = plan_work(GB_INST_WELSH, wv, e->wwork, e->witems, &e->n_wwork, &e->n_wwork_grouped))) return rc;
+  if ((rc = plan_work(GB_INST_FM, fv, e->fwork, e->fitems, &e->n_fwork, &fm_grouped))) return rc;
   {
     std::vector<PartialDesc> descs;
     for (Node* n : e->plan) {
-      if (!(n->kind == GB_INST_WELSH || n->kind == GB_INST_FM) || !n->scratch) continue;
-      const CtaWork* wk = n->kind == GB_INST_WELSH ? e->wwork.h : e->fwork.h;
-      int cnt = n->kind == GB_INST_WELSH ? e->n_wwork : e->n_fwork;
+      if (!(n->kind == GB_INST_WELSH || n->kind == GB_INST_FM) || n->partial_count == 0) continue;
       PartialDesc d;
-      d.base = n->scratch; d.out = n->buf; d.stride = mb; d.count = 0; d.pad = 0;
-      for (int i = 0; i < cnt; ++i)
-        if (wk[i].inst == n->table_index) d.count++;
+      d.base = n->scratch; d.out = n->buf; d.stride = mb; d.count = n->partial_count; d.pad = 0;
       descs.push_back(d);
     }
     e->n_partials = (int)descs.size();
@@ -990,10 +1024,14 @@ int gb_finalize(gb_engine* e) {
       CUDA_TRY(e, cudaMemcpy((void*)n->d_src_table, ptrs.data(), ptrs.size() * sizeof(double2*), cudaMemcpyHostToDevice));
     }
   }
-  CUDA_TRY(e, cudaFuncSetAttribute(welsh_kernel<kVoiceWarps, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                   (int)(kVoiceWarps * kTileStride * sizeof(double2))));
-  CUDA_TRY(e, cudaFuncSetAttribute(welsh_kernel<kVoiceWarps, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                   (int)(kVoiceWarps * kTileStride * sizeof(double2))));
+  const int welsh_smem_bytes = (int)(kVoiceWarps * kTileStride * sizeof(double2) + kParkWords * 32 * kVoiceWarps * sizeof(double));
+  CUDA_TRY(e, cudaFuncSetAttribute(welsh_kernel<8, 1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, welsh_smem_bytes));
+  CUDA_TRY(e, cudaFuncSetAttribute(welsh_kernel<8, 2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, welsh_smem_bytes));
+  CUDA_TRY(e, cudaFuncSetAttribute(welsh_kernel<8, 2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, welsh_smem_bytes));
+  CUDA_TRY(e, cudaFuncSetAttribute(welsh_kernel<4, 4, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, welsh_smem_bytes));
+  CUDA_TRY(e, cudaFuncSetAttribute(welsh_kernel<4, 4, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, welsh_smem_bytes));
+  CUDA_TRY(e, cudaFuncSetAttribute(welsh_kernel<4, 5, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, welsh_smem_bytes));
+  CUDA_TRY(e, cudaFuncSetAttribute(welsh_kernel<4, 6, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, welsh_smem_bytes));
   CUDA_TRY(e, cudaFuncSetAttribute(fm_kernel<kVoiceWarps>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                    (int)(kVoiceWarps * kTileStride * sizeof(double2))));
   CUDA_TRY(e, cudaStreamSynchronize(e->stream));
@@ -1154,6 +1192,7 @@ int render_chunk(gb_engine* e, int frames, size_t n_ev) {
     return 0;
   };
   const size_t tile_bytes = (size_t)kVoiceWarps * kTileStride * sizeof(double2);
+  const size_t welsh_smem = tile_bytes + (size_t)kParkWords * 32 * kVoiceWarps * sizeof(double);
   if (e->n_wvoice) {
     if (e->winst_dirty) {
       for (Node* n : e->plan)
@@ -1168,12 +1207,26 @@ int render_chunk(gb_engine* e, int frames, size_t n_ev) {
     if (rc) return rc;
     {
       Launch l(e, true);
-      if (e->welsh_occ == 1)
-        welsh_kernel<kVoiceWarps, 1><<<e->n_wwork, 32 * kVoiceWarps, tile_bytes, e->stream>>>(
-            e->d_winst, e->d_wvoice, e->wwork.d, e->wev.d, e->wev_off.d, f0, frames);
-      else
-        welsh_kernel<kVoiceWarps, 2><<<e->n_wwork, 32 * kVoiceWarps, tile_bytes, e->stream>>>(
-            e->d_winst, e->d_wvoice, e->wwork.d, e->wev.d, e->wev_off.d, f0, frames);
+#define GB_WELSH_LAUNCH(W_, M_, SOLO_, first_, count_)                                                                \
+  welsh_kernel<W_, M_, SOLO_><<<(count_), 32 * W_, (size_t)W_ * kTileStride * sizeof(double2) +                        \
+                                                      (size_t)kParkWords * 32 * W_ * sizeof(double), e->stream>>>(     \
+      e->d_winst, e->d_wvoice, e->wwork.d + (first_), e->witems.d, e->wev.d, e->wev_off.d, f0, frames)
+      const int ng = e->n_wwork_grouped, ns = e->n_wwork - e->n_wwork_grouped;
+      if (ng) {
+        switch (e->welsh_occ) {
+          case 1: GB_WELSH_LAUNCH(8, 1, false, 0, ng); break;
+          case 4: GB_WELSH_LAUNCH(4, 4, false, 0, ng); break;
+          case 5: GB_WELSH_LAUNCH(4, 5, false, 0, ng); break;
+          case 6: GB_WELSH_LAUNCH(4, 6, false, 0, ng); break;
+          default: GB_WELSH_LAUNCH(8, 2, false, 0, ng); break;
+        }
+      }
+      if (ns) {
+        if (ng) { e->stats.kernel_launches++; e->stats.voice_kernel_launches++; }
+        if (e->welsh_occ >= 4) GB_WELSH_LAUNCH(4, 4, true, ng, ns);
+        else GB_WELSH_LAUNCH(8, 2, true, ng, ns);
+      }
+#undef GB_WELSH_LAUNCH
     }
     e->stats.voice_samples += (uint64_t)e->n_wvoice * (uint64_t)frames;
   }
@@ -1192,7 +1245,7 @@ int render_chunk(gb_engine* e, int frames, size_t n_ev) {
     {
       Launch l(e, true);
       fm_kernel<kVoiceWarps><<<e->n_fwork, 32 * kVoiceWarps, tile_bytes, e->stream>>>(
-          e->d_finst, e->d_fvoice, e->fwork.d, e->fev.d, e->fev_off.d, f0, frames);
+          e->d_finst, e->d_fvoice, e->fwork.d, e->fitems.d, e->fev.d, e->fev_off.d, f0, frames);
     }
     e->stats.voice_samples += (uint64_t)e->n_fvoice * (uint64_t)frames;
   }

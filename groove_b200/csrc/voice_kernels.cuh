@@ -154,13 +154,34 @@ struct WelshVoice {
   double knot[6];
 };
 
+// Two kinds of CTA work.  Grouped (solo == 0): `nvoices` voices of ONE instrument starting at voice
+// `voice0`, processed in rounds of W and summed through shared memory into `out`.  Solo (solo == 1):
+// up to W unrelated (instrument, voice) pairs, items[voice0 .. voice0 + nvoices), one per warp, each
+// warp writing its own output buffer — for instruments with fewer voices than a CTA has warps
+// (e.g. a batch of one-voice patch variants).
 struct CtaWork {
-  int inst;       // index into the instrument table
-  int voice0;     // first voice (global index) handled by this CTA
-  int nvoices;    // any count; processed in rounds of W (warps per CTA)
-  int pad;
-  double2* out;   // chunk-relative output buffer (node buffer or a partial)
+  int inst;       // grouped: index into the instrument table
+  int voice0;     // grouped: first voice (global index); solo: first WarpItem
+  int nvoices;
+  int solo;
+  double2* out;   // grouped: chunk-relative output buffer (node buffer or a partial)
 };
+struct WarpItem {
+  int inst;       // index into the instrument table
+  int voice;      // global voice index
+  double2* out;   // chunk-relative output buffer (node buffer, or a partial of a 2..W-1 voice instrument)
+};
+
+// A warp copies its 256-frame tile row (or zeros) to its own output buffer, coalesced.
+__device__ __forceinline__ void warp_store_row(const double2* tile_row, bool any, double2* out, i64 fb, i64 f0,
+                                               i64 f_end, int lane) {
+#pragma unroll
+  for (int i = 0; i < kT; ++i) {
+    const int t = i * 32 + lane;
+    const i64 n = fb + t;
+    if (n < f_end) out[n - f0] = any ? tile_row[t + (t >> 3)] : make_double2(0.0, 0.0);
+  }
+}
 
 struct Phases {
   u64 p1, p2, pl;
@@ -742,35 +763,47 @@ __device__ __forceinline__ void cta_reduce_store(const double2* tiles, const int
 // the filter envelope and moving <= kKnotMaxRate per frame, every lane sounding inside single
 // envelope stages.  Everything the general fast path decides per frame is a compile-time constant
 // here; the arithmetic is identical to welsh_block_fast<COEF_KNOTS, true>.
+constexpr int kParkWords = 14;  // doubles parked per thread by welsh_block_simple (see below)
+
 template <bool LFO_AMP>
 __device__ __noinline__ void welsh_block_simple(WelshVoice* vp, const WelshInst* Ip, i64 fb, int lane, EnvSeg aseg,
-                                                EnvSeg fseg, double2* tile_row, bool accumulate) {
+                                                EnvSeg fseg, double2* tile_row, bool accumulate, double* park) {
+  // `park` = this thread's column of a [kParkWords][blockDim.x] shared array: values that are only
+  // needed after pass 1 wait there so that the oscillator constants fit in registers.
   const WelshInst& I = *Ip;
+  const int pstride = blockDim.x;
   const i64 c0 = fb + (i64)lane * kT;
   // ---- coefficient knots ----
-  SecCoef m1, m2, e1c, e2c, s1c, s2c;
-  welsh_coef_exact(I, fma(I.cut_b, env_seg_at(fseg, kT / 2), I.cut_a), m1, m2);
-  welsh_coef_exact(I, fma(I.cut_b, env_seg_at(fseg, kT), I.cut_a), e1c, e2c);
-  s1c.b0 = __shfl_up_sync(0xffffffffu, e1c.b0, 1); s1c.a1 = __shfl_up_sync(0xffffffffu, e1c.a1, 1);
-  s1c.a2 = __shfl_up_sync(0xffffffffu, e1c.a2, 1); s2c.b0 = __shfl_up_sync(0xffffffffu, e2c.b0, 1);
-  s2c.a1 = __shfl_up_sync(0xffffffffu, e2c.a1, 1); s2c.a2 = __shfl_up_sync(0xffffffffu, e2c.a2, 1);
-  if (lane == 0) {
-    if (vp->knot_frame == fb) {
-      s1c.b0 = vp->knot[0]; s1c.a1 = vp->knot[1]; s1c.a2 = vp->knot[2];
-      s2c.b0 = vp->knot[3]; s2c.a1 = vp->knot[4]; s2c.a2 = vp->knot[5];
-    } else {
-      welsh_coef_exact(I, fma(I.cut_b, env_seg_at(fseg, 0), I.cut_a), s1c, s2c);
+  Quad qb1, qa11, qa21;
+  {
+    SecCoef m1, m2, e1c, e2c, s1c, s2c;
+    welsh_coef_exact(I, fma(I.cut_b, env_seg_at(fseg, kT / 2), I.cut_a), m1, m2);
+    welsh_coef_exact(I, fma(I.cut_b, env_seg_at(fseg, kT), I.cut_a), e1c, e2c);
+    s1c.b0 = __shfl_up_sync(0xffffffffu, e1c.b0, 1); s1c.a1 = __shfl_up_sync(0xffffffffu, e1c.a1, 1);
+    s1c.a2 = __shfl_up_sync(0xffffffffu, e1c.a2, 1); s2c.b0 = __shfl_up_sync(0xffffffffu, e2c.b0, 1);
+    s2c.a1 = __shfl_up_sync(0xffffffffu, e2c.a1, 1); s2c.a2 = __shfl_up_sync(0xffffffffu, e2c.a2, 1);
+    if (lane == 0) {
+      if (vp->knot_frame == fb) {
+        s1c.b0 = vp->knot[0]; s1c.a1 = vp->knot[1]; s1c.a2 = vp->knot[2];
+        s2c.b0 = vp->knot[3]; s2c.a1 = vp->knot[4]; s2c.a2 = vp->knot[5];
+      } else {
+        welsh_coef_exact(I, fma(I.cut_b, env_seg_at(fseg, 0), I.cut_a), s1c, s2c);
+      }
     }
+    __syncwarp();
+    if (lane == 31) {
+      vp->knot[0] = e1c.b0; vp->knot[1] = e1c.a1; vp->knot[2] = e1c.a2;
+      vp->knot[3] = e2c.b0; vp->knot[4] = e2c.a1; vp->knot[5] = e2c.a2;
+    }
+    qb1 = quad_fit(s1c.b0, m1.b0, e1c.b0); qa11 = quad_fit(s1c.a1, m1.a1, e1c.a1); qa21 = quad_fit(s1c.a2, m1.a2, e1c.a2);
+    const Quad qb2 = quad_fit(s2c.b0, m2.b0, e2c.b0), qa12 = quad_fit(s2c.a1, m2.a1, e2c.a1),
+               qa22 = quad_fit(s2c.a2, m2.a2, e2c.a2);
+    park[0 * pstride] = qb2.k0; park[1 * pstride] = qb2.d1; park[2 * pstride] = qb2.d2;
+    park[3 * pstride] = qa12.k0; park[4 * pstride] = qa12.d1; park[5 * pstride] = qa12.d2;
+    park[6 * pstride] = qa22.k0; park[7 * pstride] = qa22.d1; park[8 * pstride] = qa22.d2;
+    park[9 * pstride] = aseg.q0; park[10 * pstride] = aseg.q1; park[11 * pstride] = aseg.q2;
+    park[12 * pstride] = aseg.w0; park[13 * pstride] = aseg.dw;
   }
-  __syncwarp();
-  if (lane == 31) {
-    vp->knot[0] = e1c.b0; vp->knot[1] = e1c.a1; vp->knot[2] = e1c.a2;
-    vp->knot[3] = e2c.b0; vp->knot[4] = e2c.a1; vp->knot[5] = e2c.a2;
-  }
-  const Quad qb1 = quad_fit(s1c.b0, m1.b0, e1c.b0), qa11 = quad_fit(s1c.a1, m1.a1, e1c.a1),
-             qa21 = quad_fit(s1c.a2, m1.a2, e1c.a2);
-  const Quad qb2 = quad_fit(s2c.b0, m2.b0, e2c.b0), qa12 = quad_fit(s2c.a1, m2.a1, e2c.a1),
-             qa22 = quad_fit(s2c.a2, m2.a2, e2c.a2);
   // ---- phases at c0 - 1 (closed form), LFO base angle ----
   const u64 k = (u64)(c0 - 1 - vp->anchor);
   const u64 d1 = vp->d1, d2 = vp->d2;
@@ -778,7 +811,7 @@ __device__ __noinline__ void welsh_block_simple(WelshVoice* vp, const WelshInst*
   double ls = 0.0, lc = 0.0;
   if (LFO_AMP) sincospi(2.0 * pos_of(vp->pl + (k + 1) * I.lfo_dq), &ls, &lc);
   const double mix1 = I.mix, mix2 = 1.0 - I.mix;
-  const u64 th1 = I.s1.thresh, th2 = I.s2.thresh;
+  const OscShape o1 = I.s1, o2 = I.s2;
   // ---- pass 1: oscillators + section 1 from a zero state with its homogeneous response ----
   double yp[kT], g0[kT], g1[kT];
   double ps0 = 0.0, ps1 = 0.0, h00 = 1.0, h01 = 0.0, h10 = 0.0, h11 = 1.0;
@@ -786,7 +819,7 @@ __device__ __noinline__ void welsh_block_simple(WelshVoice* vp, const WelshInst*
   for (int j = 0; j < kT; ++j) {
     p1 += d1;
     p2 += d2;
-    const double x = fma(osc_affine(I.s1, p1, th1), mix1, osc_affine(I.s2, p2, th2) * mix2);
+    const double x = fma(osc_affine(o1, p1, o1.thresh), mix1, osc_affine(o2, p2, o2.thresh) * mix2);
     const double b0 = quad_at(qb1, j), a1 = quad_at(qa11, j), a2 = quad_at(qa21, j);
     const double bx = b0 * x;
     const double y = bx + ps0;
@@ -807,20 +840,26 @@ __device__ __noinline__ void welsh_block_simple(WelshVoice* vp, const WelshInst*
   }
   const double ns0 = end0, ns1 = end1;
   // ---- pass 2: section 2 on the fixed-up section-1 output ----
-  ps0 = 0.0; ps1 = 0.0; h00 = 1.0; h01 = 0.0; h10 = 0.0; h11 = 1.0;
+  {
+    Quad qb2, qa12, qa22;
+    qb2.k0 = park[0 * pstride]; qb2.d1 = park[1 * pstride]; qb2.d2 = park[2 * pstride];
+    qa12.k0 = park[3 * pstride]; qa12.d1 = park[4 * pstride]; qa12.d2 = park[5 * pstride];
+    qa22.k0 = park[6 * pstride]; qa22.d1 = park[7 * pstride]; qa22.d2 = park[8 * pstride];
+    ps0 = 0.0; ps1 = 0.0; h00 = 1.0; h01 = 0.0; h10 = 0.0; h11 = 1.0;
 #pragma unroll
-  for (int j = 0; j < kT; ++j) {
-    const double b0 = quad_at(qb2, j), a1 = quad_at(qa12, j), a2 = quad_at(qa22, j);
-    const double x = fma(g1[j], e1, fma(g0[j], e0, yp[j]));
-    const double bx = b0 * x;
-    const double y = bx + ps0;
-    yp[j] = y; g0[j] = h00; g1[j] = h01;
-    const double n0 = fma(a1, y, fma(2.0, bx, ps1));
-    ps1 = fma(a2, y, bx);
-    ps0 = n0;
-    const double t00 = fma(a1, h00, h10), t01 = fma(a1, h01, h11);
-    h10 = a2 * h00; h11 = a2 * h01;
-    h00 = t00; h01 = t01;
+    for (int j = 0; j < kT; ++j) {
+      const double b0 = quad_at(qb2, j), a1 = quad_at(qa12, j), a2 = quad_at(qa22, j);
+      const double x = fma(g1[j], e1, fma(g0[j], e0, yp[j]));
+      const double bx = b0 * x;
+      const double y = bx + ps0;
+      yp[j] = y; g0[j] = h00; g1[j] = h01;
+      const double n0 = fma(a1, y, fma(2.0, bx, ps1));
+      ps1 = fma(a2, y, bx);
+      ps0 = n0;
+      const double t00 = fma(a1, h00, h10), t01 = fma(a1, h01, h11);
+      h10 = a2 * h00; h11 = a2 * h01;
+      h00 = t00; h01 = t01;
+    }
   }
   {
     Affine2 a;
@@ -829,11 +868,14 @@ __device__ __noinline__ void welsh_block_simple(WelshVoice* vp, const WelshInst*
     affine_lane_entry(inc, lane, vp->s[2], vp->s[3], e0, e1, end0, end1);
   }
   // ---- amplitude (envelope segment x LFO), DCA, CTA tile ----
+  EnvSeg as;
+  as.q0 = park[9 * pstride]; as.q1 = park[10 * pstride]; as.q2 = park[11 * pstride];
+  as.w0 = park[12 * pstride]; as.dw = park[13 * pstride];
   const double gl = I.gl, gr = I.gr;
   double2* row = tile_row + lane * (kT + 1);
 #pragma unroll
   for (int j = 0; j < kT; ++j) {
-    double amp = 0.5 * env_seg_at(aseg, j);
+    double amp = 0.5 * env_seg_at(as, j);
     if (LFO_AMP) amp *= fma(fma(ls, I.lfo_cos[j], lc * I.lfo_sin[j]), I.depth, 1.0);
     const double m = fma(g1[j], e1, fma(g0[j], e0, yp[j])) * amp;
     double2 o = make_double2(m * gl, m * gr);
@@ -888,38 +930,54 @@ __device__ __noinline__ void welsh_block_general(int variant, WelshVoice* vp, co
   __syncwarp();
 }
 
-// grid = number of CtaWork items; block = 32 * W threads; dynamic smem = W * kTileStride double2.
+// grid = number of CtaWork items; block = 32 * W threads;
+// dynamic smem = W * kTileStride double2 (tiles) + kParkWords * 32 * W doubles (parking columns).
 // __launch_bounds__(.., 2): two CTAs (16 warps) per SM, i.e. at most 128 registers per thread.
-template <int W, int MINB>
+template <int W, int MINB, bool SOLO>
 __global__ void __launch_bounds__(32 * W, MINB) welsh_kernel(const WelshInst* __restrict__ insts,
                                                            WelshVoice* __restrict__ voices,
                                                            const CtaWork* __restrict__ work,
+                                                           const WarpItem* __restrict__ items,
                                                            const VoiceEvent* __restrict__ events,
                                                            const int* __restrict__ ev_off, i64 f0, int nframes) {
   extern __shared__ double2 smem_tiles[];
   __shared__ int s_active[W];
-  __shared__ WelshInst sI;  // the CTA's instrument record: LDS instead of repeated global loads
+  __shared__ WelshInst sI[SOLO ? W : 1];  // instrument records: LDS instead of repeated global loads
   const CtaWork wk = work[blockIdx.x];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  {
+  constexpr bool solo = SOLO;  // compile-time: the grouped kernel carries none of the solo plumbing
+  const bool mine = !solo || warp < wk.nvoices;   // solo: does this warp have an item?
+  WarpItem item;
+  item.inst = wk.inst; item.voice = 0; item.out = nullptr;
+  if (solo && mine) item = items[wk.voice0 + warp];
+  if (!solo) {
     const int* src = reinterpret_cast<const int*>(insts + wk.inst);
-    int* dst = reinterpret_cast<int*>(&sI);
+    int* dst = reinterpret_cast<int*>(&sI[0]);
     for (int i = threadIdx.x; i < (int)(sizeof(WelshInst) / sizeof(int)); i += 32 * W) dst[i] = src[i];
+  } else if (mine) {
+    const int* src = reinterpret_cast<const int*>(insts + item.inst);
+    int* dst = reinterpret_cast<int*>(&sI[warp]);
+    for (int i = lane; i < (int)(sizeof(WelshInst) / sizeof(int)); i += 32) dst[i] = src[i];
   }
   __syncthreads();
-  const WelshInst& I = sI;
+  const WelshInst& I = sI[SOLO ? warp : 0];
   double2* tile_row = smem_tiles + warp * kTileStride;
+  // per-thread parking column behind the tiles: [kParkWords][32 * W] doubles
+  double* park = reinterpret_cast<double*>(smem_tiles + W * kTileStride) + threadIdx.x;
   const i64 f_end = f0 + nframes;
-  const bool pitch = I.routing == LFO_PITCH;
+  const bool pitch = mine && I.routing == LFO_PITCH;
   // instrument qualifies for welsh_block_simple (see its preconditions)
-  const bool simple_inst = I.s1.kind == 0 && I.s2.kind == 0 && !I.sync && I.filter_mode == FILTER_ENVELOPE &&
+  const bool simple_inst = mine && I.s1.kind == 0 && I.s2.kind == 0 && !I.sync && I.filter_mode == FILTER_ENVELOPE &&
                            (I.routing == LFO_NONE || (I.routing == LFO_AMPLITUDE && I.wl == W_SINE));
+  // voices this warp handles per block: grouped = warp, warp+W, ...; solo = its one item
+  const int g_begin = solo ? 0 : warp;
+  const int g_end = solo ? (mine ? 1 : 0) : wk.nvoices;
 #pragma unroll 1
   for (i64 fb = f0; fb < f_end; fb += kBlockFrames) {
     bool any = false;
 #pragma unroll 1
-    for (int g = warp; g < wk.nvoices; g += W) {
-      const int vi = wk.voice0 + g;
+    for (int g = g_begin; g < g_end; g += W) {
+      const int vi = solo ? item.voice : wk.voice0 + g;
       WelshVoice st = voices[vi];
       int ei = ev_off[vi];
       const int e_end = ev_off[vi + 1];
@@ -957,25 +1015,31 @@ __global__ void __launch_bounds__(32 * W, MINB) welsh_kernel(const WelshInst* __
           }
           if (__all_sync(0xffffffffu, smooth)) {
             if (simple_inst && I.routing == LFO_NONE)
-              welsh_block_simple<false>(vp, Ip, fb, lane, aseg, fseg, tile_row, any);
+              welsh_block_simple<false>(vp, Ip, fb, lane, aseg, fseg, tile_row, any, park);
             else if (simple_inst)
-              welsh_block_simple<true>(vp, Ip, fb, lane, aseg, fseg, tile_row, any);
+              welsh_block_simple<true>(vp, Ip, fb, lane, aseg, fseg, tile_row, any, park);
             else
               welsh_fast_call<COEF_KNOTS, true>(vp, Ip, fb, lane, cls, aseg, fseg, seed1, seed2, seedl, tile_row, any);
-          }
-          else
+          } else {
             welsh_fast_call<COEF_EXACT, false>(vp, Ip, fb, lane, cls, aseg, fseg, seed1, seed2, seedl, tile_row, any);
+          }
         }
       } else {
-        welsh_block_general((pitch ? 2 : 0) + (ev_here ? 1 : 0), voices + vi, insts + wk.inst, events, ei, e_end, fb, f_end, lane,
-                            seed1, seed2, seedl, tile_row, any);
+        welsh_block_general((pitch ? 2 : 0) + (ev_here ? 1 : 0), voices + vi, insts + item.inst, events, ei, e_end, fb,
+                            f_end, lane, seed1, seed2, seedl, tile_row, any);
       }
       any = true;
     }
-    if (lane == 0) s_active[warp] = any ? 1 : 0;
-    __syncthreads();
-    cta_reduce_store<W>(smem_tiles, s_active, wk.out, fb, f0, f_end);
-    __syncthreads();
+    if (solo) {
+      __syncwarp();
+      if (mine) warp_store_row(tile_row, any, item.out, fb, f0, f_end, lane);
+      __syncwarp();
+    } else {
+      if (lane == 0) s_active[warp] = any ? 1 : 0;
+      __syncthreads();
+      cta_reduce_store<W>(smem_tiles, s_active, wk.out, fb, f0, f_end);
+      __syncthreads();
+    }
   }
 }
 
@@ -1107,21 +1171,29 @@ __device__ __forceinline__ void fm_block(FmVoice& st, const FmInst& I, const Voi
 template <int W>
 __global__ void __launch_bounds__(32 * W) fm_kernel(const FmInst* __restrict__ insts, FmVoice* __restrict__ voices,
                                                      const CtaWork* __restrict__ work,
+                                                     const WarpItem* __restrict__ items,
                                                      const VoiceEvent* __restrict__ events,
                                                      const int* __restrict__ ev_off, i64 f0, int nframes) {
   extern __shared__ double2 smem_tiles[];
   __shared__ int s_active[W];
   const CtaWork wk = work[blockIdx.x];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const FmInst& I = insts[wk.inst];
+  const bool solo = wk.solo != 0;
+  const bool mine = !solo || warp < wk.nvoices;
+  WarpItem item;
+  item.inst = wk.inst; item.voice = 0; item.out = nullptr;
+  if (solo && mine) item = items[wk.voice0 + warp];
+  const FmInst& I = insts[item.inst];
   double2* tile_row = smem_tiles + warp * kTileStride;
   const i64 f_end = f0 + nframes;
+  const int g_begin = solo ? 0 : warp;
+  const int g_end = solo ? (mine ? 1 : 0) : wk.nvoices;
 #pragma unroll 1
   for (i64 fb = f0; fb < f_end; fb += kBlockFrames) {
     bool any = false;
 #pragma unroll 1
-    for (int g = warp; g < wk.nvoices; g += W) {
-      const int vi = wk.voice0 + g;
+    for (int g = g_begin; g < g_end; g += W) {
+      const int vi = solo ? item.voice : wk.voice0 + g;
       FmVoice st = voices[vi];
       int ei = ev_off[vi];
       const int e_end = ev_off[vi + 1];
@@ -1136,10 +1208,16 @@ __global__ void __launch_bounds__(32 * W) fm_kernel(const FmInst* __restrict__ i
       if (lane == 0) voices[vi] = st;
       __syncwarp();
     }
-    if (lane == 0) s_active[warp] = any ? 1 : 0;
-    __syncthreads();
-    cta_reduce_store<W>(smem_tiles, s_active, wk.out, fb, f0, f_end);
-    __syncthreads();
+    if (solo) {
+      __syncwarp();
+      if (mine) warp_store_row(tile_row, any, item.out, fb, f0, f_end, lane);
+      __syncwarp();
+    } else {
+      if (lane == 0) s_active[warp] = any ? 1 : 0;
+      __syncthreads();
+      cta_reduce_store<W>(smem_tiles, s_active, wk.out, fb, f0, f_end);
+      __syncthreads();
+    }
   }
 }
 

@@ -96,3 +96,92 @@ def cfg4_slice(voices: int, frames: int, voice_offset: int = 0) -> Cfg4:
     while voices % groups:
         groups -= 1
     return Cfg4(total_voices=voices, frames=frames, groups=groups, voice_offset=voice_offset)
+
+
+# ---------------------------------------------------------------------------------------------------
+# Config 5: 65 536 one-shot patch variants, SR 48 kHz, 2 s each, note-off at 1 s.
+# Variant j draws from splitmix64 seeded with 0x5EED + j; even j = subtractive, odd j = FM.
+CFG5_SAMPLE_RATE = 48000.0
+CFG5_FRAMES = 96000
+CFG5_NOTE_OFF = 48000
+_M64 = (1 << 64) - 1
+
+
+class _SplitMix:
+    def __init__(self, seed: int):
+        self.s = seed & _M64
+
+    def next(self) -> int:
+        self.s = (self.s + 0x9E3779B97F4A7C15) & _M64
+        z = self.s
+        z = ((z ^ (z >> 30)) * 0xBF58476D1CE4E5B9) & _M64
+        z = ((z ^ (z >> 27)) * 0x94D049BB133111EB) & _M64
+        return z ^ (z >> 31)
+
+    def u(self) -> float:
+        return (self.next() >> 11) * (1.0 / 9007199254740992.0)
+
+    def log_u(self, lo: float, hi: float) -> float:
+        return lo * (hi / lo) ** self.u()
+
+    def pick(self, seq):
+        return seq[self.next() % len(seq)]
+
+
+def cfg5_variant(j: int, gain: float = 1.0 / 256.0):
+    """(kind, params struct, MIDI key) of variant j."""
+    g = _SplitMix(0x5EED + j)
+    key = 36 + g.next() % 49
+    env4 = lambda: (g.log_u(1e-3, 1.0), g.log_u(1e-3, 1.0), g.u(), g.log_u(1e-3, 1.0))
+    pan = 2.0 * g.u() - 1.0
+    if j % 2 == 0:
+        shapes = (abi.WAVE_SAWTOOTH, abi.WAVE_SQUARE, abi.WAVE_PULSE_WIDTH, abi.WAVE_TRIANGLE)
+        p = abi.WelshParams()
+        p.oscillator_1 = abi.osc(g.pick(shapes), 0.1 + 0.8 * g.u())
+        cents = (g.u() * 100.0 - 50.0) + 1200.0 * g.pick((-2, -1, 0, 1, 2))
+        p.oscillator_2 = abi.osc(g.pick(shapes), 0.1 + 0.8 * g.u(), tune=2.0 ** (cents / 1200.0))
+        p.oscillator_2_sync = 0
+        p.oscillator_mix = g.u()
+        p.amp_envelope = abi.env(*env4())
+        p.lfo = abi.osc(abi.WAVE_SINE, frequency=0.0)
+        p.lfo_routing = abi.LFO_NONE
+        p.lfo_depth = 0.0
+        cutoff = g.log_u(40.0, 8000.0)
+        p.filter_cutoff_hz = cutoff
+        res = g.u()
+        p.filter_passband_ripple = res * res * 10.0 + 0.707
+        p.filter_cutoff_start = hz_to_pct(cutoff)
+        p.filter_cutoff_end = g.u()
+        p.filter_envelope = abi.env(*env4())
+        p.voice_dca = abi.DcaParams(1.0, 0.0)
+        p.dca = abi.DcaParams(gain, pan)
+        p.voices = 1
+        return abi.INST_WELSH, p, key
+    p = abi.FmParams()
+    p.ratio = g.pick((0.5, 1.0, 2.0, 3.0, 4.0))
+    p.beta = g.log_u(0.1, 20.0)
+    p.depth = g.u()
+    p.carrier_envelope = abi.env(*env4())
+    p.modulator_envelope = abi.env(*env4())
+    p.dca = abi.DcaParams(gain, pan)
+    p.voices = 1
+    return abi.INST_FM, p, key
+
+
+def build_cfg5(r: abi.Renderer, n_variants: int, first: int = 0, frames: int = CFG5_FRAMES,
+               note_off: int = CFG5_NOTE_OFF):
+    """Variants first .. first+n-1, each its own one-voice instrument patched into the main mixer
+    (its node buffer is the per-variant stereo output; the mixer's is the summed bus)."""
+    uids = []
+    ev = np.zeros(2 * n_variants, dtype=abi.EVENT_DTYPE)
+    for i in range(n_variants):
+        kind, p, key = cfg5_variant(first + i)
+        u = r.add_instrument(kind, p)
+        r.patch(u, abi.MAIN_MIXER)
+        uids.append(u)
+        ev[2 * i] = (0, u, abi.EV_NOTE_ON, key, 127, 0.0)
+        ev[2 * i + 1] = (note_off, u, abi.EV_NOTE_OFF, key, 0, 0.0)
+    r.finalize()
+    ev = ev[np.argsort(ev["frame"], kind="stable")]
+    r.push_events(ev)
+    return frames, uids

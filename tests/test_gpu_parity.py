@@ -182,3 +182,34 @@ def test_cfg4_slice_parity_and_linearity():
     # cfg4_slice(256) groups voices by i mod 128, the halves by i mod 128 as well: same voices
     assert np.abs(whole - parts).max() < 1e-12
     assert np.abs(whole).max() > 1e-3
+
+
+def test_cfg5_variant_batch_parity():
+    """BASELINE config 5 on a batch the oracle finishes in seconds: 96 randomised one-voice
+    subtractive / FM variants (solo-warp work items, short envelopes -> exact and general paths)."""
+    frames, note_off = 24000, 12000
+    o = OracleEngine(48000.0)
+    workloads.build_cfg5(o, 96, first=1000, frames=frames, note_off=note_off)
+    ref = o.render(frames)
+    g = gpu_engine(48000.0, max_block=frames)
+    workloads.build_cfg5(g, 96, first=1000, frames=frames, note_off=note_off)
+    out = g.render(frames)
+    g.close()
+    assert np.abs(ref).max() > 1e-3
+    check(out, ref)
+
+
+def test_cfg5_batch_is_sum_of_its_variants():
+    """Size-independent property at a larger batch: the bus of 512 variants equals the sum of the
+    buses of its two halves (independent renders)."""
+    frames, note_off = 16000, 8000
+    def run(n, first):
+        e = gpu_engine(48000.0, max_block=frames)
+        workloads.build_cfg5(e, n, first=first, frames=frames, note_off=note_off)
+        y = e.render(frames)
+        e.close()
+        return y
+    whole = run(512, 0)
+    parts = run(256, 0) + run(256, 256)
+    assert np.abs(whole).max() > 1e-2
+    assert np.abs(whole - parts).max() < 1e-12
