@@ -141,37 +141,60 @@ __device__ __forceinline__ Affine2 affine_compose(const Affine2& earlier, const 
   r.v1 = later.m10 * earlier.v0 + later.m11 * earlier.v1 + later.v1;
   return r;
 }
+// 64-bit shuffle as two explicit 32-bit shuffles (keeps the halves in a register pair).
+__device__ __forceinline__ double shfl_up_f64(double x, int delta) {
+  int lo = __shfl_up_sync(0xffffffffu, __double2loint(x), delta);
+  int hi = __shfl_up_sync(0xffffffffu, __double2hiint(x), delta);
+  return __hiloint2double(hi, lo);
+}
+__device__ __forceinline__ double shfl_idx_f64(double x, int src) {
+  int lo = __shfl_sync(0xffffffffu, __double2loint(x), src);
+  int hi = __shfl_sync(0xffffffffu, __double2hiint(x), src);
+  return __hiloint2double(hi, lo);
+}
 __device__ __forceinline__ Affine2 affine_shfl_up(const Affine2& a, int delta) {
   Affine2 r;
-  r.m00 = __shfl_up_sync(0xffffffffu, a.m00, delta);
-  r.m01 = __shfl_up_sync(0xffffffffu, a.m01, delta);
-  r.m10 = __shfl_up_sync(0xffffffffu, a.m10, delta);
-  r.m11 = __shfl_up_sync(0xffffffffu, a.m11, delta);
-  r.v0 = __shfl_up_sync(0xffffffffu, a.v0, delta);
-  r.v1 = __shfl_up_sync(0xffffffffu, a.v1, delta);
+  r.m00 = shfl_up_f64(a.m00, delta);
+  r.m01 = shfl_up_f64(a.m01, delta);
+  r.m10 = shfl_up_f64(a.m10, delta);
+  r.m11 = shfl_up_f64(a.m11, delta);
+  r.v0 = shfl_up_f64(a.v0, delta);
+  r.v1 = shfl_up_f64(a.v1, delta);
   return r;
+}
+// a <- a after e (e = the earlier map), in place.  Ordered so that every old word of `a` is dead
+// by the time its register is overwritten: one temporary per matrix row, no copies.
+__device__ __forceinline__ void affine_compose_inplace(Affine2& a, const Affine2& e) {
+  a.v0 = fma(a.m01, e.v1, fma(a.m00, e.v0, a.v0));
+  a.v1 = fma(a.m11, e.v1, fma(a.m10, e.v0, a.v1));
+  const double t0 = a.m00 * e.m01;
+  a.m00 = fma(a.m01, e.m10, a.m00 * e.m00);
+  a.m01 = fma(a.m01, e.m11, t0);
+  const double t1 = a.m10 * e.m01;
+  a.m10 = fma(a.m11, e.m10, a.m10 * e.m00);
+  a.m11 = fma(a.m11, e.m11, t1);
 }
 // Inclusive Kogge-Stone scan over the 32 lanes (lane order = time order).
 __device__ __forceinline__ Affine2 affine_warp_scan(Affine2 a, int lane) {
 #pragma unroll
   for (int d = 1; d < 32; d <<= 1) {
-    Affine2 prev = affine_shfl_up(a, d);
-    if (lane >= d) a = affine_compose(prev, a);
+    const Affine2 prev = affine_shfl_up(a, d);
+    if (lane >= d) affine_compose_inplace(a, prev);
   }
   return a;
 }
-// Given the inclusive scan and the state at the start of the warp's span, return the state at the
-// start of this lane's chunk, and (in *span_end) the state after the whole 32-lane span.
+// Given the inclusive scan and the state (s0,s1) at the start of the warp's span: the state at the
+// start of this lane's chunk (e0,e1) and after the whole 32-lane span (end0,end1).  The state after
+// lane l is incl_l applied to s; lane l's entry state is that of lane l-1 (two words to shuffle).
 __device__ __forceinline__ void affine_lane_entry(const Affine2& incl, int lane, double s0, double s1, double& e0,
                                                   double& e1, double& end0, double& end1) {
-  Affine2 ex = affine_shfl_up(incl, 1);
-  if (lane == 0) ex = affine_identity();
-  e0 = ex.m00 * s0 + ex.m01 * s1 + ex.v0;
-  e1 = ex.m10 * s0 + ex.m11 * s1 + ex.v1;
-  double t0 = incl.m00 * s0 + incl.m01 * s1 + incl.v0;
-  double t1 = incl.m10 * s0 + incl.m11 * s1 + incl.v1;
-  end0 = __shfl_sync(0xffffffffu, t0, 31);
-  end1 = __shfl_sync(0xffffffffu, t1, 31);
+  const double t0 = fma(incl.m01, s1, fma(incl.m00, s0, incl.v0));
+  const double t1 = fma(incl.m11, s1, fma(incl.m10, s0, incl.v1));
+  const double u0 = shfl_up_f64(t0, 1), u1 = shfl_up_f64(t1, 1);
+  e0 = lane == 0 ? s0 : u0;
+  e1 = lane == 0 ? s1 : u1;
+  end0 = shfl_idx_f64(t0, 31);
+  end1 = shfl_idx_f64(t1, 31);
 }
 
 // Segmented u64 sum scan (phase accumulators with resets).

@@ -291,7 +291,8 @@ struct gb_engine {
   int64_t pos = 0;
   uint32_t next_uid = 2;
   int num_sms = 148;
-  int welsh_occ = 2;        // resident CTAs per SM the Welsh kernel is compiled for (GB_WELSH_OCC=1|2)
+  int welsh_occ = 2;        // resident CTAs per SM the grouped Welsh kernel is compiled for (GB_WELSH_OCC=1|2):
+                            // 2 = 128 registers, 16 warps/SM (default, measured faster); 1 = 255 registers, 8 warps/SM
   int cta_target_mult = 2;  // CTAs per SM the voice work lists aim for (GB_CTA_MULT)
   std::map<uint32_t, std::unique_ptr<Node>> nodes;
   std::vector<Node*> plan;  // reachable nodes, sources before consumers
@@ -645,7 +646,7 @@ int gb_create(const gb_config* cfg, gb_engine** out) {
   memset(&e->stats, 0, sizeof e->stats);
   cudaDeviceProp prop;
   if (cudaGetDeviceProperties(&prop, e->device) == cudaSuccess) e->num_sms = prop.multiProcessorCount;
-  if (const char* v = getenv("GB_WELSH_OCC")) e->welsh_occ = atoi(v);  // 1,2: 8-warp CTAs; 4,5,6: 4-warp CTAs
+  if (const char* v = getenv("GB_WELSH_OCC")) e->welsh_occ = atoi(v) == 1 ? 1 : 2;
   if (const char* v = getenv("GB_CTA_MULT")) e->cta_target_mult = std::max(1, atoi(v));
   if (cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking) != cudaSuccess)
     return fail(nullptr, GB_ECUDA, "cudaStreamCreate failed");
@@ -934,7 +935,7 @@ int gb_finalize(gb_engine* e) {
     std::vector<WarpItem> items;
     if (total_voices == 0) { *count = 0; *n_grouped = 0; return 0; }
     int target = std::max(1, e->num_sms * e->cta_target_mult);
-    const int wpc = (kind == GB_INST_WELSH && e->welsh_occ >= 4) ? 4 : kVoiceWarps;  // warps per CTA
+    const int wpc = kVoiceWarps;  // warps per CTA (4-warp CTAs with tighter register caps measured slower)
     int vpc = std::max(wpc, cdiv(total_voices, target));
     vpc = cdiv(vpc, wpc) * wpc;
     for (Node* n : e->plan) {
@@ -1028,10 +1029,6 @@ int gb_finalize(gb_engine* e) {
   CUDA_TRY(e, cudaFuncSetAttribute(welsh_kernel<8, 1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, welsh_smem_bytes));
   CUDA_TRY(e, cudaFuncSetAttribute(welsh_kernel<8, 2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, welsh_smem_bytes));
   CUDA_TRY(e, cudaFuncSetAttribute(welsh_kernel<8, 2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, welsh_smem_bytes));
-  CUDA_TRY(e, cudaFuncSetAttribute(welsh_kernel<4, 4, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, welsh_smem_bytes));
-  CUDA_TRY(e, cudaFuncSetAttribute(welsh_kernel<4, 4, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, welsh_smem_bytes));
-  CUDA_TRY(e, cudaFuncSetAttribute(welsh_kernel<4, 5, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, welsh_smem_bytes));
-  CUDA_TRY(e, cudaFuncSetAttribute(welsh_kernel<4, 6, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, welsh_smem_bytes));
   CUDA_TRY(e, cudaFuncSetAttribute(fm_kernel<kVoiceWarps>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                    (int)(kVoiceWarps * kTileStride * sizeof(double2))));
   CUDA_TRY(e, cudaStreamSynchronize(e->stream));
@@ -1213,18 +1210,12 @@ int render_chunk(gb_engine* e, int frames, size_t n_ev) {
       e->d_winst, e->d_wvoice, e->wwork.d + (first_), e->witems.d, e->wev.d, e->wev_off.d, f0, frames)
       const int ng = e->n_wwork_grouped, ns = e->n_wwork - e->n_wwork_grouped;
       if (ng) {
-        switch (e->welsh_occ) {
-          case 1: GB_WELSH_LAUNCH(8, 1, false, 0, ng); break;
-          case 4: GB_WELSH_LAUNCH(4, 4, false, 0, ng); break;
-          case 5: GB_WELSH_LAUNCH(4, 5, false, 0, ng); break;
-          case 6: GB_WELSH_LAUNCH(4, 6, false, 0, ng); break;
-          default: GB_WELSH_LAUNCH(8, 2, false, 0, ng); break;
-        }
+        if (e->welsh_occ == 1) GB_WELSH_LAUNCH(8, 1, false, 0, ng);
+        else GB_WELSH_LAUNCH(8, 2, false, 0, ng);
       }
       if (ns) {
         if (ng) { e->stats.kernel_launches++; e->stats.voice_kernel_launches++; }
-        if (e->welsh_occ >= 4) GB_WELSH_LAUNCH(4, 4, true, ng, ns);
-        else GB_WELSH_LAUNCH(8, 2, true, ng, ns);
+        GB_WELSH_LAUNCH(8, 2, true, ng, ns);
       }
 #undef GB_WELSH_LAUNCH
     }

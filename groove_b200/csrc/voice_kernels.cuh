@@ -545,7 +545,11 @@ __device__ __forceinline__ double env_seg_at(const EnvSeg& g, int j) {
 
 // Lane classification for the fast path: 0 = needs the general path, 1 = all kT frames idle,
 // 2 = all kT frames sounding inside single envelope stages.
-__device__ __forceinline__ int welsh_lane_class(const WelshVoice& st, const WelshInst& I, i64 c0, i64 f_end,
+struct NoteWords {  // the part of a voice record that decides the path of a block
+  i64 n_on, n_off;
+  double la_on, la_off, lf_on, lf_off;
+};
+__device__ __forceinline__ int welsh_lane_class(const NoteWords& st, const WelshInst& I, i64 c0, i64 f_end,
                                                 EnvSeg& amp, EnvSeg& filt) {
   const i64 last = c0 + (kT - 1);
   const i64 idle_at = st.n_off + I.amp.nr;
@@ -978,17 +982,19 @@ __global__ void __launch_bounds__(32 * W, MINB) welsh_kernel(const WelshInst* __
 #pragma unroll 1
     for (int g = g_begin; g < g_end; g += W) {
       const int vi = solo ? item.voice : wk.voice0 + g;
-      WelshVoice st = voices[vi];
+      WelshVoice* vp = voices + vi;
+      NoteWords st;
+      st.n_on = vp->n_on; st.n_off = vp->n_off;
+      st.la_on = vp->la_on; st.la_off = vp->la_off; st.lf_on = vp->lf_on; st.lf_off = vp->lf_off;
       int ei = ev_off[vi];
       const int e_end = ev_off[vi + 1];
-      while (ei < e_end && events[ei].frame < fb) ++ei;  // already folded into st by earlier blocks
+      while (ei < e_end && events[ei].frame < fb) ++ei;  // already folded into the record by earlier blocks
       const bool idle = fb >= st.n_off + I.amp.nr;
       const bool ev_here = ei < e_end && events[ei].frame < fb + kBlockFrames;
       if (idle && !ev_here) continue;
+      // noise seeds are only needed off the specialised path
       const int local = vi - I.voice0;
-      const u64 seed1 = splitmix64(((u64)(unsigned)I.uid << 32) ^ (u64)(2 * local));
-      const u64 seed2 = splitmix64(((u64)(unsigned)I.uid << 32) ^ (u64)(2 * local + 1));
-      const u64 seedl = splitmix64(((u64)(unsigned)I.uid << 32) ^ 0x4C464F00ull ^ (u64)local);
+      auto seed_of = [&](u64 salt) { return splitmix64(((u64)(unsigned)I.uid << 32) ^ salt); };
       bool fast = false;
       EnvSeg aseg, fseg;
       int cls = 0;
@@ -998,13 +1004,12 @@ __global__ void __launch_bounds__(32 * W, MINB) welsh_kernel(const WelshInst* __
       }
       if (fast) {
         // the fast path changes only the filter state and the carried knot of the voice record
-        WelshVoice* vp = voices + vi;
         const WelshInst* Ip = &I;  // shared-memory copy
         if (I.filter_mode == FILTER_FIXED) {
           if (__all_sync(0xffffffffu, cls == 2))
-            welsh_fast_call<COEF_FIXED, true>(vp, Ip, fb, lane, cls, aseg, fseg, seed1, seed2, seedl, tile_row, any);
+            welsh_fast_call<COEF_FIXED, true>(vp, Ip, fb, lane, cls, aseg, fseg, seed_of((u64)(2 * local)), seed_of((u64)(2 * local + 1)), seed_of(0x4C464F00ull ^ (u64)local), tile_row, any);
           else
-            welsh_fast_call<COEF_FIXED, false>(vp, Ip, fb, lane, cls, aseg, fseg, seed1, seed2, seedl, tile_row, any);
+            welsh_fast_call<COEF_FIXED, false>(vp, Ip, fb, lane, cls, aseg, fseg, seed_of((u64)(2 * local)), seed_of((u64)(2 * local + 1)), seed_of(0x4C464F00ull ^ (u64)local), tile_row, any);
         } else {
           // knots need every lane sounding and the cutoff moving slowly enough over the lane's frames
           bool smooth = false;
@@ -1019,14 +1024,14 @@ __global__ void __launch_bounds__(32 * W, MINB) welsh_kernel(const WelshInst* __
             else if (simple_inst)
               welsh_block_simple<true>(vp, Ip, fb, lane, aseg, fseg, tile_row, any, park);
             else
-              welsh_fast_call<COEF_KNOTS, true>(vp, Ip, fb, lane, cls, aseg, fseg, seed1, seed2, seedl, tile_row, any);
+              welsh_fast_call<COEF_KNOTS, true>(vp, Ip, fb, lane, cls, aseg, fseg, seed_of((u64)(2 * local)), seed_of((u64)(2 * local + 1)), seed_of(0x4C464F00ull ^ (u64)local), tile_row, any);
           } else {
-            welsh_fast_call<COEF_EXACT, false>(vp, Ip, fb, lane, cls, aseg, fseg, seed1, seed2, seedl, tile_row, any);
+            welsh_fast_call<COEF_EXACT, false>(vp, Ip, fb, lane, cls, aseg, fseg, seed_of((u64)(2 * local)), seed_of((u64)(2 * local + 1)), seed_of(0x4C464F00ull ^ (u64)local), tile_row, any);
           }
         }
       } else {
-        welsh_block_general((pitch ? 2 : 0) + (ev_here ? 1 : 0), voices + vi, insts + item.inst, events, ei, e_end, fb,
-                            f_end, lane, seed1, seed2, seedl, tile_row, any);
+        welsh_block_general((pitch ? 2 : 0) + (ev_here ? 1 : 0), vp, insts + item.inst, events, ei, e_end, fb,
+                            f_end, lane, seed_of((u64)(2 * local)), seed_of((u64)(2 * local + 1)), seed_of(0x4C464F00ull ^ (u64)local), tile_row, any);
       }
       any = true;
     }
