@@ -290,10 +290,22 @@ def run_ours(a) -> None:
             pass
         hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
         vs_per_launch = per_rank_vs * a.steps / max(vlaunches, 1)
+        frames_per_launch = vs_per_launch / (a.variants if cfg5 else a.voices)
+        ctas_per_launch = 2 * min(128, a.voices)   # config 4: each 32-voice instrument is split over 2 CTAs
         launch_s = kern_ms * 1e-3 / max(vlaunches, 1)
         # cfg5: half the variants are FM voices (67 FLOP), launched as a second kernel per chunk
         flop_per_vs = 0.5 * (workloads.W_VOICE_FLOP + workloads.W_FM_FLOP) if cfg5 else workloads.W_VOICE_FLOP
         achieved_tflops = flop_per_vs * vs_per_launch / launch_s / 1e12
+        # DRAM traffic of the dominant kernel: from the committed ncu --set full capture (cannot be measured live),
+        # scaled to this run's voice-samples per launch
+        traffic = None
+        try:
+            with open(os.path.join(ROOT, "profiles", "r1_welsh_traffic.json")) as f:
+                tj = json.load(f)
+            if not cfg5:
+                traffic = tj["dram_bytes_per_launch"] * vs_per_launch / tj["voice_samples_per_launch"]
+        except (OSError, KeyError, ValueError):
+            pass
         # algorithmic HBM bytes: 16 B stereo f64 out per frame per CTA partial + voice state in/out
         out = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": a.steps, "warmup": max(a.warmup, 1),
@@ -314,7 +326,9 @@ def run_ours(a) -> None:
                     "h2d_bytes_per_step": int(h2d // a.steps), "d2h_bytes_per_step": int(d2h // a.steps)},
             "roofline": {
                 "bound": "fp64", "kernel": "welsh_kernel<8,2>" + (" + fm_kernel<8>" if cfg5 else ""), "achieved": achieved_tflops, "peak": fp64_peak,
-                "unit": "TFLOP/s", "frac": achieved_tflops / fp64_peak, "traffic": None,
+                "unit": "TFLOP/s", "frac": achieved_tflops / fp64_peak, "traffic": traffic,
+                "traffic_unit": "DRAM bytes per launch (ncu dram__bytes_read+write, profiles/r1_welsh_traffic.json)",
+                "algorithmic_bytes_per_launch": 16.0 * frames_per_launch * ctas_per_launch if not cfg5 else None,
                 "peak_source": "FP64 FMA microbenchmark measured live on this GPU (gb_measure_fma_peak); "
                                "MEASURED_PEAKS.json has no FP64 entry",
                 "algorithmic_flop_per_voice_sample": flop_per_vs,

@@ -1174,7 +1174,7 @@ __device__ __forceinline__ void fm_block(FmVoice& st, const FmInst& I, const Voi
 }
 
 template <int W>
-__global__ void __launch_bounds__(32 * W) fm_kernel(const FmInst* __restrict__ insts, FmVoice* __restrict__ voices,
+__global__ void __launch_bounds__(32 * W, 2) fm_kernel(const FmInst* __restrict__ insts, FmVoice* __restrict__ voices,
                                                      const CtaWork* __restrict__ work,
                                                      const WarpItem* __restrict__ items,
                                                      const VoiceEvent* __restrict__ events,
