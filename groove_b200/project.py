@@ -13,9 +13,9 @@ that plan on any block-render ABI engine.  Semantics kept from the reference:
 
 Schema drift across the reference's fixtures is accepted: `[4,4]` or `{top,bottom}`
 time signatures, `flat: [v]` or `flat: {value: v}`, `min/max` or `minimum/maximum`, `bits` or
-`bits-to-crush`, `delay` or `seconds`.  Controllers other than the pattern sequencer and control
-trips (arpeggiator, LFO controller, signal passthrough, ...) are not compiled yet and are reported in
-`Plan.skipped`.
+`bits-to-crush`, `delay` or `seconds`.  Event sources compiled: the pattern sequencer, control trips,
+the LFO controller (through `controls` links) and the arpeggiator.  The signal-passthrough (sidechain)
+controller needs an audio-rate control bus inside the engine and is reported in `Plan.skipped`.
 """
 from __future__ import annotations
 
@@ -365,6 +365,7 @@ class ProjectLoader:
         top, bottom = (ts["top"], ts["bottom"]) if isinstance(ts, dict) else (ts[0], ts[1])
         plan = Plan(project.get("title") or "", sample_rate, bpm, 0, [], [], [])
         by_uvid: Dict[str, Entity] = {}
+        controllers: Dict[str, tuple] = {}
         for dev in project.get("devices", []):
             (role, (uvid, spec)), = dev.items()
             ent = None
@@ -373,8 +374,14 @@ class ProjectLoader:
             elif role == "effect":
                 ent = self._effect(uvid, spec, plan)
             else:
-                plan.skipped.append(f"controller {uvid}: {list(spec)[0]} (event sources other than the sequencer and "
-                                    "control trips are not compiled yet)")
+                (ckind, cbody), = spec.items()
+                midi = cbody[0] if isinstance(cbody, list) and cbody else {}
+                args = cbody[1] if isinstance(cbody, list) and len(cbody) > 1 else {}
+                if ckind in ("lfo", "arpeggiator"):
+                    controllers[uvid] = (ckind, midi, args)
+                else:
+                    plan.skipped.append(f"controller {uvid}: {ckind} is not compiled (signal-passthrough needs an "
+                                        "audio-rate control bus; see DESIGN.md)")
             if ent:
                 plan.entities.append(ent)
                 by_uvid[uvid] = ent
@@ -394,6 +401,8 @@ class ProjectLoader:
         for e in plan.entities:
             if e.role == "instrument" and e.midi_in is not None:
                 by_channel.setdefault(int(e.midi_in), []).append(e)
+        arps = {int(m.get("midi-in", -1)): int(m.get("midi-out", 0))
+                for (k, m, _a) in controllers.values() if k == "arpeggiator"}
         for track in project.get("tracks", []):
             cursor = 0.0
             for pid in track.get("patterns", []):
@@ -408,9 +417,22 @@ class ProjectLoader:
                     for i, key in enumerate(row):
                         if key == 0:
                             continue
-                        for ent in by_channel.get(int(track["midi-channel"]), []):
+                        ch = int(track["midi-channel"])
+                        for ent in by_channel.get(ch, []):
                             plan.events.append((quantise(cursor + i * step), ent.uvid, abi.EV_NOTE_ON, int(key), 127, 0.0))
                             plan.events.append((quantise(cursor + (i + 1) * step), ent.uvid, abi.EV_NOTE_OFF, int(key), 0, 0.0))
+                        if ch in arps:
+                            # Arpeggiator (parity unpinned): while the input note is held it plays the major
+                            # scale key + [0,2,4,5,7,9,11,12], one note per quarter beat, each 0.2 beat long,
+                            # repeating every 2 beats, on its midi-out channel.
+                            b0, b1 = cursor + i * step, cursor + (i + 1) * step
+                            k = 0
+                            while b0 + 0.25 * k < b1 - 1e-9:
+                                nk = int(key) + (0, 2, 4, 5, 7, 9, 11, 12)[k % 8]
+                                for ent in by_channel.get(arps[ch], []):
+                                    plan.events.append((quantise(b0 + 0.25 * k), ent.uvid, abi.EV_NOTE_ON, nk, 127, 0.0))
+                                    plan.events.append((quantise(b0 + 0.25 * k + 0.2), ent.uvid, abi.EV_NOTE_OFF, nk, 0, 0.0))
+                                k += 1
                 cursor += math.ceil(longest * step / top - 1e-9) * top
             end_beats = max(end_beats, cursor)
         # control trips: one control event per 64-frame buffer while a step is active
@@ -447,8 +469,33 @@ class ProjectLoader:
                             plan.events.append((f, ent.uvid, abi.EV_CONTROL, idx, 0, a + (b - a) * t))
                     cursor += step_beats
             end_beats = max(end_beats, cursor)
-        plan.events.sort(key=lambda ev: ev[0])
         plan.frames = song_frames(end_beats, bpm, sample_rate)
+        # LFO controllers (`controls` links, settings/src/songs.rs:166-202): one control event per 64-frame
+        # buffer carrying the oscillator's value at the buffer's first frame, mapped to 0..1
+        for link in project.get("controls", []):
+            src = controllers.get(link.get("source"))
+            tgt = link.get("target", {})
+            ent = by_uvid.get(tgt.get("id"))
+            idx = CONTROL_INDEX.get(tgt.get("param"))
+            if src is None or src[0] != "lfo" or ent is None or idx is None:
+                plan.skipped.append(f"control {link.get('id')}: source/target not compiled")
+                continue
+            wf, pw = _waveform(src[2].get("waveform", "sine"))
+            hz = float(src[2].get("frequency", 1.0))
+            for f in range(0, plan.frames, BUFFER_FRAMES):
+                ph = (f * hz / sample_rate) % 1.0
+                if wf == abi.WAVE_SINE:
+                    v = math.sin(2.0 * math.pi * ph)
+                elif wf == abi.WAVE_TRIANGLE:
+                    v = 4.0 * ph - 1.0 if ph < 0.5 else 3.0 - 4.0 * ph
+                elif wf == abi.WAVE_SAWTOOTH:
+                    v = 2.0 * ph if ph < 0.5 else 2.0 * ph - 2.0
+                elif wf in (abi.WAVE_SQUARE, abi.WAVE_PULSE_WIDTH):
+                    v = 1.0 if ph < (pw if wf == abi.WAVE_PULSE_WIDTH else 0.5) else -1.0
+                else:
+                    v = 0.0
+                plan.events.append((f, ent.uvid, abi.EV_CONTROL, idx, 0, 0.5 * (v + 1.0)))
+        plan.events.sort(key=lambda ev: ev[0])
         return plan
 
     def load(self, path: str, sample_rate: float = 44100.0) -> Plan:

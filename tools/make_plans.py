@@ -22,6 +22,8 @@ PROJECTS = {
     "compressor": "projects/demos/effects/compressor.json",
     "drums-reverb": "projects/demos/effects/drums-reverb.json",
     "fm-synthesizer": "projects/demos/instruments/fm-synthesizer.json",
+    "arpeggiator": "projects/demos/controllers/arpeggiator.json",
+    "stereo-automation": "projects/demos/controllers/stereo-automation.json",
 }
 out_dir = os.path.join(ROOT, "tests", "golden", "plans")
 os.makedirs(out_dir, exist_ok=True)
