@@ -125,22 +125,6 @@ __device__ __forceinline__ void lp24_from_k(const Lp24Ripple& rp, double k, SecC
 struct Affine2 {
   double m00, m01, m10, m11, v0, v1;
 };
-__device__ __forceinline__ Affine2 affine_identity() {
-  Affine2 a;
-  a.m00 = 1.0; a.m01 = 0.0; a.m10 = 0.0; a.m11 = 1.0; a.v0 = 0.0; a.v1 = 0.0;
-  return a;
-}
-// apply `later` after `earlier`
-__device__ __forceinline__ Affine2 affine_compose(const Affine2& earlier, const Affine2& later) {
-  Affine2 r;
-  r.m00 = later.m00 * earlier.m00 + later.m01 * earlier.m10;
-  r.m01 = later.m00 * earlier.m01 + later.m01 * earlier.m11;
-  r.m10 = later.m10 * earlier.m00 + later.m11 * earlier.m10;
-  r.m11 = later.m10 * earlier.m01 + later.m11 * earlier.m11;
-  r.v0 = later.m00 * earlier.v0 + later.m01 * earlier.v1 + later.v0;
-  r.v1 = later.m10 * earlier.v0 + later.m11 * earlier.v1 + later.v1;
-  return r;
-}
 // 64-bit shuffle as two explicit 32-bit shuffles (keeps the halves in a register pair).
 __device__ __forceinline__ double shfl_up_f64(double x, int delta) {
   int lo = __shfl_up_sync(0xffffffffu, __double2loint(x), delta);

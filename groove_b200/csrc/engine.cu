@@ -1189,7 +1189,6 @@ int render_chunk(gb_engine* e, int frames, size_t n_ev) {
     return 0;
   };
   const size_t tile_bytes = (size_t)kVoiceWarps * kTileStride * sizeof(double2);
-  const size_t welsh_smem = tile_bytes + (size_t)kParkWords * 32 * kVoiceWarps * sizeof(double);
   if (e->n_wvoice) {
     if (e->winst_dirty) {
       for (Node* n : e->plan)

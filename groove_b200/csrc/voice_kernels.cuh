@@ -1173,6 +1173,72 @@ __device__ __forceinline__ void fm_block(FmVoice& st, const FmInst& I, const Voi
   }
 }
 
+// ---- FM fast path: blocks without note events in which every lane is idle or sounds inside single
+// stages of both envelopes.  Envelopes are 3 FMAs per frame; the modulator sine advances by an
+// angle-addition rotation (its phase increment is constant within a note); the carrier is exact:
+// integer-summed phase (warp scan) and sinpi.
+__device__ __forceinline__ int fm_lane_class(const FmVoice& st, const FmInst& I, i64 c0, i64 f_end, EnvSeg& car,
+                                             EnvSeg& mod) {
+  const i64 last = c0 + (kT - 1);
+  const i64 idle_at = st.n_off + I.car.nr;
+  if (c0 >= f_end || last < st.n_on || c0 >= idle_at) return 1;
+  if (!(c0 >= st.n_on && last < idle_at && last < f_end)) return 0;
+  if (!env_segment(I.car, st.n_on, st.n_off, st.lc_on, st.lc_off, c0, car)) return 0;
+  if (!env_segment(I.mod, st.n_on, st.n_off, st.lm_on, st.lm_off, c0, mod)) return 0;
+  return 2;
+}
+__device__ __forceinline__ void fm_block_fast(FmVoice& st, const FmInst& I, i64 fb, int lane, int cls,
+                                              const EnvSeg& cseg, const EnvSeg& mseg, double2* tile_row,
+                                              bool accumulate) {
+  const i64 c0 = fb + (i64)lane * kT;
+  const bool on = cls == 2;
+  u64 dc[kT];
+  u64 sum = 0;
+#pragma unroll
+  for (int j = 0; j < kT; ++j) dc[j] = 0;
+  if (on) {
+    const u64 pm0 = st.pm + (u64)(c0 - st.anchor) * st.dm;
+    double s, c, sd, cd;
+    sincospi(2.0 * pos_of(pm0), &s, &c);
+    sincospi(2.0 * (__ull2double_rn(st.dm) * (1.0 / kTwo64)), &sd, &cd);
+    const double depth = I.depth, beta = I.beta, cyc = st.cyc_c;
+#pragma unroll
+    for (int j = 0; j < kT; ++j) {
+      const double menv = env_seg_at(mseg, j);
+      const double x = __dmul_rn(__dmul_rn(__dmul_rn(s, menv), depth), beta);
+      dc[j] = cycles_to_q(__dmul_rn(cyc, __dadd_rn(1.0, x)));
+      sum += dc[j];
+      const double ns = fma(s, cd, c * sd);
+      c = fma(c, cd, -(s * sd));
+      s = ns;
+    }
+  }
+  // inclusive integer scan of the lane sums (no restarts on this path)
+  u64 inc = sum;
+#pragma unroll
+  for (int d = 1; d < 32; d <<= 1) {
+    const u64 up = __shfl_up_sync(0xffffffffu, inc, d);
+    if (lane >= d) inc += up;
+  }
+  u64 pc = st.pc + inc - sum;  // carrier phase at c0 - 1
+  st.pc = __shfl_sync(0xffffffffu, st.pc + inc, 31);
+#pragma unroll
+  for (int j = 0; j < kT; ++j) {
+    double m = 0.0;
+    if (on) {
+      pc += dc[j];
+      m = sinpi(2.0 * pos_of(pc)) * env_seg_at(cseg, j);
+    }
+    const int t = lane * kT + j;
+    double2 o = make_double2(m * I.gl, m * I.gr);
+    if (accumulate) {
+      double2 p = tile_row[t + (t >> 3)];
+      o.x += p.x; o.y += p.y;
+    }
+    tile_row[t + (t >> 3)] = o;
+  }
+}
+
 template <int W>
 __global__ void __launch_bounds__(32 * W, 2) fm_kernel(const FmInst* __restrict__ insts, FmVoice* __restrict__ voices,
                                                      const CtaWork* __restrict__ work,
@@ -1206,8 +1272,14 @@ __global__ void __launch_bounds__(32 * W, 2) fm_kernel(const FmInst* __restrict_
       bool idle = fb >= st.n_off + I.car.nr;
       bool ev_here = ei < e_end && events[ei].frame < fb + kBlockFrames;
       if (idle && !ev_here) continue;
-      if (ev_here) fm_block<true>(st, I, events, ei, e_end, fb, f_end, lane, tile_row, any);
-      else fm_block<false>(st, I, events, ei, e_end, fb, f_end, lane, tile_row, any);
+      if (ev_here) {
+        fm_block<true>(st, I, events, ei, e_end, fb, f_end, lane, tile_row, any);
+      } else {
+        EnvSeg cseg, mseg;
+        const int cls = fm_lane_class(st, I, fb + (i64)lane * kT, f_end, cseg, mseg);
+        if (__all_sync(0xffffffffu, cls != 0)) fm_block_fast(st, I, fb, lane, cls, cseg, mseg, tile_row, any);
+        else fm_block<false>(st, I, events, ei, e_end, fb, f_end, lane, tile_row, any);
+      }
       any = true;
       __syncwarp();
       if (lane == 0) voices[vi] = st;
