@@ -317,6 +317,9 @@ def run_ours(a) -> None:
                             "per-frame 24 dB LPF), 60 s at 48 kHz stereo" if (a.voices, a.seconds) == (4096, 60.0)
                             else f"config-4 recipe scaled: {a.voices} voices x {a.seconds:g} s at 48 kHz stereo",
                 "voices_per_gpu": a.voices, "frames": frames, "voice_samples_per_step": total_vs,
+                "coefficients": ("exact per frame (GB_KNOT_MAX_RATE=0)" if os.environ.get("GB_KNOT_MAX_RATE", "") in ("0", "0.0")
+                                 else "quadratic through exact knots every 4 frames when the cutoff moves <= "
+                                      + os.environ.get("GB_KNOT_MAX_RATE", "1e-5") + "/frame, else exact per frame"),
                 "max_block": a.max_block, "parallelism": f"voices sharded over {world} GPU(s); one NCCL f64 bus reduce",
                 "l2": "256 MiB device memset between steps (L2 flush); fresh engine per step",
             },

@@ -432,6 +432,8 @@ void welsh_inst_from_params(const Node& n, double sr, WelshInst* I) {
   I->log2_25_over_sr = std::log2(25.0 / sr);
   I->u_min = 1.0 / sr;
   I->u_max = 0.49;
+  I->knot_max_rate = kKnotMaxRate;
+  if (const char* v = getenv("GB_KNOT_MAX_RATE")) I->knot_max_rate = atof(v);
   for (int j = 0; j < kT; ++j) {
     uint64_t q = (uint64_t)j * I->lfo_dq;  // mod 2^64
     double ang = 6.283185307179586476925286766559 * ((double)q / 18446744073709551616.0);

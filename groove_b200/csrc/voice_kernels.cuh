@@ -139,6 +139,7 @@ struct WelshInst {
   OscShape s1, s2, sl;              // branch-free waveform descriptions (fast path)
   double log2_25_over_sr;           // fc/sr = exp2(pct*log2(800) + log2(25/sr))
   double u_min, u_max;              // clamp of fc/sr: [1/sr, 0.49]
+  double knot_max_rate;             // cutoff motion (fraction of the log range per frame) up to which knots are used
 };
 enum { FILTER_FIXED = 0, FILTER_ENVELOPE = 1, FILTER_LFO = 2 };
 
@@ -590,7 +591,7 @@ __device__ __forceinline__ double quad_at(const Quad& q, int j) {
 // sets are taken from the quadratic through exact knots every kT/2 frames instead of being evaluated
 // exactly: the interpolation error grows with the cube of the rate and is <= 1e-11 absolute here
 // (docs/ORACLE_SPEC.md, "coefficient knots").
-constexpr double kKnotMaxRate = 1.0e-5;
+constexpr double kKnotMaxRate = 1.0e-5;  // default of WelshInst::knot_max_rate (GB_KNOT_MAX_RATE overrides; 0 = always exact)
 
 enum { COEF_FIXED = 0, COEF_EXACT = 1, COEF_KNOTS = 2 };
 
@@ -1016,7 +1017,7 @@ __global__ void __launch_bounds__(32 * W, MINB) welsh_kernel(const WelshInst* __
           if (I.filter_mode == FILTER_ENVELOPE && cls == 2) {
             const double w8 = fma((double)kT, fseg.dw, fseg.w0);
             const double r0 = fabs(fma(2.0 * fseg.q2, fseg.w0, fseg.q1)), r8 = fabs(fma(2.0 * fseg.q2, w8, fseg.q1));
-            smooth = fabs(I.cut_b * fseg.dw) * fmax(r0, r8) <= kKnotMaxRate;
+            smooth = fabs(I.cut_b * fseg.dw) * fmax(r0, r8) <= I.knot_max_rate && I.knot_max_rate > 0.0;
           }
           if (__all_sync(0xffffffffu, smooth)) {
             if (simple_inst && I.routing == LFO_NONE)
