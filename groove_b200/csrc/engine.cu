@@ -262,6 +262,8 @@ struct Node {
   int table_index = -1;  // index in the welsh/fm instrument table
   int voice0 = 0, nvoices = 0;
   int partial_count = 0;  // partial output buffers in `scratch` (0 = renders straight into `buf`)
+  bool unit_gain = false; // this chunk renders at unit DCA gain; a segmented OP_DCA pass applies gain/pan
+  std::vector<std::vector<SampleVoiceHost>> done_plays;  // per sample voice: plays that ended inside this chunk
   int64_t release_frames = 0;
   SlotStore store;
   std::vector<SampleDev> samples;
@@ -315,6 +317,7 @@ struct gb_engine {
   DevBuf<VoiceEvent> wev, fev;
   DevBuf<int> wev_off, fev_off;
   DevBuf<SamplePlay> plays;
+  DevBuf<SegParam> segs;         // per-chunk parameter segment tables of all effects / instrument DCAs
   DevBuf<PartialDesc> partials;  // instruments split over several CTAs (static after finalize)
   int n_partials = 0;
   std::vector<void*> allocations;  // everything cudaMalloc'ed at finalize/load time
@@ -409,6 +412,7 @@ void welsh_inst_from_params(const Node& n, double sr, WelshInst* I) {
   double pan = p.voice_dca.pan + p.dca.pan;
   pan = pan < -1.0 ? -1.0 : (pan > 1.0 ? 1.0 : pan);
   dca_gains(p.voice_dca.gain * p.dca.gain, pan, &I->gl, &I->gr);
+  if (n.unit_gain) { I->gl = 1.0; I->gr = 1.0; }
   I->pi_over_sr = 3.141592653589793238462643383279 / sr;
   I->sr = sr;
   auto shape = [](int wf, uint64_t duty_q, OscShape* o) {
@@ -448,6 +452,7 @@ void fm_inst_from_params(const Node& n, double sr, FmInst* I) {
   I->depth = n.fp.depth;
   I->beta = n.fp.beta;
   dca_gains(n.fp.dca.gain, n.fp.dca.pan, &I->gl, &I->gr);
+  if (n.unit_gain) { I->gl = 1.0; I->gr = 1.0; }
   I->uid = (int)n.uid;
   I->voice0 = n.voice0;
 }
@@ -556,43 +561,59 @@ bool effect_accepts(const Node* n, int index) {
   }
 }
 
-// Run one effect node over chunk frames [t0,t1) with its current parameters.
-int run_effect_segment(gb_engine* e, Node* n, const SourceList& src, int frames, int t0, int t1, int64_t chunk_pos) {
-  if (t1 <= t0) return 0;
-  const int nseg = t1 - t0;
+// Kernel-ready values of an effect's (or instrument DCA's) current parameters, for one segment.
+void seg_values(gb_engine* e, const Node* n, double* v) {
+  for (int i = 0; i < 6; ++i) v[i] = 0.0;
+  switch (n->kind) {
+    case GB_FX_GAIN: v[0] = n->p[0]; break;
+    case GB_FX_LIMITER: v[0] = n->p[0]; v[1] = n->p[1]; break;
+    case GB_FX_BITCRUSHER: v[0] = std::exp2(std::floor(n->p[0])); break;
+    case GB_FX_COMPRESSOR: v[0] = n->p[0]; v[1] = n->p[1]; break;
+    case GB_FX_CHORUS: v[0] = n->p[GB_CTL_CHORUS_WET_DRY_MIX]; break;
+    case GB_FX_REVERB: v[0] = n->p[0]; break;
+    case GB_FX_LOW_PASS_24DB: {
+      SecCoef s1, s2;
+      Lp24Ripple rp = make_ripple(n->p[1]);
+      host_lp24(rp, n->p[0], e->sr, &s1, &s2);
+      v[0] = s1.b0; v[1] = s1.a1; v[2] = s1.a2; v[3] = s2.b0; v[4] = s2.a1; v[5] = s2.a2;
+    } break;
+    case GB_INST_WELSH: {
+      double pan = n->wp.voice_dca.pan + n->wp.dca.pan;
+      pan = pan < -1.0 ? -1.0 : (pan > 1.0 ? 1.0 : pan);
+      dca_gains(n->wp.voice_dca.gain * n->wp.dca.gain, pan, &v[0], &v[1]);
+    } break;
+    case GB_INST_FM: dca_gains(n->fp.dca.gain, n->fp.dca.pan, &v[0], &v[1]); break;
+    default:
+      if (n->kind >= GB_FX_LOW_PASS_12DB && n->kind <= GB_FX_HIGH_SHELF_12DB) {
+        BiquadCoefs c = host_rbj(n->kind, n->p[0], n->p[1], e->sr);
+        v[0] = c.b0; v[1] = c.b1; v[2] = c.b2; v[3] = c.a1; v[4] = c.a2;
+      }
+      break;
+  }
+}
+
+// Run one effect node over the whole chunk; `segs`/`nseg` = its parameter segment table (device).
+int run_effect(gb_engine* e, Node* n, const SourceList& src, int frames, const SegParam* segs, int nseg,
+               int64_t chunk_pos) {
   switch (n->kind) {
     case GB_FX_MIXER: {
       Launch l(e, false);
-      pointwise_kernel<<<cdiv(nseg, 256), 256, 0, e->stream>>>(src, n->buf, t0, t1, OP_SUM, 0.0, 0.0);
+      pointwise_kernel<<<cdiv(frames, 256), 256, 0, e->stream>>>(src, n->buf, frames, OP_SUM, segs, nseg);
     } break;
-    case GB_FX_GAIN: {
+    case GB_FX_GAIN: case GB_FX_LIMITER: case GB_FX_BITCRUSHER: case GB_FX_COMPRESSOR: {
+      const int op = n->kind == GB_FX_GAIN ? OP_GAIN : n->kind == GB_FX_LIMITER ? OP_LIMITER
+                   : n->kind == GB_FX_BITCRUSHER ? OP_BITCRUSHER : OP_COMPRESSOR;
       Launch l(e, false);
-      pointwise_kernel<<<cdiv(nseg, 256), 256, 0, e->stream>>>(src, n->buf, t0, t1, OP_GAIN, n->p[0], 0.0);
-    } break;
-    case GB_FX_LIMITER: {
-      Launch l(e, false);
-      pointwise_kernel<<<cdiv(nseg, 256), 256, 0, e->stream>>>(src, n->buf, t0, t1, OP_LIMITER, n->p[0], n->p[1]);
-    } break;
-    case GB_FX_BITCRUSHER: {
-      Launch l(e, false);
-      pointwise_kernel<<<cdiv(nseg, 256), 256, 0, e->stream>>>(src, n->buf, t0, t1, OP_BITCRUSHER,
-                                                                std::exp2(std::floor(n->p[0])), 0.0);
-    } break;
-    case GB_FX_COMPRESSOR: {
-      Launch l(e, false);
-      pointwise_kernel<<<cdiv(nseg, 256), 256, 0, e->stream>>>(src, n->buf, t0, t1, OP_COMPRESSOR, n->p[0], n->p[1]);
+      pointwise_kernel<<<cdiv(frames, 256), 256, 0, e->stream>>>(src, n->buf, frames, op, segs, nseg);
     } break;
     case GB_FX_LOW_PASS_24DB: {
-      Lp24Coefs c;
-      Lp24Ripple rp = make_ripple(n->p[1]);
-      host_lp24(rp, n->p[0], e->sr, &c.s1, &c.s2);
       Launch l(e, false);
-      lp24_kernel<<<1, 32 * kFxWarps, 0, e->stream>>>(src, n->buf, t0, t1, c, n->d_lp);
+      lp24_kernel<<<1, 32 * kFxWarps, 0, e->stream>>>(src, n->buf, frames, segs, nseg, n->d_lp);
     } break;
     case GB_FX_CHORUS: {
       Launch l(e, false);
-      chorus_kernel<<<cdiv(nseg, 256), 256, 0, e->stream>>>(src, n->hist[n->hist_cur], std::max(n->delay_frames, 1),
-                                                             n->taps, n->p[GB_CTL_CHORUS_WET_DRY_MIX], n->buf, t0, t1);
+      chorus_kernel<<<cdiv(frames, 256), 256, 0, e->stream>>>(src, n->hist[n->hist_cur], std::max(n->delay_frames, 1),
+                                                               n->taps, segs, nseg, n->buf, frames);
     } break;
     case GB_FX_REVERB: {
       int maxd = 0;
@@ -600,25 +621,24 @@ int run_effect_segment(gb_engine* e, Node* n, const SourceList& src, int frames,
       {
         Launch l(e, false);
         dim3 grid(cdiv(maxd, 256), 8);
-        reverb_comb_kernel<<<grid, 256, 0, e->stream>>>(src, n->rv, n->p[0], n->rv_comb_out, frames, chunk_pos, t0, t1);
+        reverb_comb_kernel<<<grid, 256, 0, e->stream>>>(src, n->rv, segs, nseg, n->rv_comb_out, frames, chunk_pos);
       }
       for (int stage = 0; stage < 2; ++stage) {
         Launch l(e, false);
         dim3 grid(cdiv(n->rv.ap_d[stage], 256), 2);
         reverb_allpass_kernel<<<grid, 256, 0, e->stream>>>(stage == 0 ? n->rv_comb_out : n->rv_ap_out[0],
                                                             stage == 0 ? 4 : 1, (size_t)frames, n->rv, stage,
-                                                            n->rv_ap_out[stage], frames, chunk_pos, t0, t1);
+                                                            n->rv_ap_out[stage], frames, chunk_pos);
       }
       {
         Launch l(e, false);
-        interleave_kernel<<<cdiv(nseg, 256), 256, 0, e->stream>>>(n->rv_ap_out[1], n->buf, frames, t0, t1);
+        interleave_kernel<<<cdiv(frames, 256), 256, 0, e->stream>>>(n->rv_ap_out[1], n->buf, frames);
       }
     } break;
     default:
       if (n->kind >= GB_FX_LOW_PASS_12DB && n->kind <= GB_FX_HIGH_SHELF_12DB) {
-        BiquadCoefs c = host_rbj(n->kind, n->p[0], n->p[1], e->sr);
         Launch l(e, false);
-        biquad_df1_kernel<<<1, 32 * kFxWarps, 0, e->stream>>>(src, n->buf, t0, t1, c, n->d_bq);
+        biquad_df1_kernel<<<1, 32 * kFxWarps, 0, e->stream>>>(src, n->buf, frames, segs, nseg, n->d_bq);
       }
       break;
   }
@@ -1113,7 +1133,13 @@ int render_chunk(gb_engine* e, int frames, size_t n_ev) {
           int v = n->store.note_on(f, key);
           const SampleDev& s = n->samples[0];
           SampleVoiceHost& sv = n->svoices[(size_t)v];
-          // a retriggered voice's previous play ends here: record it if it overlaps this chunk
+          // a retriggered voice's previous play ends here: keep it for this chunk if it overlaps it
+          n->done_plays.resize(n->svoices.size());
+          if (sv.sample >= 0 && sv.n_on < f && sv.n_end > f0) {
+            SampleVoiceHost old = sv;
+            old.n_end = std::min(old.n_end, f);
+            n->done_plays[(size_t)v].push_back(old);
+          }
           sv.sample = 0;
           sv.step_q = step_to_q32(note_hz(key) / s.root_hz * (s.sr / e->sr));
           sv.n_on = f;
@@ -1133,6 +1159,12 @@ int render_chunk(gb_engine* e, int frames, size_t n_ev) {
         if (!on || key < 0 || key >= 128 || n->key_to_voice[key] < 0) continue;
         SampleVoiceHost& sv = n->svoices[(size_t)n->key_to_voice[key]];
         const SampleDev& s = n->samples[(size_t)sv.sample];
+        n->done_plays.resize(n->svoices.size());
+        if (sv.n_on < f && sv.n_end > f0 && sv.n_on > kNever) {
+          SampleVoiceHost old = sv;
+          old.n_end = std::min(old.n_end, f);
+          n->done_plays[(size_t)n->key_to_voice[key]].push_back(old);
+        }
         sv.step_q = step_to_q32(s.sr / e->sr);
         sv.n_on = f;
         sv.n_end = f + frames_until_end(s.n, sv.step_q);
@@ -1152,19 +1184,58 @@ int render_chunk(gb_engine* e, int frames, size_t n_ev) {
   // latest play above.  Plays are therefore snapshotted per event below via `pending_plays`.
   // (handled by render splitting chunks at sampler note-ons; see split_points in gb_render.)
 
-  // ---- 2. instrument parameter changes (DCA) apply at the chunk start (chunks are split there) ----
-  for (auto& kv : controls) {
-    Node* n = kv.first;
-    if (!n->is_inst) continue;
-    for (const ControlPoint& cp : kv.second) {
-      if (n->kind == GB_INST_WELSH) {
-        if (cp.index == GB_CTL_INST_DCA_GAIN) n->wp.dca.gain = cp.raw; else n->wp.dca.pan = cp.raw;
-        e->winst_dirty = true;
-      } else if (n->kind == GB_INST_FM) {
-        if (cp.index == GB_CTL_INST_DCA_GAIN) n->fp.dca.gain = cp.raw; else n->fp.dca.pan = cp.raw;
-        e->finst_dirty = true;
-      }
+  // ---- 2. parameter segment tables: one per automated node, built on the host, one upload ----
+  struct SegRange { size_t off; int n; };
+  std::map<Node*, SegRange> seg_of;
+  std::vector<SegParam> segs_h;
+  auto apply_cp = [&](Node* n, const ControlPoint& cp) {
+    if (n->kind == GB_INST_WELSH) {
+      if (cp.index == GB_CTL_INST_DCA_GAIN) n->wp.dca.gain = cp.raw; else n->wp.dca.pan = cp.raw;
+      e->winst_dirty = true;
+    } else if (n->kind == GB_INST_FM) {
+      if (cp.index == GB_CTL_INST_DCA_GAIN) n->fp.dca.gain = cp.raw; else n->fp.dca.pan = cp.raw;
+      e->finst_dirty = true;
+    } else {
+      effect_apply_param(e, n, cp.index, cp.raw);
     }
+  };
+  auto push_seg = [&](Node* n, int t) {
+    SegParam sp;
+    sp.t0 = t; sp.pad = 0;
+    seg_values(e, n, sp.v);
+    segs_h.push_back(sp);
+  };
+  for (Node* n : e->plan) {
+    const bool inst = n->kind == GB_INST_WELSH || n->kind == GB_INST_FM;
+    if (n->is_inst && !inst) continue;
+    if (!n->is_inst && (n->kind == GB_FX_MIXER || n->kind == GB_FX_DELAY)) continue;  // no parameters
+    std::vector<ControlPoint> cps;
+    auto it = controls.find(n);
+    if (it != controls.end()) cps = it->second;
+    std::stable_sort(cps.begin(), cps.end(), [](const ControlPoint& a, const ControlPoint& b) { return a.t < b.t; });
+    size_t ci = 0;
+    while (ci < cps.size() && cps[ci].t <= 0) apply_cp(n, cps[ci++]);  // events at the chunk start
+    if (inst && ci == cps.size()) continue;  // no automation inside the chunk: the kernel applies the DCA
+    SegRange r;
+    r.off = segs_h.size();
+    push_seg(n, 0);
+    while (ci < cps.size()) {
+      const int t = cps[ci].t;
+      while (ci < cps.size() && cps[ci].t == t) apply_cp(n, cps[ci++]);
+      push_seg(n, t);
+    }
+    r.n = (int)(segs_h.size() - r.off);
+    seg_of[n] = r;
+    if (inst) {  // render at unit gain, then one segmented gain/pan pass over the instrument's buffer
+      n->unit_gain = true;
+      (n->kind == GB_INST_WELSH ? e->winst_dirty : e->finst_dirty) = true;
+    }
+  }
+  if (!segs_h.empty()) {
+    if (!e->segs.reserve(segs_h.size())) return fail(e, GB_ENOMEM, "out of memory");
+    memcpy(e->segs.h, segs_h.data(), segs_h.size() * sizeof(SegParam));
+    CUDA_TRY(e, cudaMemcpyAsync(e->segs.d, e->segs.h, segs_h.size() * sizeof(SegParam), cudaMemcpyHostToDevice, e->stream));
+    e->stats.h2d_bytes += segs_h.size() * sizeof(SegParam);
   }
 
   // ---- 3. voices ----
@@ -1241,30 +1312,36 @@ int render_chunk(gb_engine* e, int frames, size_t n_ev) {
     }
     e->stats.voice_samples += (uint64_t)e->n_fvoice * (uint64_t)frames;
   }
-  // samplers / drumkits / toy sources: one launch per instrument
+  // samplers / drumkits: one launch per instrument over this chunk's plays (voice order, then time)
   {
-    size_t total = 0;
-    for (Node* n : e->plan)
-      if (n->kind == GB_INST_SAMPLER || n->kind == GB_INST_DRUMKIT) total += n->svoices.size();
-    if (!e->plays.reserve(total + 1)) return fail(e, GB_ENOMEM, "out of memory");
-    size_t k = 0;
+    std::vector<SamplePlay> plays_h;
     std::vector<std::pair<Node*, std::pair<size_t, int>>> launches;
+    auto add_play = [&](Node* n, const SampleVoiceHost& sv) {
+      if (sv.sample < 0 || sv.n_end <= f0 || sv.n_on >= f0 + frames) return;
+      const SampleDev& s = n->samples[(size_t)sv.sample];
+      SamplePlay pl;
+      pl.n_on = sv.n_on; pl.n_end = sv.n_end; pl.step_q = sv.step_q;
+      pl.data = s.d; pl.len = s.n; pl.channels = s.channels; pl.pad = 0;
+      plays_h.push_back(pl);
+    };
     for (Node* n : e->plan) {
       if (n->kind != GB_INST_SAMPLER && n->kind != GB_INST_DRUMKIT) continue;
-      size_t k0 = k;
-      for (const SampleVoiceHost& sv : n->svoices) {
-        if (sv.sample < 0 || sv.n_end <= f0 || sv.n_on >= f0 + frames) continue;
-        const SampleDev& s = n->samples[(size_t)sv.sample];
-        SamplePlay pl;
-        pl.n_on = sv.n_on; pl.n_end = sv.n_end; pl.step_q = sv.step_q;
-        pl.data = s.d; pl.len = s.n; pl.channels = s.channels; pl.pad = 0;
-        e->plays.h[k++] = pl;
+      const size_t k0 = plays_h.size();
+      for (size_t v = 0; v < n->svoices.size(); ++v) {
+        if (v < n->done_plays.size()) {
+          for (const SampleVoiceHost& old : n->done_plays[v]) add_play(n, old);
+          n->done_plays[v].clear();
+        }
+        add_play(n, n->svoices[v]);
       }
-      launches.push_back({n, {k0, (int)(k - k0)}});
+      launches.push_back({n, {k0, (int)(plays_h.size() - k0)}});
     }
-    if (k) {
-      CUDA_TRY(e, cudaMemcpyAsync(e->plays.d, e->plays.h, k * sizeof(SamplePlay), cudaMemcpyHostToDevice, e->stream));
-      e->stats.h2d_bytes += k * sizeof(SamplePlay);
+    if (!plays_h.empty()) {
+      if (!e->plays.reserve(plays_h.size())) return fail(e, GB_ENOMEM, "out of memory");
+      memcpy(e->plays.h, plays_h.data(), plays_h.size() * sizeof(SamplePlay));
+      CUDA_TRY(e, cudaMemcpyAsync(e->plays.d, e->plays.h, plays_h.size() * sizeof(SamplePlay), cudaMemcpyHostToDevice,
+                                  e->stream));
+      e->stats.h2d_bytes += plays_h.size() * sizeof(SamplePlay);
     }
     for (auto& L : launches) {
       Launch l(e, true);
@@ -1279,12 +1356,24 @@ int render_chunk(gb_engine* e, int frames, size_t n_ev) {
     dim3 grid(cdiv(frames, 256), e->n_partials);
     reduce_partials_kernel<<<grid, 256, 0, e->stream>>>(e->partials.d, frames);
   }
-  // ---- 5. plan walk: toy sources, effects ----
+  // ---- 5. plan walk: toy sources, instrument DCA automation, effects (one launch per node) ----
   for (Node* n : e->plan) {
+    auto sr = seg_of.find(n);
+    const SegParam* segs = sr != seg_of.end() ? e->segs.d + sr->second.off : nullptr;
+    const int nseg = sr != seg_of.end() ? sr->second.n : 0;
     if (n->is_inst) {
       if (n->kind == GB_INST_TOY_SOURCE) {
         Launch l(e, false);
         fill_kernel<<<cdiv(frames, 256), 256, 0, e->stream>>>(n->buf, frames, n->tp.level_left, n->tp.level_right);
+      } else if (n->unit_gain) {
+        SourceList self;
+        memset(&self, 0, sizeof self);
+        self.n = 1;
+        self.p[0] = n->buf;
+        Launch l(e, false);
+        pointwise_kernel<<<cdiv(frames, 256), 256, 0, e->stream>>>(self, n->buf, frames, OP_DCA, segs, nseg);
+        n->unit_gain = false;  // the next chunk's instrument record carries the real gains again
+        (n->kind == GB_INST_WELSH ? e->winst_dirty : e->finst_dirty) = true;
       }
       continue;
     }
@@ -1305,23 +1394,8 @@ int render_chunk(gb_engine* e, int frames, size_t n_ev) {
       }
       continue;
     }
-    // parameter segments
-    std::vector<ControlPoint> cps;
-    auto it = controls.find(n);
-    if (it != controls.end()) cps = it->second;
-    std::stable_sort(cps.begin(), cps.end(), [](const ControlPoint& a, const ControlPoint& b) { return a.t < b.t; });
-    int t = 0;
-    size_t ci = 0;
-    while (t < frames) {
-      while (ci < cps.size() && cps[ci].t <= t) {
-        effect_apply_param(e, n, cps[ci].index, cps[ci].raw);
-        ++ci;
-      }
-      int t1 = ci < cps.size() ? std::min(cps[ci].t, frames) : frames;
-      rc = run_effect_segment(e, n, src, frames, t, t1, f0);
-      if (rc) return rc;
-      t = t1;
-    }
+    rc = run_effect(e, n, src, frames, segs, nseg, f0);
+    if (rc) return rc;
     if (n->kind == GB_FX_CHORUS && n->delay_frames > 0) {
       Launch l(e, false);
       history_update_kernel<<<cdiv(n->delay_frames, 256), 256, 0, e->stream>>>(
@@ -1339,9 +1413,7 @@ int render_chunk(gb_engine* e, int frames, size_t n_ev) {
 
 enum OutMode { OUT_F64, OUT_PCM16, OUT_DEVICE };
 
-// Split the request into chunks: at most max_block frames, and never across an event that the
-// chunk kernels take as constant (instrument DCA changes, sampler/drumkit note-ons after the first
-// at a given voice).
+// Split the request into chunks of at most max_block frames.
 int render_impl(gb_engine* e, void* out, size_t frames, size_t* done, OutMode mode) {
   if (!e) return GB_EINVAL;
   if (!e->finalized) return fail(e, GB_ESTATE, "engine is not finalized");
@@ -1362,22 +1434,8 @@ int render_impl(gb_engine* e, void* out, size_t frames, size_t* done, OutMode mo
   while (produced < frames) {
     const int64_t f0 = e->pos;
     int64_t limit = (int64_t)std::min<size_t>(frames - produced, e->max_block);
-    // find the split point, then take every event strictly before the chunk end
-    for (size_t i = 0; i < e->events.size() && e->events[i].frame < f0 + limit; ++i) {
-      const gb_event& ev = e->events[i];
-      if (ev.frame <= f0) continue;
-      Node* n = find(e, ev.uid);
-      if (!n || n->order < 0) continue;
-      bool split = false;
-      if (n->is_inst && (ev.type == GB_EV_CONTROL || ev.type == GB_EV_SET_PARAM)) split = true;
-      if ((n->kind == GB_INST_SAMPLER || n->kind == GB_INST_DRUMKIT) &&
-          (ev.type == GB_EV_NOTE_ON || ev.type == GB_EV_NOTE_OFF))
-        split = true;  // sampler plays are constant per chunk: a (re)trigger starts a new chunk
-      if (split) {
-        limit = ev.frame - f0;
-        break;
-      }
-    }
+    // every event strictly before the chunk end belongs to this chunk (events never split a chunk:
+    // parameters go through segment tables, sampler retriggers through per-chunk play lists)
     size_t n_ev = 0;
     while (n_ev < e->events.size() && e->events[n_ev].frame < f0 + limit) ++n_ev;
     int rc = render_chunk(e, (int)limit, n_ev);

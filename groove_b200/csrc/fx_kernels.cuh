@@ -32,7 +32,7 @@ __device__ __forceinline__ double2 sum_sources(const SourceList& s, int t) {
   return make_double2(l, r);
 }
 
-enum { OP_SUM = 0, OP_GAIN, OP_LIMITER, OP_BITCRUSHER, OP_COMPRESSOR };
+enum { OP_SUM = 0, OP_GAIN, OP_LIMITER, OP_BITCRUSHER, OP_COMPRESSOR, OP_DCA };
 
 __device__ __forceinline__ double op_apply(int op, double x, double a, double b) {
   switch (op) {
@@ -56,13 +56,38 @@ __device__ __forceinline__ double op_apply(int op, double x, double a, double b)
   }
 }
 
-// out[t] = op(sum of sources[t]) for t in [t0, t1)
-__global__ void __launch_bounds__(256) pointwise_kernel(SourceList src, double2* __restrict__ out, int t0, int t1,
-                                                         int op, double a, double b) {
-  int t = t0 + blockIdx.x * blockDim.x + threadIdx.x;
-  if (t >= t1) return;
+// Parameter automation is piecewise constant in time.  A chunk's parameter history for one effect is
+// a segment table in device memory: segment k holds the kernel-ready values that apply from chunk
+// frame t0[k] (t0[0] == 0) until the next segment.  One launch covers the whole chunk.
+struct SegParam {
+  int t0;
+  int pad;
+  double v[6];
+};
+__device__ __forceinline__ int seg_find(const SegParam* __restrict__ segs, int n, int t) {
+  int lo = 0, hi = n - 1;  // last k with segs[k].t0 <= t
+  while (lo < hi) {
+    int mid = (lo + hi + 1) >> 1;
+    if (segs[mid].t0 <= t) lo = mid;
+    else hi = mid - 1;
+  }
+  return lo;
+}
+
+// out[t] = op(sum of sources[t]) with the parameters of the segment covering t.
+// OP_DCA multiplies the two channels by v[0], v[1] (instrument gain/pan automation).
+__global__ void __launch_bounds__(256) pointwise_kernel(SourceList src, double2* __restrict__ out, int frames,
+                                                         int op, const SegParam* __restrict__ segs, int nseg) {
+  int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= frames) return;
   double2 v = sum_sources(src, t);
-  out[t] = make_double2(op_apply(op, v.x, a, b), op_apply(op, v.y, a, b));
+  if (op == OP_SUM) {
+    out[t] = v;
+    return;
+  }
+  const SegParam& sp = segs[nseg > 1 ? seg_find(segs, nseg, t) : 0];
+  if (op == OP_DCA) out[t] = make_double2(v.x * sp.v[0], v.y * sp.v[1]);
+  else out[t] = make_double2(op_apply(op, v.x, sp.v[0], sp.v[1]), op_apply(op, v.y, sp.v[0], sp.v[1]));
 }
 
 // out[t] = sum over a device-resident pointer table, left to right (any number of sources).
@@ -149,20 +174,20 @@ __device__ __forceinline__ void cta_entry_state(const Affine2& warp_total, Affin
   __syncthreads();
 }
 
-// One launch = one biquad effect over frames [t0,t1) of the chunk with constant coefficients.
-// One CTA of kFxWarps warps; both channels per thread.
+// One launch = one biquad effect over the whole chunk; coefficients (v[0..4] = b0,b1,b2,a1,a2) follow
+// the segment table frame by frame.  One CTA of kFxWarps warps; both channels per thread.
 __global__ void __launch_bounds__(32 * kFxWarps) biquad_df1_kernel(SourceList src, double2* __restrict__ out,
-                                                                    int t0, int t1, BiquadCoefs c,
-                                                                    BiquadState* __restrict__ state) {
+                                                                    int frames, const SegParam* __restrict__ segs,
+                                                                    int nseg, BiquadState* __restrict__ state) {
   __shared__ Affine2 sh[2][kFxWarps];
   __shared__ double2 sx[kFxRound + 2];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   BiquadState st = *state;
-  for (int r0 = t0; r0 < t1; r0 += kFxRound) {
+  for (int r0 = 0; r0 < frames; r0 += kFxRound) {
     // stage the round's input (coalesced), with the two history frames in front
     for (int i = threadIdx.x; i < kFxRound; i += blockDim.x) {
       int t = r0 + i;
-      sx[i + 2] = t < t1 ? sum_sources(src, t) : make_double2(0.0, 0.0);
+      sx[i + 2] = t < frames ? sum_sources(src, t) : make_double2(0.0, 0.0);
     }
     if (threadIdx.x == 0) {
       sx[0] = make_double2(st.x2[0], st.x2[1]);
@@ -173,21 +198,29 @@ __global__ void __launch_bounds__(32 * kFxWarps) biquad_df1_kernel(SourceList sr
     double yp[2][kFxT], g0[kFxT], g1[kFxT];
     double p0[2] = {0.0, 0.0}, p1[2] = {0.0, 0.0};
     double h00 = 1.0, h01 = 0.0, h10 = 0.0, h11 = 1.0;
-    int nvalid = t1 - (r0 + base);
+    const int nvalid = frames - (r0 + base);
+    int k = nvalid > 0 ? seg_find(segs, nseg, r0 + base) : 0;
+    int next_t0 = k + 1 < nseg ? segs[k + 1].t0 : 0x7fffffff;
+    double b0 = segs[k].v[0], b1 = segs[k].v[1], b2 = segs[k].v[2], a1 = segs[k].v[3], a2 = segs[k].v[4];
 #pragma unroll
     for (int j = 0; j < kFxT; ++j) {
       if (j < nvalid) {
+        while (r0 + base + j >= next_t0) {
+          ++k;
+          next_t0 = k + 1 < nseg ? segs[k + 1].t0 : 0x7fffffff;
+          b0 = segs[k].v[0]; b1 = segs[k].v[1]; b2 = segs[k].v[2]; a1 = segs[k].v[3]; a2 = segs[k].v[4];
+        }
         double2 x0 = sx[base + j + 2], xm1 = sx[base + j + 1], xm2 = sx[base + j];
-        double v[2] = {c.b0 * x0.x + c.b1 * xm1.x + c.b2 * xm2.x, c.b0 * x0.y + c.b1 * xm1.y + c.b2 * xm2.y};
+        double v[2] = {b0 * x0.x + b1 * xm1.x + b2 * xm2.x, b0 * x0.y + b1 * xm1.y + b2 * xm2.y};
 #pragma unroll
         for (int ch = 0; ch < 2; ++ch) {
-          double y = v[ch] - c.a1 * p0[ch] - c.a2 * p1[ch];
+          double y = v[ch] - a1 * p0[ch] - a2 * p1[ch];
           yp[ch][j] = y;
           p1[ch] = p0[ch];
           p0[ch] = y;
         }
-        // homogeneous: contribution of the entry state (y1,y2) to y[n] is row 0 of A^(j+1)
-        double t00 = -c.a1 * h00 - c.a2 * h10, t01 = -c.a1 * h01 - c.a2 * h11;
+        // homogeneous: contribution of the entry state (y1,y2) to y[n] is row 0 of the running product
+        double t00 = -a1 * h00 - a2 * h10, t01 = -a1 * h01 - a2 * h11;
         h10 = h00; h11 = h01;
         h00 = t00; h01 = t01;
         g0[j] = h00; g1[j] = h01;
@@ -202,8 +235,7 @@ __global__ void __launch_bounds__(32 * kFxWarps) biquad_df1_kernel(SourceList sr
       a.m00 = h00; a.m01 = h01; a.m10 = h10; a.m11 = h11; a.v0 = p0[ch]; a.v1 = p1[ch];
       Affine2 inc = affine_warp_scan(a, lane);
       double w0, w1, ce0, ce1;
-      Affine2 tot = inc;  // lane 31 holds the warp total
-      cta_entry_state(tot, sh[ch], warp, lane, st.y1[ch], st.y2[ch], w0, w1, ce0, ce1);
+      cta_entry_state(inc, sh[ch], warp, lane, st.y1[ch], st.y2[ch], w0, w1, ce0, ce1);
       double d0, d1;
       affine_lane_entry(inc, lane, w0, w1, e0[ch], e1[ch], d0, d1);
       endv0[ch] = ce0; endv1[ch] = ce1;
@@ -217,7 +249,7 @@ __global__ void __launch_bounds__(32 * kFxWarps) biquad_df1_kernel(SourceList sr
       }
     }
     // carry state to the next round
-    int last = min(kFxRound, t1 - r0);  // frames in this round
+    int last = min(kFxRound, frames - r0);  // frames in this round
     double2 xl1 = sx[last + 1], xl2 = sx[last];
     __syncthreads();
     st.x1[0] = xl1.x; st.x1[1] = xl1.y;
@@ -228,30 +260,32 @@ __global__ void __launch_bounds__(32 * kFxWarps) biquad_df1_kernel(SourceList sr
   if (threadIdx.x == 0) *state = st;
 }
 
-// 24 dB low-pass effect: two transposed-DF2 sections with constant coefficients.
-struct Lp24Coefs {
-  SecCoef s1, s2;
-};
+// 24 dB low-pass effect: two transposed-DF2 sections; coefficients (v[0..5] = b0,a1,a2 of section 1
+// then of section 2) follow the segment table frame by frame.
 struct Lp24State {
   double s[2][4];
 };
-__global__ void __launch_bounds__(32 * kFxWarps) lp24_kernel(SourceList src, double2* __restrict__ out, int t0,
-                                                              int t1, Lp24Coefs c, Lp24State* __restrict__ state) {
+__global__ void __launch_bounds__(32 * kFxWarps) lp24_kernel(SourceList src, double2* __restrict__ out, int frames,
+                                                              const SegParam* __restrict__ segs, int nseg,
+                                                              Lp24State* __restrict__ state) {
   __shared__ Affine2 sh[2][kFxWarps];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   Lp24State st = *state;
-  for (int r0 = t0; r0 < t1; r0 += kFxRound) {
+  for (int r0 = 0; r0 < frames; r0 += kFxRound) {
     const int base = r0 + (warp * 32 + lane) * kFxT;
-    int nvalid = t1 - base;
+    const int nvalid = frames - base;
     double sig[2][kFxT];
 #pragma unroll
     for (int j = 0; j < kFxT; ++j) {
       double2 v = j < nvalid ? sum_sources(src, base + j) : make_double2(0.0, 0.0);
       sig[0][j] = v.x; sig[1][j] = v.y;
     }
+    const int k0 = nvalid > 0 ? seg_find(segs, nseg, base) : 0;
 #pragma unroll
     for (int sec = 0; sec < 2; ++sec) {
-      const SecCoef k = sec == 0 ? c.s1 : c.s2;
+      int k = k0;
+      int next_t0 = k + 1 < nseg ? segs[k + 1].t0 : 0x7fffffff;
+      double cb0 = segs[k].v[3 * sec], ca1 = segs[k].v[3 * sec + 1], ca2 = segs[k].v[3 * sec + 2];
       double g0[kFxT], g1[kFxT];
       double p0[2] = {0.0, 0.0}, p1[2] = {0.0, 0.0};
       double h00 = 1.0, h01 = 0.0, h10 = 0.0, h11 = 1.0;
@@ -259,18 +293,23 @@ __global__ void __launch_bounds__(32 * kFxWarps) lp24_kernel(SourceList src, dou
       for (int j = 0; j < kFxT; ++j) {
         g0[j] = 0.0; g1[j] = 0.0;
         if (j < nvalid) {
+          while (base + j >= next_t0) {
+            ++k;
+            next_t0 = k + 1 < nseg ? segs[k + 1].t0 : 0x7fffffff;
+            cb0 = segs[k].v[3 * sec]; ca1 = segs[k].v[3 * sec + 1]; ca2 = segs[k].v[3 * sec + 2];
+          }
 #pragma unroll
           for (int ch = 0; ch < 2; ++ch) {
-            double bx = k.b0 * sig[ch][j];
+            double bx = cb0 * sig[ch][j];
             double y = bx + p0[ch];
             sig[ch][j] = y;
-            double n0 = 2.0 * bx + k.a1 * y + p1[ch];
-            p1[ch] = bx + k.a2 * y;
+            double n0 = 2.0 * bx + ca1 * y + p1[ch];
+            p1[ch] = bx + ca2 * y;
             p0[ch] = n0;
           }
           g0[j] = h00; g1[j] = h01;
-          double t00 = k.a1 * h00 + h10, t01 = k.a1 * h01 + h11;
-          h10 = k.a2 * h00; h11 = k.a2 * h01;
+          double t00 = ca1 * h00 + h10, t01 = ca1 * h01 + h11;
+          h10 = ca2 * h00; h11 = ca2 * h01;
           h00 = t00; h01 = t01;
         }
       }
@@ -313,10 +352,11 @@ struct ChorusTaps {
   int nv;
 };
 __global__ void __launch_bounds__(256) chorus_kernel(SourceList src, const double2* __restrict__ hist, int len,
-                                                      ChorusTaps taps, double wet, double2* __restrict__ out, int t0,
-                                                      int t1) {
-  int t = t0 + blockIdx.x * blockDim.x + threadIdx.x;
-  if (t >= t1) return;
+                                                      ChorusTaps taps, const SegParam* __restrict__ segs, int nseg,
+                                                      double2* __restrict__ out, int frames) {
+  int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= frames) return;
+  const double wet = segs[nseg > 1 ? seg_find(segs, nseg, t) : 0].v[0];
   double2 x = sum_sources(src, t);
   double al = 0.0, ar = 0.0;
   for (int i = 0; i < taps.nv; ++i) {
@@ -346,9 +386,11 @@ struct ReverbDesc {
   double* comb_ring[2][4];  // per channel, per comb: D doubles
   double* ap_ring[2][2];
 };
-__global__ void __launch_bounds__(256) reverb_comb_kernel(SourceList src, ReverbDesc d, double attenuation,
+__global__ void __launch_bounds__(256) reverb_comb_kernel(SourceList src, ReverbDesc d,
+                                                           const SegParam* __restrict__ segs, int nseg,
                                                            double* __restrict__ comb_out /* [2][4][n] */, int n,
-                                                           long long pos0, int t0, int t1) {
+                                                           long long pos0) {
+  const int t0 = 0, t1 = n;
   int comb = blockIdx.y & 3, ch = blockIdx.y >> 2;
   int D = d.comb_d[comb];
   int r = blockIdx.x * blockDim.x + threadIdx.x;
@@ -361,6 +403,7 @@ __global__ void __launch_bounds__(256) reverb_comb_kernel(SourceList src, Reverb
   double w = ring[r];
   for (int t = first; t < t1; t += D) {
     double2 x = sum_sources(src, t);
+    const double attenuation = segs[nseg > 1 ? seg_find(segs, nseg, t) : 0].v[0];
     double xa = (ch == 0 ? x.x : x.y) * attenuation;
     o[t] = w;
     w = __dadd_rn(xa, __dmul_rn(g, w));
@@ -371,7 +414,8 @@ __global__ void __launch_bounds__(256) reverb_comb_kernel(SourceList src, Reverb
 __global__ void __launch_bounds__(256) reverb_allpass_kernel(const double* __restrict__ in /* planes */, int nplanes,
                                                               size_t plane_stride, ReverbDesc d, int stage,
                                                               double* __restrict__ out /* [2][n] */, int n,
-                                                              long long pos0, int t0, int t1) {
+                                                              long long pos0) {
+  const int t0 = 0, t1 = n;
   int ch = blockIdx.y;
   int D = d.ap_d[stage];
   int r = blockIdx.x * blockDim.x + threadIdx.x;
@@ -392,9 +436,9 @@ __global__ void __launch_bounds__(256) reverb_allpass_kernel(const double* __res
   ring[r] = w;
 }
 __global__ void __launch_bounds__(256) interleave_kernel(const double* __restrict__ planes /* [2][n] */,
-                                                          double2* __restrict__ out, int n, int t0, int t1) {
-  int t = t0 + blockIdx.x * blockDim.x + threadIdx.x;
-  if (t < t1) out[t] = make_double2(planes[t], planes[(size_t)n + t]);
+                                                          double2* __restrict__ out, int n) {
+  int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t < n) out[t] = make_double2(planes[t], planes[(size_t)n + t]);
 }
 
 // ---------------------------------------------------------------- microbenchmark ---
