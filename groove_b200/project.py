@@ -72,6 +72,17 @@ CONTROL_INDEX = {
 }
 
 
+UNITS_IN_BEAT = 65536  # MusicalTime resolution (doc/designs/time.md:94-98)
+
+
+def frames_to_units(frames: int, bpm: float, sample_rate: int) -> int:
+    """MusicalTime::new_with_frames (src/mini/transport.rs:58-63): whole MusicalTime units elapsed after
+    `frames` frames.  Integer arithmetic, so the per-frame deltas telescope exactly: one second of frames
+    at 60 bpm is exactly UNITS_IN_BEAT units at any sample rate (transport.rs:157-188)."""
+    bpm_milli = int(round(bpm * 1000.0))
+    return (frames * bpm_milli * UNITS_IN_BEAT) // (60 * 1000 * int(sample_rate))
+
+
 def song_frames(beats: float, bpm: float, sample_rate: float) -> int:
     """orchestrator.rs:1723-1737: a song of `beats` beats renders ceil(beats*60/bpm*SR) frames."""
     return int(math.ceil(beats * 60.0 / bpm * sample_rate - 1e-9))

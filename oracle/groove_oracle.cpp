@@ -1312,6 +1312,18 @@ int go_render_pcm16(go_engine* e, int16_t* out, size_t frames, size_t* done) {
 
 int64_t go_position(const go_engine* e) { return e ? e->pos : -1; }
 
+// MMA (DLS level 2) concave / convex transforms — orchestration/src/util.rs:4-21.  Dead code in the
+// reference snapshot (and not on this oracle's render path: see docs/ORACLE_SPEC.md §3 for the envelope
+// shapes actually used), restated because the reference's own tests pin their bounds (util.rs:286-318).
+double go_mma_concave(double x) {
+  if (x > 1.0 - std::pow(10.0, -12.0 / 5.0)) return 1.0;
+  return -(5.0 / 12.0) * std::log10(1.0 - x);
+}
+double go_mma_convex(double x) {
+  if (x < std::pow(10.0, -12.0 / 5.0)) return 0.0;
+  return 1.0 + (5.0 / 12.0) * std::log10(x);
+}
+
 // Known-answer helpers exported for tests (unit-level checks of the restated formulas).
 double go_tune_ratio(int semitones, double cents) {  // settings/src/patches.rs:255-258
   return std::pow(2.0, ((double)semitones * 100.0 + cents) / 1200.0);

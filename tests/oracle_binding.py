@@ -46,6 +46,9 @@ def oracle_lib() -> C.CDLL:
         _lib.go_lp24_coefficients.argtypes = [C.c_double, C.c_double, C.c_double, C.c_void_p]
         _lib.go_rbj_coefficients.restype = None
         _lib.go_rbj_coefficients.argtypes = [C.c_int, C.c_double, C.c_double, C.c_double, C.c_void_p]
+        for fn in (_lib.go_mma_concave, _lib.go_mma_convex):
+            fn.restype = C.c_double
+            fn.argtypes = [C.c_double]
         _lib.go_pcm16.restype = None
         _lib.go_pcm16.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t]
     return _lib

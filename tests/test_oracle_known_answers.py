@@ -317,3 +317,29 @@ def test_fanout_evaluates_each_node_once():
         o.note_on(0, u, 60)
         return o.render(500)
     assert np.allclose(build(2), 2 * build(1), atol=1e-15)
+
+
+def test_mma_transforms_match_reference_bounds():
+    """orchestration/src/util.rs:286-318 (mma_concave_transform / mma_convex_transform), verbatim bounds."""
+    lib = oracle_lib()
+    cc, cv = lib.go_mma_concave, lib.go_mma_convex
+    assert cc(0.001) < 0.0002 and cc(0.01) < 0.019 and cc(0.1) < 0.02
+    assert 0.12 < cc(0.5) < 0.13 and cc(0.9) > 0.40 and cc(0.99) > 0.83 and cc(0.995) > 0.95
+    assert cv(0.995) > 0.999 and cv(0.99) > 0.998 and cv(0.9) > 0.98
+    assert 0.87 < cv(0.5) < 0.88 and cv(0.1) < 0.59 and cv(0.01) < 0.17 and cv(0.001) < 0.0005
+    for i in range(101):
+        x = i / 100.0
+        assert cc(x) <= x + 1e-15 and cv(x) >= x - 1e-15
+
+
+def test_transport_advances_exactly_one_beat_per_second_at_60_bpm():
+    """src/mini/transport.rs:157-188: frame-by-frame MusicalTime deltas over one second sum to
+    UNITS_IN_BEAT (65536) at every sample rate of the reference test."""
+    from groove_b200.project import UNITS_IN_BEAT, frames_to_units
+    for sr in (100, 997, 22050, 44100, 48000, 88200, 98689, 100000, 262144):
+        covered, prev = 0, 0
+        for f in range(1, sr + 1):
+            now = frames_to_units(f, 60.0, sr)
+            covered += now - prev
+            prev = now
+        assert covered == UNITS_IN_BEAT and frames_to_units(sr, 60.0, sr) == UNITS_IN_BEAT
