@@ -771,7 +771,7 @@ __device__ __forceinline__ void cta_reduce_store(const double2* tiles, const int
 constexpr int kParkWords = 14;  // doubles parked per thread by welsh_block_simple (see below)
 
 template <bool LFO_AMP>
-__device__ __noinline__ void welsh_block_simple(WelshVoice* vp, const WelshInst* Ip, i64 fb, int lane, EnvSeg aseg,
+__device__ __forceinline__ void welsh_block_simple(WelshVoice* vp, const WelshInst* Ip, i64 fb, int lane, EnvSeg aseg,
                                                 EnvSeg fseg, double2* tile_row, bool accumulate, double* park) {
   // `park` = this thread's column of a [kParkWords][blockDim.x] shared array: values that are only
   // needed after pass 1 wait there so that the oscillator constants fit in registers.
