@@ -181,6 +181,87 @@ __device__ __forceinline__ void affine_lane_entry(const Affine2& incl, int lane,
   end1 = shfl_idx_f64(t1, 31);
 }
 
+// v <- M p + v
+__device__ __forceinline__ void affine_vec_step(double& v0, double& v1, double m00, double m01, double m10,
+                                                double m11, double p0, double p1) {
+  v0 = fma(m01, p1, fma(m00, p0, v0));
+  v1 = fma(m11, p1, fma(m10, p0, v1));
+}
+// The scan the voice kernels need: lane aggregates `a` (lane order = time order) and the state (s0,s1)
+// at the start of the warp's span in; the state at the start of this lane's chunk (e0,e1) and after
+// the whole span (end0,end1) out.  The entry state is folded into lane 0's map first, so only the
+// vector part of the inclusive scan is needed at the end: the last Kogge-Stone step moves and
+// combines 2 words instead of 6.
+__device__ __forceinline__ void affine_scan_states(Affine2 a, int lane, double s0, double s1, double& e0, double& e1,
+                                                   double& end0, double& end1) {
+  if (lane == 0) affine_vec_step(a.v0, a.v1, a.m00, a.m01, a.m10, a.m11, s0, s1);
+#pragma unroll
+  for (int d = 1; d < 16; d <<= 1) {
+    const Affine2 prev = affine_shfl_up(a, d);
+    if (lane >= d) affine_compose_inplace(a, prev);
+  }
+  {
+    const double p0 = shfl_up_f64(a.v0, 16), p1 = shfl_up_f64(a.v1, 16);
+    if (lane >= 16) affine_vec_step(a.v0, a.v1, a.m00, a.m01, a.m10, a.m11, p0, p1);
+  }
+  const double u0 = shfl_up_f64(a.v0, 1), u1 = shfl_up_f64(a.v1, 1);
+  e0 = lane == 0 ? s0 : u0;
+  e1 = lane == 0 ? s1 : u1;
+  end0 = shfl_idx_f64(a.v0, 31);
+  end1 = shfl_idx_f64(a.v1, 31);
+}
+
+// ---- time-invariant stretches: every lane's span has the same homogeneous map M = A^T, so the map of a
+// 2^k-lane span is a per-instrument constant (mp[k] = M^(2^k), row-major; mp[5] = 0) and only the
+// 2-vector of zero-state end states is scanned: 4 FMAs and 2 shuffled words per step.  Lanes that a
+// Kogge-Stone step leaves alone read the zero matrix instead of being predicated off, so the FMAs
+// update the vector in place with no selects or moves.
+__device__ __forceinline__ void lti_scan_states(double v0, double v1, const double (*mp)[4], int lane, double s0,
+                                                double s1, double& e0, double& e1, double& end0, double& end1) {
+  {
+    const double* m = mp[lane == 0 ? 0 : 5];
+    const double2 r0 = *reinterpret_cast<const double2*>(m), r1 = *reinterpret_cast<const double2*>(m + 2);
+    affine_vec_step(v0, v1, r0.x, r0.y, r1.x, r1.y, s0, s1);
+  }
+#pragma unroll
+  for (int k = 0; k < 5; ++k) {
+    const int d = 1 << k;
+    const double p0 = shfl_up_f64(v0, d), p1 = shfl_up_f64(v1, d);
+    const double* m = mp[lane >= d ? k : 5];
+    const double2 r0 = *reinterpret_cast<const double2*>(m), r1 = *reinterpret_cast<const double2*>(m + 2);
+    affine_vec_step(v0, v1, r0.x, r0.y, r1.x, r1.y, p0, p1);
+  }
+  const double u0 = shfl_up_f64(v0, 1), u1 = shfl_up_f64(v1, 1);
+  e0 = lane == 0 ? s0 : u0;
+  e1 = lane == 0 ? s1 : u1;
+  end0 = shfl_idx_f64(v0, 31);
+  end1 = shfl_idx_f64(v1, 31);
+}
+
+// sin and cos of 2*pi*q/2^64 straight from a phase integer: the quadrant from the top bits, the rest
+// as a signed angle in [-pi/4, pi/4) for two Taylor forms (|error| < 1e-16; no slow path, no table).
+__device__ __forceinline__ void sincos_phase(u64 q, double* s, double* c) {
+  const u64 qr = q + (1ull << 61);  // round to the nearest quarter turn
+  const int quad = (int)(qr >> 62);
+  const i64 r = (i64)(qr & ((1ull << 62) - 1)) - (i64)(1ull << 61);
+  const double x = (double)r * (2.0 * kPi / kTwo64);
+  const double z = x * x;
+  double ps = 2.8114572543455206e-15, pc = 4.7794773323873853e-14;
+  ps = fma(ps, z, -7.6471637318198164e-13); pc = fma(pc, z, -1.1470745597729725e-11);
+  ps = fma(ps, z, 1.6059043836821613e-10);  pc = fma(pc, z, 2.0876756987868100e-09);
+  ps = fma(ps, z, -2.5052108385441720e-08); pc = fma(pc, z, -2.7557319223985888e-07);
+  ps = fma(ps, z, 2.7557319223985893e-06);  pc = fma(pc, z, 2.4801587301587302e-05);
+  ps = fma(ps, z, -1.9841269841269841e-04); pc = fma(pc, z, -1.3888888888888889e-03);
+  ps = fma(ps, z, 8.3333333333333332e-03);  pc = fma(pc, z, 4.1666666666666664e-02);
+  ps = fma(ps, z, -1.6666666666666666e-01); pc = fma(pc, z, -0.5);
+  ps = fma(ps, z, 1.0);                     pc = fma(pc, z, 1.0);
+  ps *= x;
+  const double s0 = (quad & 1) ? pc : ps;
+  const double c0 = (quad & 1) ? ps : pc;
+  *s = (quad & 2) ? -s0 : s0;
+  *c = ((quad + 1) & 2) ? -c0 : c0;
+}
+
 // Segmented u64 sum scan (phase accumulators with resets).
 struct SegSum {
   u64 sum;

@@ -441,8 +441,48 @@ void welsh_inst_from_params(const Node& n, double sr, WelshInst* I) {
   for (int j = 0; j < kT; ++j) {
     uint64_t q = (uint64_t)j * I->lfo_dq;  // mod 2^64
     double ang = 6.283185307179586476925286766559 * ((double)q / 18446744073709551616.0);
-    I->lfo_cos[j] = std::cos(ang);
-    I->lfo_sin[j] = std::sin(ang);
+    I->lfo_rot[j] = make_double2(std::cos(ang), std::sin(ang));
+  }
+  // oscillator pair with the mix and the [1,2) phase offset folded in (OscMix)
+  auto fold = [](const OscShape& o, double mix, OscMix* m) {
+    m->a_lo = mix * o.a_lo; m->b_lo = mix * (o.b_lo - o.a_lo);
+    m->a_hi = mix * o.a_hi; m->b_hi = mix * (o.b_hi - o.a_hi);
+  };
+  fold(I->s1, I->mix, &I->m1);
+  fold(I->s2, 1.0 - I->mix, &I->m2);
+  // time-invariant stretches: the resting coefficient sets and what follows from them (LtiTable)
+  {
+    SecCoef c1 = I->fixed1, c2 = I->fixed2;
+    if (I->filter_mode == FILTER_ENVELOPE) {
+      double pct = I->cut_a + I->cut_b * I->filt.sustain;
+      pct = pct < 0.0 ? 0.0 : (pct > 1.0 ? 1.0 : pct);
+      host_lp24(I->rp, 25.0 * std::exp2(pct * 9.6438561897747243), sr, &c1, &c2);
+    }
+    I->steady_after = I->filter_mode == FILTER_ENVELOPE ? std::max(I->amp.na + I->amp.nd, I->filt.na + I->filt.nd)
+                                                         : I->amp.na + I->amp.nd;
+    I->amp_rest = 0.5 * I->amp.sustain;
+    I->osc_flat = I->m1.a_lo == 0.0 && I->m1.a_hi == 0.0 && I->m2.a_lo == 0.0 && I->m2.a_hi == 0.0;
+    auto table = [](const SecCoef& c, double (*g)[2], double (*mp)[4]) {
+      double h00 = 1.0, h01 = 0.0, h10 = 0.0, h11 = 1.0;  // H = A^j, A = [[a1, 1], [a2, 0]]
+      for (int j = 0; j < kT; ++j) {
+        g[j][0] = h00; g[j][1] = h01;
+        const double t00 = c.a1 * h00 + h10, t01 = c.a1 * h01 + h11;
+        h10 = c.a2 * h00; h11 = c.a2 * h01;
+        h00 = t00; h01 = t01;
+      }
+      mp[0][0] = h00; mp[0][1] = h01; mp[0][2] = h10; mp[0][3] = h11;
+      for (int k = 1; k < 5; ++k) {
+        const double* m = mp[k - 1];
+        mp[k][0] = m[0] * m[0] + m[1] * m[2]; mp[k][1] = m[0] * m[1] + m[1] * m[3];
+        mp[k][2] = m[2] * m[0] + m[3] * m[2]; mp[k][3] = m[2] * m[1] + m[3] * m[3];
+      }
+      mp[5][0] = mp[5][1] = mp[5][2] = mp[5][3] = 0.0;
+    };
+    I->lti.c1 = c1; I->lti.c2 = c2;
+    table(c1, I->lti.g1, I->lti.mp1);
+    table(c2, I->lti.g2, I->lti.mp2);
+    I->lti_ok = 1;
+    if (const char* v = getenv("GB_LTI")) I->lti_ok = atoi(v) != 0;
   }
 }
 void fm_inst_from_params(const Node& n, double sr, FmInst* I) {

@@ -124,7 +124,27 @@ __device__ __forceinline__ void lp24_from_u(const Lp24Ripple& rp, double u, SecC
   s2.a2 = (fma(rp.c3k, sc, -ss) - n2) * i2;
 }
 
+// Both oscillators and their mix folded into one expression for the specialised blocks: with
+// P = 1 + pos(q) taken straight from the mantissa trick (no subtraction) and (a, b) the affine piece
+// selected by the phase compare,  mix1*(a1*pos1 + b1) + mix2*(a2*pos2 + b2) = A1*P1 + A2*P2 + (B1 + B2)
+// where A = mix*a and B = mix*(b - a): 3 FP64 operations per frame instead of 6.
+struct OscMix {
+  double a_lo, b_lo, a_hi, b_hi;
+};
+// Time-invariant stretches of the 24 dB filter (fixed cutoff, or the filter envelope resting at its
+// sustain level): the coefficient sets, the rows g[j] = (A^j)[0][*] that carry a lane's entry state to
+// its j-th output, and the span maps A^(kT * 2^k) for the scan are per-instrument constants, computed
+// once on the host (engine.cu, welsh_inst_from_params).
+struct alignas(16) LtiTable {
+  double g1[8][2], g2[8][2];    // kT rows per section
+  double mp1[6][4], mp2[6][4];  // row-major 2x2; entry 5 is the zero matrix (lti_scan_states)
+  SecCoef c1, c2;
+};
+
 struct WelshInst {
+  LtiTable lti;
+  OscMix m1, m2;
+  double2 lfo_rot[8];  // (cos, sin)(2*pi*j*lfo_dq/2^64): rotation table for a sine LFO
   EnvShape amp, filt;
   int w1, w2, wl, sync, routing, filter_mode, uid, voice0;
   u64 duty1_q, duty2_q, dutyl_q, lfo_dq;
@@ -135,15 +155,17 @@ struct WelshInst {
   SecCoef fixed1, fixed2;
   double gl, gr;
   double pi_over_sr, sr;
-  double lfo_cos[kT], lfo_sin[kT];  // cos/sin(2*pi*j*lfo_dq/2^64): rotation table for a sine LFO
   OscShape s1, s2, sl;              // branch-free waveform descriptions (fast path)
   double log2_25_over_sr;           // fc/sr = exp2(pct*log2(800) + log2(25/sr))
   double u_min, u_max;              // clamp of fc/sr: [1/sr, 0.49]
   double knot_max_rate;             // cutoff motion (fraction of the log range per frame) up to which knots are used
+  i64 steady_after;                 // frames after note-on from which both envelopes rest at their sustain levels
+  double amp_rest;                  // 0.5 * amp.sustain: the DCA input level of a resting voice (without LFO)
+  int lti_ok, osc_flat;             // osc_flat: both oscillators piecewise constant (OscMix slopes are 0); lti holds this instrument's resting coefficient sets (GB_LTI=0 disables the path)
 };
 enum { FILTER_FIXED = 0, FILTER_ENVELOPE = 1, FILTER_LFO = 2 };
 
-struct WelshVoice {
+struct alignas(16) WelshVoice {  // 208 bytes; field pairs at 16-byte offsets are moved as 128-bit words
   i64 n_on, n_off;
   double la_on, la_off, lf_on, lf_off;
   i64 anchor;       // frame at which p1/p2/pl are valid (closed-form path); LFO anchor always
@@ -652,7 +674,7 @@ __device__ __forceinline__ void welsh_block_fast(WelshVoice& st, const WelshInst
       double ld = 0.0;
       if (lfo_on) {
         ph.pl += I.lfo_dq;
-        double l = lfo_sine ? fma(ls, I.lfo_cos[j], lc * I.lfo_sin[j])
+        double l = lfo_sine ? fma(ls, I.lfo_rot[j].x, lc * I.lfo_rot[j].y)
                             : osc_eval(I.sl, ph.pl, I.sl.thresh, seedl, n);
         ld = l * I.depth;
       }
@@ -770,9 +792,30 @@ __device__ __forceinline__ void cta_reduce_store(const double2* tiles, const int
 // here; the arithmetic is identical to welsh_block_fast<COEF_KNOTS, true>.
 constexpr int kParkWords = 14;  // doubles parked per thread by welsh_block_simple (see below)
 
-template <bool LFO_AMP>
+// 1 + pos_of(q): the top 52 phase bits as the mantissa of a double in [1,2)
+__device__ __forceinline__ double pos1_of(u64 q) {
+  return __longlong_as_double((long long)(0x3FF0000000000000ull | (q >> 12)));
+}
+// ZERO_A: both waveforms are piecewise constant (square, pulse, debug levels, none) — no slope term.
+template <bool ZERO_A>
+__device__ __forceinline__ double osc_mix_eval(const OscMix& m1, u64 t1, u64 p1, const OscMix& m2, u64 t2, u64 p2) {
+  const bool lo1 = p1 < t1, lo2 = p2 < t2;
+  const double b = (lo1 ? m1.b_lo : m1.b_hi) + (lo2 ? m2.b_lo : m2.b_hi);
+  if (ZERO_A) return b;
+  return fma(lo1 ? m1.a_lo : m1.a_hi, pos1_of(p1), fma(lo2 ? m2.a_lo : m2.a_hi, pos1_of(p2), b));
+}
+// One frame of a transposed-DF2 section (b1 = 2 b0, b2 = b0): returns y, advances (s0, s1).
+__device__ __forceinline__ double lp_step(double b0, double a1, double a2, double x, double& s0, double& s1) {
+  const double bx = b0 * x;
+  const double y = bx + s0;
+  s0 = fma(a1, y, fma(2.0, bx, s1));
+  s1 = fma(a2, y, bx);
+  return y;
+}
+
+template <bool LFO_AMP, bool ZERO_A>
 __device__ __forceinline__ void welsh_block_simple(WelshVoice* vp, const WelshInst* Ip, i64 fb, int lane, EnvSeg aseg,
-                                                EnvSeg fseg, double2* tile_row, bool accumulate, double* park) {
+                                                EnvSeg fseg, double2* tile_row, double* park) {
   // `park` = this thread's column of a [kParkWords][blockDim.x] shared array: values that are only
   // needed after pass 1 wait there so that the oscillator constants fit in registers.
   const WelshInst& I = *Ip;
@@ -806,42 +849,44 @@ __device__ __forceinline__ void welsh_block_simple(WelshVoice* vp, const WelshIn
     park[0 * pstride] = qb2.k0; park[1 * pstride] = qb2.d1; park[2 * pstride] = qb2.d2;
     park[3 * pstride] = qa12.k0; park[4 * pstride] = qa12.d1; park[5 * pstride] = qa12.d2;
     park[6 * pstride] = qa22.k0; park[7 * pstride] = qa22.d1; park[8 * pstride] = qa22.d2;
-    park[9 * pstride] = aseg.q0; park[10 * pstride] = aseg.q1; park[11 * pstride] = aseg.q2;
+    // the amplitude envelope segment, with the DCA's 0.5 folded in
+    park[9 * pstride] = 0.5 * aseg.q0; park[10 * pstride] = 0.5 * aseg.q1; park[11 * pstride] = 0.5 * aseg.q2;
     park[12 * pstride] = aseg.w0; park[13 * pstride] = aseg.dw;
   }
   // ---- phases at c0 - 1 (closed form), LFO base angle ----
   const u64 k = (u64)(c0 - 1 - vp->anchor);
   const u64 d1 = vp->d1, d2 = vp->d2;
   u64 p1 = vp->p1 + k * d1, p2 = vp->p2 + k * d2;
-  double ls = 0.0, lc = 0.0;
-  if (LFO_AMP) sincospi(2.0 * pos_of(vp->pl + (k + 1) * I.lfo_dq), &ls, &lc);
-  const double mix1 = I.mix, mix2 = 1.0 - I.mix;
-  const OscShape o1 = I.s1, o2 = I.s2;
+  double lsd = 0.0, lcd = 0.0;  // depth * (sin, cos) of the LFO angle at the lane's first frame
+  if (LFO_AMP) {
+    double ls, lc;
+    sincos_phase(vp->pl + (k + 1) * I.lfo_dq, &ls, &lc);
+    lsd = ls * I.depth; lcd = lc * I.depth;
+  }
   // ---- pass 1: oscillators + section 1 from a zero state with its homogeneous response ----
   double yp[kT], g0[kT], g1[kT];
   double ps0 = 0.0, ps1 = 0.0, h00 = 1.0, h01 = 0.0, h10 = 0.0, h11 = 1.0;
+  {
+    const OscMix o1 = I.m1, o2 = I.m2;
+    const u64 t1 = I.s1.thresh, t2 = I.s2.thresh;
 #pragma unroll
-  for (int j = 0; j < kT; ++j) {
-    p1 += d1;
-    p2 += d2;
-    const double x = fma(osc_affine(o1, p1, o1.thresh), mix1, osc_affine(o2, p2, o2.thresh) * mix2);
-    const double b0 = quad_at(qb1, j), a1 = quad_at(qa11, j), a2 = quad_at(qa21, j);
-    const double bx = b0 * x;
-    const double y = bx + ps0;
-    yp[j] = y; g0[j] = h00; g1[j] = h01;
-    const double n0 = fma(a1, y, fma(2.0, bx, ps1));
-    ps1 = fma(a2, y, bx);
-    ps0 = n0;
-    const double t00 = fma(a1, h00, h10), t01 = fma(a1, h01, h11);
-    h10 = a2 * h00; h11 = a2 * h01;
-    h00 = t00; h01 = t01;
+    for (int j = 0; j < kT; ++j) {
+      p1 += d1;
+      p2 += d2;
+      const double x = osc_mix_eval<ZERO_A>(o1, t1, p1, o2, t2, p2);
+      const double b0 = quad_at(qb1, j), a1 = quad_at(qa11, j), a2 = quad_at(qa21, j);
+      g0[j] = h00; g1[j] = h01;
+      yp[j] = lp_step(b0, a1, a2, x, ps0, ps1);
+      const double t00 = fma(a1, h00, h10), t01 = fma(a1, h01, h11);
+      h10 = a2 * h00; h11 = a2 * h01;
+      h00 = t00; h01 = t01;
+    }
   }
   double e0, e1, end0, end1;
   {
     Affine2 a;
     a.m00 = h00; a.m01 = h01; a.m10 = h10; a.m11 = h11; a.v0 = ps0; a.v1 = ps1;
-    const Affine2 inc = affine_warp_scan(a, lane);
-    affine_lane_entry(inc, lane, vp->s[0], vp->s[1], e0, e1, end0, end1);
+    affine_scan_states(a, lane, vp->s[0], vp->s[1], e0, e1, end0, end1);
   }
   const double ns0 = end0, ns1 = end1;
   // ---- pass 2: section 2 on the fixed-up section-1 output ----
@@ -855,12 +900,8 @@ __device__ __forceinline__ void welsh_block_simple(WelshVoice* vp, const WelshIn
     for (int j = 0; j < kT; ++j) {
       const double b0 = quad_at(qb2, j), a1 = quad_at(qa12, j), a2 = quad_at(qa22, j);
       const double x = fma(g1[j], e1, fma(g0[j], e0, yp[j]));
-      const double bx = b0 * x;
-      const double y = bx + ps0;
-      yp[j] = y; g0[j] = h00; g1[j] = h01;
-      const double n0 = fma(a1, y, fma(2.0, bx, ps1));
-      ps1 = fma(a2, y, bx);
-      ps0 = n0;
+      g0[j] = h00; g1[j] = h01;
+      yp[j] = lp_step(b0, a1, a2, x, ps0, ps1);
       const double t00 = fma(a1, h00, h10), t01 = fma(a1, h01, h11);
       h10 = a2 * h00; h11 = a2 * h01;
       h00 = t00; h01 = t01;
@@ -869,8 +910,7 @@ __device__ __forceinline__ void welsh_block_simple(WelshVoice* vp, const WelshIn
   {
     Affine2 a;
     a.m00 = h00; a.m01 = h01; a.m10 = h10; a.m11 = h11; a.v0 = ps0; a.v1 = ps1;
-    const Affine2 inc = affine_warp_scan(a, lane);
-    affine_lane_entry(inc, lane, vp->s[2], vp->s[3], e0, e1, end0, end1);
+    affine_scan_states(a, lane, vp->s[2], vp->s[3], e0, e1, end0, end1);
   }
   // ---- amplitude (envelope segment x LFO), DCA, CTA tile ----
   EnvSeg as;
@@ -880,20 +920,129 @@ __device__ __forceinline__ void welsh_block_simple(WelshVoice* vp, const WelshIn
   double2* row = tile_row + lane * (kT + 1);
 #pragma unroll
   for (int j = 0; j < kT; ++j) {
-    double amp = 0.5 * env_seg_at(as, j);
-    if (LFO_AMP) amp *= fma(fma(ls, I.lfo_cos[j], lc * I.lfo_sin[j]), I.depth, 1.0);
-    const double m = fma(g1[j], e1, fma(g0[j], e0, yp[j])) * amp;
-    double2 o = make_double2(m * gl, m * gr);
-    if (accumulate) {
-      const double2 p = row[j];
-      o.x += p.x; o.y += p.y;
+    double amp = env_seg_at(as, j);
+    if (LFO_AMP) {
+      const double2 rot = I.lfo_rot[j];
+      amp *= fma(lsd, rot.x, fma(lcd, rot.y, 1.0));
     }
-    row[j] = o;
+    const double m = fma(g1[j], e1, fma(g0[j], e0, yp[j])) * amp;
+    const double2 p = row[j];  // the row holds the warp's earlier voices of this block (or zeros)
+    row[j] = make_double2(fma(m, gl, p.x), fma(m, gr, p.y));
   }
   __syncwarp();
   if (lane == 0) {
     vp->s[0] = ns0; vp->s[1] = ns1; vp->s[2] = end0; vp->s[3] = end1;
     vp->knot_frame = fb + kBlockFrames;
+  }
+  __syncwarp();
+}
+
+// ---- the time-invariant block --------------------------------------------------------------------
+// Preconditions (warp-uniform, checked by the caller): as welsh_block_simple, but the cutoff does not
+// move over the block — the instrument's filter is fixed, or every lane's filter envelope rests at its
+// sustain level.  Both coefficient sets are then the per-instrument constants of LtiTable: nothing is
+// evaluated or interpolated per frame, the homogeneous response rows come from the table instead of
+// being tracked per lane, and the scan moves 2-vectors under constant span maps.
+//   NV        voices of the same instrument rendered in lockstep by this warp (1 or 2).  Two voices
+//             give every dependent chain (recurrence, scan steps, table loads) an independent twin,
+//             which is what hides the latencies at 4 warps per scheduler.
+//   AMP_FLAT  the amplitude envelope rests too (level I.amp_rest); otherwise `aseg` is the lane's segment.
+template <bool LFO_AMP, bool ZERO_A, bool AMP_FLAT, int NV>
+__device__ __forceinline__ void welsh_block_lti(WelshVoice* const (&vp)[NV], const WelshInst* Ip, i64 fb, int lane,
+                                                const EnvSeg& aseg, double2* tile_row) {
+  static_assert(offsetof(WelshVoice, anchor) % 16 == 0 && offsetof(WelshVoice, p2) % 16 == 0 &&
+                offsetof(WelshVoice, d1) % 16 == 0 && offsetof(WelshVoice, s) % 16 == 0 && sizeof(WelshVoice) % 16 == 0,
+                "WelshVoice field pairs must sit on 16-byte boundaries");
+  const WelshInst& I = *Ip;
+  const LtiTable& L = I.lti;
+  const i64 c0 = fb + (i64)lane * kT;
+  u64 p1[NV], p2[NV], d1[NV], d2[NV];
+  double lsd[NV], lcd[NV];  // (depth x level) * (sin, cos) of the LFO angle at the lane's first frame
+  double s[NV][4];
+#pragma unroll
+  for (int v = 0; v < NV; ++v) {
+    const ulonglong2 ap = *reinterpret_cast<const ulonglong2*>(&vp[v]->anchor);  // anchor, p1
+    const ulonglong2 pp = *reinterpret_cast<const ulonglong2*>(&vp[v]->p2);      // p2, pl
+    const ulonglong2 dd = *reinterpret_cast<const ulonglong2*>(&vp[v]->d1);      // d1, d2
+    const double2 sa = *reinterpret_cast<const double2*>(&vp[v]->s[0]), sb = *reinterpret_cast<const double2*>(&vp[v]->s[2]);
+    s[v][0] = sa.x; s[v][1] = sa.y; s[v][2] = sb.x; s[v][3] = sb.y;
+    const u64 k = (u64)(c0 - 1) - ap.x;
+    d1[v] = dd.x; d2[v] = dd.y;
+    p1[v] = ap.y + k * dd.x; p2[v] = pp.x + k * dd.y;
+    lsd[v] = 0.0; lcd[v] = 0.0;
+    if (LFO_AMP) {
+      double ls, lc;
+      sincos_phase(pp.y + (k + 1) * I.lfo_dq, &ls, &lc);
+      const double dl = AMP_FLAT ? I.depth * I.amp_rest : I.depth;
+      lsd[v] = ls * dl; lcd[v] = lc * dl;
+    }
+  }
+  double yp[NV][kT];
+  double ps0[NV], ps1[NV];
+  {
+    const OscMix o1 = I.m1, o2 = I.m2;
+    const u64 t1 = I.s1.thresh, t2 = I.s2.thresh;
+    const double b0 = L.c1.b0, a1 = L.c1.a1, a2 = L.c1.a2;
+#pragma unroll
+    for (int v = 0; v < NV; ++v) { ps0[v] = 0.0; ps1[v] = 0.0; }
+#pragma unroll
+    for (int j = 0; j < kT; ++j) {
+#pragma unroll
+      for (int v = 0; v < NV; ++v) {
+        p1[v] += d1[v];
+        p2[v] += d2[v];
+        yp[v][j] = lp_step(b0, a1, a2, osc_mix_eval<ZERO_A>(o1, t1, p1[v], o2, t2, p2[v]), ps0[v], ps1[v]);
+      }
+    }
+  }
+  double e0[NV], e1[NV], end[NV][4];
+#pragma unroll
+  for (int v = 0; v < NV; ++v) lti_scan_states(ps0[v], ps1[v], L.mp1, lane, s[v][0], s[v][1], e0[v], e1[v], end[v][0], end[v][1]);
+  {
+    const double b0 = L.c2.b0, a1 = L.c2.a1, a2 = L.c2.a2;
+#pragma unroll
+    for (int v = 0; v < NV; ++v) { ps0[v] = 0.0; ps1[v] = 0.0; }
+#pragma unroll
+    for (int j = 0; j < kT; ++j) {
+      const double2 g = *reinterpret_cast<const double2*>(L.g1[j]);
+#pragma unroll
+      for (int v = 0; v < NV; ++v)
+        yp[v][j] = lp_step(b0, a1, a2, fma(g.y, e1[v], fma(g.x, e0[v], yp[v][j])), ps0[v], ps1[v]);
+    }
+  }
+#pragma unroll
+  for (int v = 0; v < NV; ++v) lti_scan_states(ps0[v], ps1[v], L.mp2, lane, s[v][2], s[v][3], e0[v], e1[v], end[v][2], end[v][3]);
+  // ---- amplitude (envelope x LFO), DCA, into the warp's tile row (voices of a pair are summed first) ----
+  EnvSeg as = aseg;
+  if (!AMP_FLAT) { as.q0 *= 0.5; as.q1 *= 0.5; as.q2 *= 0.5; }
+  const double arest = I.amp_rest;
+  const double gl = I.gl, gr = I.gr;
+  double2* row = tile_row + lane * (kT + 1);
+#pragma unroll
+  for (int j = 0; j < kT; ++j) {
+    const double2 g = *reinterpret_cast<const double2*>(L.g2[j]);
+    double2 rot = make_double2(0.0, 0.0);
+    if (LFO_AMP) rot = I.lfo_rot[j];
+    const double env = AMP_FLAT ? arest : env_seg_at(as, j);
+    double m = 0.0;
+#pragma unroll
+    for (int v = 0; v < NV; ++v) {
+      double amp = env;
+      if (LFO_AMP) amp = AMP_FLAT ? fma(lsd[v], rot.x, fma(lcd[v], rot.y, arest))
+                                  : env * fma(lsd[v], rot.x, fma(lcd[v], rot.y, 1.0));
+      m = fma(fma(g.y, e1[v], fma(g.x, e0[v], yp[v][j])), amp, m);
+    }
+    const double2 p = row[j];  // the row holds the warp's earlier voices of this block (or zeros)
+    row[j] = make_double2(fma(m, gl, p.x), fma(m, gr, p.y));
+  }
+  __syncwarp();
+  if (lane == 0) {
+#pragma unroll
+    for (int v = 0; v < NV; ++v) {
+      *reinterpret_cast<double2*>(&vp[v]->s[0]) = make_double2(end[v][0], end[v][1]);
+      *reinterpret_cast<double2*>(&vp[v]->s[2]) = make_double2(end[v][2], end[v][3]);
+      vp[v]->knot_frame = kNever;  // no coefficient knot is carried out of a time-invariant block
+    }
   }
   __syncwarp();
 }
@@ -972,69 +1121,142 @@ __global__ void __launch_bounds__(32 * W, MINB) welsh_kernel(const WelshInst* __
   const i64 f_end = f0 + nframes;
   const bool pitch = mine && I.routing == LFO_PITCH;
   // instrument qualifies for welsh_block_simple (see its preconditions)
-  const bool simple_inst = mine && I.s1.kind == 0 && I.s2.kind == 0 && !I.sync && I.filter_mode == FILTER_ENVELOPE &&
-                           (I.routing == LFO_NONE || (I.routing == LFO_AMPLITUDE && I.wl == W_SINE));
+  const bool lin_inst = mine && I.s1.kind == 0 && I.s2.kind == 0 && !I.sync &&
+                        (I.routing == LFO_NONE || (I.routing == LFO_AMPLITUDE && I.wl == W_SINE));
+  const bool simple_inst = lin_inst && I.filter_mode == FILTER_ENVELOPE;
+  // instrument qualifies for welsh_block_lti whenever its cutoff rests (see its preconditions)
+  const bool lti_inst = lin_inst && I.lti_ok && (I.filter_mode == FILTER_FIXED || I.filter_mode == FILTER_ENVELOPE);
   // voices this warp handles per block: grouped = warp, warp+W, ...; solo = its one item
   const int g_begin = solo ? 0 : warp;
   const int g_end = solo ? (mine ? 1 : 0) : wk.nvoices;
 #pragma unroll 1
   for (i64 fb = f0; fb < f_end; fb += kBlockFrames) {
     bool any = false;
+    // Voices are taken two at a time (g and g + W): when both rest — no note events for them in this
+    // chunk, both envelopes at their sustain levels for the whole block — the pair is rendered in
+    // lockstep by welsh_block_lti<.., 2>.  The test reads two words of each record.
 #pragma unroll 1
-    for (int g = g_begin; g < g_end; g += W) {
-      const int vi = solo ? item.voice : wk.voice0 + g;
-      WelshVoice* vp = voices + vi;
-      NoteWords st;
-      st.n_on = vp->n_on; st.n_off = vp->n_off;
-      st.la_on = vp->la_on; st.la_off = vp->la_off; st.lf_on = vp->lf_on; st.lf_off = vp->lf_off;
-      int ei = ev_off[vi];
-      const int e_end = ev_off[vi + 1];
-      while (ei < e_end && events[ei].frame < fb) ++ei;  // already folded into the record by earlier blocks
-      const bool idle = fb >= st.n_off + I.amp.nr;
-      const bool ev_here = ei < e_end && events[ei].frame < fb + kBlockFrames;
-      if (idle && !ev_here) continue;
-      // noise seeds are only needed off the specialised path
-      const int local = vi - I.voice0;
-      auto seed_of = [&](u64 salt) { return splitmix64(((u64)(unsigned)I.uid << 32) ^ salt); };
-      bool fast = false;
-      EnvSeg aseg, fseg;
-      int cls = 0;
-      if (!pitch && !ev_here) {
-        cls = welsh_lane_class(st, I, fb + (i64)lane * kT, f_end, aseg, fseg);
-        fast = __all_sync(0xffffffffu, cls != 0);
+    for (int g = g_begin; g < g_end; g += 2 * W) {
+      const int nv = (!solo && g + W < g_end) ? 2 : 1;
+      int vis[2];
+      bool rest[2];
+      vis[0] = solo ? item.voice : wk.voice0 + g;
+      vis[1] = nv == 2 ? vis[0] + W : vis[0];
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        const longlong2 on_off = *reinterpret_cast<const longlong2*>(&voices[vis[h]].n_on);
+        const i64 last = on_off.y < f_end ? on_off.y : f_end;
+        rest[h] = lti_inst && ev_off[vis[h]] == ev_off[vis[h] + 1] && fb >= on_off.x + I.steady_after &&
+                  fb + kBlockFrames <= last;
       }
-      if (fast) {
-        // the fast path changes only the filter state and the carried knot of the voice record
-        const WelshInst* Ip = &I;  // shared-memory copy
-        if (I.filter_mode == FILTER_FIXED) {
-          if (__all_sync(0xffffffffu, cls == 2))
-            welsh_fast_call<COEF_FIXED, true>(vp, Ip, fb, lane, cls, aseg, fseg, seed_of((u64)(2 * local)), seed_of((u64)(2 * local + 1)), seed_of(0x4C464F00ull ^ (u64)local), tile_row, any);
-          else
-            welsh_fast_call<COEF_FIXED, false>(vp, Ip, fb, lane, cls, aseg, fseg, seed_of((u64)(2 * local)), seed_of((u64)(2 * local + 1)), seed_of(0x4C464F00ull ^ (u64)local), tile_row, any);
-        } else {
-          // knots need every lane sounding and the cutoff moving slowly enough over the lane's frames
-          bool smooth = false;
-          if (I.filter_mode == FILTER_ENVELOPE && cls == 2) {
-            const double w8 = fma((double)kT, fseg.dw, fseg.w0);
-            const double r0 = fabs(fma(2.0 * fseg.q2, fseg.w0, fseg.q1)), r8 = fabs(fma(2.0 * fseg.q2, w8, fseg.q1));
-            smooth = fabs(I.cut_b * fseg.dw) * fmax(r0, r8) <= I.knot_max_rate && I.knot_max_rate > 0.0;
-          }
-          if (__all_sync(0xffffffffu, smooth)) {
-            if (simple_inst && I.routing == LFO_NONE)
-              welsh_block_simple<false>(vp, Ip, fb, lane, aseg, fseg, tile_row, any, park);
-            else if (simple_inst)
-              welsh_block_simple<true>(vp, Ip, fb, lane, aseg, fseg, tile_row, any, park);
-            else
-              welsh_fast_call<COEF_KNOTS, true>(vp, Ip, fb, lane, cls, aseg, fseg, seed_of((u64)(2 * local)), seed_of((u64)(2 * local + 1)), seed_of(0x4C464F00ull ^ (u64)local), tile_row, any);
-          } else {
-            welsh_fast_call<COEF_EXACT, false>(vp, Ip, fb, lane, cls, aseg, fseg, seed_of((u64)(2 * local)), seed_of((u64)(2 * local + 1)), seed_of(0x4C464F00ull ^ (u64)local), tile_row, any);
-          }
+      if (rest[0] || (nv == 2 && rest[1])) {
+        if (!any) {  // the specialised blocks always accumulate into the warp's tile row
+          double2* row = tile_row + lane * (kT + 1);
+#pragma unroll
+          for (int j = 0; j < kT; ++j) row[j] = make_double2(0.0, 0.0);
+          any = true;
         }
-      } else {
-        welsh_block_general((pitch ? 2 : 0) + (ev_here ? 1 : 0), vp, insts + item.inst, events, ei, e_end, fb,
-                            f_end, lane, seed_of((u64)(2 * local)), seed_of((u64)(2 * local + 1)), seed_of(0x4C464F00ull ^ (u64)local), tile_row, any);
+        EnvSeg none;
+        none.q0 = 0.0; none.q1 = 0.0; none.q2 = 0.0; none.w0 = 0.0; none.dw = 0.0;
+#define GB_LTI_REST(NV_, ARR_)                                                                                   \
+  do {                                                                                                           \
+    if (I.osc_flat) {                                                                                            \
+      if (I.routing == LFO_NONE) welsh_block_lti<false, true, true, NV_>(ARR_, &I, fb, lane, none, tile_row);    \
+      else welsh_block_lti<true, true, true, NV_>(ARR_, &I, fb, lane, none, tile_row);                           \
+    } else {                                                                                                     \
+      if (I.routing == LFO_NONE) welsh_block_lti<false, false, true, NV_>(ARR_, &I, fb, lane, none, tile_row);   \
+      else welsh_block_lti<true, false, true, NV_>(ARR_, &I, fb, lane, none, tile_row);                          \
+    }                                                                                                            \
+  } while (0)
+        if (nv == 2 && rest[0] && rest[1]) {
+          WelshVoice* const two[2] = {voices + vis[0], voices + vis[1]};
+          GB_LTI_REST(2, two);
+          continue;
+        }
+        WelshVoice* const one[1] = {voices + (rest[0] ? vis[0] : vis[1])};
+        GB_LTI_REST(1, one);
+#undef GB_LTI_REST
       }
-      any = true;
+#pragma unroll 1
+      for (int h = 0; h < nv; ++h) {
+        if (rest[h]) continue;
+        const int vi = vis[h];
+        WelshVoice* vp = voices + vi;
+        NoteWords st;
+        st.n_on = vp->n_on; st.n_off = vp->n_off;
+        st.la_on = vp->la_on; st.la_off = vp->la_off; st.lf_on = vp->lf_on; st.lf_off = vp->lf_off;
+        int ei = ev_off[vi];
+        const int e_end = ev_off[vi + 1];
+        while (ei < e_end && events[ei].frame < fb) ++ei;  // already folded into the record by earlier blocks
+        const bool idle = fb >= st.n_off + I.amp.nr;
+        const bool ev_here = ei < e_end && events[ei].frame < fb + kBlockFrames;
+        if (idle && !ev_here) continue;
+        // noise seeds are only needed off the specialised path
+        const int local = vi - I.voice0;
+        auto seed_of = [&](u64 salt) { return splitmix64(((u64)(unsigned)I.uid << 32) ^ salt); };
+        bool fast = false;
+        EnvSeg aseg, fseg;
+        int cls = 0;
+        if (!pitch && !ev_here) {
+          cls = welsh_lane_class(st, I, fb + (i64)lane * kT, f_end, aseg, fseg);
+          fast = __all_sync(0xffffffffu, cls != 0);
+        }
+        bool lti = false;
+        if (fast && lti_inst) {
+          // every lane sounding, and the cutoff at rest: fixed filter, or the filter envelope at its sustain level
+          const bool rest = cls == 2 && (I.filter_mode == FILTER_FIXED ||
+                                         (fseg.q1 == 0.0 && fseg.q2 == 0.0 && fseg.q0 == I.filt.sustain));
+          lti = __all_sync(0xffffffffu, rest);
+        }
+        if ((lti || fast) && !any) {  // the specialised blocks always accumulate into the warp's tile row
+          double2* row = tile_row + lane * (kT + 1);
+  #pragma unroll
+          for (int j = 0; j < kT; ++j) row[j] = make_double2(0.0, 0.0);
+        }
+        if (lti) {
+          WelshVoice* const one[1] = {vp};
+          if (I.osc_flat) {
+            if (I.routing == LFO_NONE) welsh_block_lti<false, true, false, 1>(one, &I, fb, lane, aseg, tile_row);
+            else welsh_block_lti<true, true, false, 1>(one, &I, fb, lane, aseg, tile_row);
+          } else {
+            if (I.routing == LFO_NONE) welsh_block_lti<false, false, false, 1>(one, &I, fb, lane, aseg, tile_row);
+            else welsh_block_lti<true, false, false, 1>(one, &I, fb, lane, aseg, tile_row);
+          }
+        } else if (fast) {
+          // the fast path changes only the filter state and the carried knot of the voice record
+          const WelshInst* Ip = &I;  // shared-memory copy
+          if (I.filter_mode == FILTER_FIXED) {
+            if (__all_sync(0xffffffffu, cls == 2))
+              welsh_fast_call<COEF_FIXED, true>(vp, Ip, fb, lane, cls, aseg, fseg, seed_of((u64)(2 * local)), seed_of((u64)(2 * local + 1)), seed_of(0x4C464F00ull ^ (u64)local), tile_row, true);
+            else
+              welsh_fast_call<COEF_FIXED, false>(vp, Ip, fb, lane, cls, aseg, fseg, seed_of((u64)(2 * local)), seed_of((u64)(2 * local + 1)), seed_of(0x4C464F00ull ^ (u64)local), tile_row, any);
+          } else {
+            // knots need every lane sounding and the cutoff moving slowly enough over the lane's frames
+            bool smooth = false;
+            if (I.filter_mode == FILTER_ENVELOPE && cls == 2) {
+              const double w8 = fma((double)kT, fseg.dw, fseg.w0);
+              const double r0 = fabs(fma(2.0 * fseg.q2, fseg.w0, fseg.q1)), r8 = fabs(fma(2.0 * fseg.q2, w8, fseg.q1));
+              smooth = fabs(I.cut_b * fseg.dw) * fmax(r0, r8) <= I.knot_max_rate && I.knot_max_rate > 0.0;
+            }
+            if (__all_sync(0xffffffffu, smooth)) {
+              if (simple_inst && I.osc_flat) {
+                if (I.routing == LFO_NONE) welsh_block_simple<false, true>(vp, Ip, fb, lane, aseg, fseg, tile_row, park);
+                else welsh_block_simple<true, true>(vp, Ip, fb, lane, aseg, fseg, tile_row, park);
+              } else if (simple_inst) {
+                if (I.routing == LFO_NONE) welsh_block_simple<false, false>(vp, Ip, fb, lane, aseg, fseg, tile_row, park);
+                else welsh_block_simple<true, false>(vp, Ip, fb, lane, aseg, fseg, tile_row, park);
+              } else
+                welsh_fast_call<COEF_KNOTS, true>(vp, Ip, fb, lane, cls, aseg, fseg, seed_of((u64)(2 * local)), seed_of((u64)(2 * local + 1)), seed_of(0x4C464F00ull ^ (u64)local), tile_row, any);
+            } else {
+              welsh_fast_call<COEF_EXACT, false>(vp, Ip, fb, lane, cls, aseg, fseg, seed_of((u64)(2 * local)), seed_of((u64)(2 * local + 1)), seed_of(0x4C464F00ull ^ (u64)local), tile_row, any);
+            }
+          }
+        } else {
+          welsh_block_general((pitch ? 2 : 0) + (ev_here ? 1 : 0), vp, insts + item.inst, events, ei, e_end, fb,
+                              f_end, lane, seed_of((u64)(2 * local)), seed_of((u64)(2 * local + 1)), seed_of(0x4C464F00ull ^ (u64)local), tile_row, any);
+        }
+        any = true;
+      }
     }
     if (solo) {
       __syncwarp();

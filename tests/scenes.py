@@ -116,6 +116,43 @@ def scene_welsh_variants(r: abi.Renderer) -> int:
     return 16000
 
 
+def scene_welsh_sustain(r: abi.Renderer) -> int:
+    """Long notes whose filter envelope reaches its sustain level (the cutoff rests: the engine's
+    time-invariant block), fixed-cutoff filters, releases that set the cutoff moving again, and
+    retriggers in the middle of a resting stretch."""
+    fast_filt = (0.0, 0.01, 0.6, 0.05)
+    cfgs = [
+        dict(w1=abi.WAVE_PULSE_WIDTH, pw1=0.1, w2=abi.WAVE_SQUARE, mix=0.5, routing=abi.LFO_AMPLITUDE, depth=0.05,
+             lfo_hz=7.5, filt=fast_filt, amp=(0.06, 0.0, 1.0, 0.0), cutoff_start=hz_to_pct(40.0), cutoff_end=0.9),
+        dict(w1=abi.WAVE_SAWTOOTH, w2=abi.WAVE_TRIANGLE, tune2=1.0029, routing=abi.LFO_NONE, filt=fast_filt,
+             amp=(0.001, 0.05, 0.8, 0.02), ripple=2.5, cutoff_start=0.2, cutoff_end=0.4),
+        dict(w1=abi.WAVE_TRIANGLE, w2=abi.WAVE_PULSE_WIDTH, pw2=0.8, mix=0.3, cutoff_end=0.0, cutoff_hz=700.0,
+             routing=abi.LFO_AMPLITUDE, depth=0.5, lfo_hz=11.0),
+        dict(w1=abi.WAVE_SQUARE, w2=abi.WAVE_SAWTOOTH, filt=(0.0, 0.0, 1.0, 0.0), cutoff_start=0.1, cutoff_end=1.0,
+             ripple=10.707, amp=(0.0, 0.0, 1.0, 0.0)),
+        dict(w1=abi.WAVE_SAWTOOTH, w2=abi.WAVE_SINE, filt=fast_filt, routing=abi.LFO_NONE),       # sine: not this path
+        dict(w1=abi.WAVE_SAWTOOTH, w2=abi.WAVE_SQUARE, filt=(0.0, 0.005, 0.0, 0.005), cutoff_start=0.15, cutoff_end=0.7),
+    ]
+    uids = []
+    for i, c in enumerate(cfgs):
+        u = r.add_instrument(abi.INST_WELSH, generic_welsh(voices=3, gain=0.4, pan=-0.5 + 0.2 * i, **c))
+        r.patch(u, abi.MAIN_MIXER)
+        uids.append(u)
+    r.finalize()
+    ev = []
+    for i, u in enumerate(uids):
+        base = 53 * i
+        ev += [(base + 3, u, abi.EV_NOTE_ON, 40 + 3 * i, 127, 0.0),
+               (base + 900, u, abi.EV_NOTE_ON, 47 + 3 * i, 127, 0.0),
+               (base + 6000, u, abi.EV_NOTE_ON, 40 + 3 * i, 127, 0.0),     # retrigger a resting voice
+               (base + 9001, u, abi.EV_NOTE_OFF, 47 + 3 * i, 0, 0.0),
+               (base + 15000, u, abi.EV_NOTE_OFF, 40 + 3 * i, 0, 0.0),
+               (base + 15400, u, abi.EV_NOTE_ON, 52 + 3 * i, 127, 0.0),
+               (base + 21000, u, abi.EV_NOTE_OFF, 52 + 3 * i, 0, 0.0)]
+    r.push_events(ev)
+    return 24000
+
+
 def fm_params(ratio=2.0, depth=1.0, beta=1.0, car=(0.01, 0.1, 0.8, 0.2), mod=(0.0, 0.3, 0.4, 0.3),
               gain=1.0, pan=0.0, voices=4) -> abi.FmParams:
     p = abi.FmParams()
@@ -237,6 +274,7 @@ def scene_graph_toys(r: abi.Renderer) -> int:
 ALL_SCENES = {
     "cello_chord": scene_cello_chord,
     "welsh_variants": scene_welsh_variants,
+    "welsh_sustain": scene_welsh_sustain,
     "fm": scene_fm,
     "drums_and_sampler": scene_drums_and_sampler,
     "effects_rack": scene_effects_rack,
