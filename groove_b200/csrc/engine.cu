@@ -33,6 +33,7 @@ using namespace gbk;
 namespace {
 
 constexpr int kVoiceWarps = 8;  // warps per voice CTA
+constexpr int kRestSmemMax = 96 * 1024;  // dynamic shared memory cap of welsh_rest_kernel (tiles + cached voice state)
 constexpr uint32_t kDefaultMaxBlock = 1u << 16;
 
 std::string g_create_err;
@@ -293,8 +294,6 @@ struct gb_engine {
   int64_t pos = 0;
   uint32_t next_uid = 2;
   int num_sms = 148;
-  int welsh_occ = 2;        // resident CTAs per SM the grouped Welsh kernel is compiled for (GB_WELSH_OCC=1|2):
-                            // 2 = 128 registers, 16 warps/SM (default, measured faster); 1 = 255 registers, 8 warps/SM
   int cta_target_mult = 2;  // CTAs per SM the voice work lists aim for (GB_CTA_MULT)
   std::map<uint32_t, std::unique_ptr<Node>> nodes;
   std::vector<Node*> plan;  // reachable nodes, sources before consumers
@@ -314,6 +313,8 @@ struct gb_engine {
   DevBuf<WarpItem> witems, fitems;  // solo-warp work items (instruments with fewer voices than a CTA has warps)
   int n_wwork = 0, n_fwork = 0;
   int n_wwork_grouped = 0;  // wwork[0 .. n_wwork_grouped) are grouped CTAs, the rest solo CTAs
+  std::vector<Node*> wwork_node;  // instrument of each grouped Welsh CTA
+  DevBuf<int> widx;               // per chunk: grouped Welsh CTAs sorted into resting (4 variants) and general
   DevBuf<VoiceEvent> wev, fev;
   DevBuf<int> wev_off, fev_off;
   DevBuf<SamplePlay> plays;
@@ -458,6 +459,16 @@ void welsh_inst_from_params(const Node& n, double sr, WelshInst* I) {
       pct = pct < 0.0 ? 0.0 : (pct > 1.0 ? 1.0 : pct);
       host_lp24(I->rp, 25.0 * std::exp2(pct * 9.6438561897747243), sr, &c1, &c2);
     }
+    for (int l = 0; l < 32; ++l) {
+      uint64_t q = (uint64_t)(l * kT) * I->lfo_dq;
+      double ang = 6.283185307179586476925286766559 * ((double)q / 18446744073709551616.0);
+      I->lane_rot[l] = make_double2(std::cos(ang), std::sin(ang));
+    }
+    {
+      uint64_t q = (uint64_t)kBlockFrames * I->lfo_dq;
+      double ang = 6.283185307179586476925286766559 * ((double)q / 18446744073709551616.0);
+      I->block_rot = make_double2(std::cos(ang), std::sin(ang));
+    }
     I->steady_after = I->filter_mode == FILTER_ENVELOPE ? std::max(I->amp.na + I->amp.nd, I->filt.na + I->filt.nd)
                                                          : I->amp.na + I->amp.nd;
     I->amp_rest = 0.5 * I->amp.sustain;
@@ -483,6 +494,13 @@ void welsh_inst_from_params(const Node& n, double sr, WelshInst* I) {
     table(c2, I->lti.g2, I->lti.mp2);
     I->lti_ok = 1;
     if (const char* v = getenv("GB_LTI")) I->lti_ok = atoi(v) != 0;
+    // welsh_rest_kernel variant: same preconditions as welsh_block_lti (see voice_kernels.cuh)
+    const bool lin = I->s1.kind == 0 && I->s2.kind == 0 && !I->sync &&
+                     (I->routing == LFO_NONE || (I->routing == LFO_AMPLITUDE && I->wl == W_SINE));
+    I->rest_class = -1;
+    if (lin && I->lti_ok && (I->filter_mode == FILTER_FIXED || I->filter_mode == FILTER_ENVELOPE))
+      I->rest_class = (I->routing == LFO_AMPLITUDE ? 2 : 0) + (I->osc_flat ? 1 : 0);
+    if (const char* v = getenv("GB_REST_KERNEL")) if (atoi(v) == 0) I->rest_class = -1;
   }
 }
 void fm_inst_from_params(const Node& n, double sr, FmInst* I) {
@@ -517,6 +535,7 @@ void resolve_spans(gb_engine* e) {
     float ms = 0.f;
     cudaEventElapsedTime(&ms, sp.a, sp.b);
     if (sp.what == 1) e->stats.voice_kernel_ms += ms;
+    else if (sp.what == 3) { e->stats.voice_kernel_ms += ms; e->stats.rest_kernel_ms += ms; }
     else if (sp.what == 0) e->stats.fx_kernel_ms += ms;
     else e->stats.render_ms += ms;
     e->event_pool.push_back({sp.a, sp.b});
@@ -528,10 +547,11 @@ struct Launch {  // per-launch accounting (+ optional CUDA-event timing on the e
   gb_engine* e;
   bool timed;
   size_t index;
-  Launch(gb_engine* e_, bool voice) : e(e_) {
+  Launch(gb_engine* e_, bool voice, bool rest = false) : e(e_) {
     e->stats.kernel_launches++;
     if (voice) e->stats.voice_kernel_launches++;
-    timed = span_begin(e, voice ? 1 : 0);
+    if (rest) e->stats.rest_kernel_launches++;
+    timed = span_begin(e, rest ? 3 : voice ? 1 : 0);
     index = e->spans.size() - 1;
   }
   ~Launch() {
@@ -708,7 +728,6 @@ int gb_create(const gb_config* cfg, gb_engine** out) {
   memset(&e->stats, 0, sizeof e->stats);
   cudaDeviceProp prop;
   if (cudaGetDeviceProperties(&prop, e->device) == cudaSuccess) e->num_sms = prop.multiProcessorCount;
-  if (const char* v = getenv("GB_WELSH_OCC")) e->welsh_occ = atoi(v) == 1 ? 1 : 2;
   if (const char* v = getenv("GB_CTA_MULT")) e->cta_target_mult = std::max(1, atoi(v));
   if (cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking) != cudaSuccess)
     return fail(nullptr, GB_ECUDA, "cudaStreamCreate failed");
@@ -1000,6 +1019,7 @@ int gb_finalize(gb_engine* e) {
     const int wpc = kVoiceWarps;  // warps per CTA (4-warp CTAs with tighter register caps measured slower)
     int vpc = std::max(wpc, cdiv(total_voices, target));
     vpc = cdiv(vpc, wpc) * wpc;
+    if (const char* v = getenv("GB_VPC")) vpc = std::max(1, atoi(v));  // tests: force the voices-per-CTA split
     for (Node* n : e->plan) {
       if (n->kind != kind) continue;
       if (n->nvoices < wpc) {
@@ -1034,6 +1054,7 @@ int gb_finalize(gb_engine* e) {
         w.solo = 0;
         w.out = ncta == 1 ? n->buf : n->scratch + (size_t)c * mb;
         work.push_back(w);
+        if (kind == GB_INST_WELSH) e->wwork_node.push_back(n);
         v += w.nvoices;
       }
     }
@@ -1059,6 +1080,7 @@ int gb_finalize(gb_engine* e) {
   };
   int rc;
   int fm_grouped = 0;
+  e->wwork_node.clear();
   if ((rc = plan_work(GB_INST_WELSH, wv, e->wwork, e->witems, &e->n_wwork, &e->n_wwork_grouped))) return rc;
   if ((rc = plan_work(GB_INST_FM, fv, e->fwork, e->fitems, &e->n_fwork, &fm_grouped))) return rc;
   {
@@ -1088,9 +1110,12 @@ int gb_finalize(gb_engine* e) {
     }
   }
   const int welsh_smem_bytes = (int)(kVoiceWarps * kTileStride * sizeof(double2) + kParkWords * 32 * kVoiceWarps * sizeof(double));
-  CUDA_TRY(e, cudaFuncSetAttribute(welsh_kernel<8, 1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, welsh_smem_bytes));
   CUDA_TRY(e, cudaFuncSetAttribute(welsh_kernel<8, 2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, welsh_smem_bytes));
   CUDA_TRY(e, cudaFuncSetAttribute(welsh_kernel<8, 2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, welsh_smem_bytes));
+  CUDA_TRY(e, cudaFuncSetAttribute(welsh_rest_kernel<8, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kRestSmemMax));
+  CUDA_TRY(e, cudaFuncSetAttribute(welsh_rest_kernel<8, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kRestSmemMax));
+  CUDA_TRY(e, cudaFuncSetAttribute(welsh_rest_kernel<8, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kRestSmemMax));
+  CUDA_TRY(e, cudaFuncSetAttribute(welsh_rest_kernel<8, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kRestSmemMax));
   CUDA_TRY(e, cudaFuncSetAttribute(fm_kernel<kVoiceWarps>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                    (int)(kVoiceWarps * kTileStride * sizeof(double2))));
   CUDA_TRY(e, cudaStreamSynchronize(e->stream));
@@ -1315,21 +1340,66 @@ int render_chunk(gb_engine* e, int frames, size_t n_ev) {
     int rc = upload_events(wlists, e->wev, e->wev_off, any_w);
     if (rc) return rc;
     {
-      Launch l(e, true);
-#define GB_WELSH_LAUNCH(W_, M_, SOLO_, first_, count_)                                                                \
-  welsh_kernel<W_, M_, SOLO_><<<(count_), 32 * W_, (size_t)W_ * kTileStride * sizeof(double2) +                        \
-                                                      (size_t)kParkWords * 32 * W_ * sizeof(double), e->stream>>>(     \
-      e->d_winst, e->d_wvoice, e->wwork.d + (first_), e->witems.d, e->wev.d, e->wev_off.d, f0, frames)
+      // Sort the grouped CTAs of this chunk: a CTA whose voices all rest for the whole chunk (note held
+      // since before the chunk with both envelopes at their sustain levels, no note event inside it)
+      // goes to welsh_rest_kernel, the others to welsh_kernel.  Host knowledge only: note frames are
+      // integers tracked by the slot stores.
       const int ng = e->n_wwork_grouped, ns = e->n_wwork - e->n_wwork_grouped;
+      std::vector<int> lists[5];  // 0..3 = resting variants, 4 = general
+      const bool chunk_ok = frames % kBlockFrames == 0;
+      size_t rest_voices_max = 0;
+      uint64_t rest_voices = 0;
+      for (int i = 0; i < ng; ++i) {
+        const CtaWork& w = e->wwork.h[i];
+        const Node* n = e->wwork_node[(size_t)i];
+        const WelshInst& I = e->h_winst[(size_t)n->table_index];
+        bool rest = chunk_ok && I.rest_class >= 0 &&
+                    kVoiceWarps * kTileStride * sizeof(double2) + (size_t)w.nvoices * sizeof(RestState) <= (size_t)kRestSmemMax;
+        for (int v = 0; rest && v < w.nvoices; ++v) {
+          const Slot& sl = n->store.slots[(size_t)(w.voice0 - n->voice0 + v)];
+          rest = wlists[(size_t)(w.voice0 + v)].empty() && sl.held && sl.on_frame > kNever &&
+                 sl.on_frame + I.steady_after <= f0;
+        }
+        lists[rest ? I.rest_class : 4].push_back(i);
+        if (rest) {
+          rest_voices_max = std::max(rest_voices_max, (size_t)w.nvoices);
+          rest_voices += (uint64_t)w.nvoices;
+        }
+      }
       if (ng) {
-        if (e->welsh_occ == 1) GB_WELSH_LAUNCH(8, 1, false, 0, ng);
-        else GB_WELSH_LAUNCH(8, 2, false, 0, ng);
+        if (!e->widx.reserve((size_t)ng)) return fail(e, GB_ENOMEM, "out of memory");
+        size_t k = 0;
+        for (auto& l : lists)
+          for (int i : l) e->widx.h[k++] = i;
+        CUDA_TRY(e, cudaMemcpyAsync(e->widx.d, e->widx.h, (size_t)ng * sizeof(int), cudaMemcpyHostToDevice, e->stream));
+        e->stats.h2d_bytes += (size_t)ng * sizeof(int);
+      }
+      const size_t rest_smem = (size_t)kVoiceWarps * kTileStride * sizeof(double2) + rest_voices_max * sizeof(RestState);
+      size_t off = 0;
+#define GB_REST_LAUNCH(CLS_, LFO_, FLAT_)                                                                            \
+  if (!lists[CLS_].empty()) {                                                                                        \
+    Launch l(e, true, true);                                                                                         \
+    welsh_rest_kernel<8, LFO_, FLAT_><<<(int)lists[CLS_].size(), 32 * 8, rest_smem, e->stream>>>(                      \
+        e->d_winst, e->d_wvoice, e->wwork.d, e->widx.d + off, f0, frames);                                           \
+    off += lists[CLS_].size();                                                                                       \
+  }
+      GB_REST_LAUNCH(0, false, false)
+      GB_REST_LAUNCH(1, false, true)
+      GB_REST_LAUNCH(2, true, false)
+      GB_REST_LAUNCH(3, true, true)
+#undef GB_REST_LAUNCH
+      e->stats.rest_voice_samples += rest_voices * (uint64_t)frames;
+      const size_t welsh_smem = (size_t)kVoiceWarps * kTileStride * sizeof(double2) + (size_t)kParkWords * 32 * kVoiceWarps * sizeof(double);
+      if (!lists[4].empty()) {
+        Launch l(e, true);
+        welsh_kernel<8, 2, false><<<(int)lists[4].size(), 32 * 8, welsh_smem, e->stream>>>(
+            e->d_winst, e->d_wvoice, e->wwork.d, e->witems.d, e->wev.d, e->wev_off.d, f0, frames, e->widx.d + off);
       }
       if (ns) {
-        if (ng) { e->stats.kernel_launches++; e->stats.voice_kernel_launches++; }
-        GB_WELSH_LAUNCH(8, 2, true, ng, ns);
+        Launch l(e, true);
+        welsh_kernel<8, 2, true><<<ns, 32 * 8, welsh_smem, e->stream>>>(
+            e->d_winst, e->d_wvoice, e->wwork.d + ng, e->witems.d, e->wev.d, e->wev_off.d, f0, frames, nullptr);
       }
-#undef GB_WELSH_LAUNCH
     }
     e->stats.voice_samples += (uint64_t)e->n_wvoice * (uint64_t)frames;
   }
@@ -1474,6 +1544,9 @@ int render_impl(gb_engine* e, void* out, size_t frames, size_t* done, OutMode mo
   while (produced < frames) {
     const int64_t f0 = e->pos;
     int64_t limit = (int64_t)std::min<size_t>(frames - produced, e->max_block);
+    // long ragged chunks are cut at a block multiple (the remainder becomes its own small chunk), so
+    // that resting voices can take welsh_rest_kernel, which renders whole blocks only
+    if (limit >= 16 * kBlockFrames && limit % kBlockFrames) limit -= limit % kBlockFrames;
     // every event strictly before the chunk end belongs to this chunk (events never split a chunk:
     // parameters go through segment tables, sampler retriggers through per-chunk play lists)
     size_t n_ev = 0;

@@ -159,6 +159,9 @@ struct WelshInst {
   double log2_25_over_sr;           // fc/sr = exp2(pct*log2(800) + log2(25/sr))
   double u_min, u_max;              // clamp of fc/sr: [1/sr, 0.49]
   double knot_max_rate;             // cutoff motion (fraction of the log range per frame) up to which knots are used
+  double2 lane_rot[32];             // (cos, sin)(2*pi*kT*l*lfo_dq/2^64): a lane's LFO angle relative to its block
+  double2 block_rot;                // (cos, sin)(2*pi*kBlockFrames*lfo_dq/2^64): one block further
+  int rest_class, pad_rc;           // welsh_rest_kernel variant (2*lfo_amp + zero_a), -1 = the instrument does not qualify
   i64 steady_after;                 // frames after note-on from which both envelopes rest at their sustain levels
   double amp_rest;                  // 0.5 * amp.sustain: the DCA input level of a resting voice (without LFO)
   int lti_ok, osc_flat;             // osc_flat: both oscillators piecewise constant (OscMix slopes are 0); lti holds this instrument's resting coefficient sets (GB_LTI=0 disables the path)
@@ -1093,11 +1096,12 @@ __global__ void __launch_bounds__(32 * W, MINB) welsh_kernel(const WelshInst* __
                                                            const CtaWork* __restrict__ work,
                                                            const WarpItem* __restrict__ items,
                                                            const VoiceEvent* __restrict__ events,
-                                                           const int* __restrict__ ev_off, i64 f0, int nframes) {
+                                                           const int* __restrict__ ev_off, i64 f0, int nframes,
+                                                           const int* __restrict__ idx) {
   extern __shared__ double2 smem_tiles[];
   __shared__ int s_active[W];
   __shared__ WelshInst sI[SOLO ? W : 1];  // instrument records: LDS instead of repeated global loads
-  const CtaWork wk = work[blockIdx.x];
+  const CtaWork wk = work[idx ? idx[blockIdx.x] : blockIdx.x];  // idx: this chunk's subset of the work list
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   constexpr bool solo = SOLO;  // compile-time: the grouped kernel carries none of the solo plumbing
   const bool mine = !solo || warp < wk.nvoices;   // solo: does this warp have an item?
@@ -1268,6 +1272,211 @@ __global__ void __launch_bounds__(32 * W, MINB) welsh_kernel(const WelshInst* __
       cta_reduce_store<W>(smem_tiles, s_active, wk.out, fb, f0, f_end);
       __syncthreads();
     }
+  }
+}
+
+// ---- the resting-voice kernel ----------------------------------------------------------------------
+// The host knows every voice's note frames, so per chunk it sorts the grouped CTAs: those whose voices
+// all rest for the WHOLE chunk (note held since before the chunk, both envelopes at their sustain
+// levels, no note event in the chunk, chunk a multiple of kBlockFrames) come here, the others go to
+// welsh_kernel.  Here nothing is decided per block: the voice state lives in shared memory for the
+// duration of the launch (phases advance by integer adds, the LFO by a rotation, the filter state
+// straight from the scan), two voices run in lockstep per warp, and the only global traffic of the
+// block loop is the CTA's 16-byte-per-frame output.
+struct alignas(16) RestState {
+  u64 p1, p2;     // oscillator phases at the frame before the current block
+  u64 d1, d2;
+  double s[4];    // filter state at the start of the current block
+  double ls, lc;  // depth * level * (sin, cos) of the LFO angle at the first frame of the current block
+};
+
+// Exclusive form of lti_scan_states: the lanes' zero-state end vectors are shifted up by one lane with
+// the span's entry state entering at lane 0, so the inclusive scan yields each lane's entry state
+// directly.  Returns the state after the whole span in lane 31's (x0, x1).
+__device__ __forceinline__ void lti_scan_entry(double v0, double v1, const double (*mp)[4], int lane, double s0,
+                                               double s1, double& e0, double& e1, double& x0, double& x1) {
+  double u0 = shfl_up_f64(v0, 1), u1 = shfl_up_f64(v1, 1);
+  u0 = lane == 0 ? s0 : u0;
+  u1 = lane == 0 ? s1 : u1;
+#pragma unroll
+  for (int k = 0; k < 5; ++k) {
+    const int d = 1 << k;
+    const double p0 = shfl_up_f64(u0, d), p1 = shfl_up_f64(u1, d);
+    const double* m = mp[lane >= d ? k : 5];
+    const double2 r0 = *reinterpret_cast<const double2*>(m), r1 = *reinterpret_cast<const double2*>(m + 2);
+    affine_vec_step(u0, u1, r0.x, r0.y, r1.x, r1.y, p0, p1);
+  }
+  e0 = u0; e1 = u1;
+  const double2 r0 = *reinterpret_cast<const double2*>(mp[0]), r1 = *reinterpret_cast<const double2*>(mp[0] + 2);
+  x0 = v0; x1 = v1;
+  affine_vec_step(x0, x1, r0.x, r0.y, r1.x, r1.y, u0, u1);
+}
+
+template <bool LFO_AMP, bool ZERO_A, int NV, bool ACC>
+__device__ __forceinline__ void welsh_rest_block(RestState* const (&rs)[NV], const WelshInst& I, int lane,
+                                                 double2* tile_row) {
+  const LtiTable& L = I.lti;
+  u64 p1[NV], p2[NV], d1[NV], d2[NV];
+  double lsd[NV], lcd[NV];
+  double s[NV][4];
+#pragma unroll
+  for (int v = 0; v < NV; ++v) {
+    const ulonglong2 pp = *reinterpret_cast<const ulonglong2*>(&rs[v]->p1);
+    const ulonglong2 dd = *reinterpret_cast<const ulonglong2*>(&rs[v]->d1);
+    const double2 sa = *reinterpret_cast<const double2*>(&rs[v]->s[0]), sb = *reinterpret_cast<const double2*>(&rs[v]->s[2]);
+    s[v][0] = sa.x; s[v][1] = sa.y; s[v][2] = sb.x; s[v][3] = sb.y;
+    d1[v] = dd.x; d2[v] = dd.y;
+    const u64 k = (u64)(lane * kT);
+    p1[v] = pp.x + k * dd.x; p2[v] = pp.y + k * dd.y;
+    lsd[v] = 0.0; lcd[v] = 0.0;
+    if (LFO_AMP) {
+      const double2 ph = *reinterpret_cast<const double2*>(&rs[v]->ls);
+      const double2 r = I.lane_rot[lane];
+      lsd[v] = fma(ph.x, r.x, ph.y * r.y);
+      lcd[v] = fma(ph.y, r.x, -(ph.x * r.y));
+    }
+  }
+  double yp[NV][kT];
+  double ps0[NV], ps1[NV];
+  {
+    const OscMix o1 = I.m1, o2 = I.m2;
+    const u64 t1 = I.s1.thresh, t2 = I.s2.thresh;
+    const double b0 = L.c1.b0, a1 = L.c1.a1, a2 = L.c1.a2;
+#pragma unroll
+    for (int v = 0; v < NV; ++v) { ps0[v] = 0.0; ps1[v] = 0.0; }
+#pragma unroll
+    for (int j = 0; j < kT; ++j) {
+#pragma unroll
+      for (int v = 0; v < NV; ++v) {
+        p1[v] += d1[v];
+        p2[v] += d2[v];
+        yp[v][j] = lp_step(b0, a1, a2, osc_mix_eval<ZERO_A>(o1, t1, p1[v], o2, t2, p2[v]), ps0[v], ps1[v]);
+      }
+    }
+  }
+  double e0[NV], e1[NV], x[NV][4];
+#pragma unroll
+  for (int v = 0; v < NV; ++v) lti_scan_entry(ps0[v], ps1[v], L.mp1, lane, s[v][0], s[v][1], e0[v], e1[v], x[v][0], x[v][1]);
+  {
+    const double b0 = L.c2.b0, a1 = L.c2.a1, a2 = L.c2.a2;
+#pragma unroll
+    for (int v = 0; v < NV; ++v) { ps0[v] = 0.0; ps1[v] = 0.0; }
+#pragma unroll
+    for (int j = 0; j < kT; ++j) {
+      const double2 g = *reinterpret_cast<const double2*>(L.g1[j]);
+#pragma unroll
+      for (int v = 0; v < NV; ++v)
+        yp[v][j] = lp_step(b0, a1, a2, fma(g.y, e1[v], fma(g.x, e0[v], yp[v][j])), ps0[v], ps1[v]);
+    }
+  }
+#pragma unroll
+  for (int v = 0; v < NV; ++v) lti_scan_entry(ps0[v], ps1[v], L.mp2, lane, s[v][2], s[v][3], e0[v], e1[v], x[v][2], x[v][3]);
+  const double arest = I.amp_rest;
+  const double gl = I.gl, gr = I.gr;
+  double2* row = tile_row + lane * (kT + 1);
+#pragma unroll
+  for (int j = 0; j < kT; ++j) {
+    const double2 g = *reinterpret_cast<const double2*>(L.g2[j]);
+    double2 rot = make_double2(0.0, 0.0);
+    if (LFO_AMP) rot = I.lfo_rot[j];
+    double m = 0.0;
+#pragma unroll
+    for (int v = 0; v < NV; ++v) {
+      const double amp = LFO_AMP ? fma(lsd[v], rot.x, fma(lcd[v], rot.y, arest)) : arest;
+      const double y = fma(g.y, e1[v], fma(g.x, e0[v], yp[v][j]));
+      m = v == 0 ? y * amp : fma(y, amp, m);
+    }
+    if (ACC) {
+      const double2 p = row[j];
+      row[j] = make_double2(fma(m, gl, p.x), fma(m, gr, p.y));
+    } else {
+      row[j] = make_double2(m * gl, m * gr);
+    }
+  }
+  // ---- advance the cached state by one block ----
+#pragma unroll
+  for (int v = 0; v < NV; ++v) {
+    if (lane == 31) {
+      *reinterpret_cast<double2*>(&rs[v]->s[0]) = make_double2(x[v][0], x[v][1]);
+      *reinterpret_cast<double2*>(&rs[v]->s[2]) = make_double2(x[v][2], x[v][3]);
+    }
+    if (lane == 0) {
+      *reinterpret_cast<ulonglong2*>(&rs[v]->p1) =
+          make_ulonglong2(p1[v] + (u64)(kBlockFrames - kT) * d1[v], p2[v] + (u64)(kBlockFrames - kT) * d2[v]);
+      if (LFO_AMP) {
+        const double2 r = I.block_rot;  // lane 0's (lsd, lcd) is the block phasor itself (lane_rot[0] = (1, 0))
+        *reinterpret_cast<double2*>(&rs[v]->ls) =
+            make_double2(fma(lsd[v], r.x, lcd[v] * r.y), fma(lcd[v], r.x, -(lsd[v] * r.y)));
+      }
+    }
+  }
+  __syncwarp();
+}
+
+// grid = number of resting CTAs of this variant; block = 32 * W threads;
+// dynamic smem = W * kTileStride double2 (tiles) + max_voices RestState.  nframes is a multiple of kBlockFrames.
+template <int W, bool LFO_AMP, bool ZERO_A>
+__global__ void __launch_bounds__(32 * W, 2) welsh_rest_kernel(const WelshInst* __restrict__ insts,
+                                                             WelshVoice* __restrict__ voices,
+                                                             const CtaWork* __restrict__ work,
+                                                             const int* __restrict__ idx, i64 f0, int nframes) {
+  extern __shared__ double2 smem_tiles[];
+  __shared__ int s_active[W];
+  __shared__ WelshInst sI;
+  const CtaWork wk = work[idx[blockIdx.x]];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  {
+    const int* src = reinterpret_cast<const int*>(insts + wk.inst);
+    int* dst = reinterpret_cast<int*>(&sI);
+    for (int i = threadIdx.x; i < (int)(sizeof(WelshInst) / sizeof(int)); i += 32 * W) dst[i] = src[i];
+  }
+  __syncthreads();
+  const WelshInst& I = sI;
+  RestState* cache = reinterpret_cast<RestState*>(smem_tiles + W * kTileStride);
+  for (int t = threadIdx.x; t < wk.nvoices; t += 32 * W) {
+    const WelshVoice* vp = voices + wk.voice0 + t;
+    RestState r;
+    const u64 k = (u64)(f0 - 1 - vp->anchor);
+    r.d1 = vp->d1; r.d2 = vp->d2;
+    r.p1 = vp->p1 + k * r.d1; r.p2 = vp->p2 + k * r.d2;
+    r.s[0] = vp->s[0]; r.s[1] = vp->s[1]; r.s[2] = vp->s[2]; r.s[3] = vp->s[3];
+    r.ls = 0.0; r.lc = 0.0;
+    if (LFO_AMP) {
+      double ls, lc;
+      sincos_phase(vp->pl + (k + 1) * I.lfo_dq, &ls, &lc);
+      const double dl = I.depth * I.amp_rest;
+      r.ls = ls * dl; r.lc = lc * dl;
+    }
+    cache[t] = r;
+  }
+  if (lane == 0) s_active[warp] = warp < wk.nvoices ? 1 : 0;
+  __syncthreads();
+  double2* tile_row = smem_tiles + warp * kTileStride;
+  const i64 f_end = f0 + nframes;
+#pragma unroll 1
+  for (i64 fb = f0; fb < f_end; fb += kBlockFrames) {
+    bool first = true;
+#pragma unroll 1
+    for (int g = warp; g < wk.nvoices; g += 2 * W) {
+      if (g + W < wk.nvoices) {
+        RestState* const two[2] = {cache + g, cache + g + W};
+        if (first) welsh_rest_block<LFO_AMP, ZERO_A, 2, false>(two, I, lane, tile_row);
+        else welsh_rest_block<LFO_AMP, ZERO_A, 2, true>(two, I, lane, tile_row);
+      } else {
+        RestState* const one[1] = {cache + g};
+        if (first) welsh_rest_block<LFO_AMP, ZERO_A, 1, false>(one, I, lane, tile_row);
+        else welsh_rest_block<LFO_AMP, ZERO_A, 1, true>(one, I, lane, tile_row);
+      }
+      first = false;
+    }
+    __syncthreads();
+    cta_reduce_store<W>(smem_tiles, s_active, wk.out, fb, f0, f_end);
+    __syncthreads();
+  }
+  for (int t = threadIdx.x; t < wk.nvoices; t += 32 * W) {
+    WelshVoice* vp = voices + wk.voice0 + t;
+    vp->s[0] = cache[t].s[0]; vp->s[1] = cache[t].s[1]; vp->s[2] = cache[t].s[2]; vp->s[3] = cache[t].s[3];
+    vp->knot_frame = kNever;
   }
 }
 

@@ -264,6 +264,9 @@ typedef struct {
   uint64_t voice_samples;        /* voice x frame units the voice kernels covered */
   uint64_t h2d_bytes;
   uint64_t d2h_bytes;
+  uint64_t rest_kernel_launches; /* of the voice kernel launches: the resting-voice kernel (time-invariant stretches) */
+  double rest_kernel_ms;         /* ... its share of voice_kernel_ms */
+  uint64_t rest_voice_samples;   /* ... and of voice_samples */
 } gb_stats;
 int gb_get_stats(gb_engine* e, gb_stats* out);
 int gb_reset_stats(gb_engine* e);

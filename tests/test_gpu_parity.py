@@ -213,3 +213,51 @@ def test_cfg5_batch_is_sum_of_its_variants():
     parts = run(256, 0) + run(256, 256)
     assert np.abs(whole).max() > 1e-2
     assert np.abs(whole - parts).max() < 1e-12
+
+
+@pytest.mark.parametrize("vpc", [None, "24", "16"])
+def test_resting_voices_kernel(vpc, monkeypatch):
+    """Chunks in which every voice of a CTA rests (note held, both envelopes at sustain, no events in the
+    chunk) go to welsh_rest_kernel: voice state cached in shared memory across the chunk, two voices per
+    warp.  Instruments with 41 / 16 / 9 voices and forced voices-per-CTA splits cover the paired, the
+    single and the accumulate variants, all four (LFO, flat-oscillator) classes, and the hand-over to and
+    from the general kernel at note-on / note-off chunks."""
+    if vpc:
+        monkeypatch.setenv("GB_VPC", vpc)
+    fast_filt = (0.0, 0.01, 0.6, 0.05)
+    cfgs = [
+        (41, dict(w1=abi.WAVE_PULSE_WIDTH, pw1=0.1, w2=abi.WAVE_SQUARE, mix=0.5, routing=abi.LFO_AMPLITUDE, depth=0.05,
+                  lfo_hz=7.5, filt=fast_filt, amp=(0.02, 0.0, 1.0, 0.0), cutoff_start=scenes.hz_to_pct(40.0), cutoff_end=0.9)),
+        (16, dict(w1=abi.WAVE_SAWTOOTH, w2=abi.WAVE_TRIANGLE, tune2=1.0029, routing=abi.LFO_NONE, filt=fast_filt,
+                  amp=(0.001, 0.02, 0.8, 0.02), ripple=2.5, cutoff_start=0.2, cutoff_end=0.4)),
+        (9, dict(w1=abi.WAVE_TRIANGLE, w2=abi.WAVE_PULSE_WIDTH, pw2=0.8, mix=0.3, cutoff_end=0.0, cutoff_hz=700.0,
+                 routing=abi.LFO_AMPLITUDE, depth=0.5, lfo_hz=11.0, amp=(0.0, 0.01, 0.9, 0.01))),
+        (12, dict(w1=abi.WAVE_SQUARE, w2=abi.WAVE_PULSE_WIDTH, pw2=0.3, routing=abi.LFO_NONE, filt=fast_filt,
+                  amp=(0.0, 0.0, 1.0, 0.0), cutoff_start=0.3, cutoff_end=0.8)),
+    ]
+    frames = 6 * 4096 + 700
+
+    def scene(r):
+        uids = []
+        for i, (nv, c) in enumerate(cfgs):
+            u = r.add_instrument(abi.INST_WELSH, scenes.generic_welsh(voices=nv, gain=0.05, pan=-0.6 + 0.4 * i, **c))
+            r.patch(u, abi.MAIN_MIXER)
+            uids.append(u)
+        r.finalize()
+        for i, (nv, _) in enumerate(cfgs):
+            for v in range(nv):
+                r.note_on(5 + 7 * v + i, uids[i], 30 + v)
+                r.note_off(4 * 4096 + 100 + 3 * v, uids[i], 30 + v)
+        return frames
+
+    o = OracleEngine(48000.0)
+    scene(o)
+    ref = o.render(frames)
+    g = gpu_engine(48000.0, max_block=4096)
+    scene(g)
+    out = g.render(frames)
+    st = g.stats()
+    g.close()
+    assert st.rest_kernel_launches >= 6, "chunks 1..3 should have taken the resting-voice kernel"
+    assert st.rest_voice_samples > 0
+    check(out, ref)
