@@ -51,6 +51,7 @@ def parse_args():
                     help="cfg4 = BASELINE config 4 (headline); cfg5 = batch of one-shot patch variants")
     ap.add_argument("--variants", type=int, default=8192, help="cfg5: variants per GPU (config 5: 65536 over 8 GPUs)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-time-varying", action="store_true", help="skip the secondary always-moving-cutoff leg")
     ap.add_argument("--cpu-sample-voices", type=int, default=256)
     ap.add_argument("--cpu-sample-seconds", type=float, default=4.0)
     return ap.parse_args()
@@ -208,7 +209,7 @@ def run_ours(a) -> None:
             return None
         return parallel.reduce_bus(parallel.device_bus_tensor(eng, local), dst=0)
 
-    def one_step(mode: str):
+    def one_step(mode: str, step_cfg=None):
         """Build config 4 and render it.  Engine construction (allocation, plan, host-side event list)
         is setup and stays outside the timed span; the per-chunk event upload (H2D) and the result
         download (D2H) happen inside the render call, i.e. inside the e2e span."""
@@ -217,7 +218,7 @@ def run_ours(a) -> None:
         if cfg5:
             workloads.build_cfg5(eng, a.variants, first=rank * a.variants)
         else:
-            workloads.build_cfg4(eng, cfg)
+            workloads.build_cfg4(eng, step_cfg or cfg)
         flush.zero_()
         barrier()
         t0 = time.perf_counter()
@@ -246,6 +247,7 @@ def run_ours(a) -> None:
     barrier()
     sampler = ClockSampler(local) if rank == 0 else None
     dev_ms, kern_ms, launches, vlaunches, wall_dev = 0.0, 0.0, 0, 0, 0.0
+    rest_ms, rest_launches, rest_vs = 0.0, 0, 0
     t_region = time.perf_counter()
     for _ in range(a.steps):
         wall, st = one_step("device")
@@ -253,6 +255,9 @@ def run_ours(a) -> None:
         kern_ms += st.voice_kernel_ms
         launches += st.kernel_launches
         vlaunches += st.voice_kernel_launches
+        rest_ms += st.rest_kernel_ms
+        rest_launches += st.rest_kernel_launches
+        rest_vs += st.rest_voice_samples
         wall_dev += wall
     barrier()
     region_s = time.perf_counter() - t_region
@@ -264,6 +269,24 @@ def run_ours(a) -> None:
         d2h += st.d2h_bytes if world == 1 else (frames * 16 if rank == 0 else 0)
     barrier()
     clocks = sampler.stop() if sampler else None
+    # secondary leg (N = 1, config 4 only): the same recipe with the filter-envelope decay stretched past
+    # the note, so the cutoff moves on every frame of every note and no voice ever rests — the
+    # time-varying path (welsh_kernel's knot-interpolated block) on its own
+    tv = None
+    if world == 1 and not cfg5 and not a.no_time_varying:
+        from dataclasses import replace
+        tv_frames = min(frames, 12 * 48000)
+        tv_cfg = replace(cfg, frames=tv_frames, note_off_base=int(tv_frames * 2_400_000 / 2_880_000), filter_decay=120.0)
+        saved = frames
+        frames = tv_frames
+        one_step("device", tv_cfg)
+        t_ms, t_kern, t_vl = 0.0, 0.0, 0
+        for _ in range(2):
+            _, st = one_step("device", tv_cfg)
+            t_ms += st.render_ms; t_kern += st.voice_kernel_ms; t_vl += st.voice_kernel_launches
+        frames = saved
+        tv = {"ms": t_ms / 2, "kern_ms": t_kern / 2, "launches": t_vl // 2, "voice_samples": tv_cfg.voice_samples,
+              "sounding_voice_samples": a.voices * tv_cfg.note_off_base, "seconds": tv_frames / 48000.0}
 
     # max over ranks
     vals = torch.tensor([dev_ms, wall_dev, e2e_wall, kern_ms], dtype=torch.float64, device="cuda")
@@ -289,21 +312,30 @@ def run_ours(a) -> None:
         except OSError:
             pass
         hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
-        vs_per_launch = per_rank_vs * a.steps / max(vlaunches, 1)
+        # Dominant kernel.  Config 4: welsh_rest_kernel (resting voices; 90+ % of the step) — its launches and
+        # the voice-samples they covered are counted by the engine.  Otherwise: all voice-kernel launches.
+        use_rest = (not cfg5) and rest_launches > 0 and rest_ms > 0.5 * kern_ms
+        if use_rest:
+            k_ms, k_launches, k_vs = rest_ms, rest_launches, rest_vs
+            k_name = "welsh_rest_kernel<8,lfo,flat>"
+        else:
+            k_ms, k_launches, k_vs = kern_ms, vlaunches, per_rank_vs * a.steps
+            k_name = "welsh_kernel<8,2>" + (" + fm_kernel<8>" if cfg5 else "")
+        vs_per_launch = k_vs / max(k_launches, 1)
         frames_per_launch = vs_per_launch / (a.variants if cfg5 else a.voices)
         ctas_per_launch = 2 * min(128, a.voices)   # config 4: each 32-voice instrument is split over 2 CTAs
-        launch_s = kern_ms * 1e-3 / max(vlaunches, 1)
+        launch_s = k_ms * 1e-3 / max(k_launches, 1)
         # cfg5: half the variants are FM voices (67 FLOP), launched as a second kernel per chunk
         flop_per_vs = 0.5 * (workloads.W_VOICE_FLOP + workloads.W_FM_FLOP) if cfg5 else workloads.W_VOICE_FLOP
         achieved_tflops = flop_per_vs * vs_per_launch / launch_s / 1e12
-        # DRAM traffic of the dominant kernel: from the committed ncu --set full capture (cannot be measured live),
-        # scaled to this run's voice-samples per launch
-        traffic = None
+        # DRAM traffic and executed-instruction facts of the dominant kernel: from the committed ncu --set full
+        # capture (cannot be measured live), traffic scaled to this run's voice-samples per launch
+        traffic, prof = None, {}
         try:
             with open(os.path.join(ROOT, "profiles", "r1_welsh_traffic.json")) as f:
-                tj = json.load(f)
+                prof = json.load(f)
             if not cfg5:
-                traffic = tj["dram_bytes_per_launch"] * vs_per_launch / tj["voice_samples_per_launch"]
+                traffic = prof["dram_bytes_per_launch"] * vs_per_launch / prof["voice_samples_per_launch"]
         except (OSError, KeyError, ValueError):
             pass
         # algorithmic HBM bytes: 16 B stereo f64 out per frame per CTA partial + voice state in/out
@@ -328,7 +360,7 @@ def run_ours(a) -> None:
             "e2e": {"value": e2e_value, "unit": UNIT, "ms_per_step": e2e_wall / a.steps * 1e3,
                     "h2d_bytes_per_step": int(h2d // a.steps), "d2h_bytes_per_step": int(d2h // a.steps)},
             "roofline": {
-                "bound": "fp64", "kernel": "welsh_kernel<8,2>" + (" + fm_kernel<8>" if cfg5 else ""), "achieved": achieved_tflops, "peak": fp64_peak,
+                "bound": "fp64", "kernel": k_name, "achieved": achieved_tflops, "peak": fp64_peak,
                 "unit": "TFLOP/s", "frac": achieved_tflops / fp64_peak, "traffic": traffic,
                 "traffic_unit": "DRAM bytes per launch (ncu dram__bytes_read+write, profiles/r1_welsh_traffic.json)",
                 "algorithmic_bytes_per_launch": 16.0 * frames_per_launch * ctas_per_launch if not cfg5 else None,
@@ -336,13 +368,33 @@ def run_ours(a) -> None:
                                "MEASURED_PEAKS.json has no FP64 entry",
                 "algorithmic_flop_per_voice_sample": flop_per_vs,
                 "voice_samples_per_launch": vs_per_launch, "launch_ms": launch_s * 1e3,
-                "kernel_share_of_step": kern_ms * 1e-3 / a.steps / step_s if world == 1 else None,
+                "kernel_share_of_step": k_ms * 1e-3 / a.steps / step_s if world == 1 else None,
+                "all_voice_kernels_share_of_step": kern_ms * 1e-3 / a.steps / step_s if world == 1 else None,
+                "note": "achieved counts the ALGORITHMIC 150 FLOP per voice-sample of the reference's per-frame loop "
+                        "(SURVEY.md 8d). While a voice rests (envelopes at sustain) its cutoff does not move, so this "
+                        "kernel takes the coefficient sets and scan maps from per-instrument tables instead of "
+                        "re-deriving them per frame: it executes fewer FP64 instructions than the algorithmic count, "
+                        "which is why frac can exceed what the pipe utilisation alone would give; see "
+                        "executed_fp64_instr_per_voice_sample / fp64_pipe_active_pct (ncu) and the time_varying leg.",
+                "executed_fp64_instr_per_voice_sample": prof.get("fp64_instr_per_voice_sample"),
+                "fp64_pipe_active_pct": prof.get("fp64_pipe_active_pct"),
+                "issue_active_pct": prof.get("issue_active_pct"),
                 "fp32_peak_tflops": fp32_peak,
                 "hbm": {"peak_gbs": hbm_peak, "peak_source": "MEASURED_PEAKS.json" if peaks else "fallback 6650"},
             },
             "clocks": clocks,
             "timed_region_s": region_s,
         }
+        if tv:
+            tv_launch_s = tv["kern_ms"] * 1e-3 / max(tv["launches"], 1)
+            tv_ach = workloads.W_VOICE_FLOP * tv["voice_samples"] / max(tv["launches"], 1) / tv_launch_s / 1e12
+            out["time_varying"] = {
+                "what": f"config-4 recipe, {tv['seconds']:g} s, filter-envelope decay stretched to 120 s: the cutoff moves "
+                        "on every frame of every note, no voice rests (welsh_kernel, knot-interpolated coefficients)",
+                "value": tv["voice_samples"] / (tv["ms"] * 1e-3), "unit": UNIT, "ms_per_step": tv["ms"],
+                "roofline": {"bound": "fp64", "kernel": "welsh_kernel<8,2>", "achieved": tv_ach, "peak": fp64_peak,
+                             "unit": "TFLOP/s", "frac": tv_ach / fp64_peak, "launch_ms": tv_launch_s * 1e3},
+            }
         if not a.no_cpu_baseline:
             out["cpu_baseline"] = cpu_baseline_single(a.cpu_sample_voices, a.cpu_sample_seconds)
         print(json.dumps(out), flush=True)

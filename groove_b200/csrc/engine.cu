@@ -38,26 +38,50 @@ constexpr uint32_t kDefaultMaxBlock = 1u << 16;
 
 std::string g_create_err;
 
+// Host staging is rotated over kStageSlots chunks so that the host can enqueue chunk i+1 .. i+3 while
+// chunk i's uploads are still in flight (no stream synchronisation per chunk).
+constexpr int kStageSlots = 4;
+
 template <typename T>
-struct DevBuf {  // growable device array with a pinned host mirror for uploads
+struct DevBuf {  // growable device array with pinned host mirrors (one per staging slot) for uploads
   T* d = nullptr;
-  T* h = nullptr;
+  T* h = nullptr;  // the mirror of the current staging slot
+  T* hs[kStageSlots] = {nullptr, nullptr, nullptr, nullptr};
   size_t cap = 0;
+  int slot = 0;
   ~DevBuf() { release(); }
   void release() {
     if (d) cudaFree(d);
-    if (h) cudaFreeHost(h);
+    for (T*& p : hs) {
+      if (p) cudaFreeHost(p);
+      p = nullptr;
+    }
     d = nullptr; h = nullptr; cap = 0;
+  }
+  void use_slot(int s) {
+    slot = s;
+    h = hs[s];
   }
   bool reserve(size_t n) {
     if (n <= cap) return true;
     size_t ncap = std::max<size_t>(n, cap * 2 + 16);
-    T* nd = nullptr; T* nh = nullptr;
-    if (cudaMalloc(&nd, ncap * sizeof(T)) != cudaSuccess) return false;
-    if (cudaMallocHost(&nh, ncap * sizeof(T)) != cudaSuccess) { cudaFree(nd); return false; }
+    cudaDeviceSynchronize();  // growth is rare; uploads from the old mirrors may still be in flight
+    T* nd = nullptr;
+    T* nh[kStageSlots] = {nullptr, nullptr, nullptr, nullptr};
+    bool ok = cudaMalloc(&nd, ncap * sizeof(T)) == cudaSuccess;
+    for (int i = 0; ok && i < kStageSlots; ++i) ok = cudaMallocHost(&nh[i], ncap * sizeof(T)) == cudaSuccess;
+    if (!ok) {
+      if (nd) cudaFree(nd);
+      for (T* p : nh)
+        if (p) cudaFreeHost(p);
+      return false;
+    }
     if (d) cudaFree(d);
-    if (h) cudaFreeHost(h);
-    d = nd; h = nh; cap = ncap;
+    for (int i = 0; i < kStageSlots; ++i) {
+      if (hs[i]) cudaFreeHost(hs[i]);
+      hs[i] = nh[i];
+    }
+    d = nd; cap = ncap; h = hs[slot];
     return true;
   }
 };
@@ -290,6 +314,11 @@ struct gb_engine {
   double sr = 44100.0;
   uint32_t max_block = kDefaultMaxBlock;
   cudaStream_t stream = nullptr;
+  cudaStream_t copy_stream = nullptr;               // device -> host result copies, overlapped with the next chunks
+  cudaEvent_t stage_done[kStageSlots] = {};          // chunk i's work enqueued on `stream` (guards staging slot i % kStageSlots)
+  cudaEvent_t d2d_done[kStageSlots] = {}, d2h_done[kStageSlots] = {};
+  double2* ring = nullptr;                           // pinned: kStageSlots x max_block frames (host-buffer renders)
+  uint64_t chunk_seq = 0;
   bool finalized = false;
   int64_t pos = 0;
   uint32_t next_uid = 2;
@@ -729,8 +758,15 @@ int gb_create(const gb_config* cfg, gb_engine** out) {
   cudaDeviceProp prop;
   if (cudaGetDeviceProperties(&prop, e->device) == cudaSuccess) e->num_sms = prop.multiProcessorCount;
   if (const char* v = getenv("GB_CTA_MULT")) e->cta_target_mult = std::max(1, atoi(v));
-  if (cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking) != cudaSuccess)
+  if (cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking) != cudaSuccess ||
+      cudaStreamCreateWithFlags(&e->copy_stream, cudaStreamNonBlocking) != cudaSuccess)
     return fail(nullptr, GB_ECUDA, "cudaStreamCreate failed");
+  for (int i = 0; i < kStageSlots; ++i) {
+    if (cudaEventCreateWithFlags(&e->stage_done[i], cudaEventDisableTiming) != cudaSuccess ||
+        cudaEventCreateWithFlags(&e->d2d_done[i], cudaEventDisableTiming) != cudaSuccess ||
+        cudaEventCreateWithFlags(&e->d2h_done[i], cudaEventDisableTiming) != cudaSuccess)
+      return fail(nullptr, GB_ECUDA, "cudaEventCreate failed");
+  }
   auto mixer = std::make_unique<Node>();
   mixer->uid = GB_MAIN_MIXER;
   mixer->kind = GB_FX_MIXER;
@@ -743,6 +779,14 @@ void gb_destroy(gb_engine* e) {
   if (!e) return;
   cudaSetDevice(e->device);
   if (e->stream) cudaStreamSynchronize(e->stream);
+  if (e->copy_stream) cudaStreamSynchronize(e->copy_stream);
+  for (int i = 0; i < kStageSlots; ++i) {
+    if (e->stage_done[i]) cudaEventDestroy(e->stage_done[i]);
+    if (e->d2d_done[i]) cudaEventDestroy(e->d2d_done[i]);
+    if (e->d2h_done[i]) cudaEventDestroy(e->d2h_done[i]);
+  }
+  if (e->ring) cudaFreeHost(e->ring);
+  if (e->copy_stream) cudaStreamDestroy(e->copy_stream);
   for (void* p : e->allocations) cudaFree(p);
   if (e->d_full) cudaFree(e->d_full);
   if (e->d_pcm) cudaFree(e->d_pcm);
@@ -1151,6 +1195,11 @@ struct ControlPoint {
 // e->events[0 .. n_ev).
 int render_chunk(gb_engine* e, int frames, size_t n_ev) {
   const int64_t f0 = e->pos;
+  // staging slot of this chunk: wait until the chunk that used it kStageSlots chunks ago has been consumed
+  const int slot = (int)(e->chunk_seq % kStageSlots);
+  if (e->chunk_seq >= (uint64_t)kStageSlots) CUDA_TRY(e, cudaEventSynchronize(e->stage_done[slot]));
+  e->widx.use_slot(slot); e->wev.use_slot(slot); e->fev.use_slot(slot); e->wev_off.use_slot(slot);
+  e->fev_off.use_slot(slot); e->plays.use_slot(slot); e->segs.use_slot(slot);
   // ---- 1. resolve events ----
   std::vector<std::vector<VoiceEvent>> wlists((size_t)e->n_wvoice), flists((size_t)e->n_fvoice);
   std::map<Node*, std::vector<ControlPoint>> controls;
@@ -1517,6 +1566,8 @@ int render_chunk(gb_engine* e, int frames, size_t n_ev) {
   Node* root = find(e, GB_MAIN_MIXER);
   e->last_out = root->buf;
   e->last_frames = (size_t)frames;
+  CUDA_TRY(e, cudaEventRecord(e->stage_done[slot], e->stream));
+  e->chunk_seq++;
   e->pos += frames;
   return 0;
 }
@@ -1529,18 +1580,34 @@ int render_impl(gb_engine* e, void* out, size_t frames, size_t* done, OutMode mo
   if (!e->finalized) return fail(e, GB_ESTATE, "engine is not finalized");
   if (frames && !out && mode != OUT_DEVICE) return fail(e, GB_EINVAL, "null output buffer");
   cudaSetDevice(e->device);
-  if (mode == OUT_DEVICE || mode == OUT_PCM16) {
-    if (frames > e->full_cap) {
-      if (e->d_full) cudaFree(e->d_full);
-      e->d_full = nullptr;
-      e->full_cap = 0;
-      CUDA_TRY(e, cudaMalloc(&e->d_full, std::max<size_t>(frames, 1) * sizeof(double2)));
-      e->full_cap = frames;
-    }
+  // every mode gathers the chunks in d_full (device); host-buffer renders stream it back from there
+  if (frames > e->full_cap) {
+    CUDA_TRY(e, cudaStreamSynchronize(e->stream));
+    CUDA_TRY(e, cudaStreamSynchronize(e->copy_stream));
+    if (e->d_full) cudaFree(e->d_full);
+    e->d_full = nullptr;
+    e->full_cap = 0;
+    CUDA_TRY(e, cudaMalloc(&e->d_full, std::max<size_t>(frames, 1) * sizeof(double2)));
+    e->full_cap = frames;
   }
+  if (mode == OUT_F64 && !e->ring)
+    CUDA_TRY(e, cudaMallocHost(&e->ring, (size_t)kStageSlots * e->max_block * sizeof(double2)));
   size_t produced = 0;
   const bool call_timed = span_begin(e, 2);
   const size_t call_span = e->spans.size() - 1;
+  // Chunks are enqueued without waiting for each other.  For host-buffer renders chunk i's result goes
+  // d_full -> pinned ring slot on the copy stream while chunks i+1.. compute, and the host moves a ring
+  // slot into the caller's (pageable) buffer just before the slot is reused.
+  struct Pending { size_t off, n; int slot; };
+  std::vector<Pending> pending;
+  uint64_t out_seq = 0;
+  auto drain_one = [&]() -> int {
+    const Pending p = pending.front();
+    pending.erase(pending.begin());
+    CUDA_TRY(e, cudaEventSynchronize(e->d2h_done[p.slot]));
+    memcpy((double*)out + 2 * p.off, e->ring + (size_t)p.slot * e->max_block, p.n * sizeof(double2));
+    return 0;
+  };
   while (produced < frames) {
     const int64_t f0 = e->pos;
     int64_t limit = (int64_t)std::min<size_t>(frames - produced, e->max_block);
@@ -1554,18 +1621,26 @@ int render_impl(gb_engine* e, void* out, size_t frames, size_t* done, OutMode mo
     int rc = render_chunk(e, (int)limit, n_ev);
     if (rc) return rc;
     const size_t n = (size_t)limit;
+    CUDA_TRY(e, cudaMemcpyAsync(e->d_full + produced, e->last_out, n * sizeof(double2), cudaMemcpyDeviceToDevice,
+                                e->stream));
     if (mode == OUT_F64) {
-      CUDA_TRY(e, cudaMemcpyAsync((double*)out + 2 * produced, e->last_out, n * sizeof(double2), cudaMemcpyDeviceToHost,
-                                  e->stream));
-      CUDA_TRY(e, cudaStreamSynchronize(e->stream));
+      const int rslot = (int)(out_seq++ % kStageSlots);
+      if (pending.size() == (size_t)kStageSlots && (rc = drain_one())) return rc;
+      CUDA_TRY(e, cudaEventRecord(e->d2d_done[rslot], e->stream));
+      CUDA_TRY(e, cudaStreamWaitEvent(e->copy_stream, e->d2d_done[rslot], 0));
+      CUDA_TRY(e, cudaMemcpyAsync(e->ring + (size_t)rslot * e->max_block, e->d_full + produced, n * sizeof(double2),
+                                  cudaMemcpyDeviceToHost, e->copy_stream));
+      CUDA_TRY(e, cudaEventRecord(e->d2h_done[rslot], e->copy_stream));
+      pending.push_back({produced, n, rslot});
       e->stats.d2h_bytes += n * sizeof(double2);
-    } else {
-      CUDA_TRY(e, cudaMemcpyAsync(e->d_full + produced, e->last_out, n * sizeof(double2), cudaMemcpyDeviceToDevice,
-                                  e->stream));
-      CUDA_TRY(e, cudaStreamSynchronize(e->stream));
     }
     produced += n;
   }
+  while (!pending.empty()) {
+    int rc = drain_one();
+    if (rc) return rc;
+  }
+  if (mode != OUT_PCM16) CUDA_TRY(e, cudaStreamSynchronize(e->stream));
   if (mode == OUT_PCM16 && frames) {
     if (frames > e->pcm_cap) {
       if (e->d_pcm) cudaFree(e->d_pcm);

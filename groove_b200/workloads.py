@@ -26,7 +26,7 @@ def hz_to_pct(hz: float) -> float:
     return max(0.0, min(1.0, math.log(hz / 25.0) / LOG800))
 
 
-def cello_params(voices: int, gain: float, pan: float) -> abi.WelshParams:
+def cello_params(voices: int, gain: float, pan: float, filter_decay: float = 3.29) -> abi.WelshParams:
     """assets/patches/welsh/cello.json mapped as settings/src/patches.rs:87-170 does (release := decay)."""
     p = abi.WelshParams()
     p.oscillator_1 = abi.osc(abi.WAVE_PULSE_WIDTH, 0.1)
@@ -41,7 +41,7 @@ def cello_params(voices: int, gain: float, pan: float) -> abi.WelshParams:
     p.filter_passband_ripple = 0.707
     p.filter_cutoff_start = hz_to_pct(40.0)
     p.filter_cutoff_end = 0.9
-    p.filter_envelope = abi.env(0.0, 3.29, 0.78, 3.29)
+    p.filter_envelope = abi.env(0.0, filter_decay, 0.78, filter_decay)
     p.voice_dca = abi.DcaParams(1.0, 0.0)
     p.dca = abi.DcaParams(gain, pan)
     p.voices = voices
@@ -56,6 +56,8 @@ class Cfg4:
     note_off_base: int = 2_400_000
     groups: int = 128          # instruments; voice i belongs to instrument i mod groups
     voice_offset: int = 0      # first global voice index (multi-GPU shards use rank * total_voices)
+    filter_decay: float = 3.29 # cello.json's filter-envelope decay (s); bench.py's "time_varying" leg stretches it
+                               # past the note length so that the cutoff never rests
 
     @property
     def voice_samples(self) -> int:
@@ -70,7 +72,7 @@ def build_cfg4(r: abi.Renderer, cfg: Cfg4) -> int:
     for q in range(cfg.groups):
         i0 = cfg.voice_offset + q
         pan = -1.0 + 2.0 * (i0 % 64) / 63.0
-        u = r.add_instrument(abi.INST_WELSH, cello_params(per, 1.0 / 4096.0, pan))
+        u = r.add_instrument(abi.INST_WELSH, cello_params(per, 1.0 / 4096.0, pan, cfg.filter_decay))
         r.patch(u, abi.MAIN_MIXER)
         uids.append(u)
     r.finalize()
