@@ -26,6 +26,8 @@ FX_DELAY, FX_CHORUS, FX_REVERB = 37, 38, 39
 FX_LOW_PASS_12DB, FX_HIGH_PASS_12DB, FX_BAND_PASS_12DB, FX_BAND_STOP_12DB = 40, 41, 42, 43
 FX_ALL_PASS_12DB, FX_PEAKING_EQ_12DB, FX_LOW_SHELF_12DB, FX_HIGH_SHELF_12DB = 44, 45, 46, 47
 FX_LOW_PASS_24DB = 48
+FX_SIGNAL_PASSTHROUGH = 49
+CONTROL_PERIOD = 64
 BIQUAD_KINDS = tuple(range(40, 48))
 
 WAVE_NONE, WAVE_SINE, WAVE_SQUARE, WAVE_PULSE_WIDTH, WAVE_TRIANGLE = 0, 1, 2, 3, 4
@@ -139,7 +141,7 @@ ABI_SYMBOLS = (
     "create", "destroy", "last_error", "add_instrument", "add_effect", "load_sample", "patch", "finalize",
     "push_events", "render_block", "render_pcm16", "render_device", "last_device_buffer", "read_last", "position",
     "save_state",
-    "restore_state", "get_stats", "reset_stats", "set_timing", "measure_fma_peak",
+    "restore_state", "get_stats", "reset_stats", "set_timing", "measure_fma_peak", "link_control",
 )
 
 
@@ -259,6 +261,10 @@ class Renderer:
         """Patch a source -> ... -> sink cable (settings/src/songs.rs:134-164)."""
         for a, b in zip(uids[:-1], uids[1:]):
             self.patch(a, b)
+
+    def link_control(self, source: int, target: int, control_index: int):
+        """Control link from a signal-passthrough node (sidechain): include/groove_b200.h, gb_link_control."""
+        self._check(self._f("link_control")(self._h, source, target, control_index))
 
     def finalize(self):
         self._check(self._f("finalize")(self._h))

@@ -342,6 +342,14 @@ struct gb_engine {
   DevBuf<WarpItem> witems, fitems;  // solo-warp work items (instruments with fewer voices than a CTA has warps)
   int n_wwork = 0, n_fwork = 0;
   int n_wwork_grouped = 0;  // wwork[0 .. n_wwork_grouped) are grouped CTAs, the rest solo CTAs
+  struct Link {                   // gb_link_control: signal-passthrough source -> effect parameter
+    uint32_t src, dst;
+    int index;
+    SegParam* d_table = nullptr;  // the target's parameter table of the current chunk (device-built)
+    double* d_state = nullptr;    // 2 x {control value, last l, last r, have-last}: ping-pong per chunk
+    int cur = 0;
+  };
+  std::vector<Link> links;
   std::vector<Node*> wwork_node;  // instrument of each grouped Welsh CTA
   DevBuf<int> widx;               // per chunk: grouped Welsh CTAs sorted into resting (4 variants) and general
   DevBuf<VoiceEvent> wev, fev;
@@ -685,7 +693,7 @@ void seg_values(gb_engine* e, const Node* n, double* v) {
 int run_effect(gb_engine* e, Node* n, const SourceList& src, int frames, const SegParam* segs, int nseg,
                int64_t chunk_pos) {
   switch (n->kind) {
-    case GB_FX_MIXER: {
+    case GB_FX_MIXER: case GB_FX_SIGNAL_PASSTHROUGH: {
       Launch l(e, false);
       pointwise_kernel<<<cdiv(frames, 256), 256, 0, e->stream>>>(src, n->buf, frames, OP_SUM, segs, nseg);
     } break;
@@ -851,7 +859,7 @@ int gb_add_effect(gb_engine* e, int32_t kind, const void* params, size_t size, u
   n->kind = kind;
 #define NEED(T) if (!params || size != sizeof(T)) return fail(e, GB_EINVAL, "bad effect params size for kind %d", kind)
   switch (kind) {
-    case GB_FX_MIXER: break;
+    case GB_FX_MIXER: case GB_FX_SIGNAL_PASSTHROUGH: break;
     case GB_FX_GAIN: NEED(gb_gain_params); n->p[0] = ((const gb_gain_params*)params)->ceiling; break;
     case GB_FX_LIMITER:
       NEED(gb_limiter_params);
@@ -966,10 +974,48 @@ int gb_patch(gb_engine* e, uint32_t src, uint32_t dst) {
   return 0;
 }
 
+int gb_link_control(gb_engine* e, uint32_t src, uint32_t dst, int32_t index) {
+  if (!e) return GB_EINVAL;
+  if (e->finalized) return fail(e, GB_ESTATE, "engine is finalized");
+  Node* s = find(e, src);
+  Node* d = find(e, dst);
+  if (!s || !d) return fail(e, GB_ENOENT, "unknown uid");
+  if (s->kind != GB_FX_SIGNAL_PASSTHROUGH) return fail(e, GB_EINVAL, "link source is not a signal-passthrough node");
+  if (!(d->kind == GB_FX_GAIN || d->kind == GB_FX_LIMITER || d->kind == GB_FX_COMPRESSOR) || !effect_accepts(d, index))
+    return fail(e, GB_EINVAL, "link target must be a gain, limiter or compressor parameter");
+  for (auto& l : e->links)
+    if (l.dst == dst) return fail(e, GB_EINVAL, "target already has a control link");
+  gb_engine::Link l;
+  l.src = src; l.dst = dst; l.index = index;
+  e->links.push_back(l);
+  return 0;
+}
+
 int gb_finalize(gb_engine* e) {
   if (!e) return GB_EINVAL;
   if (e->finalized) return fail(e, GB_ESTATE, "engine is already finalized");
   cudaSetDevice(e->device);
+  // Scheduling edges: a link target must run after its source.  Only sources that the main mixer reaches
+  // through patch cables count (unpatched entities never render, orchestrator.rs:378-430).
+  std::map<uint32_t, std::vector<uint32_t>> children;
+  {
+    std::map<uint32_t, bool> reach;
+    std::vector<uint32_t> todo{GB_MAIN_MIXER};
+    reach[GB_MAIN_MIXER] = true;
+    while (!todo.empty()) {
+      Node* n = find(e, todo.back());
+      todo.pop_back();
+      if (!n) continue;
+      for (uint32_t c : n->sources)
+        if (!reach[c]) { reach[c] = true; todo.push_back(c); }
+    }
+    for (auto& kv : e->nodes) {
+      std::vector<uint32_t>& ch = children[kv.first];
+      for (auto& l : e->links)
+        if (l.dst == kv.first && reach[l.src] && reach[l.dst]) ch.push_back(l.src);
+      for (uint32_t c : kv.second->sources) ch.push_back(c);
+    }
+  }
   // post-order DFS from the main mixer: sources before consumers; detects cycles.
   std::map<uint32_t, int> color;
   std::vector<std::pair<Node*, size_t>> st;
@@ -979,17 +1025,18 @@ int gb_finalize(gb_engine* e) {
   e->plan.clear();
   while (!st.empty()) {
     auto& top = st.back();
-    if (top.second >= top.first->sources.size()) {
+    const std::vector<uint32_t>& kids = children[top.first->uid];
+    if (top.second >= kids.size()) {
       color[top.first->uid] = 2;
       top.first->order = (int)e->plan.size();
       e->plan.push_back(top.first);
       st.pop_back();
       continue;
     }
-    uint32_t cu = top.first->sources[top.second++];
+    uint32_t cu = kids[top.second++];
     Node* c = find(e, cu);
     if (!c) continue;
-    if (color[cu] == 1) return fail(e, GB_EGRAPH, "patch graph has a cycle");
+    if (color[cu] == 1) return fail(e, GB_EGRAPH, "patch graph (with control links) has a cycle");
     if (color[cu] == 0) {
       color[cu] = 1;
       st.push_back({c, 0});
@@ -1031,6 +1078,16 @@ int gb_finalize(gb_engine* e) {
           return rc;
       }
     }
+  }
+  for (auto& l : e->links) {
+    Node* sn = find(e, l.src);
+    Node* dn = find(e, l.dst);
+    if (!sn || !dn || sn->order < 0 || dn->order < 0) continue;
+    int rc = dev_alloc(e, &l.d_table, mb / GB_CONTROL_PERIOD + 3);
+    if (rc) return rc;
+    if ((rc = dev_alloc(e, &l.d_state, 8))) return rc;
+    const double init[8] = {dn->p[l.index], 0.0, 0.0, 0.0, dn->p[l.index], 0.0, 0.0, 0.0};
+    CUDA_TRY(e, cudaMemcpy(l.d_state, init, sizeof init, cudaMemcpyHostToDevice));
   }
   // voice state: every voice starts idle
   e->n_wvoice = wv;
@@ -1322,10 +1379,17 @@ int render_chunk(gb_engine* e, int frames, size_t n_ev) {
   for (Node* n : e->plan) {
     const bool inst = n->kind == GB_INST_WELSH || n->kind == GB_INST_FM;
     if (n->is_inst && !inst) continue;
-    if (!n->is_inst && (n->kind == GB_FX_MIXER || n->kind == GB_FX_DELAY)) continue;  // no parameters
+    if (!n->is_inst && (n->kind == GB_FX_MIXER || n->kind == GB_FX_DELAY || n->kind == GB_FX_SIGNAL_PASSTHROUGH))
+      continue;  // no parameters
     std::vector<ControlPoint> cps;
     auto it = controls.find(n);
     if (it != controls.end()) cps = it->second;
+    bool linked = false;
+    for (auto& l : e->links) linked |= l.dst == n->uid && l.d_table;
+    if (linked) {  // the table of a link target is built on the device (plan walk); host points apply up front
+      for (auto& cp : cps) apply_cp(n, cp);
+      continue;
+    }
     std::stable_sort(cps.begin(), cps.end(), [](const ControlPoint& a, const ControlPoint& b) { return a.t < b.t; });
     size_t ci = 0;
     while (ci < cps.size() && cps[ci].t <= 0) apply_cp(n, cps[ci++]);  // events at the chunk start
@@ -1553,7 +1617,26 @@ int render_chunk(gb_engine* e, int frames, size_t n_ev) {
       }
       continue;
     }
-    rc = run_effect(e, n, src, frames, segs, nseg, f0);
+    const SegParam* use_segs = segs;
+    int use_nseg = nseg;
+    for (auto& l : e->links) {
+      if (l.dst != n->uid || !l.d_table) continue;
+      Node* sn = find(e, l.src);
+      const int first = (int)((GB_CONTROL_PERIOD - f0 % GB_CONTROL_PERIOD) % GB_CONTROL_PERIOD);
+      const int nb = first < frames ? (frames - first + GB_CONTROL_PERIOD - 1) / GB_CONTROL_PERIOD : 0;
+      const int ns = nb + (first == 0 ? 0 : 1);
+      SegParam base;
+      base.t0 = 0; base.pad = 0;
+      seg_values(e, n, base.v);
+      Launch lk(e, false);
+      sidechain_table_kernel<<<cdiv(std::max(ns, 1), 128), 128, 0, e->stream>>>(
+          sn->buf, frames, first, GB_CONTROL_PERIOD, std::max(ns, 1), base, l.index, l.d_table, l.d_state + 4 * l.cur,
+          l.d_state + 4 * (l.cur ^ 1), (long long)f0);
+      l.cur ^= 1;
+      use_segs = l.d_table;
+      use_nseg = std::max(ns, 1);
+    }
+    rc = run_effect(e, n, src, frames, use_segs, use_nseg, f0);
     if (rc) return rc;
     if (n->kind == GB_FX_CHORUS && n->delay_frames > 0) {
       Launch l(e, false);
@@ -1754,6 +1837,8 @@ int for_each_state_region(gb_engine* e, F&& fn) {
       }
     }
   }
+  for (auto& l : e->links)  // the current half of the ping-pong link state
+    if (l.d_state && (rc = fn(l.d_state + 4 * l.cur, 4 * sizeof(double)))) return rc;
   return 0;
 }
 }  // namespace

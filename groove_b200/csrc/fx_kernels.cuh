@@ -90,6 +90,46 @@ __global__ void __launch_bounds__(256) pointwise_kernel(SourceList src, double2*
   else out[t] = make_double2(op_apply(op, v.x, sp.v[0], sp.v[1]), op_apply(op, v.y, sp.v[0], sp.v[1]));
 }
 
+// Sidechain (signal-passthrough source -> effect parameter, gb_link_control): the target's parameter table
+// of this chunk is built on the device from the source's output.  Control boundaries are the absolute
+// frames that are multiples of `period`; the value taken at boundary t is min(1, |mono|) of the source at
+// t - 1 (for t = 0: the last frame of the previous chunk, carried in `state_in`).  state = {current
+// control value, last l, last r, have-last flag}; `state_out` receives the values for the next chunk.
+// first = chunk-relative frame of the first boundary (0 .. period-1); nseg = segments to write.
+__global__ void __launch_bounds__(128) sidechain_table_kernel(const double2* __restrict__ src, int frames, int first,
+                                                               int period, int nseg, SegParam base, int slot,
+                                                               SegParam* __restrict__ table,
+                                                               const double* __restrict__ state_in,
+                                                               double* __restrict__ state_out, long long f0) {
+  const int k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= nseg) return;
+  SegParam sp = base;
+  double value;
+  if (k == 0) {
+    sp.t0 = 0;
+    value = state_in[0];
+    if (first == 0 && f0 > 0 && state_in[3] != 0.0) {
+      const double m = fabs(0.5 * (state_in[1] + state_in[2]));
+      value = m > 1.0 ? 1.0 : m;
+    }
+  } else {
+    const int t = first + (k - (first == 0 ? 0 : 1)) * period;
+    sp.t0 = t;
+    const double2 v = src[t - 1];
+    const double m = fabs(0.5 * (v.x + v.y));
+    value = m > 1.0 ? 1.0 : m;
+  }
+  sp.v[slot] = value;
+  table[k] = sp;
+  if (k == nseg - 1) {
+    const double2 last = src[frames - 1];
+    state_out[0] = value;
+    state_out[1] = last.x;
+    state_out[2] = last.y;
+    state_out[3] = 1.0;
+  }
+}
+
 // out[t] = sum over a device-resident pointer table, left to right (any number of sources).
 __global__ void __launch_bounds__(256) sum_table_kernel(const double2* const* __restrict__ ptrs, int n,
                                                          double2* __restrict__ out, int frames) {

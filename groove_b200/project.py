@@ -15,7 +15,8 @@ Schema drift across the reference's fixtures is accepted: `[4,4]
 time signatures, `flat: [v]` or `flat: {value: v}`, `min/max` or `minimum/maximum`, `bits` or
 `bits-to-crush`, `delay` or `seconds`.  Event sources compiled: the pattern sequencer, control trips,
 the LFO controller (through `controls` links) and the arpeggiator.  The signal-passthrough (sidechain)
-controller needs an audio-rate control bus inside the engine and is reported in `Plan.skipped`.
+controller is not an event source: it becomes a pass-through node in its patch chain plus a control link
+(`Plan.links`) that the engine evaluates from the rendered signal (`gb_link_control`).
 """
 from __future__ import annotations
 
@@ -181,12 +182,13 @@ class Plan:
     cables: List[List[str]]
     events: List[Tuple[int, str, int, int, int, float]]   # (frame, uvid, type, a, b, value)
     skipped: List[str] = field(default_factory=list)
+    links: List[Tuple[str, str, int]] = field(default_factory=list)   # (source uvid, target uvid, control index)
 
     def to_json(self) -> str:
         return json.dumps({
             "title": self.title, "sample_rate": self.sample_rate, "bpm": self.bpm, "frames": self.frames,
             "entities": [e.__dict__ for e in self.entities], "cables": self.cables, "events": self.events,
-            "skipped": self.skipped}, indent=None, separators=(",", ":"))
+            "skipped": self.skipped, "links": self.links}, indent=None, separators=(",", ":"))
 
     @staticmethod
     def from_json(text: str) -> "Plan":
@@ -194,7 +196,7 @@ class Plan:
         ents = [Entity(uvid=e["uvid"], role=e["role"], kind=e["kind"], params=e["params"], midi_in=e["midi_in"],
                        samples=[tuple(s) for s in e["samples"]]) for e in d["entities"]]
         return Plan(d["title"], d["sample_rate"], d["bpm"], d["frames"], ents, d["cables"],
-                    [tuple(e) for e in d["events"]], d.get("skipped", []))
+                    [tuple(e) for e in d["events"]], d.get("skipped", []), [tuple(l) for l in d.get("links", [])])
 
 
 def _osc_tune(tune) -> Tuple[float, Optional[int]]:
@@ -304,7 +306,7 @@ def _env4(e: Optional[dict], default=(0.0, 0.0, 1.0, 0.0)) -> List[float]:
 
 def effect_struct(kind: int, p: dict):
     g = lambda *names, default=0.0: next((float(p[n]) for n in names if n in p), default)
-    if kind == abi.FX_MIXER:
+    if kind in (abi.FX_MIXER, abi.FX_SIGNAL_PASSTHROUGH):
         return None
     if kind == abi.FX_GAIN:
         return abi.GainParams(g("ceiling", default=1.0))
@@ -390,9 +392,13 @@ class ProjectLoader:
                 args = cbody[1] if isinstance(cbody, list) and len(cbody) > 1 else {}
                 if ckind in ("lfo", "arpeggiator"):
                     controllers[uvid] = (ckind, midi, args)
+                elif ckind == "signal-passthrough-controller":
+                    # patched into a chain like an effect (settings/src/controllers.rs:110-111,181-187); the
+                    # engine evaluates its control links from the rendered signal (gb_link_control)
+                    controllers[uvid] = (ckind, midi, args)
+                    ent = Entity(uvid, "effect", abi.FX_SIGNAL_PASSTHROUGH, {})
                 else:
-                    plan.skipped.append(f"controller {uvid}: {ckind} is not compiled (signal-passthrough needs an "
-                                        "audio-rate control bus; see DESIGN.md)")
+                    plan.skipped.append(f"controller {uvid}: {ckind} is not compiled")
             if ent:
                 plan.entities.append(ent)
                 by_uvid[uvid] = ent
@@ -488,6 +494,9 @@ class ProjectLoader:
             tgt = link.get("target", {})
             ent = by_uvid.get(tgt.get("id"))
             idx = CONTROL_INDEX.get(tgt.get("param"))
+            if src is not None and src[0] == "signal-passthrough-controller" and ent is not None and idx is not None:
+                plan.links.append((link.get("source"), ent.uvid, idx))
+                continue
             if src is None or src[0] != "lfo" or ent is None or idx is None:
                 plan.skipped.append(f"control {link.get('id')}: source/target not compiled")
                 continue
@@ -549,6 +558,9 @@ def build_plan(r: abi.Renderer, plan: Plan, samples) -> Dict[str, int]:
         for a, b in zip(cable[:-1], cable[1:]):
             if a in uid and b in uid:
                 r.patch(uid[a], uid[b])
+    for src, dst, idx in plan.links:
+        if src in uid and dst in uid:
+            r.link_control(uid[src], uid[dst], idx)
     r.finalize()
     ev = np.zeros(len(plan.events), dtype=abi.EVENT_DTYPE)
     k = 0

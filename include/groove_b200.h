@@ -76,7 +76,10 @@ typedef enum {
   GB_FX_PEAKING_EQ_12DB = 45, /* {cutoff, db-gain} */
   GB_FX_LOW_SHELF_12DB = 46,  /* {cutoff, db-gain} */
   GB_FX_HIGH_SHELF_12DB = 47, /* {cutoff, db-gain} */
-  GB_FX_LOW_PASS_24DB = 48    /* gb_lowpass24_params {cutoff, passband-ripple} */
+  GB_FX_LOW_PASS_24DB = 48,   /* gb_lowpass24_params {cutoff, passband-ripple} */
+  GB_FX_SIGNAL_PASSTHROUGH = 49 /* no params — SignalPassthroughController (settings/src/controllers.rs:110-111,181-187):
+                                   sits in a patch chain, passes audio through unchanged, and is the SOURCE of control
+                                   links (gb_link_control): the sidechain of projects/demos/controllers/sidechain.json */
 } gb_kind;
 
 /* uid of the main mixer every engine starts with (orchestrator.rs:104,543-546) */
@@ -250,6 +253,17 @@ int gb_last_device_buffer(gb_engine* e, void** device_ptr, size_t* frames);
 /* Copy the most recent device-resident render (<= frames of it) to the host. */
 int gb_read_last(gb_engine* e, double* out_interleaved_lr, size_t frames);
 int64_t gb_position(const gb_engine* e);         /* frames rendered so far */
+
+/* Control link from an audio-rate source: replaces Orchestrator::link_control_by_name
+ * (orchestration/src/orchestrator.rs:207-234) for a SignalPassthroughController source.  Controllers do
+ * their work once per caller buffer (handle_work, orchestrator.rs:631-708; 64 frames in groove-cli), so
+ * at every absolute frame n > 0 that is a multiple of GB_CONTROL_PERIOD the target's parameter
+ * `control_index` is set to the control value min(1, |(l + r) / 2|) of the source's output at frame
+ * n - 1.  `source_uid` must be a GB_FX_SIGNAL_PASSTHROUGH node, `target_uid` a gain, limiter or
+ * compressor (one link per target).  Call before gb_finalize.  A linked parameter is owned by its link:
+ * GB_EV_CONTROL events for it are ignored from the first boundary on. */
+#define GB_CONTROL_PERIOD 64
+int gb_link_control(gb_engine* e, uint32_t source_uid, uint32_t target_uid, int32_t control_index);
 /* Serialise all time-varying state.  Call with buf == NULL to query the size. */
 int gb_save_state(gb_engine* e, void* buf, size_t* size);
 int gb_restore_state(gb_engine* e, const void* buf, size_t size);

@@ -656,6 +656,9 @@ struct ToySource : Entity {
 
 // -- effects ---------------------------------------------------------------------
 struct Mixer : Entity {};
+// SignalPassthroughController (settings/src/controllers.rs:110-111,181-187; source ABSENT): patched into a
+// chain like an effect, passes the audio through; its last output is what control links read.
+struct SignalPassthrough : Entity {};
 struct Gain : Entity {
   double ceiling;
   Stereo transform_audio(Stereo in) override {
@@ -1016,6 +1019,8 @@ struct go_engine {
   std::map<uint32_t, std::unique_ptr<Entity>> store;
   std::map<uint32_t, std::vector<uint32_t>> patches;  // effect uid -> sources, in patch order
   std::vector<gb_event> events;                       // pending, sorted by frame (stable)
+  struct Link { uint32_t src, dst; int index; };
+  std::vector<Link> links;                            // control links from signal-passthrough nodes
   std::string err;
 };
 static std::string g_create_err;
@@ -1086,6 +1091,7 @@ int go_add_effect(go_engine* e, int32_t kind, const void* params, size_t size, u
 #define NEED(T) if (!params || size != sizeof(T)) return fail(e, GB_EINVAL, "bad effect params size")
   switch (kind) {
     case GB_FX_MIXER: ent = std::make_unique<Mixer>(); break;
+    case GB_FX_SIGNAL_PASSTHROUGH: ent = std::make_unique<SignalPassthrough>(); break;
     case GB_FX_GAIN: {
       NEED(gb_gain_params);
       auto g = std::make_unique<Gain>();
@@ -1176,6 +1182,22 @@ int go_patch(go_engine* e, uint32_t src, uint32_t dst) {
   if (src == dst) return fail(e, GB_EGRAPH, "cannot patch a device to itself");
   auto& v = e->patches[dst];
   if (std::find(v.begin(), v.end(), src) == v.end()) v.push_back(src);
+  return 0;
+}
+
+// Orchestrator::link_control_by_name (orchestration/src/orchestrator.rs:207-234) for an audio-rate source.
+int go_link_control(go_engine* e, uint32_t src, uint32_t dst, int32_t index) {
+  if (!e) return GB_EINVAL;
+  if (e->finalized) return fail(e, GB_ESTATE, "engine is finalized");
+  auto s = e->store.find(src), d = e->store.find(dst);
+  if (s == e->store.end() || d == e->store.end()) return fail(e, GB_ENOENT, "unknown uid");
+  if (s->second->kind != GB_FX_SIGNAL_PASSTHROUGH) return fail(e, GB_EINVAL, "link source is not a signal-passthrough node");
+  const int k = d->second->kind;
+  if (!(k == GB_FX_GAIN || k == GB_FX_LIMITER || k == GB_FX_COMPRESSOR) || index < 0 || index > (k == GB_FX_GAIN ? 0 : 1))
+    return fail(e, GB_EINVAL, "link target must be a gain, limiter or compressor parameter");
+  for (auto& l : e->links)
+    if (l.dst == dst) return fail(e, GB_EINVAL, "target already has a control link");
+  e->links.push_back({src, dst, index});
   return 0;
 }
 
@@ -1277,6 +1299,16 @@ int go_render_block(go_engine* e, double* out, size_t frames, size_t* done) {
         case GB_EV_CONTROL: ent->control(ev.a, ev.value); break;
         case GB_EV_SET_PARAM: ent->set_param(ev.a, ev.value); break;
         default: break;
+      }
+    }
+    // controllers work once per buffer (handle_work, orchestrator.rs:631-708; GB_CONTROL_PERIOD frames):
+    // a signal-passthrough source hands the magnitude of its latest output to its link targets
+    if (n > 0 && n % GB_CONTROL_PERIOD == 0) {
+      for (auto& l : e->links) {
+        Entity* src = e->store[l.src].get();
+        if (src->memo_frame != n - 1) continue;  // not reached from the main mixer: it never rendered
+        double v = std::fabs(0.5 * (src->memo.l + src->memo.r));
+        e->store[l.dst]->control(l.index, v > 1.0 ? 1.0 : v);
       }
     }
     Stereo s = gather_frame(e, n);

@@ -271,6 +271,40 @@ def scene_graph_toys(r: abi.Renderer) -> int:
     return 100
 
 
+def scene_sidechain(r: abi.Renderer) -> int:
+    """projects/demos/controllers/sidechain.json in miniature: the magnitude of one chain's signal, sampled at
+    every 64-frame control boundary, drives a compressor threshold, a gain ceiling and a limiter maximum
+    of other chains (gb_link_control)."""
+    drums = r.add_instrument(abi.INST_FM, fm_params(ratio=3.0, beta=4.0, car=(0.0, 0.05, 0.0, 0.05), gain=0.9))
+    tap = r.add_effect(abi.FX_SIGNAL_PASSTHROUGH)
+    tap2 = r.add_effect(abi.FX_SIGNAL_PASSTHROUGH)
+    bass = r.add_instrument(abi.INST_WELSH, generic_welsh(w1=abi.WAVE_SAWTOOTH, w2=abi.WAVE_SQUARE, voices=2, gain=0.8))
+    comp = r.add_effect(abi.FX_COMPRESSOR, abi.CompressorParams(1.0, 0.2, 0.0, 0.0))
+    pad = r.add_instrument(abi.INST_WELSH, generic_welsh(w1=abi.WAVE_TRIANGLE, w2=abi.WAVE_SAWTOOTH, voices=2, gain=0.5, pan=0.4))
+    gain = r.add_effect(abi.FX_GAIN, abi.GainParams(1.0))
+    lim = r.add_effect(abi.FX_LIMITER, abi.LimiterParams(0.0, 1.0))
+    dead = r.add_effect(abi.FX_SIGNAL_PASSTHROUGH)      # never patched: its link must stay silent
+    g2 = r.add_effect(abi.FX_GAIN, abi.GainParams(0.7))
+    r.patch_chain([drums, tap, abi.MAIN_MIXER])
+    r.patch_chain([bass, comp, abi.MAIN_MIXER])
+    r.patch_chain([pad, gain, lim, tap2, abi.MAIN_MIXER])
+    r.patch_chain([bass, g2, abi.MAIN_MIXER])
+    r.link_control(tap, comp, 0)
+    r.link_control(tap, gain, 0)
+    r.link_control(tap, lim, 1)
+    r.link_control(dead, g2, 0)
+    r.finalize()
+    ev = []
+    for k in range(6):
+        ev.append((1 + 2500 * k, drums, abi.EV_NOTE_ON, 36 + k, 127, 0.0))
+        ev.append((900 + 2500 * k, drums, abi.EV_NOTE_OFF, 36 + k, 0, 0.0))
+    ev += [(0, bass, abi.EV_NOTE_ON, 40, 127, 0.0), (7000, bass, abi.EV_NOTE_ON, 47, 127, 0.0),
+           (13000, bass, abi.EV_NOTE_OFF, 40, 0, 0.0), (13500, bass, abi.EV_NOTE_OFF, 47, 0, 0.0),
+           (100, pad, abi.EV_NOTE_ON, 60, 127, 0.0), (12000, pad, abi.EV_NOTE_OFF, 60, 0, 0.0)]
+    r.push_events(ev)
+    return 15000
+
+
 ALL_SCENES = {
     "cello_chord": scene_cello_chord,
     "welsh_variants": scene_welsh_variants,
@@ -279,4 +313,5 @@ ALL_SCENES = {
     "drums_and_sampler": scene_drums_and_sampler,
     "effects_rack": scene_effects_rack,
     "graph_toys": scene_graph_toys,
+    "sidechain": scene_sidechain,
 }

@@ -261,3 +261,27 @@ def test_resting_voices_kernel(vpc, monkeypatch):
     assert st.rest_kernel_launches >= 6, "chunks 1..3 should have taken the resting-voice kernel"
     assert st.rest_voice_samples > 0
     check(out, ref)
+
+
+@pytest.mark.parametrize("max_block", [0, 100, 64])
+def test_sidechain_link_known_answer_on_gpu(max_block):
+    """The oracle's sidechain known answer (tests/test_oracle_known_answers.py) on the CUDA engine: the
+    target's parameter table is built on the device from the source's rendered signal, across chunk
+    boundaries that do and do not coincide with the 64-frame control boundaries."""
+    g = gpu_engine(max_block=max_block)
+    a = g.add_instrument(abi.INST_TOY_SOURCE, abi.ToySourceParams(0.3, 0.3))
+    b = g.add_instrument(abi.INST_TOY_SOURCE, abi.ToySourceParams(0.5, 0.5))
+    tap = g.add_effect(abi.FX_SIGNAL_PASSTHROUGH)
+    gain = g.add_effect(abi.FX_GAIN, abi.GainParams(1.0))
+    g.patch_chain([b, gain, abi.MAIN_MIXER])        # the target is patched first: the link must reorder the plan
+    g.patch_chain([a, tap, abi.MAIN_MIXER])
+    g.link_control(tap, gain, 0)
+    with pytest.raises(Exception):
+        g.link_control(tap, gain, 0)
+    with pytest.raises(Exception):
+        g.link_control(gain, gain, 0)
+    g.finalize()
+    y = np.concatenate([g.render(37), g.render(163)])
+    g.close()
+    assert np.allclose(y[:64], 0.3 + 0.5 * 1.0, atol=1e-15)
+    assert np.allclose(y[64:], 0.3 + 0.5 * 0.3, atol=1e-15)

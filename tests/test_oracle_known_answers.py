@@ -343,3 +343,40 @@ def test_transport_advances_exactly_one_beat_per_second_at_60_bpm():
             covered += now - prev
             prev = now
         assert covered == UNITS_IN_BEAT and frames_to_units(sr, 60.0, sr) == UNITS_IN_BEAT
+
+
+def test_sidechain_link_known_answer():
+    """Signal-passthrough control link (include/groove_b200.h, gb_link_control): a constant 0.3 source through a
+    passthrough node drives the ceiling of a gain on a constant 0.5 source.  Controllers work once per
+    64-frame buffer (orchestrator.rs:631-708), so the first buffer still has the initial ceiling 1.0:
+    0.3 + 0.5 * 1.0, and every later frame 0.3 + 0.5 * 0.3.  An unpatched source never fires its link."""
+    o = OracleEngine()
+    a = o.add_instrument(abi.INST_TOY_SOURCE, abi.ToySourceParams(0.3, 0.3))
+    b = o.add_instrument(abi.INST_TOY_SOURCE, abi.ToySourceParams(0.5, 0.5))
+    c = o.add_instrument(abi.INST_TOY_SOURCE, abi.ToySourceParams(0.25, 0.25))
+    tap = o.add_effect(abi.FX_SIGNAL_PASSTHROUGH)
+    dead = o.add_effect(abi.FX_SIGNAL_PASSTHROUGH)
+    g = o.add_effect(abi.FX_GAIN, abi.GainParams(1.0))
+    g2 = o.add_effect(abi.FX_GAIN, abi.GainParams(1.0))
+    o.patch_chain([a, tap, abi.MAIN_MIXER])
+    o.patch_chain([b, g, abi.MAIN_MIXER])
+    o.patch_chain([c, g2, abi.MAIN_MIXER])
+    o.patch(a, dead)                       # dead has an input but no path to the main mixer
+    o.link_control(tap, g, 0)
+    o.link_control(dead, g2, 0)
+    o.finalize()
+    y = o.render(200)
+    assert np.allclose(y[:64], 0.3 + 0.5 * 1.0 + 0.25, atol=1e-15)
+    assert np.allclose(y[64:], 0.3 + 0.5 * 0.3 + 0.25, atol=1e-15)
+    # errors: wrong source kind, unsupported target, second link on one target
+    o = OracleEngine()
+    tap = o.add_effect(abi.FX_SIGNAL_PASSTHROUGH)
+    g = o.add_effect(abi.FX_GAIN, abi.GainParams(1.0))
+    d = o.add_effect(abi.FX_DELAY, abi.DelayParams(0.1))
+    with pytest.raises(Exception):
+        o.link_control(g, g, 0)
+    with pytest.raises(Exception):
+        o.link_control(tap, d, 0)
+    o.link_control(tap, g, 0)
+    with pytest.raises(Exception):
+        o.link_control(tap, g, 0)

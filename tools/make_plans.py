@@ -24,6 +24,7 @@ PROJECTS = {
     "fm-synthesizer": "projects/demos/instruments/fm-synthesizer.json",
     "arpeggiator": "projects/demos/controllers/arpeggiator.json",
     "stereo-automation": "projects/demos/controllers/stereo-automation.json",
+    "sidechain": "projects/demos/controllers/sidechain.json",
 }
 out_dir = os.path.join(ROOT, "tests", "golden", "plans")
 os.makedirs(out_dir, exist_ok=True)
