@@ -1089,6 +1089,8 @@ int gb_finalize(gb_engine* e) {
     const double init[8] = {dn->p[l.index], 0.0, 0.0, 0.0, dn->p[l.index], 0.0, 0.0, 0.0};
     CUDA_TRY(e, cudaMemcpy(l.d_state, init, sizeof init, cudaMemcpyHostToDevice));
   }
+  // pinned ring for host-buffer renders (render_impl): allocated here so that no render call pays for it
+  if (!e->ring) CUDA_TRY(e, cudaMallocHost(&e->ring, (size_t)kStageSlots * e->max_block * sizeof(double2)));
   // voice state: every voice starts idle
   e->n_wvoice = wv;
   e->n_fvoice = fv;
@@ -1673,7 +1675,7 @@ int render_impl(gb_engine* e, void* out, size_t frames, size_t* done, OutMode mo
     CUDA_TRY(e, cudaMalloc(&e->d_full, std::max<size_t>(frames, 1) * sizeof(double2)));
     e->full_cap = frames;
   }
-  if (mode == OUT_F64 && !e->ring)
+  if (mode == OUT_F64 && !e->ring)  // normally allocated by gb_finalize
     CUDA_TRY(e, cudaMallocHost(&e->ring, (size_t)kStageSlots * e->max_block * sizeof(double2)));
   size_t produced = 0;
   const bool call_timed = span_begin(e, 2);

@@ -1050,6 +1050,25 @@ __device__ __forceinline__ void welsh_block_lti(WelshVoice* const (&vp)[NV], con
   __syncwarp();
 }
 
+// Out-of-line forms of the specialised blocks for the solo-warp kernel.  There every warp of a CTA is a
+// different instrument at a different stage of its note, so the warps of an SM are spread over many of
+// the kernel's code paths at once; with every block inlined (and cloned per call site) the live code
+// was 340 KB and 75 % of the stall samples were instruction-cache misses (`no_instructions`).  One
+// shared copy per variant keeps the working set small; the grouped kernel, whose warps march in step,
+// keeps the inlined forms (no ABI register saves on its hot path).
+template <bool LFO_AMP, bool ZERO_A, bool AMP_FLAT>
+__device__ __noinline__ void welsh_block_lti_ool(WelshVoice* vp, const WelshInst* Ip, i64 fb, int lane,
+                                                 const EnvSeg* aseg, double2* tile_row) {
+  WelshVoice* const one[1] = {vp};
+  welsh_block_lti<LFO_AMP, ZERO_A, AMP_FLAT, 1>(one, Ip, fb, lane, *aseg, tile_row);
+}
+template <bool LFO_AMP, bool ZERO_A>
+__device__ __noinline__ void welsh_block_simple_ool(WelshVoice* vp, const WelshInst* Ip, i64 fb, int lane,
+                                                    const EnvSeg* aseg, const EnvSeg* fseg, double2* tile_row,
+                                                    double* park) {
+  welsh_block_simple<LFO_AMP, ZERO_A>(vp, Ip, fb, lane, *aseg, *fseg, tile_row, park);
+}
+
 // Each coefficient mode of the fast path is its own out-of-line function: separate register
 // allocation and instruction footprint per mode, one call per 256-frame block.
 template <int CMODE, bool ALL_ON>
@@ -1136,8 +1155,8 @@ __global__ void __launch_bounds__(32 * W, MINB) welsh_kernel(const WelshInst* __
 #pragma unroll 1
   for (i64 fb = f0; fb < f_end; fb += kBlockFrames) {
     bool any = false;
-    // Voices are taken two at a time (g and g + W): when both rest — no note events for them in this
-    // chunk, both envelopes at their sustain levels for the whole block — the pair is rendered in
+    // Voices are taken two at a time (g and g + W): when both rest — no note event for them in this
+    // block, both envelopes at their sustain levels for the whole block — the pair is rendered in
     // lockstep by welsh_block_lti<.., 2>.  The test reads two words of each record.
 #pragma unroll 1
     for (int g = g_begin; g < g_end; g += 2 * W) {
@@ -1150,8 +1169,13 @@ __global__ void __launch_bounds__(32 * W, MINB) welsh_kernel(const WelshInst* __
       for (int h = 0; h < 2; ++h) {
         const longlong2 on_off = *reinterpret_cast<const longlong2*>(&voices[vis[h]].n_on);
         const i64 last = on_off.y < f_end ? on_off.y : f_end;
-        rest[h] = lti_inst && ev_off[vis[h]] == ev_off[vis[h] + 1] && fb >= on_off.x + I.steady_after &&
-                  fb + kBlockFrames <= last;
+        rest[h] = lti_inst && fb >= on_off.x + I.steady_after && fb + kBlockFrames <= last;
+        if (rest[h]) {  // ... and no note event inside this block (earlier ones are folded into the record)
+          int ei = ev_off[vis[h]];
+          const int e_end = ev_off[vis[h] + 1];
+          while (ei < e_end && events[ei].frame < fb) ++ei;
+          rest[h] = !(ei < e_end && events[ei].frame < fb + kBlockFrames);
+        }
       }
       if (rest[0] || (nv == 2 && rest[1])) {
         if (!any) {  // the specialised blocks always accumulate into the warp's tile row
@@ -1162,6 +1186,10 @@ __global__ void __launch_bounds__(32 * W, MINB) welsh_kernel(const WelshInst* __
         }
         EnvSeg none;
         none.q0 = 0.0; none.q1 = 0.0; none.q2 = 0.0; none.w0 = 0.0; none.dw = 0.0;
+        if constexpr (SOLO) {  // one voice per warp; shared out-of-line copies, general oscillator form only
+          if (I.routing == LFO_NONE) welsh_block_lti_ool<false, false, true>(voices + vis[0], &I, fb, lane, &none, tile_row);
+          else welsh_block_lti_ool<true, false, true>(voices + vis[0], &I, fb, lane, &none, tile_row);
+        } else {
 #define GB_LTI_REST(NV_, ARR_)                                                                                   \
   do {                                                                                                           \
     if (I.osc_flat) {                                                                                            \
@@ -1172,14 +1200,15 @@ __global__ void __launch_bounds__(32 * W, MINB) welsh_kernel(const WelshInst* __
       else welsh_block_lti<true, false, true, NV_>(ARR_, &I, fb, lane, none, tile_row);                          \
     }                                                                                                            \
   } while (0)
-        if (nv == 2 && rest[0] && rest[1]) {
-          WelshVoice* const two[2] = {voices + vis[0], voices + vis[1]};
-          GB_LTI_REST(2, two);
-          continue;
-        }
-        WelshVoice* const one[1] = {voices + (rest[0] ? vis[0] : vis[1])};
-        GB_LTI_REST(1, one);
+          if (nv == 2 && rest[0] && rest[1]) {
+            WelshVoice* const two[2] = {voices + vis[0], voices + vis[1]};
+            GB_LTI_REST(2, two);
+            continue;
+          }
+          WelshVoice* const one[1] = {voices + (rest[0] ? vis[0] : vis[1])};
+          GB_LTI_REST(1, one);
 #undef GB_LTI_REST
+        }
       }
 #pragma unroll 1
       for (int h = 0; h < nv; ++h) {
@@ -1218,13 +1247,18 @@ __global__ void __launch_bounds__(32 * W, MINB) welsh_kernel(const WelshInst* __
           for (int j = 0; j < kT; ++j) row[j] = make_double2(0.0, 0.0);
         }
         if (lti) {
-          WelshVoice* const one[1] = {vp};
-          if (I.osc_flat) {
-            if (I.routing == LFO_NONE) welsh_block_lti<false, true, false, 1>(one, &I, fb, lane, aseg, tile_row);
-            else welsh_block_lti<true, true, false, 1>(one, &I, fb, lane, aseg, tile_row);
+          if constexpr (SOLO) {
+            if (I.routing == LFO_NONE) welsh_block_lti_ool<false, false, false>(vp, &I, fb, lane, &aseg, tile_row);
+            else welsh_block_lti_ool<true, false, false>(vp, &I, fb, lane, &aseg, tile_row);
           } else {
-            if (I.routing == LFO_NONE) welsh_block_lti<false, false, false, 1>(one, &I, fb, lane, aseg, tile_row);
-            else welsh_block_lti<true, false, false, 1>(one, &I, fb, lane, aseg, tile_row);
+            WelshVoice* const one[1] = {vp};
+            if (I.osc_flat) {
+              if (I.routing == LFO_NONE) welsh_block_lti<false, true, false, 1>(one, &I, fb, lane, aseg, tile_row);
+              else welsh_block_lti<true, true, false, 1>(one, &I, fb, lane, aseg, tile_row);
+            } else {
+              if (I.routing == LFO_NONE) welsh_block_lti<false, false, false, 1>(one, &I, fb, lane, aseg, tile_row);
+              else welsh_block_lti<true, false, false, 1>(one, &I, fb, lane, aseg, tile_row);
+            }
           }
         } else if (fast) {
           // the fast path changes only the filter state and the carried knot of the voice record
@@ -1243,10 +1277,13 @@ __global__ void __launch_bounds__(32 * W, MINB) welsh_kernel(const WelshInst* __
               smooth = fabs(I.cut_b * fseg.dw) * fmax(r0, r8) <= I.knot_max_rate && I.knot_max_rate > 0.0;
             }
             if (__all_sync(0xffffffffu, smooth)) {
-              if (simple_inst && I.osc_flat) {
+              if (SOLO && simple_inst) {
+                if (I.routing == LFO_NONE) welsh_block_simple_ool<false, false>(vp, Ip, fb, lane, &aseg, &fseg, tile_row, park);
+                else welsh_block_simple_ool<true, false>(vp, Ip, fb, lane, &aseg, &fseg, tile_row, park);
+              } else if (!SOLO && simple_inst && I.osc_flat) {
                 if (I.routing == LFO_NONE) welsh_block_simple<false, true>(vp, Ip, fb, lane, aseg, fseg, tile_row, park);
                 else welsh_block_simple<true, true>(vp, Ip, fb, lane, aseg, fseg, tile_row, park);
-              } else if (simple_inst) {
+              } else if (!SOLO && simple_inst) {
                 if (I.routing == LFO_NONE) welsh_block_simple<false, false>(vp, Ip, fb, lane, aseg, fseg, tile_row, park);
                 else welsh_block_simple<true, false>(vp, Ip, fb, lane, aseg, fseg, tile_row, park);
               } else
