@@ -1430,7 +1430,8 @@ __device__ __forceinline__ void welsh_rest_block(RestState* const (&rs)[NV], con
       row[j] = make_double2(m * gl, m * gr);
     }
   }
-  // ---- advance the cached state by one block ----
+  // ---- advance the cached state by one block (every lane has read it: order the writes after the reads) ----
+  __syncwarp();
 #pragma unroll
   for (int v = 0; v < NV; ++v) {
     if (lane == 31) {

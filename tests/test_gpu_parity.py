@@ -285,3 +285,34 @@ def test_sidechain_link_known_answer_on_gpu(max_block):
     g.close()
     assert np.allclose(y[:64], 0.3 + 0.5 * 1.0, atol=1e-15)
     assert np.allclose(y[64:], 0.3 + 0.5 * 0.3, atol=1e-15)
+
+
+def test_resting_paths_agree_at_size(monkeypatch):
+    """Size-independent property at a larger size than the oracle can check: the three ways the engine
+    renders a resting voice — welsh_rest_kernel (whole chunks), welsh_block_lti inside welsh_kernel (per
+    block, GB_REST_KERNEL=0) and the knot-interpolated moving-cutoff block evaluated at a cutoff that
+    happens not to move (GB_LTI=0) — agree far inside the parity tolerance on 2048 config-4 voices over
+    a stretch that runs from the filter decay into the resting state."""
+    frames = 5 * 65536
+    cfg = workloads.cfg4_slice(2048, frames)      # 128 instruments x 16 voices: grouped CTAs
+    cfg.note_off_base = 4 * 65536 + 1000
+
+    def run(env):
+        for k in ("GB_REST_KERNEL", "GB_LTI"):
+            monkeypatch.delenv(k, raising=False)
+        for k, v in env.items():
+            monkeypatch.setenv(k, v)
+        e = gpu_engine(48000.0)
+        workloads.build_cfg4(e, cfg)
+        y = e.render(frames)
+        st = e.stats()
+        e.close()
+        return y, st
+
+    a, sa = run({})
+    b, sb = run({"GB_REST_KERNEL": "0"})
+    c, sc = run({"GB_LTI": "0"})
+    assert sa.rest_kernel_launches > 0 and sb.rest_kernel_launches == 0 and sc.rest_kernel_launches == 0
+    assert np.abs(a).max() > 1e-3
+    assert np.abs(a - b).max() < 1e-12
+    assert np.abs(a - c).max() < 1e-10
