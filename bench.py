@@ -13,9 +13,15 @@ Printed JSON (one line, rank 0):
              each render call), inputs resident in HBM, result left in HBM;
   e2e        the same metric through the C ABI with host buffers: events pushed from host memory
              and the f64 stereo result copied back to a host buffer inside the timed region;
-  roofline   dominant kernel (welsh_kernel) against the FP64 vector pipe, which is what binds this
-             path: achieved = 150 FLOP x voice-samples per launch / CUDA-event
-             launch time; peak = FP64 FMA microbenchmark measured live on the same GPU;
+  roofline   dominant kernel (config 4: welsh_rest_kernel, the resting-voice kernel) against the FP64
+             vector pipe, which is what binds this path: achieved = the ALGORITHMIC
+             150 FLOP x voice-samples its launches covered / their CUDA-event time; peak = FP64 FMA
+             microbenchmark measured live on the same GPU.  The kernel executes fewer FP64 instructions
+             than the algorithmic count (the resting cutoff makes the per-frame coefficient work
+             redundant: DESIGN.md §3.1a), so the executed count and the ncu pipe utilisation are
+             reported beside it;
+  time_varying  (N = 1) the same recipe with the filter decay stretched past the note — the cutoff moves
+             on every frame, no voice rests: value and roofline of welsh_kernel's moving-cutoff path;
   cpu_baseline  the CPU oracle (reference-structured restatement) on a bounded sample, 1 core.
 """
 from __future__ import annotations

@@ -279,6 +279,10 @@ struct Node {
   double2* buf = nullptr;         // chunk output (max_block frames)
   double2* scratch = nullptr;     // pre-reduction when > kMaxSources inputs / partial sums
   const double2** d_src_table = nullptr;  // device table of source buffers (> kMaxSources inputs)
+  const double2** d_src_table_fused = nullptr;  // the same with split instruments replaced by their partial buffers
+  int n_src_fused = 0;
+  int consumers = 0;           // plan nodes that read this node's buffer
+  bool fuse_partials = false;  // split instrument whose only consumer sums its partials itself (no reduce pass)
   // --- instruments ---
   gb_welsh_params wp;
   gb_fm_params fp;
@@ -351,6 +355,7 @@ struct gb_engine {
   };
   std::vector<Link> links;
   std::vector<Node*> wwork_node;  // instrument of each grouped Welsh CTA
+  std::vector<char> wwork_zero;   // ... its output buffer currently holds zeros (idle CTAs are not launched)
   DevBuf<int> widx;               // per chunk: grouped Welsh CTAs sorted into resting (4 variants) and general
   DevBuf<VoiceEvent> wev, fev;
   DevBuf<int> wev_off, fev_off;
@@ -358,6 +363,10 @@ struct gb_engine {
   DevBuf<SegParam> segs;         // per-chunk parameter segment tables of all effects / instrument DCAs
   DevBuf<PartialDesc> partials;  // instruments split over several CTAs (static after finalize)
   int n_partials = 0;
+  DevBuf<PartialDesc> partials_nf;  // ... without those whose consumer sums the partials itself (fuse_partials)
+  int n_partials_nf = 0;
+  bool fused_sums = false;          // this chunk: consumers read partial buffers directly
+  bool fused_sums_enabled = true;   // GB_FUSED_SUMS=0 switches the shortcut off (A/B measurements)
   std::vector<void*> allocations;  // everything cudaMalloc'ed at finalize/load time
 
   double2* last_out = nullptr;  // main mixer buffer of the last chunk
@@ -615,7 +624,10 @@ int gather_sources(gb_engine* e, Node* n, int frames, SourceList* out) {
   {
     // the pointer table was uploaded at finalize (sources never change afterwards)
     Launch l(e, false);
-    sum_table_kernel<<<cdiv(frames, 256), 256, 0, e->stream>>>(n->d_src_table, (int)ptrs.size(), n->scratch, frames);
+    if (e->fused_sums && n->d_src_table_fused)
+      sum_table_kernel<<<cdiv(frames, 256), 256, 0, e->stream>>>(n->d_src_table_fused, n->n_src_fused, n->scratch, frames);
+    else
+      sum_table_kernel<<<cdiv(frames, 256), 256, 0, e->stream>>>(n->d_src_table, (int)ptrs.size(), n->scratch, frames);
   }
   out->n = 1;
   out->p[0] = n->scratch;
@@ -766,6 +778,7 @@ int gb_create(const gb_config* cfg, gb_engine** out) {
   cudaDeviceProp prop;
   if (cudaGetDeviceProperties(&prop, e->device) == cudaSuccess) e->num_sms = prop.multiProcessorCount;
   if (const char* v = getenv("GB_CTA_MULT")) e->cta_target_mult = std::max(1, atoi(v));
+  if (const char* v = getenv("GB_FUSED_SUMS")) e->fused_sums_enabled = atoi(v) != 0;
   if (cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking) != cudaSuccess ||
       cudaStreamCreateWithFlags(&e->copy_stream, cudaStreamNonBlocking) != cudaSuccess)
     return fail(nullptr, GB_ECUDA, "cudaStreamCreate failed");
@@ -1200,16 +1213,51 @@ int gb_finalize(gb_engine* e) {
       memcpy(e->partials.h, descs.data(), descs.size() * sizeof(PartialDesc));
       CUDA_TRY(e, cudaMemcpy(e->partials.d, e->partials.h, descs.size() * sizeof(PartialDesc), cudaMemcpyHostToDevice));
     }
+    for (Node* n : e->plan)
+      if (!n->is_inst)
+        for (uint32_t su : n->sources) {
+          Node* sn = find(e, su);
+          if (sn && sn->order >= 0) sn->consumers++;
+        }
     for (Node* n : e->plan) {
       if (n->is_inst || (int)n->sources.size() <= kMaxSources) continue;
-      std::vector<const double2*> ptrs;
+      std::vector<const double2*> ptrs, fused;
       for (uint32_t su : n->sources) {
         Node* sn = find(e, su);
-        if (sn && sn->order >= 0 && sn->buf) ptrs.push_back(sn->buf);
+        if (!(sn && sn->order >= 0 && sn->buf)) continue;
+        ptrs.push_back(sn->buf);
+        // a split instrument read by this node only: sum its partial buffers here instead of reducing
+        // them into its node buffer first (one pass over HBM less)
+        if ((sn->kind == GB_INST_WELSH || sn->kind == GB_INST_FM) && sn->partial_count > 0 && sn->consumers == 1) {
+          sn->fuse_partials = true;
+          for (int k = 0; k < sn->partial_count; ++k) fused.push_back(sn->scratch + (size_t)k * mb);
+        } else {
+          fused.push_back(sn->buf);
+        }
       }
       int rc2 = dev_alloc(e, &n->d_src_table, ptrs.size());
       if (rc2) return rc2;
       CUDA_TRY(e, cudaMemcpy((void*)n->d_src_table, ptrs.data(), ptrs.size() * sizeof(double2*), cudaMemcpyHostToDevice));
+      if (fused.size() != ptrs.size()) {
+        if ((rc2 = dev_alloc(e, &n->d_src_table_fused, fused.size()))) return rc2;
+        CUDA_TRY(e, cudaMemcpy((void*)n->d_src_table_fused, fused.data(), fused.size() * sizeof(double2*), cudaMemcpyHostToDevice));
+        n->n_src_fused = (int)fused.size();
+      }
+    }
+    {
+      std::vector<PartialDesc> nf;
+      for (Node* n : e->plan) {
+        if (!(n->kind == GB_INST_WELSH || n->kind == GB_INST_FM) || n->partial_count == 0 || n->fuse_partials) continue;
+        PartialDesc d;
+        d.base = n->scratch; d.out = n->buf; d.stride = mb; d.count = n->partial_count; d.pad = 0;
+        nf.push_back(d);
+      }
+      e->n_partials_nf = (int)nf.size();
+      if (!nf.empty()) {
+        if (!e->partials_nf.reserve(nf.size())) return fail(e, GB_ENOMEM, "out of memory");
+        memcpy(e->partials_nf.h, nf.data(), nf.size() * sizeof(PartialDesc));
+        CUDA_TRY(e, cudaMemcpy(e->partials_nf.d, e->partials_nf.h, nf.size() * sizeof(PartialDesc), cudaMemcpyHostToDevice));
+      }
     }
   }
   const int welsh_smem_bytes = (int)(kVoiceWarps * kTileStride * sizeof(double2) + kParkWords * 32 * kVoiceWarps * sizeof(double));
@@ -1460,7 +1508,8 @@ int render_chunk(gb_engine* e, int frames, size_t n_ev) {
       // goes to welsh_rest_kernel, the others to welsh_kernel.  Host knowledge only: note frames are
       // integers tracked by the slot stores.
       const int ng = e->n_wwork_grouped, ns = e->n_wwork - e->n_wwork_grouped;
-      std::vector<int> lists[5];  // 0..3 = resting variants, 4 = general
+      std::vector<int> lists[5];  // 0..3 = resting variants, 4 = general (idle CTAs are not launched at all)
+      e->wwork_zero.resize((size_t)ng, 0);
       const bool chunk_ok = frames % kBlockFrames == 0;
       size_t rest_voices_max = 0;
       uint64_t rest_voices = 0;
@@ -1475,6 +1524,20 @@ int render_chunk(gb_engine* e, int frames, size_t n_ev) {
           rest = wlists[(size_t)(w.voice0 + v)].empty() && sl.held && sl.on_frame > kNever &&
                  sl.on_frame + I.steady_after <= f0;
         }
+        // idle: every voice silent for the whole chunk and no note event in it — the CTA's output is zeros
+        bool idle = !rest;
+        for (int v = 0; idle && v < w.nvoices; ++v) {
+          const Slot& sl = n->store.slots[(size_t)(w.voice0 - n->voice0 + v)];
+          idle = wlists[(size_t)(w.voice0 + v)].empty() && !sl.held && f0 >= sl.idle_at;
+        }
+        if (idle) {
+          if (!e->wwork_zero[(size_t)i]) {
+            CUDA_TRY(e, cudaMemsetAsync(w.out, 0, (size_t)e->max_block * sizeof(double2), e->stream));
+            e->wwork_zero[(size_t)i] = 1;
+          }
+          continue;
+        }
+        e->wwork_zero[(size_t)i] = 0;
         lists[rest ? I.rest_class : 4].push_back(i);
         if (rest) {
           rest_voices_max = std::max(rest_voices_max, (size_t)w.nvoices);
@@ -1486,8 +1549,10 @@ int render_chunk(gb_engine* e, int frames, size_t n_ev) {
         size_t k = 0;
         for (auto& l : lists)
           for (int i : l) e->widx.h[k++] = i;
-        CUDA_TRY(e, cudaMemcpyAsync(e->widx.d, e->widx.h, (size_t)ng * sizeof(int), cudaMemcpyHostToDevice, e->stream));
-        e->stats.h2d_bytes += (size_t)ng * sizeof(int);
+        if (k) {
+          CUDA_TRY(e, cudaMemcpyAsync(e->widx.d, e->widx.h, k * sizeof(int), cudaMemcpyHostToDevice, e->stream));
+          e->stats.h2d_bytes += k * sizeof(int);
+        }
       }
       const size_t rest_smem = (size_t)kVoiceWarps * kTileStride * sizeof(double2) + rest_voices_max * sizeof(RestState);
       size_t off = 0;
@@ -1576,10 +1641,16 @@ int render_chunk(gb_engine* e, int frames, size_t n_ev) {
     }
   }
   // ---- 4. partial sums of instruments split over several CTAs: one launch for all of them ----
-  if (e->n_partials) {
+  // (instruments whose only consumer sums the partials itself skip this pass, unless one of them needs
+  // its node buffer for a gain/pan automation pass in this chunk)
+  e->fused_sums = e->fused_sums_enabled;
+  for (Node* n : e->plan)
+    if (n->fuse_partials && n->unit_gain) e->fused_sums = false;
+  const int n_red = e->fused_sums ? e->n_partials_nf : e->n_partials;
+  if (n_red) {
     Launch l(e, false);
-    dim3 grid(cdiv(frames, 256), e->n_partials);
-    reduce_partials_kernel<<<grid, 256, 0, e->stream>>>(e->partials.d, frames);
+    dim3 grid(cdiv(frames, 256), n_red);
+    reduce_partials_kernel<<<grid, 256, 0, e->stream>>>(e->fused_sums ? e->partials_nf.d : e->partials.d, frames);
   }
   // ---- 5. plan walk: toy sources, instrument DCA automation, effects (one launch per node) ----
   for (Node* n : e->plan) {
