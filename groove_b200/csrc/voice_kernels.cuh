@@ -1329,24 +1329,39 @@ struct alignas(16) RestState {
 
 // Exclusive form of lti_scan_states: the lanes' zero-state end vectors are shifted up by one lane with
 // the span's entry state entering at lane 0, so the inclusive scan yields each lane's entry state
-// directly.  Returns the state after the whole span in lane 31's (x0, x1).
-__device__ __forceinline__ void lti_scan_entry(double v0, double v1, const double (*mp)[4], int lane, double s0,
-                                               double s1, double& e0, double& e1, double& x0, double& x1) {
-  double u0 = shfl_up_f64(v0, 1), u1 = shfl_up_f64(v1, 1);
-  u0 = lane == 0 ? s0 : u0;
-  u1 = lane == 0 ? s1 : u1;
+// directly.  The state after the whole span comes out in lane 31's x.  NV voices of one instrument are
+// scanned together: they share the span maps, so each step loads its matrix once.  sec = 0 / 1 picks the
+// state words (s[v][2 sec], s[v][2 sec + 1]) and the result words of x.
+template <int NV>
+__device__ __forceinline__ void lti_scan_entry(const double (&v0)[NV], const double (&v1)[NV], const double (*mp)[4],
+                                               int lane, const double (&s)[NV][4], int sec, double (&e0)[NV],
+                                               double (&e1)[NV], double (&x)[NV][4]) {
+  double u0[NV], u1[NV];
+#pragma unroll
+  for (int v = 0; v < NV; ++v) {
+    u0[v] = shfl_up_f64(v0[v], 1);
+    u1[v] = shfl_up_f64(v1[v], 1);
+    u0[v] = lane == 0 ? s[v][2 * sec] : u0[v];
+    u1[v] = lane == 0 ? s[v][2 * sec + 1] : u1[v];
+  }
 #pragma unroll
   for (int k = 0; k < 5; ++k) {
     const int d = 1 << k;
-    const double p0 = shfl_up_f64(u0, d), p1 = shfl_up_f64(u1, d);
     const double* m = mp[lane >= d ? k : 5];
     const double2 r0 = *reinterpret_cast<const double2*>(m), r1 = *reinterpret_cast<const double2*>(m + 2);
-    affine_vec_step(u0, u1, r0.x, r0.y, r1.x, r1.y, p0, p1);
+#pragma unroll
+    for (int v = 0; v < NV; ++v) {
+      const double p0 = shfl_up_f64(u0[v], d), p1 = shfl_up_f64(u1[v], d);
+      affine_vec_step(u0[v], u1[v], r0.x, r0.y, r1.x, r1.y, p0, p1);
+    }
   }
-  e0 = u0; e1 = u1;
   const double2 r0 = *reinterpret_cast<const double2*>(mp[0]), r1 = *reinterpret_cast<const double2*>(mp[0] + 2);
-  x0 = v0; x1 = v1;
-  affine_vec_step(x0, x1, r0.x, r0.y, r1.x, r1.y, u0, u1);
+#pragma unroll
+  for (int v = 0; v < NV; ++v) {
+    e0[v] = u0[v]; e1[v] = u1[v];
+    x[v][2 * sec] = v0[v]; x[v][2 * sec + 1] = v1[v];
+    affine_vec_step(x[v][2 * sec], x[v][2 * sec + 1], r0.x, r0.y, r1.x, r1.y, u0[v], u1[v]);
+  }
 }
 
 template <bool LFO_AMP, bool ZERO_A, int NV, bool ACC>
@@ -1392,8 +1407,7 @@ __device__ __forceinline__ void welsh_rest_block(RestState* const (&rs)[NV], con
     }
   }
   double e0[NV], e1[NV], x[NV][4];
-#pragma unroll
-  for (int v = 0; v < NV; ++v) lti_scan_entry(ps0[v], ps1[v], L.mp1, lane, s[v][0], s[v][1], e0[v], e1[v], x[v][0], x[v][1]);
+  lti_scan_entry<NV>(ps0, ps1, L.mp1, lane, s, 0, e0, e1, x);
   {
     const double b0 = L.c2.b0, a1 = L.c2.a1, a2 = L.c2.a2;
 #pragma unroll
@@ -1406,8 +1420,7 @@ __device__ __forceinline__ void welsh_rest_block(RestState* const (&rs)[NV], con
         yp[v][j] = lp_step(b0, a1, a2, fma(g.y, e1[v], fma(g.x, e0[v], yp[v][j])), ps0[v], ps1[v]);
     }
   }
-#pragma unroll
-  for (int v = 0; v < NV; ++v) lti_scan_entry(ps0[v], ps1[v], L.mp2, lane, s[v][2], s[v][3], e0[v], e1[v], x[v][2], x[v][3]);
+  lti_scan_entry<NV>(ps0, ps1, L.mp2, lane, s, 1, e0, e1, x);
   const double arest = I.amp_rest;
   const double gl = I.gl, gr = I.gr;
   double2* row = tile_row + lane * (kT + 1);
