@@ -1329,20 +1329,21 @@ struct alignas(16) RestState {
 
 // Exclusive form of lti_scan_states: the lanes' zero-state end vectors are shifted up by one lane with
 // the span's entry state entering at lane 0, so the inclusive scan yields each lane's entry state
-// directly.  The state after the whole span comes out in lane 31's x.  NV voices of one instrument are
-// scanned together: they share the span maps, so each step loads its matrix once.  sec = 0 / 1 picks the
-// state words (s[v][2 sec], s[v][2 sec + 1]) and the result words of x.
+// directly.  NV voices of one instrument are scanned together: they share the span maps, so each step
+// loads its matrix once.  sec = 0 / 1 picks the cached state words (s[2 sec], s[2 sec + 1]): lane 0 reads
+// them as the span's entry state, lane 31 replaces them by the state after the span.
 template <int NV>
 __device__ __forceinline__ void lti_scan_entry(const double (&v0)[NV], const double (&v1)[NV], const double (*mp)[4],
-                                               int lane, const double (&s)[NV][4], int sec, double (&e0)[NV],
-                                               double (&e1)[NV], double (&x)[NV][4]) {
+                                               int lane, RestState* const (&rs)[NV], int sec, double (&e0)[NV],
+                                               double (&e1)[NV]) {
   double u0[NV], u1[NV];
 #pragma unroll
   for (int v = 0; v < NV; ++v) {
+    const double2 st = *reinterpret_cast<const double2*>(&rs[v]->s[2 * sec]);  // only lane 0 uses it
     u0[v] = shfl_up_f64(v0[v], 1);
     u1[v] = shfl_up_f64(v1[v], 1);
-    u0[v] = lane == 0 ? s[v][2 * sec] : u0[v];
-    u1[v] = lane == 0 ? s[v][2 * sec + 1] : u1[v];
+    u0[v] = lane == 0 ? st.x : u0[v];
+    u1[v] = lane == 0 ? st.y : u1[v];
   }
 #pragma unroll
   for (int k = 0; k < 5; ++k) {
@@ -1355,47 +1356,50 @@ __device__ __forceinline__ void lti_scan_entry(const double (&v0)[NV], const dou
       affine_vec_step(u0[v], u1[v], r0.x, r0.y, r1.x, r1.y, p0, p1);
     }
   }
-  const double2 r0 = *reinterpret_cast<const double2*>(mp[0]), r1 = *reinterpret_cast<const double2*>(mp[0] + 2);
 #pragma unroll
-  for (int v = 0; v < NV; ++v) {
-    e0[v] = u0[v]; e1[v] = u1[v];
-    x[v][2 * sec] = v0[v]; x[v][2 * sec + 1] = v1[v];
-    affine_vec_step(x[v][2 * sec], x[v][2 * sec + 1], r0.x, r0.y, r1.x, r1.y, u0[v], u1[v]);
+  for (int v = 0; v < NV; ++v) { e0[v] = u0[v]; e1[v] = u1[v]; }
+  __syncwarp();      // lane 0 has read the old state
+  if (lane == 31) {  // state after the whole span: this lane's map applied to its entry state
+    const double2 r0 = *reinterpret_cast<const double2*>(mp[0]), r1 = *reinterpret_cast<const double2*>(mp[0] + 2);
+#pragma unroll
+    for (int v = 0; v < NV; ++v) {
+      double x0 = v0[v], x1 = v1[v];
+      affine_vec_step(x0, x1, r0.x, r0.y, r1.x, r1.y, u0[v], u1[v]);
+      *reinterpret_cast<double2*>(&rs[v]->s[2 * sec]) = make_double2(x0, x1);
+    }
   }
 }
 
 template <bool LFO_AMP, bool ZERO_A, int NV, bool ACC>
 __device__ __forceinline__ void welsh_rest_block(RestState* const (&rs)[NV], const WelshInst& I, int lane,
                                                  double2* tile_row) {
+  // Cached state is read where it is needed and written back as soon as its new value exists, so that
+  // phases, filter states and the LFO phasor do not occupy registers across the whole block.
   const LtiTable& L = I.lti;
-  u64 p1[NV], p2[NV], d1[NV], d2[NV];
-  double lsd[NV], lcd[NV];
-  double s[NV][4];
-#pragma unroll
-  for (int v = 0; v < NV; ++v) {
-    const ulonglong2 pp = *reinterpret_cast<const ulonglong2*>(&rs[v]->p1);
-    const ulonglong2 dd = *reinterpret_cast<const ulonglong2*>(&rs[v]->d1);
-    const double2 sa = *reinterpret_cast<const double2*>(&rs[v]->s[0]), sb = *reinterpret_cast<const double2*>(&rs[v]->s[2]);
-    s[v][0] = sa.x; s[v][1] = sa.y; s[v][2] = sb.x; s[v][3] = sb.y;
-    d1[v] = dd.x; d2[v] = dd.y;
-    const u64 k = (u64)(lane * kT);
-    p1[v] = pp.x + k * dd.x; p2[v] = pp.y + k * dd.y;
-    lsd[v] = 0.0; lcd[v] = 0.0;
-    if (LFO_AMP) {
-      const double2 ph = *reinterpret_cast<const double2*>(&rs[v]->ls);
-      const double2 r = I.lane_rot[lane];
-      lsd[v] = fma(ph.x, r.x, ph.y * r.y);
-      lcd[v] = fma(ph.y, r.x, -(ph.x * r.y));
-    }
-  }
   double yp[NV][kT];
   double ps0[NV], ps1[NV];
+  // ---- pass 1: oscillators + section 1 from a zero state; phases advance by one block ----
   {
+    u64 p1[NV], p2[NV], d1[NV], d2[NV];
+#pragma unroll
+    for (int v = 0; v < NV; ++v) {
+      const ulonglong2 pp = *reinterpret_cast<const ulonglong2*>(&rs[v]->p1);
+      const ulonglong2 dd = *reinterpret_cast<const ulonglong2*>(&rs[v]->d1);
+      d1[v] = dd.x; d2[v] = dd.y;
+      const u64 k = (u64)(lane * kT);
+      p1[v] = pp.x + k * dd.x; p2[v] = pp.y + k * dd.y;
+      ps0[v] = 0.0; ps1[v] = 0.0;
+    }
+    __syncwarp();  // every lane has read the block's base phases
+    if (lane == 0) {
+#pragma unroll
+      for (int v = 0; v < NV; ++v)
+        *reinterpret_cast<ulonglong2*>(&rs[v]->p1) =
+            make_ulonglong2(p1[v] + (u64)kBlockFrames * d1[v], p2[v] + (u64)kBlockFrames * d2[v]);
+    }
     const OscMix o1 = I.m1, o2 = I.m2;
     const u64 t1 = I.s1.thresh, t2 = I.s2.thresh;
     const double b0 = L.c1.b0, a1 = L.c1.a1, a2 = L.c1.a2;
-#pragma unroll
-    for (int v = 0; v < NV; ++v) { ps0[v] = 0.0; ps1[v] = 0.0; }
 #pragma unroll
     for (int j = 0; j < kT; ++j) {
 #pragma unroll
@@ -1406,8 +1410,9 @@ __device__ __forceinline__ void welsh_rest_block(RestState* const (&rs)[NV], con
       }
     }
   }
-  double e0[NV], e1[NV], x[NV][4];
-  lti_scan_entry<NV>(ps0, ps1, L.mp1, lane, s, 0, e0, e1, x);
+  double e0[NV], e1[NV];
+  lti_scan_entry<NV>(ps0, ps1, L.mp1, lane, rs, 0, e0, e1);
+  // ---- pass 2: section 2 on the fixed-up section-1 output ----
   {
     const double b0 = L.c2.b0, a1 = L.c2.a1, a2 = L.c2.a2;
 #pragma unroll
@@ -1420,7 +1425,30 @@ __device__ __forceinline__ void welsh_rest_block(RestState* const (&rs)[NV], con
         yp[v][j] = lp_step(b0, a1, a2, fma(g.y, e1[v], fma(g.x, e0[v], yp[v][j])), ps0[v], ps1[v]);
     }
   }
-  lti_scan_entry<NV>(ps0, ps1, L.mp2, lane, s, 1, e0, e1, x);
+  lti_scan_entry<NV>(ps0, ps1, L.mp2, lane, rs, 1, e0, e1);
+  // ---- LFO phasor of this lane; the cached one advances by one block ----
+  double lsd[NV], lcd[NV];
+#pragma unroll
+  for (int v = 0; v < NV; ++v) {
+    lsd[v] = 0.0; lcd[v] = 0.0;
+    if (LFO_AMP) {
+      const double2 ph = *reinterpret_cast<const double2*>(&rs[v]->ls);
+      const double2 r = I.lane_rot[lane];
+      lsd[v] = fma(ph.x, r.x, ph.y * r.y);
+      lcd[v] = fma(ph.y, r.x, -(ph.x * r.y));
+    }
+  }
+  if (LFO_AMP) {
+    __syncwarp();  // every lane has read the block's phasor
+    if (lane == 0) {
+      const double2 r = I.block_rot;  // lane 0's (lsd, lcd) is the block phasor itself (lane_rot[0] = (1, 0))
+#pragma unroll
+      for (int v = 0; v < NV; ++v)
+        *reinterpret_cast<double2*>(&rs[v]->ls) =
+            make_double2(fma(lsd[v], r.x, lcd[v] * r.y), fma(lcd[v], r.x, -(lsd[v] * r.y)));
+    }
+  }
+  // ---- amplitude, DCA, into the warp's tile row (the voices of a pair are summed first) ----
   const double arest = I.amp_rest;
   const double gl = I.gl, gr = I.gr;
   double2* row = tile_row + lane * (kT + 1);
@@ -1441,24 +1469,6 @@ __device__ __forceinline__ void welsh_rest_block(RestState* const (&rs)[NV], con
       row[j] = make_double2(fma(m, gl, p.x), fma(m, gr, p.y));
     } else {
       row[j] = make_double2(m * gl, m * gr);
-    }
-  }
-  // ---- advance the cached state by one block (every lane has read it: order the writes after the reads) ----
-  __syncwarp();
-#pragma unroll
-  for (int v = 0; v < NV; ++v) {
-    if (lane == 31) {
-      *reinterpret_cast<double2*>(&rs[v]->s[0]) = make_double2(x[v][0], x[v][1]);
-      *reinterpret_cast<double2*>(&rs[v]->s[2]) = make_double2(x[v][2], x[v][3]);
-    }
-    if (lane == 0) {
-      *reinterpret_cast<ulonglong2*>(&rs[v]->p1) =
-          make_ulonglong2(p1[v] + (u64)(kBlockFrames - kT) * d1[v], p2[v] + (u64)(kBlockFrames - kT) * d2[v]);
-      if (LFO_AMP) {
-        const double2 r = I.block_rot;  // lane 0's (lsd, lcd) is the block phasor itself (lane_rot[0] = (1, 0))
-        *reinterpret_cast<double2*>(&rs[v]->ls) =
-            make_double2(fma(lsd[v], r.x, lcd[v] * r.y), fma(lcd[v], r.x, -(lsd[v] * r.y)));
-      }
     }
   }
   __syncwarp();
