@@ -357,6 +357,8 @@ struct gb_engine {
   std::vector<Node*> wwork_node;  // instrument of each grouped Welsh CTA
   std::vector<char> wwork_zero;   // ... its output buffer currently holds zeros (idle CTAs are not launched)
   DevBuf<int> widx;               // per chunk: grouped Welsh CTAs sorted into resting (4 variants) and general
+  std::vector<int> widx_on_device;  // what widx.d currently holds (unchanged lists are not uploaded again)
+  bool wev_empty_on_device = false, fev_empty_on_device = false;  // the event offset tables on the device are all zero
   DevBuf<VoiceEvent> wev, fev;
   DevBuf<int> wev_off, fev_off;
   DevBuf<SamplePlay> plays;
@@ -1468,8 +1470,12 @@ int render_chunk(gb_engine* e, int frames, size_t n_ev) {
 
   // ---- 3. voices ----
   auto upload_events = [&](std::vector<std::vector<VoiceEvent>>& lists, DevBuf<VoiceEvent>& evb, DevBuf<int>& offb,
-                           bool any) -> int {
+                           bool any, bool* empty_on_device) -> int {
     size_t nv = lists.size(), total = 0;
+    // a chunk without note events needs the all-zero offset table: if that is what the device already
+    // holds, nothing is uploaded (every small copy costs the stream several microseconds)
+    if (!any && *empty_on_device) return 0;
+    *empty_on_device = !any;
     if (!offb.reserve(nv + 1)) return fail(e, GB_ENOMEM, "out of memory");
     if (any)
       for (auto& l : lists) total += l.size();
@@ -1500,7 +1506,7 @@ int render_chunk(gb_engine* e, int frames, size_t n_ev) {
       e->stats.h2d_bytes += e->h_winst.size() * sizeof(WelshInst);
       e->winst_dirty = false;
     }
-    int rc = upload_events(wlists, e->wev, e->wev_off, any_w);
+    int rc = upload_events(wlists, e->wev, e->wev_off, any_w, &e->wev_empty_on_device);
     if (rc) return rc;
     {
       // Sort the grouped CTAs of this chunk: a CTA whose voices all rest for the whole chunk (note held
@@ -1546,12 +1552,14 @@ int render_chunk(gb_engine* e, int frames, size_t n_ev) {
       }
       if (ng) {
         if (!e->widx.reserve((size_t)ng)) return fail(e, GB_ENOMEM, "out of memory");
-        size_t k = 0;
-        for (auto& l : lists)
-          for (int i : l) e->widx.h[k++] = i;
-        if (k) {
+        std::vector<int> flat;
+        for (auto& l : lists) flat.insert(flat.end(), l.begin(), l.end());
+        const size_t k = flat.size();
+        if (k && flat != e->widx_on_device) {
+          memcpy(e->widx.h, flat.data(), k * sizeof(int));
           CUDA_TRY(e, cudaMemcpyAsync(e->widx.d, e->widx.h, k * sizeof(int), cudaMemcpyHostToDevice, e->stream));
           e->stats.h2d_bytes += k * sizeof(int);
+          e->widx_on_device = flat;
         }
       }
       const size_t rest_smem = (size_t)kVoiceWarps * kTileStride * sizeof(double2) + rest_voices_max * sizeof(RestState);
@@ -1593,7 +1601,7 @@ int render_chunk(gb_engine* e, int frames, size_t n_ev) {
       e->stats.h2d_bytes += e->h_finst.size() * sizeof(FmInst);
       e->finst_dirty = false;
     }
-    int rc = upload_events(flists, e->fev, e->fev_off, any_f);
+    int rc = upload_events(flists, e->fev, e->fev_off, any_f, &e->fev_empty_on_device);
     if (rc) return rc;
     {
       Launch l(e, true);

@@ -316,3 +316,42 @@ def test_resting_paths_agree_at_size(monkeypatch):
     assert np.abs(a).max() > 1e-3
     assert np.abs(a - b).max() < 1e-12
     assert np.abs(a - c).max() < 1e-10
+
+
+def test_split_instruments_summed_by_their_consumer(monkeypatch):
+    """Instruments split over several CTAs write partial buffers.  When their only consumer sums more than
+    kMaxSources inputs from a pointer table, the table lists the partial buffers themselves and the
+    separate reduce pass is skipped (GB_FUSED_SUMS=0 restores it).  Both against the oracle; idle CTAs at
+    the end of the render are not launched at all (their buffers are zeroed once)."""
+    monkeypatch.setenv("GB_VPC", "8")
+    frames = 9000
+
+    def scene(r):
+        uids = []
+        for i in range(12):
+            p = scenes.generic_welsh(w1=abi.WAVE_SAWTOOTH, w2=abi.WAVE_PULSE_WIDTH, pw2=0.3, voices=20, gain=0.05,
+                                     pan=-0.9 + 0.15 * i, filt=(0.0, 0.02, 0.5, 0.02), amp=(0.002, 0.01, 0.8, 0.01))
+            u = r.add_instrument(abi.INST_WELSH, p)
+            r.patch(u, abi.MAIN_MIXER)
+            uids.append(u)
+        r.finalize()
+        for i, u in enumerate(uids):
+            for v in range(20):
+                r.note_on(3 * i + 11 * v, u, 30 + v)
+                r.note_off(5000 + 7 * v + i, u, 30 + v)
+        return frames
+
+    o = OracleEngine(48000.0)
+    scene(o)
+    ref = o.render(frames)
+    outs = []
+    for fused in ("1", "0"):
+        monkeypatch.setenv("GB_FUSED_SUMS", fused)
+        g = gpu_engine(48000.0, max_block=1024)
+        scene(g)
+        outs.append(g.render(frames))
+        g.close()
+    check(outs[0], ref)
+    check(outs[1], ref)
+    assert np.abs(outs[0] - outs[1]).max() < 1e-14
+    assert np.all(outs[0][-1024:] == 0.0)     # idle tail

@@ -46,7 +46,7 @@ def child(lib: str, seconds: float, voices: int, reps: int, out_npy: str, filter
         st = e.stats()
         r = {"render_ms": st.render_ms, "voice_kernel_ms": st.voice_kernel_ms, "launches": st.voice_kernel_launches,
              "rest_ms": getattr(st, "rest_kernel_ms", 0.0), "rest_launches": getattr(st, "rest_kernel_launches", 0),
-             "rest_vs": getattr(st, "rest_voice_samples", 0)}
+             "rest_vs": getattr(st, "rest_voice_samples", 0), "fx_ms": st.fx_kernel_ms, "all_launches": st.kernel_launches}
         e.close()
         if best is None or r["voice_kernel_ms"] < best["voice_kernel_ms"]:
             best = r
@@ -92,7 +92,7 @@ def main():
             ref = y
         diff = float(np.abs(y - ref).max())
         print(f"{os.path.basename(lib):28s} launch {r['launch_ms']:.3f} ms  render {r['render_ms']:.2f} ms  "
-              f"{r['vs_per_s']:.3e} vs/s  rest {r.get('rest_ms', 0) / max(r.get('rest_launches', 0), 1):.3f} ms x {r.get('rest_launches', 0)}  peak {np.abs(y).max():.4f}  maxdiff_vs_first {diff:.3e}", flush=True)
+              f"{r['vs_per_s']:.3e} vs/s  rest {r.get('rest_ms', 0) / max(r.get('rest_launches', 0), 1):.3f} ms x {r.get('rest_launches', 0)}  voice {r['voice_kernel_ms']:.2f} fx {r.get('fx_ms', 0):.2f} gap {r['render_ms'] - r['voice_kernel_ms'] - r.get('fx_ms', 0):.2f} ms ({r.get('all_launches', 0)} launches)  peak {np.abs(y).max():.4f}  maxdiff_vs_first {diff:.3e}", flush=True)
 
 
 if __name__ == "__main__":
