@@ -253,7 +253,7 @@ def run_ours(a) -> None:
     barrier()
     sampler = ClockSampler(local) if rank == 0 else None
     dev_ms, kern_ms, launches, vlaunches, wall_dev = 0.0, 0.0, 0, 0, 0.0
-    rest_ms, rest_launches, rest_vs = 0.0, 0, 0
+    rest_ms, rest_launches, rest_vs, fx_ms = 0.0, 0, 0, 0.0
     t_region = time.perf_counter()
     for _ in range(a.steps):
         wall, st = one_step("device")
@@ -264,6 +264,7 @@ def run_ours(a) -> None:
         rest_ms += st.rest_kernel_ms
         rest_launches += st.rest_kernel_launches
         rest_vs += st.rest_voice_samples
+        fx_ms += st.fx_kernel_ms
         wall_dev += wall
     barrier()
     region_s = time.perf_counter() - t_region
@@ -382,6 +383,12 @@ def run_ours(a) -> None:
                         "re-deriving them per frame: it executes fewer FP64 instructions than the algorithmic count, "
                         "which is why frac can exceed what the pipe utilisation alone would give; see "
                         "executed_fp64_instr_per_voice_sample / fp64_pipe_active_pct (ncu) and the time_varying leg.",
+                "executed": ({"fp64_flop_per_voice_sample": prof["fp64_flop_per_voice_sample"],
+                              "tflops": prof["fp64_flop_per_voice_sample"] * vs_per_launch / launch_s / 1e12,
+                              "frac": prof["fp64_flop_per_voice_sample"] * vs_per_launch / launch_s / 1e12 / fp64_peak,
+                              "what": "FP64 FLOP the kernel actually executes per voice-sample (ncu opcode mix: "
+                                      "2 per DFMA, 1 per DMUL / DADD) over the same launch time"}
+                             if use_rest and "fp64_flop_per_voice_sample" in prof else None),
                 "executed_fp64_instr_per_voice_sample": prof.get("fp64_instr_per_voice_sample"),
                 "fp64_pipe_active_pct": prof.get("fp64_pipe_active_pct"),
                 "issue_active_pct": prof.get("issue_active_pct"),
@@ -391,6 +398,15 @@ def run_ours(a) -> None:
             "clocks": clocks,
             "timed_region_s": region_s,
         }
+        if not cfg5 and world == 1 and fx_ms > 0:
+            # the mixdown side of the step: split instruments' partial buffers summed into the mixer bus
+            # (sum_table_kernel + the mixer's pointwise pass), HBM-bound: 16 B per partial per frame
+            chunks = -(-frames // a.max_block)
+            mix_bytes = (ctas_per_launch + 1 + 2) * 16.0 * frames
+            out["mixdown"] = {"kernel": "sum_table_kernel + pointwise_kernel", "bound": "hbm",
+                              "bytes_per_step": mix_bytes, "ms_per_step": fx_ms / a.steps,
+                              "achieved": mix_bytes / (fx_ms / a.steps * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
+                              "frac": mix_bytes / (fx_ms / a.steps * 1e-3) / 1e9 / hbm_peak, "chunks": chunks}
         if tv:
             tv_launch_s = tv["kern_ms"] * 1e-3 / max(tv["launches"], 1)
             tv_ach = workloads.W_VOICE_FLOP * tv["voice_samples"] / max(tv["launches"], 1) / tv_launch_s / 1e12

@@ -610,7 +610,7 @@ struct Launch {  // per-launch accounting (+ optional CUDA-event timing on the e
 inline int cdiv(int a, int b) { return (a + b - 1) / b; }
 
 // Sum a node's inputs.  Up to kMaxSources go straight into the consuming kernel; more are
-// pre-reduced left to right into the node's scratch buffer.
+// pre-reduced (sum_table_kernel: four interleaved row sums, added in row order) into the node's scratch buffer.
 int gather_sources(gb_engine* e, Node* n, int frames, SourceList* out) {
   std::vector<const double2*> ptrs;
   for (uint32_t s : n->sources) {
@@ -627,9 +627,9 @@ int gather_sources(gb_engine* e, Node* n, int frames, SourceList* out) {
     // the pointer table was uploaded at finalize (sources never change afterwards)
     Launch l(e, false);
     if (e->fused_sums && n->d_src_table_fused)
-      sum_table_kernel<<<cdiv(frames, 256), 256, 0, e->stream>>>(n->d_src_table_fused, n->n_src_fused, n->scratch, frames);
+      sum_table_kernel<<<cdiv(frames, kSumFrames), kSumRows * kSumFrames, 0, e->stream>>>(n->d_src_table_fused, n->n_src_fused, n->scratch, frames);
     else
-      sum_table_kernel<<<cdiv(frames, 256), 256, 0, e->stream>>>(n->d_src_table, (int)ptrs.size(), n->scratch, frames);
+      sum_table_kernel<<<cdiv(frames, kSumFrames), kSumRows * kSumFrames, 0, e->stream>>>(n->d_src_table, (int)ptrs.size(), n->scratch, frames);
   }
   out->n = 1;
   out->p[0] = n->scratch;
@@ -1474,7 +1474,7 @@ int render_chunk(gb_engine* e, int frames, size_t n_ev) {
     size_t nv = lists.size(), total = 0;
     // a chunk without note events needs the all-zero offset table: if that is what the device already
     // holds, nothing is uploaded (every small copy costs the stream several microseconds)
-    if (!any && *empty_on_device) return 0;
+    if (!any && *empty_on_device && offb.cap >= nv + 1) return 0;
     *empty_on_device = !any;
     if (!offb.reserve(nv + 1)) return fail(e, GB_ENOMEM, "out of memory");
     if (any)
@@ -1551,6 +1551,7 @@ int render_chunk(gb_engine* e, int frames, size_t n_ev) {
         }
       }
       if (ng) {
+        if (e->widx.cap < (size_t)ng) e->widx_on_device.clear();  // a new device buffer holds nothing yet
         if (!e->widx.reserve((size_t)ng)) return fail(e, GB_ENOMEM, "out of memory");
         std::vector<int> flat;
         for (auto& l : lists) flat.insert(flat.end(), l.begin(), l.end());

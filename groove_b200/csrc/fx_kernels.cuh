@@ -130,17 +130,41 @@ __global__ void __launch_bounds__(128) sidechain_table_kernel(const double2* __r
   }
 }
 
-// out[t] = sum over a device-resident pointer table, left to right (any number of sources).
-__global__ void __launch_bounds__(256) sum_table_kernel(const double2* const* __restrict__ ptrs, int n,
-                                                         double2* __restrict__ out, int frames) {
-  int t = blockIdx.x * blockDim.x + threadIdx.x;
-  if (t >= frames) return;
+// out[t] = sum over a device-resident pointer table (any number of sources).  HBM-bound: 16 bytes per
+// source per frame.  A block covers 64 frames with 4 thread rows; row r sums sources r, r+4, r+8, ...
+// (4 loads in flight each, so 16 per frame) and row 0 adds the four row sums in row order — a fixed
+// summation order, independent of the launch.
+constexpr int kSumRows = 4, kSumFrames = 64;
+__global__ void __launch_bounds__(kSumRows * kSumFrames) sum_table_kernel(const double2* const* __restrict__ ptrs, int n,
+                                                                          double2* __restrict__ out, int frames) {
+  __shared__ double2 part[kSumRows][kSumFrames];
+  const int tx = threadIdx.x % kSumFrames, row = threadIdx.x / kSumFrames;
+  const int t = blockIdx.x * kSumFrames + tx;
   double l = 0.0, r = 0.0;
-  for (int k = 0; k < n; ++k) {
-    double2 v = ptrs[k][t];
-    l += v.x; r += v.y;
+  if (t < frames) {
+    int k = row;
+    for (; k + 3 * kSumRows < n; k += 4 * kSumRows) {
+      const double2 a = ptrs[k][t], b = ptrs[k + kSumRows][t], c = ptrs[k + 2 * kSumRows][t], d = ptrs[k + 3 * kSumRows][t];
+      l += a.x; r += a.y;
+      l += b.x; r += b.y;
+      l += c.x; r += c.y;
+      l += d.x; r += d.y;
+    }
+    for (; k < n; k += kSumRows) {
+      const double2 a = ptrs[k][t];
+      l += a.x; r += a.y;
+    }
   }
-  out[t] = make_double2(l, r);
+  part[row][tx] = make_double2(l, r);
+  __syncthreads();
+  if (row == 0 && t < frames) {
+#pragma unroll
+    for (int q = 1; q < kSumRows; ++q) {
+      l += part[q][tx].x;
+      r += part[q][tx].y;
+    }
+    out[t] = make_double2(l, r);
+  }
 }
 // One launch for every instrument whose voices are split over several CTAs: blockIdx.y picks the
 // instrument; its partial buffers are `count` planes `stride` frames apart.
