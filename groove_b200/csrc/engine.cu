@@ -776,6 +776,7 @@ int gb_create(const gb_config* cfg, gb_engine** out) {
   e->device = cfg->device;
   e->sr = cfg->sample_rate;
   e->max_block = cfg->max_block ? cfg->max_block : kDefaultMaxBlock;
+  if (e->max_block > (1u << 20)) e->max_block = 1u << 20;  // node buffers and the pinned ring are sized by it
   memset(&e->stats, 0, sizeof e->stats);
   cudaDeviceProp prop;
   if (cudaGetDeviceProperties(&prop, e->device) == cudaSuccess) e->num_sms = prop.multiProcessorCount;
