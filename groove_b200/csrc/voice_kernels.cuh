@@ -47,10 +47,15 @@ __device__ __forceinline__ double osc_affine(const OscShape& o, u64 q, u64 thres
   const bool lo = q < thresh;
   return fma(lo ? o.a_lo : o.a_hi, pos_of(q), lo ? o.b_lo : o.b_hi);
 }
+// sine and noise oscillators: one shared out-of-line copy (the library sinpi is ~100 instructions, and the
+// fast block evaluates up to three oscillators at each of its kT unrolled frames)
+__device__ __noinline__ double osc_other_ool(int kind, u64 q, u64 seed, i64 frame) {
+  if (kind == 1) return sinpi(2.0 * pos_of(q));
+  return __ull2double_rn(splitmix64(seed + (u64)frame) >> 11) * (1.0 / 4503599627370496.0) - 1.0;
+}
 __device__ __forceinline__ double osc_eval(const OscShape& o, u64 q, u64 thresh, u64 seed, i64 frame) {
   if (o.kind == 0) return osc_affine(o, q, thresh);
-  if (o.kind == 1) return sinpi(2.0 * pos_of(q));
-  return __ull2double_rn(splitmix64(seed + (u64)frame) >> 11) * (1.0 / 4503599627370496.0) - 1.0;
+  return osc_other_ool(o.kind, q, seed, frame);
 }
 
 // ---- range-specialised elementary functions for the cutoff -> coefficient map ----------------------
@@ -267,6 +272,16 @@ __device__ __noinline__ WelshVoice welsh_fold(WelshVoice st, const WelshInst* Ip
   return st;
 }
 
+// Shared out-of-line copies of the heavy per-frame pieces of the general block: its loops are unrolled
+// over the lane's kT frames, and with the waveform switch (library sinpi inside) and the coefficient map
+// inlined at every frame one variant of the block was 9 k instructions — an instruction-cache problem
+// wherever the warps of an SM sit in different blocks (solo-warp kernel).  The general block runs for
+// note events, envelope stage boundaries and pitch-LFO voices; a call per frame is noise there.
+__device__ __noinline__ double wave_value_ool(int wf, u64 q, u64 duty_q, u64 seed, i64 frame) {
+  return wave_value(wf, q, duty_q, seed, frame);
+}
+__device__ __noinline__ void welsh_coef_exact_ool(const WelshInst* Ip, double pct, SecCoef* c1, SecCoef* c2);
+
 // One warp step: kBlockFrames frames of one voice starting at frame fb (absolute), valid frames < f_end.
 // `st` is the warp-uniform voice state at fb; on return it is the state at fb + kBlockFrames.
 // EV (warp-uniform) = this voice has note events inside the block; the EV=false instantiation is
@@ -321,7 +336,7 @@ __device__ __forceinline__ void welsh_block(WelshVoice& st, const WelshInst& I, 
       if (play) {
         pplay |= 1u << j;
         u64 pl = ps.pl + (u64)(n - ps.anchor) * I.lfo_dq;
-        double l = wave_value(I.wl, pl, I.dutyl_q, seedl, n);
+        double l = wave_value_ool(I.wl, pl, I.dutyl_q, seedl, n);
         f = exp2(l * I.depth);
         if (reset_bits & (1u << j)) { a1.sum = 0; a1.reset = 1; }
         else a1.sum += cycles_to_q(ps.cyc1 * f);
@@ -407,7 +422,7 @@ __device__ __forceinline__ void welsh_block(WelshVoice& st, const WelshInst& I, 
         u64 pl;
         if (PITCH) pl = ls.pl + (u64)(n - ls.anchor) * I.lfo_dq;
         else { ph.pl += I.lfo_dq; pl = ph.pl; }
-        ld = wave_value(I.wl, pl, I.dutyl_q, seedl, n) * I.depth;
+        ld = wave_value_ool(I.wl, pl, I.dutyl_q, seedl, n) * I.depth;
       }
       // oscillators
       if (PITCH) {
@@ -435,8 +450,8 @@ __device__ __forceinline__ void welsh_block(WelshVoice& st, const WelshInst& I, 
         du1 = cycles_to_q(a);
         du2 = cycles_to_q(b);
       }
-      double o1 = wave_value(I.w1, ph.p1, du1, seed1, n);
-      double o2 = wave_value(I.w2, ph.p2, du2, seed2, n);
+      double o1 = wave_value_ool(I.w1, ph.p1, du1, seed1, n);
+      double o2 = wave_value_ool(I.w2, ph.p2, du2, seed2, n);
       double x = o1 * I.mix + o2 * (1.0 - I.mix);
       // filter coefficients
       SecCoef c1 = I.fixed1, c2 = I.fixed2;
@@ -448,12 +463,7 @@ __device__ __forceinline__ void welsh_block(WelshVoice& st, const WelshInst& I, 
         } else {
           pct = I.cut_a * (1.0 + ld);
         }
-        pct = pct < 0.0 ? 0.0 : (pct > 1.0 ? 1.0 : pct);
-        double fc = 25.0 * exp2(pct * kLog2_800);
-        double fmax = 0.49 * I.sr;
-        fc = fc > fmax ? fmax : fc;
-        fc = fc < 1.0 ? 1.0 : fc;
-        lp24_from_k(I.rp, tan(fc * I.pi_over_sr), c1, c2);
+        welsh_coef_exact_ool(&I, pct, &c1, &c2);  // clamps pct to [0,1] and fc to [1 Hz, 0.49 sr]
       }
       sb0[j] = c2.b0; sa1[j] = c2.a1; sa2[j] = c2.a2;
       // amplitude
@@ -597,6 +607,10 @@ __device__ __forceinline__ void welsh_coef_exact(const WelshInst& I, double pct,
   lp24_from_u(I.rp, u, c1, c2);
 }
 
+__device__ __noinline__ void welsh_coef_exact_ool(const WelshInst* Ip, double pct, SecCoef* c1, SecCoef* c2) {
+  welsh_coef_exact(*Ip, pct, *c1, *c2);
+}
+
 // Quadratic through (0,k0), (kT/2,k4), (kT,k8) in Newton form: c(j) = k0 + j*(d1 + (j - kT/2)*d2).
 struct Quad {
   double k0, d1, d2;
@@ -702,7 +716,7 @@ __device__ __forceinline__ void welsh_block_fast(WelshVoice& st, const WelshInst
         SecCoef c2;
         const double pct = I.filter_mode == FILTER_ENVELOPE ? fma(I.cut_b, env_seg_at(fseg, j), I.cut_a)
                                                             : I.cut_a * (1.0 + ld);
-        welsh_coef_exact(I, pct, c1, c2);
+        welsh_coef_exact_ool(&I, pct, &c1, &c2);  // one shared copy: this block is unrolled over kT frames
         sb0[j] = c2.b0; sa1[j] = c2.a1; sa2[j] = c2.a2;
       } else if (CMODE == COEF_KNOTS) {
         c1.b0 = quad_at(qb1, j); c1.a1 = quad_at(qa11, j); c1.a2 = quad_at(qa21, j);
