@@ -10,7 +10,8 @@ shard (weak scaling) and the stereo buses are summed onto rank 0 with one NCCL f
 
 Printed JSON (one line, rank 0):
   value      whole-job voice-samples/s, device-timed (CUDA events on the engine's stream around
-             each render call), inputs resident in HBM, result left in HBM;
+             each render call; at N > 1 plus CUDA events around the NCCL bus reduce, max over
+             ranks), inputs resident in HBM, result left in HBM;
   e2e        the same metric through the C ABI with host buffers: events pushed from host memory
              and the f64 stereo result copied back to a host buffer inside the timed region;
   roofline   dominant kernel (config 4: welsh_rest_kernel, the resting-voice kernel) against the FP64
@@ -228,10 +229,16 @@ def run_ours(a) -> None:
         flush.zero_()
         barrier()
         t0 = time.perf_counter()
+        reduce_ms = 0.0
         if mode == "device":
-            eng.render_device(frames)
-            bus_reduce(eng)
-            torch.cuda.synchronize()
+            eng.render_device(frames)        # returns with the engine's stream drained
+            if world > 1:                    # the bus reduce, device-timed on the stream NCCL is enqueued from
+                ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                ev0.record()
+                bus_reduce(eng)
+                ev1.record()
+                torch.cuda.synchronize()
+                reduce_ms = ev0.elapsed_time(ev1)
         else:
             if world == 1:
                 eng.render(frames, host_out)
@@ -244,6 +251,7 @@ def run_ours(a) -> None:
         wall = time.perf_counter() - t0
         st = eng.stats()
         eng.close()
+        st.reduce_ms = reduce_ms
         return wall, st
 
     # warm-up (both modes), then the timed steps
@@ -258,7 +266,7 @@ def run_ours(a) -> None:
     t_region = time.perf_counter()
     for _ in range(a.steps):
         wall, st = one_step("device")
-        dev_ms += st.render_ms
+        dev_ms += st.render_ms + st.reduce_ms   # device time of the step: render (engine events) + bus reduce
         kern_ms += st.voice_kernel_ms
         launches += st.kernel_launches
         vlaunches += st.voice_kernel_launches
@@ -301,8 +309,9 @@ def run_ours(a) -> None:
     if world > 1:
         dist.all_reduce(vals, op=dist.ReduceOp.MAX)
     dev_ms, wall_dev, e2e_wall, kern_ms = [float(x) for x in vals.tolist()]
-    # N > 1: the reduce is outside the engine's events, so the step time is the synchronized wall time
-    step_s = (dev_ms * 1e-3 if world == 1 else wall_dev) / a.steps
+    # device-timed at every N (max over ranks): CUDA events around the render on the engine's stream plus,
+    # at N > 1, CUDA events around the NCCL bus reduce; e2e below is wall clock
+    step_s = dev_ms * 1e-3 / a.steps
     per_rank_vs = a.variants * frames if cfg5 else cfg.voice_samples
     total_vs = per_rank_vs * world
     value = total_vs / step_s
