@@ -355,3 +355,48 @@ def test_split_instruments_summed_by_their_consumer(monkeypatch):
     check(outs[1], ref)
     assert np.abs(outs[0] - outs[1]).max() < 1e-14
     assert np.all(outs[0][-1024:] == 0.0)     # idle tail
+
+
+def test_save_restore_across_resting_chunks_and_sidechain():
+    """State save / restore in the middle of a render whose chunks use the resting-voice kernel and a
+    sidechain link (device-side link state, cached filter state written back per chunk), and the
+    multi-chunk PCM16 path: the resumed render continues bit-identically."""
+    def scene(r):
+        u = r.add_instrument(abi.INST_WELSH, scenes.generic_welsh(
+            w1=abi.WAVE_PULSE_WIDTH, pw1=0.2, w2=abi.WAVE_SQUARE, voices=16, gain=0.1, routing=abi.LFO_AMPLITUDE,
+            depth=0.1, lfo_hz=6.0, filt=(0.0, 0.01, 0.6, 0.05), amp=(0.002, 0.0, 1.0, 0.01)))
+        tap = r.add_effect(abi.FX_SIGNAL_PASSTHROUGH)
+        d = r.add_instrument(abi.INST_FM, scenes.fm_params(car=(0.0, 0.08, 0.0, 0.08), gain=0.8))
+        comp = r.add_effect(abi.FX_COMPRESSOR, abi.CompressorParams(1.0, 0.3, 0.0, 0.0))
+        r.patch_chain([d, tap, abi.MAIN_MIXER])
+        r.patch_chain([u, comp, abi.MAIN_MIXER])
+        r.link_control(tap, comp, 0)
+        r.finalize()
+        for v in range(16):
+            r.note_on(2 + v, u, 36 + v)
+            r.note_off(14000 + v, u, 36 + v)
+        for k in range(5):
+            r.note_on(100 + 3000 * k, d, 40 + k)
+            r.note_off(1500 + 3000 * k, d, 40 + k)
+        return 16384
+
+    g = gpu_engine(48000.0, max_block=2048)
+    n = scene(g)
+    first = g.render(6144).copy()
+    blob = g.save_state()
+    rest_a = g.render(n - 6144).copy()
+    st = g.stats()
+    g.restore_state(blob)
+    rest_b = g.render(n - 6144).copy()
+    g.close()
+    assert st.rest_kernel_launches > 0
+    assert np.array_equal(rest_a, rest_b)
+    o = OracleEngine(48000.0)
+    scene(o)
+    ref = o.render(n)
+    check(np.concatenate([first, rest_a]), ref)
+    g = gpu_engine(48000.0, max_block=2048)
+    scene(g)
+    pcm = g.render_pcm16(n)
+    g.close()
+    assert int(np.abs(pcm.astype(np.int32) - pcm16(np.clip(ref, -1.0, 1.0)).astype(np.int32)).max()) <= 1
