@@ -339,6 +339,12 @@ def test_split_instruments_summed_by_their_consumer(monkeypatch):
             for v in range(20):
                 r.note_on(3 * i + 11 * v, u, 30 + v)
                 r.note_off(5000 + 7 * v + i, u, 30 + v)
+        # gain / pan automation on a split instrument (its node buffer is needed for the DCA pass: the
+        # shortcut must step aside for that chunk), and an instrument that wakes up again after idling
+        r.control(2048 + 64, uids[3], 0, 0.5)      # GB_CTL_INST_DCA_GAIN
+        r.control(3000, uids[3], 1, 0.9)           # GB_CTL_INST_DCA_PAN
+        r.note_on(7300, uids[5], 50)
+        r.note_off(7900, uids[5], 50)
         return frames
 
     o = OracleEngine(48000.0)
@@ -354,7 +360,7 @@ def test_split_instruments_summed_by_their_consumer(monkeypatch):
     check(outs[0], ref)
     check(outs[1], ref)
     assert np.abs(outs[0] - outs[1]).max() < 1e-14
-    assert np.all(outs[0][-1024:] == 0.0)     # idle tail
+    assert np.all(outs[0][-512:] == 0.0)      # idle tail
 
 
 def test_save_restore_across_resting_chunks_and_sidechain():
