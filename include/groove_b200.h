@@ -37,7 +37,7 @@
 extern "C" {
 #endif
 
-#define GB_ABI_VERSION 1
+#define GB_ABI_VERSION 2 /* 2: gb_link_control, GB_FX_SIGNAL_PASSTHROUGH, gb_stats grew (rest_kernel_*) */
 
 /* ---- error codes --------------------------------------------------------- */
 enum {
