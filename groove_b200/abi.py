@@ -133,7 +133,8 @@ class Stats(C.Structure):
     _fields_ = [("kernel_launches", C.c_uint64), ("voice_kernel_launches", C.c_uint64),
                 ("voice_kernel_ms", C.c_double), ("fx_kernel_ms", C.c_double), ("render_ms", C.c_double),
                 ("voice_samples", C.c_uint64), ("h2d_bytes", C.c_uint64), ("d2h_bytes", C.c_uint64),
-                ("rest_kernel_launches", C.c_uint64), ("rest_kernel_ms", C.c_double), ("rest_voice_samples", C.c_uint64)]
+                ("rest_kernel_launches", C.c_uint64), ("rest_kernel_ms", C.c_double), ("rest_voice_samples", C.c_uint64),
+                ("sweep_kernel_launches", C.c_uint64), ("sweep_kernel_ms", C.c_double), ("sweep_voice_samples", C.c_uint64)]
 
 
 # every symbol include/groove_b200.h declares (suffix after the prefix)

@@ -549,6 +549,12 @@ void welsh_inst_from_params(const Node& n, double sr, WelshInst* I) {
     if (lin && I->lti_ok && (I->filter_mode == FILTER_FIXED || I->filter_mode == FILTER_ENVELOPE))
       I->rest_class = (I->routing == LFO_AMPLITUDE ? 2 : 0) + (I->osc_flat ? 1 : 0);
     if (const char* v = getenv("GB_REST_KERNEL")) if (atoi(v) == 0) I->rest_class = -1;
+    // welsh_sweep_kernel: the knot path of a moving filter envelope; the frequency clamp must stay out of
+    // reach (0.49 sr >= 20 kHz) so that the coefficient trajectory of a stage is smooth
+    I->sweep_class = -1;
+    if (lin && I->filter_mode == FILTER_ENVELOPE && I->knot_max_rate > 0.0 && 0.49 * sr >= 20000.0)
+      I->sweep_class = (I->routing == LFO_AMPLITUDE ? 2 : 0) + (I->osc_flat ? 1 : 0);
+    if (const char* v = getenv("GB_SWEEP_KERNEL")) if (atoi(v) == 0) I->sweep_class = -1;
   }
 }
 void fm_inst_from_params(const Node& n, double sr, FmInst* I) {
@@ -584,6 +590,7 @@ void resolve_spans(gb_engine* e) {
     cudaEventElapsedTime(&ms, sp.a, sp.b);
     if (sp.what == 1) e->stats.voice_kernel_ms += ms;
     else if (sp.what == 3) { e->stats.voice_kernel_ms += ms; e->stats.rest_kernel_ms += ms; }
+    else if (sp.what == 4) { e->stats.voice_kernel_ms += ms; e->stats.sweep_kernel_ms += ms; }
     else if (sp.what == 0) e->stats.fx_kernel_ms += ms;
     else e->stats.render_ms += ms;
     e->event_pool.push_back({sp.a, sp.b});
@@ -595,11 +602,12 @@ struct Launch {  // per-launch accounting (+ optional CUDA-event timing on the e
   gb_engine* e;
   bool timed;
   size_t index;
-  Launch(gb_engine* e_, bool voice, bool rest = false) : e(e_) {
+  Launch(gb_engine* e_, bool voice, int special = 0) : e(e_) {  // special: 1 = resting kernel, 2 = sweeping kernel
     e->stats.kernel_launches++;
     if (voice) e->stats.voice_kernel_launches++;
-    if (rest) e->stats.rest_kernel_launches++;
-    timed = span_begin(e, rest ? 3 : voice ? 1 : 0);
+    if (special == 1) e->stats.rest_kernel_launches++;
+    if (special == 2) e->stats.sweep_kernel_launches++;
+    timed = span_begin(e, special == 1 ? 3 : special == 2 ? 4 : voice ? 1 : 0);
     index = e->spans.size() - 1;
   }
   ~Launch() {
@@ -1270,6 +1278,10 @@ int gb_finalize(gb_engine* e) {
   CUDA_TRY(e, cudaFuncSetAttribute(welsh_rest_kernel<8, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kRestSmemMax));
   CUDA_TRY(e, cudaFuncSetAttribute(welsh_rest_kernel<8, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kRestSmemMax));
   CUDA_TRY(e, cudaFuncSetAttribute(welsh_rest_kernel<8, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kRestSmemMax));
+  CUDA_TRY(e, cudaFuncSetAttribute(welsh_sweep_kernel<8, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kRestSmemMax));
+  CUDA_TRY(e, cudaFuncSetAttribute(welsh_sweep_kernel<8, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kRestSmemMax));
+  CUDA_TRY(e, cudaFuncSetAttribute(welsh_sweep_kernel<8, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kRestSmemMax));
+  CUDA_TRY(e, cudaFuncSetAttribute(welsh_sweep_kernel<8, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kRestSmemMax));
   CUDA_TRY(e, cudaFuncSetAttribute(fm_kernel<kVoiceWarps>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                    (int)(kVoiceWarps * kTileStride * sizeof(double2))));
   CUDA_TRY(e, cudaStreamSynchronize(e->stream));
@@ -1515,11 +1527,11 @@ int render_chunk(gb_engine* e, int frames, size_t n_ev) {
       // goes to welsh_rest_kernel, the others to welsh_kernel.  Host knowledge only: note frames are
       // integers tracked by the slot stores.
       const int ng = e->n_wwork_grouped, ns = e->n_wwork - e->n_wwork_grouped;
-      std::vector<int> lists[5];  // 0..3 = resting variants, 4 = general (idle CTAs are not launched at all)
+      std::vector<int> lists[9];  // 0..3 = resting variants, 4 = general, 5..8 = sweeping variants (idle CTAs are not launched)
       e->wwork_zero.resize((size_t)ng, 0);
       const bool chunk_ok = frames % kBlockFrames == 0;
-      size_t rest_voices_max = 0;
-      uint64_t rest_voices = 0;
+      size_t rest_voices_max = 0, sweep_voices_max = 0;
+      uint64_t rest_voices = 0, sweep_voices = 0;
       for (int i = 0; i < ng; ++i) {
         const CtaWork& w = e->wwork.h[i];
         const Node* n = e->wwork_node[(size_t)i];
@@ -1545,6 +1557,30 @@ int render_chunk(gb_engine* e, int frames, size_t n_ev) {
           continue;
         }
         e->wwork_zero[(size_t)i] = 0;
+        // sweeping: every voice held since before the chunk, no note event in it, the filter envelope inside one
+        // moving stage and the amplitude envelope inside one stage for the whole chunk, the cutoff slow enough
+        // for coefficient knots (the bound uses the stage's steepest slope)
+        bool sweep = !rest && chunk_ok && I.sweep_class >= 0 &&
+                     kVoiceWarps * kTileStride * sizeof(double2) + (size_t)w.nvoices * sizeof(SweepState) <= (size_t)kRestSmemMax;
+        auto stage_of = [](const EnvShape& sh, int64_t k) { return k < sh.na ? 0 : (k - sh.na < sh.nd ? 1 : 2); };
+        for (int v = 0; sweep && v < w.nvoices; ++v) {
+          const Slot& sl = n->store.slots[(size_t)(w.voice0 - n->voice0 + v)];
+          sweep = wlists[(size_t)(w.voice0 + v)].empty() && sl.held && sl.on_frame > kNever && sl.on_frame <= f0;
+          if (!sweep) break;
+          const int64_t k0 = f0 - sl.on_frame, k1 = k0 + frames - 1;
+          const int sa = stage_of(I.amp, k0), sf = stage_of(I.filt, k0);
+          sweep = sa == stage_of(I.amp, k1) && sf == stage_of(I.filt, k1) && sf != 2;
+          if (sweep) {
+            const double slope = sf == 0 ? 2.0 * I.filt.inv_na : 2.0 * (1.0 - I.filt.sustain) * I.filt.inv_nd;
+            sweep = std::fabs(I.cut_b) * slope <= I.knot_max_rate;
+          }
+        }
+        if (sweep) {
+          lists[5 + I.sweep_class].push_back(i);
+          sweep_voices_max = std::max(sweep_voices_max, (size_t)w.nvoices);
+          sweep_voices += (uint64_t)w.nvoices;
+          continue;
+        }
         lists[rest ? I.rest_class : 4].push_back(i);
         if (rest) {
           rest_voices_max = std::max(rest_voices_max, (size_t)w.nvoices);
@@ -1568,7 +1604,7 @@ int render_chunk(gb_engine* e, int frames, size_t n_ev) {
       size_t off = 0;
 #define GB_REST_LAUNCH(CLS_, LFO_, FLAT_)                                                                            \
   if (!lists[CLS_].empty()) {                                                                                        \
-    Launch l(e, true, true);                                                                                         \
+    Launch l(e, true, 1);                                                                                            \
     welsh_rest_kernel<8, LFO_, FLAT_><<<(int)lists[CLS_].size(), 32 * 8, rest_smem, e->stream>>>(                      \
         e->d_winst, e->d_wvoice, e->wwork.d, e->widx.d + off, f0, frames);                                           \
     off += lists[CLS_].size();                                                                                       \
@@ -1579,12 +1615,27 @@ int render_chunk(gb_engine* e, int frames, size_t n_ev) {
       GB_REST_LAUNCH(3, true, true)
 #undef GB_REST_LAUNCH
       e->stats.rest_voice_samples += rest_voices * (uint64_t)frames;
+      e->stats.sweep_voice_samples += sweep_voices * (uint64_t)frames;
       const size_t welsh_smem = (size_t)kVoiceWarps * kTileStride * sizeof(double2) + (size_t)kParkWords * 32 * kVoiceWarps * sizeof(double);
       if (!lists[4].empty()) {
         Launch l(e, true);
         welsh_kernel<8, 2, false><<<(int)lists[4].size(), 32 * 8, welsh_smem, e->stream>>>(
             e->d_winst, e->d_wvoice, e->wwork.d, e->witems.d, e->wev.d, e->wev_off.d, f0, frames, e->widx.d + off);
       }
+      off += lists[4].size();
+      const size_t sweep_smem = (size_t)kVoiceWarps * kTileStride * sizeof(double2) + sweep_voices_max * sizeof(SweepState);
+#define GB_SWEEP_LAUNCH(CLS_, LFO_, FLAT_)                                                                           \
+  if (!lists[5 + CLS_].empty()) {                                                                                    \
+    Launch l(e, true, 2);                                                                                            \
+    welsh_sweep_kernel<8, LFO_, FLAT_><<<(int)lists[5 + CLS_].size(), 32 * 8, sweep_smem, e->stream>>>(                \
+        e->d_winst, e->d_wvoice, e->wwork.d, e->widx.d + off, f0, frames);                                           \
+    off += lists[5 + CLS_].size();                                                                                   \
+  }
+      GB_SWEEP_LAUNCH(0, false, false)
+      GB_SWEEP_LAUNCH(1, false, true)
+      GB_SWEEP_LAUNCH(2, true, false)
+      GB_SWEEP_LAUNCH(3, true, true)
+#undef GB_SWEEP_LAUNCH
       if (ns) {
         Launch l(e, true);
         welsh_kernel<8, 2, true><<<ns, 32 * 8, welsh_smem, e->stream>>>(

@@ -166,7 +166,7 @@ struct WelshInst {
   double knot_max_rate;             // cutoff motion (fraction of the log range per frame) up to which knots are used
   double2 lane_rot[32];             // (cos, sin)(2*pi*kT*l*lfo_dq/2^64): a lane's LFO angle relative to its block
   double2 block_rot;                // (cos, sin)(2*pi*kBlockFrames*lfo_dq/2^64): one block further
-  int rest_class, pad_rc;           // welsh_rest_kernel variant (2*lfo_amp + zero_a), -1 = the instrument does not qualify
+  int rest_class, sweep_class;      // welsh_rest_kernel / welsh_sweep_kernel variant (2*lfo_amp + zero_a), -1 = does not qualify
   i64 steady_after;                 // frames after note-on from which both envelopes rest at their sustain levels
   double amp_rest;                  // 0.5 * amp.sustain: the DCA input level of a resting voice (without LFO)
   int lti_ok, osc_flat;             // osc_flat: both oscillators piecewise constant (OscMix slopes are 0); lti holds this instrument's resting coefficient sets (GB_LTI=0 disables the path)
@@ -1542,6 +1542,241 @@ __global__ void __launch_bounds__(32 * W, 2) welsh_rest_kernel(const WelshInst* 
         if (first) welsh_rest_block<LFO_AMP, ZERO_A, 1, false>(one, I, lane, tile_row);
         else welsh_rest_block<LFO_AMP, ZERO_A, 1, true>(one, I, lane, tile_row);
       }
+      first = false;
+    }
+    __syncthreads();
+    cta_reduce_store<W>(smem_tiles, s_active, wk.out, fb, f0, f_end);
+    __syncthreads();
+  }
+  for (int t = threadIdx.x; t < wk.nvoices; t += 32 * W) {
+    WelshVoice* vp = voices + wk.voice0 + t;
+    vp->s[0] = cache[t].s[0]; vp->s[1] = cache[t].s[1]; vp->s[2] = cache[t].s[2]; vp->s[3] = cache[t].s[3];
+    vp->knot_frame = kNever;
+  }
+}
+
+// ---- the sweeping-voice kernel ---------------------------------------------------------------------
+// The moving-cutoff counterpart of welsh_rest_kernel: CTAs whose voices are all held for the whole chunk
+// with the filter envelope inside ONE moving stage (attack or decay), the amplitude envelope inside one
+// stage, no note event in the chunk and the cutoff moving slowly enough for coefficient knots.  Again
+// the host decides (note frames and stage lengths are integers), nothing is classified per block, and
+// the voice state lives in shared memory for the launch.  Per block a lane evaluates ONE exact
+// coefficient set (at the end of its kT frames); with its two predecessors' sets — the lane's own start
+// and the start of the lane before, carried across blocks — a one-sided quadratic gives the per-frame
+// a1, a2 of both sections (error 8x that of welsh_block_simple's centred form: <= 1e-10 at the knot
+// threshold), and b0 follows from the unity DC gain of each section: 4 b0 = 1 - a1 - a2.
+struct alignas(16) SweepState {
+  u64 p1, p2;     // oscillator phases at the frame before the current block
+  u64 d1, d2;
+  double s[4];    // filter state at the start of the current block
+  double ls, lc;  // depth * (sin, cos) of the LFO angle at the first frame of the current block
+  double aq0, aq1, aq2, aw, adw;  // amplitude stage (0.5 folded in): level = q0 + w (q1 + q2 w), w = aw + t adw, t = frame - f0
+  double fq0, fq1, fq2, fw, fdw;  // filter-envelope stage, same form
+  double kn[2][4];                // carried knots (a1, a2 of section 1, a1, a2 of section 2) at frames fb - kT and fb
+};
+
+// Stage parameters of a HELD note whose envelope stays inside one stage from frame f on (env_segment
+// without the per-lane containment tests: the host has checked the whole chunk).
+__device__ __forceinline__ void env_stage_held(const EnvShape& sh, i64 n_on, double l_on, i64 f, double& q0, double& q1,
+                                               double& q2, double& w0, double& dw) {
+  const i64 k = f - n_on;
+  q1 = 0.0; q2 = 0.0; w0 = 0.0; dw = 0.0;
+  if (k < sh.na) {
+    w0 = (double)k * sh.inv_na; dw = sh.inv_na;
+    q0 = l_on; q1 = 2.0 * (1.0 - l_on); q2 = -(1.0 - l_on);
+  } else if (k - sh.na < sh.nd) {
+    w0 = 1.0 - (double)(k - sh.na) * sh.inv_nd; dw = -sh.inv_nd;
+    q0 = sh.sustain; q2 = 1.0 - sh.sustain;
+  } else {
+    q0 = sh.sustain;
+  }
+}
+// a1, a2 of both sections for an UNCLAMPED cutoff fraction (the knot before a stage's first frame is
+// the stage's own formula continued backwards; the frequency clamp still applies)
+__device__ __forceinline__ void welsh_knot(const WelshInst& I, double pct, double (&k)[4]) {
+  double u = exp2_ranged(fma(pct, kLog2_800, I.log2_25_over_sr));
+  u = u > I.u_max ? I.u_max : u;
+  u = u < I.u_min ? I.u_min : u;
+  SecCoef c1, c2;
+  lp24_from_u(I.rp, u, c1, c2);
+  k[0] = c1.a1; k[1] = c1.a2; k[2] = c2.a1; k[3] = c2.a2;
+}
+
+template <bool LFO_AMP, bool ZERO_A, bool ACC>
+__device__ __forceinline__ void welsh_sweep_block(SweepState* rs, const WelshInst& I, int lane, int t0,
+                                                  double2* tile_row) {
+  // t0 = first frame of the block relative to the chunk start
+  const int tl = t0 + lane * kT;  // the lane's first frame
+  // ---- coefficient knots: exact at the lane's end, the two before it from the neighbours / the cache ----
+  double d1q[4], d2q[4], k0q[4];
+  {
+    double e[4];
+    const double w8 = fma((double)(tl + kT), rs->fdw, rs->fw);
+    welsh_knot(I, fma(I.cut_b, fma(w8, fma(rs->fq2, w8, rs->fq1), rs->fq0), I.cut_a), e);
+    const double4 c0 = *reinterpret_cast<const double4*>(rs->kn[0]), c1 = *reinterpret_cast<const double4*>(rs->kn[1]);
+    const double cm2[4] = {c0.x, c0.y, c0.z, c0.w}, cm1[4] = {c1.x, c1.y, c1.z, c1.w};
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      double sv = shfl_up_f64(e[i], 1), pv = shfl_up_f64(e[i], 2);
+      sv = lane == 0 ? cm1[i] : sv;
+      pv = lane == 0 ? cm2[i] : (lane == 1 ? cm1[i] : pv);
+      k0q[i] = sv;
+      d1q[i] = (e[i] - pv) * (1.0 / (2 * kT));
+      d2q[i] = ((e[i] - sv) - (sv - pv)) * (1.0 / (2 * kT * kT));
+    }
+    __syncwarp();  // every lane has read the carried knots
+    if (lane >= 30) *reinterpret_cast<double4*>(rs->kn[lane - 30]) = make_double4(e[0], e[1], e[2], e[3]);
+  }
+  auto coef = [&](int i, int j) { return fma((double)j, fma((double)j, d2q[i], d1q[i]), k0q[i]); };
+  // ---- pass 1: oscillators + section 1 from a zero state with its homogeneous response ----
+  double yp[kT], g0[kT], g1[kT];
+  double ps0 = 0.0, ps1 = 0.0, h00 = 1.0, h01 = 0.0, h10 = 0.0, h11 = 1.0;
+  {
+    const ulonglong2 pp = *reinterpret_cast<const ulonglong2*>(&rs->p1);
+    const ulonglong2 dd = *reinterpret_cast<const ulonglong2*>(&rs->d1);
+    const u64 k = (u64)(lane * kT);
+    u64 p1 = pp.x + k * dd.x, p2 = pp.y + k * dd.y;
+    __syncwarp();  // every lane has read the block's base phases
+    if (lane == 0)
+      *reinterpret_cast<ulonglong2*>(&rs->p1) =
+          make_ulonglong2(p1 + (u64)kBlockFrames * dd.x, p2 + (u64)kBlockFrames * dd.y);
+    const OscMix o1 = I.m1, o2 = I.m2;
+    const u64 t1 = I.s1.thresh, t2 = I.s2.thresh;
+#pragma unroll
+    for (int j = 0; j < kT; ++j) {
+      p1 += dd.x;
+      p2 += dd.y;
+      const double x = osc_mix_eval<ZERO_A>(o1, t1, p1, o2, t2, p2);
+      const double a1 = coef(0, j), a2 = coef(1, j);
+      const double b0 = fma(-0.25, a1 + a2, 0.25);
+      g0[j] = h00; g1[j] = h01;
+      yp[j] = lp_step(b0, a1, a2, x, ps0, ps1);
+      const double t00 = fma(a1, h00, h10), t01 = fma(a1, h01, h11);
+      h10 = a2 * h00; h11 = a2 * h01;
+      h00 = t00; h01 = t01;
+    }
+  }
+  double e0, e1, end0, end1;
+  {
+    Affine2 a;
+    a.m00 = h00; a.m01 = h01; a.m10 = h10; a.m11 = h11; a.v0 = ps0; a.v1 = ps1;
+    const double2 st = *reinterpret_cast<const double2*>(&rs->s[0]);  // only lane 0 uses it
+    affine_scan_states(a, lane, st.x, st.y, e0, e1, end0, end1);
+    __syncwarp();
+    if (lane == 0) *reinterpret_cast<double2*>(&rs->s[0]) = make_double2(end0, end1);
+  }
+  // ---- pass 2: section 2 on the fixed-up section-1 output ----
+  ps0 = 0.0; ps1 = 0.0; h00 = 1.0; h01 = 0.0; h10 = 0.0; h11 = 1.0;
+#pragma unroll
+  for (int j = 0; j < kT; ++j) {
+    const double a1 = coef(2, j), a2 = coef(3, j);
+    const double b0 = fma(-0.25, a1 + a2, 0.25);
+    const double x = fma(g1[j], e1, fma(g0[j], e0, yp[j]));
+    g0[j] = h00; g1[j] = h01;
+    yp[j] = lp_step(b0, a1, a2, x, ps0, ps1);
+    const double t00 = fma(a1, h00, h10), t01 = fma(a1, h01, h11);
+    h10 = a2 * h00; h11 = a2 * h01;
+    h00 = t00; h01 = t01;
+  }
+  {
+    Affine2 a;
+    a.m00 = h00; a.m01 = h01; a.m10 = h10; a.m11 = h11; a.v0 = ps0; a.v1 = ps1;
+    const double2 st = *reinterpret_cast<const double2*>(&rs->s[2]);
+    affine_scan_states(a, lane, st.x, st.y, e0, e1, end0, end1);
+    __syncwarp();
+    if (lane == 0) *reinterpret_cast<double2*>(&rs->s[2]) = make_double2(end0, end1);
+  }
+  // ---- LFO phasor of this lane; the cached one advances by one block ----
+  double lsd = 0.0, lcd = 0.0;
+  if (LFO_AMP) {
+    const double2 ph = *reinterpret_cast<const double2*>(&rs->ls);
+    const double2 r = I.lane_rot[lane];
+    lsd = fma(ph.x, r.x, ph.y * r.y);
+    lcd = fma(ph.y, r.x, -(ph.x * r.y));
+    __syncwarp();
+    if (lane == 0) {
+      const double2 br = I.block_rot;
+      *reinterpret_cast<double2*>(&rs->ls) = make_double2(fma(lsd, br.x, lcd * br.y), fma(lcd, br.x, -(lsd * br.y)));
+    }
+  }
+  // ---- amplitude (stage x LFO), DCA, into the warp's tile row ----
+  const double aq0 = rs->aq0, aq1 = rs->aq1, aq2 = rs->aq2, aw = rs->aw, adw = rs->adw;
+  const double gl = I.gl, gr = I.gr;
+  double2* row = tile_row + lane * (kT + 1);
+#pragma unroll
+  for (int j = 0; j < kT; ++j) {
+    const double w = fma((double)(tl + j), adw, aw);
+    double amp = fma(w, fma(aq2, w, aq1), aq0);
+    if (LFO_AMP) {
+      const double2 rot = I.lfo_rot[j];
+      amp *= fma(lsd, rot.x, fma(lcd, rot.y, 1.0));
+    }
+    const double m = fma(g1[j], e1, fma(g0[j], e0, yp[j])) * amp;
+    if (ACC) {
+      const double2 p = row[j];
+      row[j] = make_double2(fma(m, gl, p.x), fma(m, gr, p.y));
+    } else {
+      row[j] = make_double2(m * gl, m * gr);
+    }
+  }
+  __syncwarp();
+}
+
+// grid = number of sweeping CTAs of this variant; block = 32 * W threads;
+// dynamic smem = W * kTileStride double2 (tiles) + max_voices SweepState.  nframes is a multiple of kBlockFrames.
+template <int W, bool LFO_AMP, bool ZERO_A>
+__global__ void __launch_bounds__(32 * W, 2) welsh_sweep_kernel(const WelshInst* __restrict__ insts,
+                                                              WelshVoice* __restrict__ voices,
+                                                              const CtaWork* __restrict__ work,
+                                                              const int* __restrict__ idx, i64 f0, int nframes) {
+  extern __shared__ double2 smem_tiles[];
+  __shared__ int s_active[W];
+  __shared__ WelshInst sI;
+  const CtaWork wk = work[idx[blockIdx.x]];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  {
+    const int* src = reinterpret_cast<const int*>(insts + wk.inst);
+    int* dst = reinterpret_cast<int*>(&sI);
+    for (int i = threadIdx.x; i < (int)(sizeof(WelshInst) / sizeof(int)); i += 32 * W) dst[i] = src[i];
+  }
+  __syncthreads();
+  const WelshInst& I = sI;
+  SweepState* cache = reinterpret_cast<SweepState*>(smem_tiles + W * kTileStride);
+  for (int t = threadIdx.x; t < wk.nvoices; t += 32 * W) {
+    const WelshVoice* vp = voices + wk.voice0 + t;
+    SweepState r;
+    const u64 k = (u64)(f0 - 1 - vp->anchor);
+    r.d1 = vp->d1; r.d2 = vp->d2;
+    r.p1 = vp->p1 + k * r.d1; r.p2 = vp->p2 + k * r.d2;
+    r.s[0] = vp->s[0]; r.s[1] = vp->s[1]; r.s[2] = vp->s[2]; r.s[3] = vp->s[3];
+    r.ls = 0.0; r.lc = 0.0;
+    if (LFO_AMP) {
+      double ls, lc;
+      sincos_phase(vp->pl + (k + 1) * I.lfo_dq, &ls, &lc);
+      r.ls = ls * I.depth; r.lc = lc * I.depth;
+    }
+    env_stage_held(I.amp, vp->n_on, vp->la_on, f0, r.aq0, r.aq1, r.aq2, r.aw, r.adw);
+    r.aq0 *= 0.5; r.aq1 *= 0.5; r.aq2 *= 0.5;
+    env_stage_held(I.filt, vp->n_on, vp->lf_on, f0, r.fq0, r.fq1, r.fq2, r.fw, r.fdw);
+#pragma unroll
+    for (int q = 0; q < 2; ++q) {  // knots at f0 - kT and f0: the stage's formula, continued backwards
+      const double w = fma((double)((q - 1) * kT), r.fdw, r.fw);
+      welsh_knot(I, fma(I.cut_b, fma(w, fma(r.fq2, w, r.fq1), r.fq0), I.cut_a), r.kn[q]);
+    }
+    cache[t] = r;
+  }
+  if (lane == 0) s_active[warp] = warp < wk.nvoices ? 1 : 0;
+  __syncthreads();
+  double2* tile_row = smem_tiles + warp * kTileStride;
+  const i64 f_end = f0 + nframes;
+  int t0 = 0;
+#pragma unroll 1
+  for (i64 fb = f0; fb < f_end; fb += kBlockFrames, t0 += kBlockFrames) {
+    bool first = true;
+#pragma unroll 1
+    for (int g = warp; g < wk.nvoices; g += W) {
+      if (first) welsh_sweep_block<LFO_AMP, ZERO_A, false>(cache + g, I, lane, t0, tile_row);
+      else welsh_sweep_block<LFO_AMP, ZERO_A, true>(cache + g, I, lane, t0, tile_row);
       first = false;
     }
     __syncthreads();

@@ -281,6 +281,9 @@ typedef struct {
   uint64_t rest_kernel_launches; /* of the voice kernel launches: the resting-voice kernel (time-invariant stretches) */
   double rest_kernel_ms;         /* ... its share of voice_kernel_ms */
   uint64_t rest_voice_samples;   /* ... and of voice_samples */
+  uint64_t sweep_kernel_launches; /* likewise for the sweeping-voice kernel (one moving envelope stage per chunk) */
+  double sweep_kernel_ms;
+  uint64_t sweep_voice_samples;
 } gb_stats;
 int gb_get_stats(gb_engine* e, gb_stats* out);
 int gb_reset_stats(gb_engine* e);

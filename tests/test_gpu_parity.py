@@ -298,7 +298,7 @@ def test_resting_paths_agree_at_size(monkeypatch):
     cfg.note_off_base = 4 * 65536 + 1000
 
     def run(env):
-        for k in ("GB_REST_KERNEL", "GB_LTI"):
+        for k in ("GB_REST_KERNEL", "GB_LTI", "GB_SWEEP_KERNEL"):
             monkeypatch.delenv(k, raising=False)
         for k, v in env.items():
             monkeypatch.setenv(k, v)
@@ -312,10 +312,13 @@ def test_resting_paths_agree_at_size(monkeypatch):
     a, sa = run({})
     b, sb = run({"GB_REST_KERNEL": "0"})
     c, sc = run({"GB_LTI": "0"})
+    d, sd = run({"GB_SWEEP_KERNEL": "0"})
     assert sa.rest_kernel_launches > 0 and sb.rest_kernel_launches == 0 and sc.rest_kernel_launches == 0
+    assert sa.sweep_kernel_launches > 0 and sd.sweep_kernel_launches == 0   # chunks 1-2: filter decay, no events
     assert np.abs(a).max() > 1e-3
     assert np.abs(a - b).max() < 1e-12
     assert np.abs(a - c).max() < 1e-10
+    assert np.abs(a - d).max() < 1e-10      # one-sided vs centred coefficient knots
 
 
 def test_split_instruments_summed_by_their_consumer(monkeypatch):
@@ -406,3 +409,49 @@ def test_save_restore_across_resting_chunks_and_sidechain():
     pcm = g.render_pcm16(n)
     g.close()
     assert int(np.abs(pcm.astype(np.int32) - pcm16(np.clip(ref, -1.0, 1.0)).astype(np.int32)).max()) <= 1
+
+
+@pytest.mark.parametrize("vpc", [None, "16"])
+def test_sweeping_voices_kernel(vpc, monkeypatch):
+    """Chunks in which every voice of a CTA is held inside one moving stage of the filter envelope (and
+    one stage of the amplitude envelope) with no note event go to welsh_sweep_kernel: one exact
+    coefficient knot per lane, one-sided quadratic, b0 from the unity DC gain.  Attack and decay stages,
+    LFO and flat-oscillator variants, a retriggered note (attack from a non-zero level), against the oracle."""
+    if vpc:
+        monkeypatch.setenv("GB_VPC", vpc)
+    cfgs = [
+        (24, dict(w1=abi.WAVE_PULSE_WIDTH, pw1=0.1, w2=abi.WAVE_SQUARE, mix=0.5, routing=abi.LFO_AMPLITUDE, depth=0.05,
+                  lfo_hz=7.5, filt=(0.0, 2.0, 0.7, 2.0), amp=(0.02, 0.0, 1.0, 0.0), cutoff_start=scenes.hz_to_pct(40.0),
+                  cutoff_end=0.9)),
+        (16, dict(w1=abi.WAVE_SAWTOOTH, w2=abi.WAVE_TRIANGLE, tune2=1.0029, routing=abi.LFO_NONE, filt=(3.0, 0.5, 0.3, 0.5),
+                  amp=(0.3, 0.4, 0.6, 0.1), ripple=2.5, cutoff_start=0.2, cutoff_end=0.6)),
+        (9, dict(w1=abi.WAVE_SQUARE, w2=abi.WAVE_PULSE_WIDTH, pw2=0.3, routing=abi.LFO_NONE, filt=(2.5, 0.4, 0.5, 0.3),
+                 amp=(0.0, 0.0, 1.0, 0.0), cutoff_start=0.3, cutoff_end=0.8)),
+    ]
+    frames = 10 * 4096 + 300
+
+    def scene(r):
+        uids = []
+        for i, (nv, c) in enumerate(cfgs):
+            u = r.add_instrument(abi.INST_WELSH, scenes.generic_welsh(voices=nv, gain=0.05, pan=-0.5 + 0.5 * i, **c))
+            r.patch(u, abi.MAIN_MIXER)
+            uids.append(u)
+        r.finalize()
+        for i, (nv, _) in enumerate(cfgs):
+            for v in range(nv):
+                r.note_on(5 + 7 * v + i, uids[i], 30 + v)
+                r.note_off(9 * 4096 + 100 + 3 * v, uids[i], 30 + v)
+            r.note_on(3 * 4096 + 17, uids[i], 30)      # retrigger: the attack restarts from the current level
+        return frames
+
+    o = OracleEngine(48000.0)
+    scene(o)
+    ref = o.render(frames)
+    g = gpu_engine(48000.0, max_block=4096)
+    scene(g)
+    out = g.render(frames)
+    st = g.stats()
+    g.close()
+    assert st.sweep_kernel_launches >= 6
+    assert st.sweep_voice_samples > 0
+    check(out, ref)
