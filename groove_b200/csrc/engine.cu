@@ -369,6 +369,7 @@ struct gb_engine {
   int n_partials_nf = 0;
   bool fused_sums = false;          // this chunk: consumers read partial buffers directly
   bool fused_sums_enabled = true;   // GB_FUSED_SUMS=0 switches the shortcut off (A/B measurements)
+  bool chunk_cuts = true;           // GB_CHUNK_CUTS=0: chunks of max_block regardless of voice transitions
   std::vector<void*> allocations;  // everything cudaMalloc'ed at finalize/load time
 
   double2* last_out = nullptr;  // main mixer buffer of the last chunk
@@ -790,6 +791,7 @@ int gb_create(const gb_config* cfg, gb_engine** out) {
   if (cudaGetDeviceProperties(&prop, e->device) == cudaSuccess) e->num_sms = prop.multiProcessorCount;
   if (const char* v = getenv("GB_CTA_MULT")) e->cta_target_mult = std::max(1, atoi(v));
   if (const char* v = getenv("GB_FUSED_SUMS")) e->fused_sums_enabled = atoi(v) != 0;
+  if (const char* v = getenv("GB_CHUNK_CUTS")) e->chunk_cuts = atoi(v) != 0;
   if (cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking) != cudaSuccess ||
       cudaStreamCreateWithFlags(&e->copy_stream, cudaStreamNonBlocking) != cudaSuccess)
     return fail(nullptr, GB_ECUDA, "cudaStreamCreate failed");
@@ -1791,6 +1793,55 @@ int render_chunk(gb_engine* e, int frames, size_t n_ev) {
 
 enum OutMode { OUT_F64, OUT_PCM16, OUT_DEVICE };
 
+// Where to end the chunk that starts at f0 (at most `limit` frames).  The resting and the sweeping
+// kernels take a CTA only if its voices keep their state for the WHOLE chunk, so chunks are cut at the
+// host-known transitions of the Welsh voices — note events and envelope stage boundaries (integer
+// frames).  Transitions come in clusters (the voices of a chord, a beat); a chunk either ends just
+// before a cluster (a pure stretch, left to the specialised kernels) or covers one cluster.  All cuts
+// are multiples of kBlockFrames from f0; stretches shorter than kMinZone frames are not split off.
+int64_t chunk_cut(gb_engine* e, int64_t f0, int64_t limit) {
+  constexpr int64_t kMinZone = 16 * kBlockFrames;
+  if (limit < 2 * kMinZone || e->n_wwork_grouped == 0 || !e->chunk_cuts) return limit;
+  std::vector<int64_t> tr;
+  const int64_t f1 = f0 + limit;
+  for (const gb_event& ev : e->events) {  // sorted by frame
+    if (ev.frame >= f1) break;
+    if (ev.frame <= f0 || (ev.type != GB_EV_NOTE_ON && ev.type != GB_EV_NOTE_OFF)) continue;
+    const Node* n = find(e, ev.uid);
+    if (n && n->kind == GB_INST_WELSH && n->order >= 0) tr.push_back(ev.frame);
+  }
+  for (const Node* n : e->plan) {
+    if (n->kind != GB_INST_WELSH || n->nvoices < kVoiceWarps) continue;
+    const WelshInst& I = e->h_winst[(size_t)n->table_index];
+    if (I.rest_class < 0 && I.sweep_class < 0) continue;
+    const int64_t b[4] = {I.amp.na, I.amp.na + I.amp.nd, I.filt.na, I.filt.na + I.filt.nd};
+    for (const Slot& sl : n->store.slots) {
+      if (!sl.held) {  // releasing: the voice falls idle at idle_at
+        if (sl.idle_at > f0 && sl.idle_at < f1) tr.push_back(sl.idle_at);
+        continue;
+      }
+      if (sl.on_frame <= kNever) continue;
+      for (int64_t d : b) {
+        const int64_t t = sl.on_frame + d;
+        if (t > f0 && t < f1) tr.push_back(t);
+      }
+    }
+  }
+  if (tr.empty()) return limit;
+  std::sort(tr.begin(), tr.end());
+  auto up = [&](int64_t t) { return (t - f0 + kBlockFrames - 1) / kBlockFrames * kBlockFrames; };
+  const int64_t first = (tr.front() - f0) / kBlockFrames * kBlockFrames;  // whole blocks before the first transition
+  if (first >= kMinZone) return first;
+  // the chunk starts inside (or just before) a cluster: run to its end
+  int64_t last = tr.front();
+  for (int64_t t : tr) {
+    if (t - last >= kMinZone) break;
+    last = t;
+  }
+  const int64_t cut = up(last + 1);
+  return cut >= limit || limit - cut < kMinZone ? limit : cut;
+}
+
 // Split the request into chunks of at most max_block frames.
 int render_impl(gb_engine* e, void* out, size_t frames, size_t* done, OutMode mode) {
   if (!e) return GB_EINVAL;
@@ -1831,6 +1882,7 @@ int render_impl(gb_engine* e, void* out, size_t frames, size_t* done, OutMode mo
     // long ragged chunks are cut at a block multiple (the remainder becomes its own small chunk), so
     // that resting voices can take welsh_rest_kernel, which renders whole blocks only
     if (limit >= 16 * kBlockFrames && limit % kBlockFrames) limit -= limit % kBlockFrames;
+    limit = chunk_cut(e, f0, limit);
     // every event strictly before the chunk end belongs to this chunk (events never split a chunk:
     // parameters go through segment tables, sampler retriggers through per-chunk play lists)
     size_t n_ev = 0;
