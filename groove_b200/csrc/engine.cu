@@ -539,6 +539,13 @@ void welsh_inst_from_params(const Node& n, double sr, WelshInst* I) {
       mp[5][0] = mp[5][1] = mp[5][2] = mp[5][3] = 0.0;
     };
     I->lti.c1 = c1; I->lti.c2 = c2;
+    auto scaled = [](const OscMix& m, double k) {
+      OscMix r;
+      r.a_lo = m.a_lo * k; r.b_lo = m.b_lo * k; r.a_hi = m.a_hi * k; r.b_hi = m.b_hi * k;
+      return r;
+    };
+    I->m1b = scaled(I->m1, c1.b0);
+    I->m2b = scaled(I->m2, c1.b0);
     table(c1, I->lti.g1, I->lti.mp1);
     table(c2, I->lti.g2, I->lti.mp2);
     I->lti_ok = 1;

@@ -149,6 +149,7 @@ struct alignas(16) LtiTable {
 struct WelshInst {
   LtiTable lti;
   OscMix m1, m2;
+  OscMix m1b, m2b;  // m1, m2 scaled by lti.c1.b0: the time-invariant blocks get section 1's b0*x straight from the selects
   double2 lfo_rot[8];  // (cos, sin)(2*pi*j*lfo_dq/2^64): rotation table for a sine LFO
   EnvShape amp, filt;
   int w1, w2, wl, sync, routing, filter_mode, uid, voice0;
@@ -830,6 +831,14 @@ __device__ __forceinline__ double lp_step(double b0, double a1, double a2, doubl
   return y;
 }
 
+// the same with bx = b0 * x supplied by the caller
+__device__ __forceinline__ double lp_step_bx(double bx, double a1, double a2, double& s0, double& s1) {
+  const double y = bx + s0;
+  s0 = fma(a1, y, fma(2.0, bx, s1));
+  s1 = fma(a2, y, bx);
+  return y;
+}
+
 template <bool LFO_AMP, bool ZERO_A>
 __device__ __forceinline__ void welsh_block_simple(WelshVoice* vp, const WelshInst* Ip, i64 fb, int lane, EnvSeg aseg,
                                                 EnvSeg fseg, double2* tile_row, double* park) {
@@ -997,9 +1006,9 @@ __device__ __forceinline__ void welsh_block_lti(WelshVoice* const (&vp)[NV], con
   double yp[NV][kT];
   double ps0[NV], ps1[NV];
   {
-    const OscMix o1 = I.m1, o2 = I.m2;
+    const OscMix o1 = I.m1b, o2 = I.m2b;  // pre-scaled by section 1's b0
     const u64 t1 = I.s1.thresh, t2 = I.s2.thresh;
-    const double b0 = L.c1.b0, a1 = L.c1.a1, a2 = L.c1.a2;
+    const double a1 = L.c1.a1, a2 = L.c1.a2;
 #pragma unroll
     for (int v = 0; v < NV; ++v) { ps0[v] = 0.0; ps1[v] = 0.0; }
 #pragma unroll
@@ -1008,7 +1017,7 @@ __device__ __forceinline__ void welsh_block_lti(WelshVoice* const (&vp)[NV], con
       for (int v = 0; v < NV; ++v) {
         p1[v] += d1[v];
         p2[v] += d2[v];
-        yp[v][j] = lp_step(b0, a1, a2, osc_mix_eval<ZERO_A>(o1, t1, p1[v], o2, t2, p2[v]), ps0[v], ps1[v]);
+        yp[v][j] = lp_step_bx(osc_mix_eval<ZERO_A>(o1, t1, p1[v], o2, t2, p2[v]), a1, a2, ps0[v], ps1[v]);
       }
     }
   }
@@ -1411,16 +1420,16 @@ __device__ __forceinline__ void welsh_rest_block(RestState* const (&rs)[NV], con
         *reinterpret_cast<ulonglong2*>(&rs[v]->p1) =
             make_ulonglong2(p1[v] + (u64)kBlockFrames * d1[v], p2[v] + (u64)kBlockFrames * d2[v]);
     }
-    const OscMix o1 = I.m1, o2 = I.m2;
+    const OscMix o1 = I.m1b, o2 = I.m2b;  // pre-scaled by section 1's b0
     const u64 t1 = I.s1.thresh, t2 = I.s2.thresh;
-    const double b0 = L.c1.b0, a1 = L.c1.a1, a2 = L.c1.a2;
+    const double a1 = L.c1.a1, a2 = L.c1.a2;
 #pragma unroll
     for (int j = 0; j < kT; ++j) {
 #pragma unroll
       for (int v = 0; v < NV; ++v) {
         p1[v] += d1[v];
         p2[v] += d2[v];
-        yp[v][j] = lp_step(b0, a1, a2, osc_mix_eval<ZERO_A>(o1, t1, p1[v], o2, t2, p2[v]), ps0[v], ps1[v]);
+        yp[v][j] = lp_step_bx(osc_mix_eval<ZERO_A>(o1, t1, p1[v], o2, t2, p2[v]), a1, a2, ps0[v], ps1[v]);
       }
     }
   }
