@@ -546,8 +546,15 @@ void welsh_inst_from_params(const Node& n, double sr, WelshInst* I) {
     };
     I->m1b = scaled(I->m1, c1.b0);
     I->m2b = scaled(I->m2, c1.b0);
+    I->m1bb = scaled(I->m1, c1.b0 * c2.b0);
+    I->m2bb = scaled(I->m2, c1.b0 * c2.b0);
     table(c1, I->lti.g1, I->lti.mp1);
     table(c2, I->lti.g2, I->lti.mp2);
+    for (int j = 0; j < kT; ++j) {
+      I->lti.g1b[j][0] = I->lti.g1[j][0] * c2.b0;
+      I->lti.g1b[j][1] = I->lti.g1[j][1] * c2.b0;
+    }
+    I->lti.inv_b0_2 = 1.0 / c2.b0;
     I->lti_ok = 1;
     if (const char* v = getenv("GB_LTI")) I->lti_ok = atoi(v) != 0;
     // welsh_rest_kernel variant: same preconditions as welsh_block_lti (see voice_kernels.cuh)

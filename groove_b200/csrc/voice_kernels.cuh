@@ -142,6 +142,8 @@ struct OscMix {
 // once on the host (engine.cu, welsh_inst_from_params).
 struct alignas(16) LtiTable {
   double g1[8][2], g2[8][2];    // kT rows per section
+  double g1b[8][2];             // g1 scaled by section 2's b0 (welsh_rest_block feeds section 2 with b0*x directly)
+  double inv_b0_2, pad_lti;     // 1 / c2.b0
   double mp1[6][4], mp2[6][4];  // row-major 2x2; entry 5 is the zero matrix (lti_scan_states)
   SecCoef c1, c2;
 };
@@ -150,6 +152,7 @@ struct WelshInst {
   LtiTable lti;
   OscMix m1, m2;
   OscMix m1b, m2b;  // m1, m2 scaled by lti.c1.b0: the time-invariant blocks get section 1's b0*x straight from the selects
+  OscMix m1bb, m2bb;  // ... and by lti.c2.b0 on top (welsh_rest_block: section 1 runs pre-scaled for section 2)
   double2 lfo_rot[8];  // (cos, sin)(2*pi*j*lfo_dq/2^64): rotation table for a sine LFO
   EnvShape amp, filt;
   int w1, w2, wl, sync, routing, filter_mode, uid, voice0;
@@ -1420,7 +1423,11 @@ __device__ __forceinline__ void welsh_rest_block(RestState* const (&rs)[NV], con
         *reinterpret_cast<ulonglong2*>(&rs[v]->p1) =
             make_ulonglong2(p1[v] + (u64)kBlockFrames * d1[v], p2[v] + (u64)kBlockFrames * d2[v]);
     }
-    const OscMix o1 = I.m1b, o2 = I.m2b;  // pre-scaled by section 1's b0
+    // The zero-state run of section 1 is linear in its input, so it runs pre-scaled by both sections' b0:
+    // its outputs are then section 2's b0*x (up to the entry-state term, whose rows g1b carry the same
+    // factor) and only the lane's end vector is scaled back for the scan: 2 multiplies per lane instead
+    // of 2 per frame.
+    const OscMix o1 = I.m1bb, o2 = I.m2bb;
     const u64 t1 = I.s1.thresh, t2 = I.s2.thresh;
     const double a1 = L.c1.a1, a2 = L.c1.a2;
 #pragma unroll
@@ -1432,20 +1439,23 @@ __device__ __forceinline__ void welsh_rest_block(RestState* const (&rs)[NV], con
         yp[v][j] = lp_step_bx(osc_mix_eval<ZERO_A>(o1, t1, p1[v], o2, t2, p2[v]), a1, a2, ps0[v], ps1[v]);
       }
     }
+    const double inv = L.inv_b0_2;
+#pragma unroll
+    for (int v = 0; v < NV; ++v) { ps0[v] *= inv; ps1[v] *= inv; }
   }
   double e0[NV], e1[NV];
   lti_scan_entry<NV>(ps0, ps1, L.mp1, lane, rs, 0, e0, e1);
   // ---- pass 2: section 2 on the fixed-up section-1 output ----
   {
-    const double b0 = L.c2.b0, a1 = L.c2.a1, a2 = L.c2.a2;
+    const double a1 = L.c2.a1, a2 = L.c2.a2;
 #pragma unroll
     for (int v = 0; v < NV; ++v) { ps0[v] = 0.0; ps1[v] = 0.0; }
 #pragma unroll
     for (int j = 0; j < kT; ++j) {
-      const double2 g = *reinterpret_cast<const double2*>(L.g1[j]);
+      const double2 g = *reinterpret_cast<const double2*>(L.g1b[j]);
 #pragma unroll
       for (int v = 0; v < NV; ++v)
-        yp[v][j] = lp_step(b0, a1, a2, fma(g.y, e1[v], fma(g.x, e0[v], yp[v][j])), ps0[v], ps1[v]);
+        yp[v][j] = lp_step_bx(fma(g.y, e1[v], fma(g.x, e0[v], yp[v][j])), a1, a2, ps0[v], ps1[v]);
     }
   }
   lti_scan_entry<NV>(ps0, ps1, L.mp2, lane, rs, 1, e0, e1);
