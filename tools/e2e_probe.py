@@ -6,7 +6,7 @@ from groove_b200 import Engine, workloads
 frames = 2_880_000
 cfg = workloads.Cfg4()
 out = np.empty((frames, 2))
-for mode in ("host", "device", "host", "device", "host", "host"):
+for mode in ("host", "device", "host", "host", "host", "host", "host", "host", "device", "host"):
     e = Engine(48000.0, max_block=1 << 16)
     e.set_timing(True)
     workloads.build_cfg4(e, cfg)
