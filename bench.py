@@ -278,9 +278,11 @@ def run_ours(a) -> None:
     barrier()
     region_s = time.perf_counter() - t_region
     e2e_wall, h2d, d2h = 0.0, 0, 0
+    e2e_steps_ms = []
     for _ in range(a.steps):
         wall, st = one_step("e2e")
         e2e_wall += wall
+        e2e_steps_ms.append(round(wall * 1e3, 3))
         h2d += st.h2d_bytes
         d2h += st.d2h_bytes if world == 1 else (frames * 16 if rank == 0 else 0)
     barrier()
@@ -369,7 +371,8 @@ def run_ours(a) -> None:
                             else f"config-4 recipe scaled: {a.voices} voices x {a.seconds:g} s at 48 kHz stereo",
                 "voices_per_gpu": a.voices, "frames": frames, "voice_samples_per_step": total_vs,
                 "coefficients": ("exact per frame (GB_KNOT_MAX_RATE=0)" if os.environ.get("GB_KNOT_MAX_RATE", "") in ("0", "0.0")
-                                 else "quadratic through exact knots every 4 frames when the cutoff moves <= "
+                                 else "per-instrument tables while a voice rests; otherwise quadratic through exact knots "
+                                      "(every 8 frames in welsh_sweep_kernel, every 4 in welsh_kernel) when the cutoff moves <= "
                                       + os.environ.get("GB_KNOT_MAX_RATE", "1e-5") + "/frame, else exact per frame"),
                 "max_block": a.max_block, "parallelism": f"voices sharded over {world} GPU(s); one NCCL f64 bus reduce",
                 "l2": "256 MiB device memset between steps (L2 flush); fresh engine per step",
@@ -377,6 +380,7 @@ def run_ours(a) -> None:
             "realtime_factor": value / ((a.variants if cfg5 else a.voices) * world * 48000.0),
             "gpu_launches": int(launches // a.steps),
             "e2e": {"value": e2e_value, "unit": UNIT, "ms_per_step": e2e_wall / a.steps * 1e3,
+                    "ms_steps_rank0": e2e_steps_ms,   # wall clock of each timed step (host effects show up here)
                     "h2d_bytes_per_step": int(h2d // a.steps), "d2h_bytes_per_step": int(d2h // a.steps)},
             "roofline": {
                 "bound": "fp64", "kernel": k_name, "achieved": achieved_tflops, "peak": fp64_peak,
