@@ -1815,7 +1815,10 @@ enum OutMode { OUT_F64, OUT_PCM16, OUT_DEVICE };
 // are multiples of kBlockFrames from f0; stretches shorter than kMinZone frames are not split off.
 int64_t chunk_cut(gb_engine* e, int64_t f0, int64_t limit) {
   constexpr int64_t kMinZone = 16 * kBlockFrames;
-  if (limit < 2 * kMinZone || e->n_wwork_grouped == 0 || !e->chunk_cuts) return limit;
+  // cuts pay off when the Welsh voices dominate a chunk; with a handful of voices the extra launches cost
+  // more than the specialised kernels save (a 16-voice song went from 28 to 210 launches)
+  constexpr int kMinCutVoices = 256;
+  if (limit < 2 * kMinZone || e->n_wwork_grouped == 0 || !e->chunk_cuts || e->n_wvoice < kMinCutVoices) return limit;
   std::vector<int64_t> tr;
   const int64_t f1 = f0 + limit;
   for (const gb_event& ev : e->events) {  // sorted by frame

@@ -298,7 +298,7 @@ def test_resting_paths_agree_at_size(monkeypatch):
     cfg.note_off_base = 4 * 65536 + 1000
 
     def run(env):
-        for k in ("GB_REST_KERNEL", "GB_LTI", "GB_SWEEP_KERNEL"):
+        for k in ("GB_REST_KERNEL", "GB_LTI", "GB_SWEEP_KERNEL", "GB_CHUNK_CUTS"):
             monkeypatch.delenv(k, raising=False)
         for k, v in env.items():
             monkeypatch.setenv(k, v)
@@ -313,12 +313,15 @@ def test_resting_paths_agree_at_size(monkeypatch):
     b, sb = run({"GB_REST_KERNEL": "0"})
     c, sc = run({"GB_LTI": "0"})
     d, sd = run({"GB_SWEEP_KERNEL": "0"})
+    f, sf = run({"GB_CHUNK_CUTS": "0"})       # chunks of max_block instead of cuts at the transition clusters
     assert sa.rest_kernel_launches > 0 and sb.rest_kernel_launches == 0 and sc.rest_kernel_launches == 0
     assert sa.sweep_kernel_launches > 0 and sd.sweep_kernel_launches == 0   # chunks 1-2: filter decay, no events
     assert np.abs(a).max() > 1e-3
     assert np.abs(a - b).max() < 1e-12
     assert np.abs(a - c).max() < 1e-10
     assert np.abs(a - d).max() < 1e-10      # one-sided vs centred coefficient knots
+    assert np.abs(a - f).max() < 1e-10
+    assert sf.kernel_launches < sa.kernel_launches
 
 
 def test_split_instruments_summed_by_their_consumer(monkeypatch):
