@@ -634,7 +634,9 @@ inline int cdiv(int a, int b) { return (a + b - 1) / b; }
 
 // Sum a node's inputs.  Up to kMaxSources go straight into the consuming kernel; more are
 // pre-reduced (sum_table_kernel: four interleaved row sums, added in row order) into the node's scratch buffer.
-int gather_sources(gb_engine* e, Node* n, int frames, SourceList* out) {
+// A plain sum node (mixer, signal-passthrough) with a source table needs no pass of its own: the table
+// sum is written straight into its node buffer and *done is set.
+int gather_sources(gb_engine* e, Node* n, int frames, SourceList* out, bool* done = nullptr) {
   std::vector<const double2*> ptrs;
   for (uint32_t s : n->sources) {
     Node* sn = find(e, s);
@@ -649,10 +651,13 @@ int gather_sources(gb_engine* e, Node* n, int frames, SourceList* out) {
   {
     // the pointer table was uploaded at finalize (sources never change afterwards)
     Launch l(e, false);
+    const bool plain = done && (n->kind == GB_FX_MIXER || n->kind == GB_FX_SIGNAL_PASSTHROUGH);
+    double2* dst = plain ? n->buf : n->scratch;
     if (e->fused_sums && n->d_src_table_fused)
-      sum_table_kernel<<<cdiv(frames, kSumFrames), kSumRows * kSumFrames, 0, e->stream>>>(n->d_src_table_fused, n->n_src_fused, n->scratch, frames);
+      sum_table_kernel<<<cdiv(frames, kSumFrames), kSumRows * kSumFrames, 0, e->stream>>>(n->d_src_table_fused, n->n_src_fused, dst, frames);
     else
-      sum_table_kernel<<<cdiv(frames, kSumFrames), kSumRows * kSumFrames, 0, e->stream>>>(n->d_src_table, (int)ptrs.size(), n->scratch, frames);
+      sum_table_kernel<<<cdiv(frames, kSumFrames), kSumRows * kSumFrames, 0, e->stream>>>(n->d_src_table, (int)ptrs.size(), dst, frames);
+    if (plain) *done = true;
   }
   out->n = 1;
   out->p[0] = n->scratch;
@@ -1751,8 +1756,10 @@ int render_chunk(gb_engine* e, int frames, size_t n_ev) {
       continue;
     }
     SourceList src;
-    int rc = gather_sources(e, n, frames, &src);
+    bool summed = false;
+    int rc = gather_sources(e, n, frames, &src, &summed);
     if (rc) return rc;
+    if (summed) continue;  // plain sum node: its buffer is already the table sum
     if (n->kind == GB_FX_DELAY) {
       {
         Launch l(e, false);
