@@ -327,7 +327,17 @@ struct gb_engine {
   int64_t pos = 0;
   uint32_t next_uid = 2;
   int num_sms = 148;
-  int cta_target_mult = 2;  // CTAs per SM the voice work lists aim for (GB_CTA_MULT)
+  // Developer switches (A/B measurements, path-agreement tests): read from the environment ONCE, in
+  // gb_create; nothing on the render path calls getenv.
+  struct Options {
+    int cta_target_mult = 2;      // GB_CTA_MULT: CTAs per SM the voice work lists aim for
+    int vpc = 0;                  // GB_VPC: force the voices-per-CTA split (0 = automatic)
+    double knot_max_rate = -1.0;  // GB_KNOT_MAX_RATE: < 0 = kKnotMaxRate; 0 = exact coefficients every frame
+    bool lti = true;              // GB_LTI=0: no time-invariant blocks
+    bool rest_kernel = true;      // GB_REST_KERNEL=0
+    bool sweep_kernel = true;     // GB_SWEEP_KERNEL=0
+    int min_cut_voices = 256;     // GB_MIN_CUT_VOICES: chunk cuts only for engines with at least this many Welsh voices
+  } opt;
   std::map<uint32_t, std::unique_ptr<Node>> nodes;
   std::vector<Node*> plan;  // reachable nodes, sources before consumers
   std::vector<gb_event> events;
@@ -385,7 +395,7 @@ struct gb_engine {
   bool timing = false;
   // CUDA-event pairs recorded around launches / render calls on the engine stream; resolved
   // lazily (gb_get_stats) so that timing never serialises the stream.
-  struct TimedSpan { cudaEvent_t a, b; int what; };  // what: 0 = fx kernel, 1 = voice kernel, 2 = render call
+  struct TimedSpan { cudaEvent_t a, b; int what; bool closed; };  // what: 0 = fx kernel, 1 = voice kernel, 2 = render call
   std::vector<TimedSpan> spans;
   std::vector<std::pair<cudaEvent_t, cudaEvent_t>> event_pool;
 };
@@ -425,7 +435,7 @@ Node* find(gb_engine* e, uint32_t uid) {
   return it == e->nodes.end() ? nullptr : it->second.get();
 }
 
-void welsh_inst_from_params(const Node& n, double sr, WelshInst* I) {
+void welsh_inst_from_params(const Node& n, double sr, const gb_engine::Options& opt, WelshInst* I) {
   const gb_welsh_params& p = n.wp;
   const double top = 1.0 - 1.0 / 9007199254740992.0;
   memset(I, 0, sizeof *I);
@@ -486,8 +496,7 @@ void welsh_inst_from_params(const Node& n, double sr, WelshInst* I) {
   I->log2_25_over_sr = std::log2(25.0 / sr);
   I->u_min = 1.0 / sr;
   I->u_max = 0.49;
-  I->knot_max_rate = kKnotMaxRate;
-  if (const char* v = getenv("GB_KNOT_MAX_RATE")) I->knot_max_rate = atof(v);
+  I->knot_max_rate = opt.knot_max_rate >= 0.0 ? opt.knot_max_rate : kKnotMaxRate;
   for (int j = 0; j < kT; ++j) {
     uint64_t q = (uint64_t)j * I->lfo_dq;  // mod 2^64
     double ang = 6.283185307179586476925286766559 * ((double)q / 18446744073709551616.0);
@@ -555,21 +564,20 @@ void welsh_inst_from_params(const Node& n, double sr, WelshInst* I) {
       I->lti.g1b[j][1] = I->lti.g1[j][1] * c2.b0;
     }
     I->lti.inv_b0_2 = 1.0 / c2.b0;
-    I->lti_ok = 1;
-    if (const char* v = getenv("GB_LTI")) I->lti_ok = atoi(v) != 0;
+    I->lti_ok = opt.lti ? 1 : 0;
     // welsh_rest_kernel variant: same preconditions as welsh_block_lti (see voice_kernels.cuh)
     const bool lin = I->s1.kind == 0 && I->s2.kind == 0 && !I->sync &&
                      (I->routing == LFO_NONE || (I->routing == LFO_AMPLITUDE && I->wl == W_SINE));
     I->rest_class = -1;
     if (lin && I->lti_ok && (I->filter_mode == FILTER_FIXED || I->filter_mode == FILTER_ENVELOPE))
       I->rest_class = (I->routing == LFO_AMPLITUDE ? 2 : 0) + (I->osc_flat ? 1 : 0);
-    if (const char* v = getenv("GB_REST_KERNEL")) if (atoi(v) == 0) I->rest_class = -1;
+    if (!opt.rest_kernel) I->rest_class = -1;
     // welsh_sweep_kernel: the knot path of a moving filter envelope; the frequency clamp must stay out of
     // reach (0.49 sr >= 20 kHz) so that the coefficient trajectory of a stage is smooth
     I->sweep_class = -1;
     if (lin && I->filter_mode == FILTER_ENVELOPE && I->knot_max_rate > 0.0 && 0.49 * sr >= 20000.0)
       I->sweep_class = (I->routing == LFO_AMPLITUDE ? 2 : 0) + (I->osc_flat ? 1 : 0);
-    if (const char* v = getenv("GB_SWEEP_KERNEL")) if (atoi(v) == 0) I->sweep_class = -1;
+    if (!opt.sweep_kernel) I->sweep_class = -1;
   }
 }
 void fm_inst_from_params(const Node& n, double sr, FmInst* I) {
@@ -593,16 +601,21 @@ bool span_begin(gb_engine* e, int what) {
   } else {
     if (cudaEventCreate(&ev.first) != cudaSuccess || cudaEventCreate(&ev.second) != cudaSuccess) return false;
   }
-  cudaEventRecord(ev.first, e->stream);
-  e->spans.push_back({ev.first, ev.second, what});
+  if (cudaEventRecord(ev.first, e->stream) != cudaSuccess) {  // timing is best effort: an untimed launch, not a failed one
+    e->event_pool.push_back(ev);
+    return false;
+  }
+  e->spans.push_back({ev.first, ev.second, what, false});
   return true;
 }
-void span_end(gb_engine* e, size_t index) { cudaEventRecord(e->spans[index].b, e->stream); }
+void span_end(gb_engine* e, size_t index) {
+  e->spans[index].closed = cudaEventRecord(e->spans[index].b, e->stream) == cudaSuccess;
+}
 void resolve_spans(gb_engine* e) {
   for (auto& sp : e->spans) {
-    cudaEventSynchronize(sp.b);
     float ms = 0.f;
-    cudaEventElapsedTime(&ms, sp.a, sp.b);
+    if (!sp.closed || cudaEventSynchronize(sp.b) != cudaSuccess || cudaEventElapsedTime(&ms, sp.a, sp.b) != cudaSuccess)
+      ms = 0.f;  // a span whose events could not be recorded contributes nothing
     if (sp.what == 1) e->stats.voice_kernel_ms += ms;
     else if (sp.what == 3) { e->stats.voice_kernel_ms += ms; e->stats.rest_kernel_ms += ms; }
     else if (sp.what == 4) { e->stats.voice_kernel_ms += ms; e->stats.sweep_kernel_ms += ms; }
@@ -808,7 +821,13 @@ int gb_create(const gb_config* cfg, gb_engine** out) {
   memset(&e->stats, 0, sizeof e->stats);
   cudaDeviceProp prop;
   if (cudaGetDeviceProperties(&prop, e->device) == cudaSuccess) e->num_sms = prop.multiProcessorCount;
-  if (const char* v = getenv("GB_CTA_MULT")) e->cta_target_mult = std::max(1, atoi(v));
+  if (const char* v = getenv("GB_CTA_MULT")) e->opt.cta_target_mult = std::max(1, atoi(v));
+  if (const char* v = getenv("GB_VPC")) e->opt.vpc = std::max(1, atoi(v));
+  if (const char* v = getenv("GB_KNOT_MAX_RATE")) e->opt.knot_max_rate = std::max(0.0, atof(v));
+  if (const char* v = getenv("GB_LTI")) e->opt.lti = atoi(v) != 0;
+  if (const char* v = getenv("GB_REST_KERNEL")) e->opt.rest_kernel = atoi(v) != 0;
+  if (const char* v = getenv("GB_SWEEP_KERNEL")) e->opt.sweep_kernel = atoi(v) != 0;
+  if (const char* v = getenv("GB_MIN_CUT_VOICES")) e->opt.min_cut_voices = std::max(1, atoi(v));
   if (const char* v = getenv("GB_FUSED_SUMS")) e->fused_sums_enabled = atoi(v) != 0;
   if (const char* v = getenv("GB_CHUNK_CUTS")) e->chunk_cuts = atoi(v) != 0;
   if (cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking) != cudaSuccess ||
@@ -978,6 +997,10 @@ int gb_load_sample(gb_engine* e, uint32_t uid, uint8_t key, const double* frames
   Node* n = find(e, uid);
   if (!n) return fail(e, GB_ENOENT, "unknown uid %u", uid);
   if (n->kind != GB_INST_SAMPLER && n->kind != GB_INST_DRUMKIT) return fail(e, GB_EINVAL, "entity does not take samples");
+  // the sample table is part of the plan (voice count, state blob layout): frozen by gb_finalize
+  if (e->finalized) return fail(e, GB_ESTATE, "engine is finalized");
+  if (n->kind == GB_INST_DRUMKIT && key >= 128) return fail(e, GB_EINVAL, "bad key");
+  if (!(sample_rate > 0.0)) return fail(e, GB_EINVAL, "bad sample rate");
   cudaSetDevice(e->device);
   SampleDev s;
   s.n = n_frames;
@@ -985,15 +1008,24 @@ int gb_load_sample(gb_engine* e, uint32_t uid, uint8_t key, const double* frames
   s.sr = sample_rate;
   size_t bytes = n_frames * (size_t)channels * sizeof(double);
   CUDA_TRY(e, cudaMalloc(&s.d, bytes));
+  if (cudaMemcpy(s.d, frames, bytes, cudaMemcpyHostToDevice) != cudaSuccess) {
+    cudaFree(s.d);
+    return fail(e, GB_ECUDA, "sample upload failed");
+  }
   e->allocations.push_back(s.d);
-  CUDA_TRY(e, cudaMemcpy(s.d, frames, bytes, cudaMemcpyHostToDevice));
   e->stats.h2d_bytes += bytes;
+  auto release = [&](SampleDev& old) {  // a replaced sample's buffer is freed now, not at destroy
+    auto it = std::find(e->allocations.begin(), e->allocations.end(), (void*)old.d);
+    if (it != e->allocations.end()) e->allocations.erase(it);
+    cudaFree(old.d);
+    old.d = nullptr;
+  };
   if (n->kind == GB_INST_SAMPLER) {
     s.root_hz = root_hz > 0.0 ? root_hz : (n->sp.root_hz > 0.0 ? n->sp.root_hz : 440.0);
+    for (SampleDev& old : n->samples) release(old);
     n->samples.clear();
     n->samples.push_back(s);
   } else {
-    if (key >= 128) return fail(e, GB_EINVAL, "bad key");
     if (n->key_to_voice[key] < 0) {
       n->key_to_voice[key] = (int)n->svoices.size();
       n->samples.push_back(s);
@@ -1001,7 +1033,9 @@ int gb_load_sample(gb_engine* e, uint32_t uid, uint8_t key, const double* frames
       v.sample = (int)n->samples.size() - 1;
       n->svoices.push_back(v);
     } else {
-      n->samples[n->svoices[n->key_to_voice[key]].sample] = s;
+      SampleDev& slot = n->samples[(size_t)n->svoices[(size_t)n->key_to_voice[key]].sample];
+      release(slot);
+      slot = s;
     }
   }
   return 0;
@@ -1040,6 +1074,17 @@ int gb_finalize(gb_engine* e) {
   if (!e) return GB_EINVAL;
   if (e->finalized) return fail(e, GB_ESTATE, "engine is already finalized");
   cudaSetDevice(e->device);
+  // a finalize that failed half-way may be retried: start from a clean plan
+  e->plan.clear();
+  e->h_winst.clear();
+  e->h_finst.clear();
+  e->wwork_node.clear();
+  for (auto& kv : e->nodes) {
+    kv.second->consumers = 0;
+    kv.second->order = -1;
+    kv.second->fuse_partials = false;
+    kv.second->partial_count = 0;
+  }
   // Scheduling edges: a link target must run after its source.  Only sources that the main mixer reaches
   // through patch cables count (unpatched entities never render, orchestrator.rs:378-430).
   std::map<uint32_t, std::vector<uint32_t>> children;
@@ -1163,11 +1208,11 @@ int gb_finalize(gb_engine* e) {
     std::vector<CtaWork> work;
     std::vector<WarpItem> items;
     if (total_voices == 0) { *count = 0; *n_grouped = 0; return 0; }
-    int target = std::max(1, e->num_sms * e->cta_target_mult);
+    int target = std::max(1, e->num_sms * e->opt.cta_target_mult);
     const int wpc = kVoiceWarps;  // warps per CTA (4-warp CTAs with tighter register caps measured slower)
     int vpc = std::max(wpc, cdiv(total_voices, target));
     vpc = cdiv(vpc, wpc) * wpc;
-    if (const char* v = getenv("GB_VPC")) vpc = std::max(1, atoi(v));  // tests: force the voices-per-CTA split
+    if (e->opt.vpc > 0) vpc = e->opt.vpc;  // tests: force the voices-per-CTA split
     for (Node* n : e->plan) {
       if (n->kind != kind) continue;
       if (n->nvoices < wpc) {
@@ -1437,9 +1482,9 @@ int render_chunk(gb_engine* e, int frames, size_t n_ev) {
   }
   e->events.erase(e->events.begin(), e->events.begin() + (long)n_ev);
 
-  // NOTE on sampler retriggers inside a chunk: a voice restarted twice in one chunk keeps only the
-  // latest play above.  Plays are therefore snapshotted per event below via `pending_plays`.
-  // (handled by render splitting chunks at sampler note-ons; see split_points in gb_render.)
+  // Sampler retriggers inside a chunk do not split it: when a voice is restarted, its previous play is
+  // truncated at the retrigger frame and kept in Node::done_plays for this chunk's play list (step 3),
+  // so a voice restarted several times in one chunk contributes every one of its plays.
 
   // ---- 2. parameter segment tables: one per automated node, built on the host, one upload ----
   struct SegRange { size_t off; int n; };
@@ -1533,7 +1578,7 @@ int render_chunk(gb_engine* e, int frames, size_t n_ev) {
   if (e->n_wvoice) {
     if (e->winst_dirty) {
       for (Node* n : e->plan)
-        if (n->kind == GB_INST_WELSH) welsh_inst_from_params(*n, e->sr, &e->h_winst[(size_t)n->table_index]);
+        if (n->kind == GB_INST_WELSH) welsh_inst_from_params(*n, e->sr, e->opt, &e->h_winst[(size_t)n->table_index]);
       CUDA_TRY(e, cudaMemcpyAsync(e->d_winst, e->h_winst.data(), e->h_winst.size() * sizeof(WelshInst),
                                   cudaMemcpyHostToDevice, e->stream));
       CUDA_TRY(e, cudaStreamSynchronize(e->stream));  // h_winst is pageable
@@ -1824,8 +1869,7 @@ int64_t chunk_cut(gb_engine* e, int64_t f0, int64_t limit) {
   constexpr int64_t kMinZone = 16 * kBlockFrames;
   // cuts pay off when the Welsh voices dominate a chunk; with a handful of voices the extra launches cost
   // more than the specialised kernels save (a 16-voice song went from 28 to 210 launches)
-  constexpr int kMinCutVoices = 256;
-  if (limit < 2 * kMinZone || e->n_wwork_grouped == 0 || !e->chunk_cuts || e->n_wvoice < kMinCutVoices) return limit;
+  if (limit < 2 * kMinZone || e->n_wwork_grouped == 0 || !e->chunk_cuts || e->n_wvoice < e->opt.min_cut_voices) return limit;
   std::vector<int64_t> tr;
   const int64_t f1 = f0 + limit;
   for (const gb_event& ev : e->events) {  // sorted by frame

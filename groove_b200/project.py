@@ -230,11 +230,13 @@ def welsh_params_from_patch(patch: dict, voices: int = 8) -> dict:
     w2, pw2 = _waveform(o2["waveform"])
     t1, _ = _osc_tune(o1.get("tune", {}))
     t2, note2 = _osc_tune(o2.get("tune", {}))
+    # oscillator-2-track=false: the reference sets the fixed frequency only on a throwaway Oscillator that
+    # is used for the mix count (patches.rs:92-101); the WelshVoiceParams it returns carry
+    # oscillator_2 = {waveform, frequency_tune (Note -> ratio 1.0), ..Default} (patches.rs:118-122), so
+    # oscillator 2 still tracks the note at ratio 1.0.  Reproduced as is; the panic is kept.
     fixed2 = 0.0
-    if w2 != abi.WAVE_NONE and not patch.get("oscillator-2-track", True):
-        if note2 is None:
-            raise ValueError("Patch configured without oscillator 2 tracking, but tune is not a note specification")
-        fixed2 = 440.0 * 2.0 ** ((note2 - 69) / 12.0)
+    if w2 != abi.WAVE_NONE and not patch.get("oscillator-2-track", True) and note2 is None:
+        raise ValueError("Patch configured without oscillator 2 tracking, but tune is not a note specification")
     n_osc = (w1 != abi.WAVE_NONE) + (w2 != abi.WAVE_NONE) + (float(patch.get("noise", 0.0)) > 0.0)
     m1, m2 = float(o1.get("mix-pct", 1.0)), float(o2.get("mix-pct", 1.0))
     if n_osc == 0:

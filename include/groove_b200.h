@@ -233,7 +233,8 @@ const char* gb_last_error(const gb_engine* e);   /* e may be NULL: error of the 
 
 int gb_add_instrument(gb_engine* e, int32_t kind, const void* params, size_t params_size, uint32_t* uid);
 int gb_add_effect(gb_engine* e, int32_t kind, const void* params, size_t params_size, uint32_t* uid);
-/* frames: interleaved when channels == 2; values in [-1,1). key: MIDI key for a drumkit, 0 for a sampler. */
+/* frames: interleaved when channels == 2; values in [-1,1). key: MIDI key for a drumkit, 0 for a sampler.
+   Call before gb_finalize (the sample table is part of the frozen plan): GB_ESTATE afterwards. */
 int gb_load_sample(gb_engine* e, uint32_t uid, uint8_t key, const double* frames, size_t n_frames,
                    int32_t channels, double sample_rate, double root_hz);
 /* source -> destination; destination must be an effect (orchestrator.rs:263-304). */

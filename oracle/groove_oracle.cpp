@@ -1168,6 +1168,7 @@ int go_load_sample(go_engine* e, uint32_t uid, uint8_t key, const double* frames
   if (!e || !frames || n == 0 || (channels != 1 && channels != 2)) return fail(e, GB_EINVAL, "bad sample");
   auto it = e->store.find(uid);
   if (it == e->store.end()) return fail(e, GB_ENOENT, "unknown uid");
+  if (e->finalized) return fail(e, GB_ESTATE, "engine is finalized");
   int rc = it->second->load_sample(key, frames, n, channels, sample_rate, root_hz);
   if (rc) return fail(e, rc, "entity does not take samples");
   return 0;

@@ -305,8 +305,25 @@ def scene_sidechain(r: abi.Renderer) -> int:
     return 15000
 
 
+def scene_cello_held_chord(r: abi.Renderer) -> int:
+    """Config 4's recipe in miniature: one 16-voice cello instrument (grouped CTAs), every note held from the
+    first frames to near the end.  Rendered in 4096-frame chunks this walks the voices through the general
+    kernel (note-ons, envelope stage boundaries, note-offs), welsh_sweep_kernel (filter decay, 3.29 s) and
+    welsh_rest_kernel (both envelopes at sustain)."""
+    u = r.add_instrument(abi.INST_WELSH, cello_params(voices=16, gain=1.0 / 16.0, pan=-0.3))
+    r.patch(u, abi.MAIN_MIXER)
+    r.finalize()
+    ev = []
+    for i in range(16):
+        ev.append((64 * i, u, abi.EV_NOTE_ON, 36 + i, 127, 0.0))
+        ev.append((180000 + 64 * i, u, abi.EV_NOTE_OFF, 36 + i, 0, 0.0))
+    r.push_events(ev)
+    return 200000
+
+
 ALL_SCENES = {
     "cello_chord": scene_cello_chord,
+    "cello_held_chord": scene_cello_held_chord,
     "welsh_variants": scene_welsh_variants,
     "welsh_sustain": scene_welsh_sustain,
     "fm": scene_fm,

@@ -97,6 +97,20 @@ def test_welsh_patch_mapping_quirks():
     cello = project.welsh_params_from_patch(json.load(open(os.path.join(REF, "assets/patches/welsh/cello.json"))))
     assert cello["mix"] == 0.5 and cello["lfo_depth"] == pytest.approx(0.05) and cello["cutoff_end"] == pytest.approx(0.9)
     assert cello["amp"] == [pytest.approx(0.06), 0.0, 1.0, 0.0] and cello["filt"][3] == pytest.approx(3.29)
+    # oscillator-2-track=false (patches.rs:92-101): the fixed frequency lands on a throwaway oscillator only;
+    # the returned voice params keep oscillator 2 tracking the note at ratio 1.0 (tune = Note)
+    untracked = 0
+    for path in sorted(glob.glob(os.path.join(REF, "assets/patches/welsh/*.json"))):
+        patch = json.load(open(path))
+        if patch.get("oscillator-2-track", True) or patch["oscillator-2"]["waveform"] == "none":
+            continue
+        try:
+            p = project.welsh_params_from_patch(patch)
+        except ValueError:
+            continue
+        untracked += 1
+        assert p["fixed2"] == 0.0 and p["tune2"] == 1.0, path
+    assert untracked >= 3   # the other untracked patches panic in the reference too (tune is not a Note)
 
 
 def test_json5_subset_parser():
