@@ -21,6 +21,7 @@ OK, EINVAL, ENOENT, ESTATE, ENODEV, ECUDA, ENOMEM, EGRAPH = 0, -1, -2, -3, -4, -
 
 # --- kinds ---------------------------------------------------------------------
 INST_WELSH, INST_FM, INST_SAMPLER, INST_DRUMKIT, INST_TOY_SOURCE = 1, 2, 3, 4, 5
+INST_OSCILLATOR, INST_ENVELOPE = 6, 7
 FX_MIXER, FX_GAIN, FX_LIMITER, FX_BITCRUSHER, FX_COMPRESSOR = 32, 33, 34, 35, 36
 FX_DELAY, FX_CHORUS, FX_REVERB = 37, 38, 39
 FX_LOW_PASS_12DB, FX_HIGH_PASS_12DB, FX_BAND_PASS_12DB, FX_BAND_STOP_12DB = 40, 41, 42, 43
@@ -76,6 +77,14 @@ class DrumkitParams(C.Structure):
 
 class ToySourceParams(C.Structure):
     _fields_ = [("level_left", C.c_double), ("level_right", C.c_double)]
+
+
+class OscillatorSourceParams(C.Structure):
+    _fields_ = [("oscillator", OscillatorParams)]
+
+
+class EnvelopeSourceParams(C.Structure):
+    _fields_ = [("envelope", EnvelopeParams)]
 
 
 class GainParams(C.Structure):

@@ -105,6 +105,30 @@ inline void dca_gains(double gain, double pan, double* gl, double* gr) {
   *gl = gain * (1.0 - a * a);
   *gr = gain * (1.0 - b * b);
 }
+// host copies of dsp.cuh's env_pre / env_level (levels at note events of a GB_INST_ENVELOPE device)
+inline double h_env_pre(const EnvShape& s, int64_t n_on, double l_on, int64_t n) {
+  const int64_t k = n - n_on;
+  if (k < s.na) {
+    const double t = (double)k / (double)s.na;
+    return l_on + (1.0 - l_on) * (t * (2.0 - t));
+  }
+  const int64_t k2 = k - s.na;
+  if (k2 < s.nd) {
+    const double u = 1.0 - (double)k2 / (double)s.nd;
+    return s.sustain + (1.0 - s.sustain) * (u * u);
+  }
+  return s.sustain;
+}
+inline double h_env_level(const EnvShape& s, int64_t n_on, int64_t n_off, double l_on, double l_off, int64_t n) {
+  if (n < n_on) return 0.0;
+  if (n < n_off) return h_env_pre(s, n_on, l_on, n);
+  const int64_t k = n - n_off;
+  if (k < s.nr) {
+    const double u = 1.0 - (double)k / (double)s.nr;
+    return l_off * (u * u);
+  }
+  return 0.0;
+}
 inline EnvShape make_shape(const gb_envelope_params& p, double sr) {
   EnvShape s;
   s.na = frames_of(p.attack, sr);
@@ -288,6 +312,12 @@ struct Node {
   gb_fm_params fp;
   gb_sampler_params sp;
   gb_toy_source_params tp;
+  gb_oscillator_source_params osp;
+  gb_envelope_source_params esp;
+  struct EnvHost {  // GB_INST_ENVELOPE: note state tracked on the host (integer frames + two levels)
+    int64_t n_on = kNever, n_off = kNever;
+    double l_on = 0.0, l_off = 0.0;
+  } envh;
   int table_index = -1;  // index in the welsh/fm instrument table
   int voice0 = 0, nvoices = 0;
   int partial_count = 0;  // partial output buffers in `scratch` (0 = renders straight into `buf`)
@@ -906,6 +936,14 @@ int gb_add_instrument(gb_engine* e, int32_t kind, const void* params, size_t siz
       if (!params || size != sizeof(gb_toy_source_params)) return fail(e, GB_EINVAL, "bad toy params size");
       n->tp = *(const gb_toy_source_params*)params;
       break;
+    case GB_INST_OSCILLATOR:
+      if (!params || size != sizeof(gb_oscillator_source_params)) return fail(e, GB_EINVAL, "bad oscillator params size");
+      n->osp = *(const gb_oscillator_source_params*)params;
+      break;
+    case GB_INST_ENVELOPE:
+      if (!params || size != sizeof(gb_envelope_source_params)) return fail(e, GB_EINVAL, "bad envelope params size");
+      n->esp = *(const gb_envelope_source_params*)params;
+      break;
     default:
       return fail(e, GB_EINVAL, "unknown instrument kind %d", kind);
   }
@@ -1391,6 +1429,10 @@ int render_chunk(gb_engine* e, int frames, size_t n_ev) {
   // ---- 1. resolve events ----
   std::vector<std::vector<VoiceEvent>> wlists((size_t)e->n_wvoice), flists((size_t)e->n_fvoice);
   std::map<Node*, std::vector<ControlPoint>> controls;
+  std::map<Node*, std::vector<std::pair<int, Node::EnvHost>>> env_points;  // GB_INST_ENVELOPE: (chunk frame, state from there on)
+  std::map<Node*, Node::EnvHost> env_entry;  // ... state at the start of the chunk
+  for (Node* n : e->plan)
+    if (n->kind == GB_INST_ENVELOPE) env_entry[n] = n->envh;
   bool any_w = false, any_f = false;
   for (size_t i = 0; i < n_ev; ++i) {
     const gb_event& ev = e->events[i];
@@ -1457,6 +1499,19 @@ int render_chunk(gb_engine* e, int frames, size_t n_ev) {
             }
           }
         }
+      } else if (n->kind == GB_INST_ENVELOPE) {
+        const EnvShape sh = make_shape(n->esp.envelope, e->sr);
+        Node::EnvHost& h = n->envh;
+        if (on) {
+          h.l_on = h_env_level(sh, h.n_on, h.n_off, h.l_on, h.l_off, f);
+          h.n_on = f;
+          h.n_off = kHeld;
+        } else {
+          if (h.n_off != kHeld) continue;
+          h.l_off = h_env_pre(sh, h.n_on, h.l_on, f);
+          h.n_off = f;
+        }
+        env_points[n].push_back({(int)(f - f0), h});
       } else if (n->kind == GB_INST_DRUMKIT) {
         if (!on || key < 0 || key >= 128 || n->key_to_voice[key] < 0) continue;
         SampleVoiceHost& sv = n->svoices[(size_t)n->key_to_voice[key]];
@@ -1539,6 +1594,24 @@ int render_chunk(gb_engine* e, int frames, size_t n_ev) {
       n->unit_gain = true;
       (n->kind == GB_INST_WELSH ? e->winst_dirty : e->finst_dirty) = true;
     }
+  }
+  for (Node* n : e->plan) {  // envelope devices: one segment per note event of the chunk
+    if (n->kind != GB_INST_ENVELOPE) continue;
+    SegRange r;
+    r.off = segs_h.size();
+    auto seg = [&](int t, const Node::EnvHost& h) {
+      SegParam sp;
+      sp.t0 = t; sp.pad = 0;
+      sp.v[0] = h.l_on; sp.v[1] = h.l_off; sp.v[2] = (double)h.n_on; sp.v[3] = (double)h.n_off; sp.v[4] = 0.0; sp.v[5] = 0.0;
+      if (t == 0 && segs_h.size() > r.off) segs_h.back() = sp;  // an event on the chunk's first frame replaces the entry state
+      else segs_h.push_back(sp);
+    };
+    seg(0, env_entry[n]);
+    auto it = env_points.find(n);
+    if (it != env_points.end())
+      for (auto& pt : it->second) seg(pt.first, pt.second);
+    r.n = (int)(segs_h.size() - r.off);
+    seg_of[n] = r;
   }
   if (!segs_h.empty()) {
     if (!e->segs.reserve(segs_h.size())) return fail(e, GB_ENOMEM, "out of memory");
@@ -1788,6 +1861,21 @@ int render_chunk(gb_engine* e, int frames, size_t n_ev) {
       if (n->kind == GB_INST_TOY_SOURCE) {
         Launch l(e, false);
         fill_kernel<<<cdiv(frames, 256), 256, 0, e->stream>>>(n->buf, frames, n->tp.level_left, n->tp.level_right);
+      } else if (n->kind == GB_INST_OSCILLATOR) {
+        const double top = 1.0 - 1.0 / 9007199254740992.0;
+        OscSourceDesc d;
+        d.waveform = n->osp.oscillator.waveform; d.pad = 0;
+        d.dq = h_cycles_to_q(n->osp.oscillator.frequency / e->sr);
+        d.duty_q = h_cycles_to_q(std::min(clamp01(n->osp.oscillator.pulse_width), top));
+        d.seed = splitmix64((uint64_t)n->uid << 32);
+        Launch l(e, true);
+        oscillator_source_kernel<<<cdiv(frames, 256), 256, 0, e->stream>>>(d, n->buf, f0, frames);
+        e->stats.voice_samples += (uint64_t)frames;
+      } else if (n->kind == GB_INST_ENVELOPE) {
+        Launch l(e, true);
+        envelope_source_kernel<<<cdiv(frames, 256), 256, 0, e->stream>>>(make_shape(n->esp.envelope, e->sr), segs, nseg,
+                                                                          n->buf, f0, frames);
+        e->stats.voice_samples += (uint64_t)frames;
       } else if (n->unit_gain) {
         SourceList self;
         memset(&self, 0, sizeof self);
@@ -2104,7 +2192,7 @@ int gb_save_state(gb_engine* e, void* buf, size_t* size) {
   cudaSetDevice(e->device);
   CUDA_TRY(e, cudaStreamSynchronize(e->stream));
   Blob b;
-  uint64_t magic = 0x31305453424700ull;  // "GBST01"
+  uint64_t magic = 0x32305453424700ull;  // "GBST02"
   b.put(magic);
   b.put(e->pos);
   b.put(e->n_wvoice);
@@ -2122,6 +2210,7 @@ int gb_save_state(gb_engine* e, void* buf, size_t* size) {
     uint32_t nsv = (uint32_t)n->svoices.size();
     b.put(nsv);
     for (auto& s : n->svoices) b.put(s);
+    b.put(n->envh);
   }
   uint64_t nev = e->events.size();
   b.put(nev);
@@ -2149,7 +2238,7 @@ int gb_restore_state(gb_engine* e, const void* buf, size_t size) {
   uint32_t nplan = 0;
   int64_t pos = 0;
   r.get(&magic); r.get(&pos); r.get(&nw); r.get(&nf); r.get(&nplan);
-  if (!r.ok || magic != 0x31305453424700ull || nw != e->n_wvoice || nf != e->n_fvoice || nplan != e->plan.size())
+  if (!r.ok || magic != 0x32305453424700ull || nw != e->n_wvoice || nf != e->n_fvoice || nplan != e->plan.size())
     return fail(e, GB_EINVAL, "state blob does not match this engine");
   for (Node* n : e->plan) {
     uint32_t uid = 0, ns = 0, nsv = 0;
@@ -2164,6 +2253,7 @@ int gb_restore_state(gb_engine* e, const void* buf, size_t size) {
     r.get(&nsv);
     if (nsv != n->svoices.size()) return fail(e, GB_EINVAL, "state blob sample-voice mismatch");
     for (auto& s : n->svoices) r.get(&s);
+    r.get(&n->envh);
   }
   uint64_t nev = 0;
   r.get(&nev);

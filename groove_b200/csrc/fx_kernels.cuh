@@ -192,6 +192,31 @@ __global__ void __launch_bounds__(256) fill_kernel(double2* __restrict__ out, in
   if (t < n) out[t] = make_double2(l, r);
 }
 
+// ---- bare oscillator / envelope devices (GB_INST_OSCILLATOR, GB_INST_ENVELOPE) ----------------------
+// Both are closed forms of the absolute frame, so they need no device state: the oscillator runs free
+// from frame 0 (phase(n) = n * dq mod 2^64), the envelope's note state per segment of the chunk comes
+// from the host (note frames are integers; v = {l_on, l_off, n_on, n_off}, frames exact in a double).
+struct OscSourceDesc {
+  int waveform, pad;
+  u64 dq, duty_q, seed;
+};
+__global__ void __launch_bounds__(256) oscillator_source_kernel(OscSourceDesc d, double2* __restrict__ out, i64 f0,
+                                                                 int frames) {
+  int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= frames) return;
+  const i64 n = f0 + t;
+  const double v = wave_value(d.waveform, (u64)n * d.dq, d.duty_q, d.seed, n);
+  out[t] = make_double2(v, v);
+}
+__global__ void __launch_bounds__(256) envelope_source_kernel(EnvShape sh, const SegParam* __restrict__ segs, int nseg,
+                                                               double2* __restrict__ out, i64 f0, int frames) {
+  int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= frames) return;
+  const SegParam& sp = segs[nseg > 1 ? seg_find(segs, nseg, t) : 0];
+  const double v = env_level(sh, (i64)sp.v[2], (i64)sp.v[3], sp.v[0], sp.v[1], f0 + t);
+  out[t] = make_double2(v, v);
+}
+
 // f64 stereo -> 16-bit PCM: (x * 32767.0) as i16 — truncate toward zero, saturate, NaN -> 0
 // (orchestration/src/helpers.rs:78,90-91).
 __device__ __forceinline__ short pcm16_of(double x) {

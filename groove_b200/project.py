@@ -152,6 +152,33 @@ def read_wav(path: str) -> Tuple[np.ndarray, float]:
     return x, float(sr)
 
 
+def wav_root_note(path: str) -> Optional[int]:
+    """MIDI root note from a WAV file's metadata, or None: the `smpl` chunk's MIDI unity note, else the
+    `acid` chunk's root note when its flags say it is valid (bit 1).  README.md:82-84: "If it can figure
+    out the root frequency from the WAV file's metadata, then it will play the sample at the right
+    adjusted frequency"; test-data/samples/riff-acidized.wav carries an acid chunk with root note 57."""
+    import struct
+    with open(path, "rb") as f:
+        b = f.read()
+    if len(b) < 12 or b[:4] != b"RIFF" or b[8:12] != b"WAVE":
+        return None
+    smpl = acid = None
+    i = 12
+    while i + 8 <= len(b):
+        cid, size = b[i:i + 4], struct.unpack("<I", b[i + 4:i + 8])[0]
+        body = b[i + 8:i + 8 + size]
+        if cid == b"smpl" and len(body) >= 16:
+            note = struct.unpack("<I", body[12:16])[0]
+            if 0 <= note < 128:
+                smpl = int(note)
+        elif cid == b"acid" and len(body) >= 6:
+            flags, note = struct.unpack("<IH", body[:6])
+            if flags & 0x02 and note < 128:
+                acid = int(note)
+        i += 8 + size + (size & 1)
+    return smpl if smpl is not None else acid
+
+
 def write_wav16(path: str, pcm: np.ndarray, sample_rate: float) -> None:
     """16-bit stereo PCM writer (orchestration/src/helpers.rs:74-97)."""
     with wave.open(path, "wb") as w:
@@ -352,8 +379,13 @@ class ProjectLoader:
             e.samples = [(k, v, 0.0) for k, v in sorted(KIT_707.items())]
             return e
         if kind_name == "sampler":
-            e = Entity(uvid, "instrument", abi.INST_SAMPLER, {"root": float(args.get("root", 0.0)), "voices": 8}, midi)
-            e.samples = [(0, args["filename"], float(args.get("root", 0.0)))]
+            # root: the project's value if positive, else the WAV file's own metadata (README.md:82-84), else the
+            # engine default (440 Hz)
+            root = float(args.get("root", 0.0))
+            if not root > 0.0:
+                root = self.sample_root_hz(args["filename"])
+            e = Entity(uvid, "instrument", abi.INST_SAMPLER, {"root": root, "voices": 8}, midi)
+            e.samples = [(0, args["filename"], root)]
             return e
         if kind_name == "fm-synthesizer":
             dca = args.get("dca", {})
@@ -362,6 +394,17 @@ class ProjectLoader:
                 "beta": float(args.get("beta", 1.0)), "car": _env4(args.get("carrier-envelope")),
                 "mod": _env4(args.get("modulator-envelope")), "gain": float(dca.get("gain", 1.0)),
                 "pan": float(dca.get("pan", 0.0)), "voices": 8}, midi)
+        # "oscillator" / "envelope": bare Oscillator / Envelope devices of the older fixtures (58 + 1 projects under
+        # projects/demos/); the variants are gone from InstrumentSettings (settings/src/instruments.rs:24-39) but "a
+        # loader must accept the union" (SURVEY.md §5).  The body is a one-element list: midi-in and the parameters
+        # share one object.
+        flat = body[0] if isinstance(body, list) and body else {}
+        if kind_name == "oscillator":
+            wf, pw = _waveform(flat.get("waveform", "sine"))
+            return Entity(uvid, "instrument", abi.INST_OSCILLATOR,
+                          {"waveform": wf, "pw": pw, "hz": float(flat.get("frequency", 0.0))}, midi)
+        if kind_name == "envelope":
+            return Entity(uvid, "instrument", abi.INST_ENVELOPE, {"env": _env4(flat)}, midi)
         plan.skipped.append(f"instrument {uvid}: type {kind_name!r} is not in InstrumentSettings (settings/src/instruments.rs:24-39)")
         return None
 
@@ -524,12 +567,23 @@ class ProjectLoader:
         with open(path) as f:
             return self.compile(parse_json5(f.read()), sample_rate)
 
-    def sample(self, name: str) -> Tuple[np.ndarray, float]:
+    def _sample_path(self, name: str) -> str:
         for cand in (os.path.join(self.assets, "samples", "elphnt.io", "707", name + ".wav"),
                      os.path.join(self.assets, "samples", name), os.path.join(self.assets, name)):
             if os.path.exists(cand):
-                return read_wav(cand)
+                return cand
         raise FileNotFoundError(name)
+
+    def sample(self, name: str) -> Tuple[np.ndarray, float]:
+        return read_wav(self._sample_path(name))
+
+    def sample_root_hz(self, name: str) -> float:
+        """Root frequency from the file's metadata (smpl / acid chunk), 0.0 if it has none."""
+        try:
+            note = wav_root_note(self._sample_path(name))
+        except FileNotFoundError:
+            return 0.0
+        return 440.0 * 2.0 ** ((note - 69) / 12.0) if note is not None else 0.0
 
 
 def build_plan(r: abi.Renderer, plan: Plan, samples) -> Dict[str, int]:
@@ -544,6 +598,11 @@ def build_plan(r: abi.Renderer, plan: Plan, samples) -> Dict[str, int]:
                 s = abi.FmParams(p["ratio"], p["depth"], p["beta"], abi.env(*p["car"]), abi.env(*p["mod"]),
                                  abi.DcaParams(p["gain"], p["pan"]), p["voices"], 0)
                 uid[e.uvid] = r.add_instrument(e.kind, s)
+            elif e.kind == abi.INST_OSCILLATOR:
+                p = e.params
+                uid[e.uvid] = r.add_instrument(e.kind, abi.OscillatorSourceParams(abi.osc(p["waveform"], p["pw"], frequency=p["hz"])))
+            elif e.kind == abi.INST_ENVELOPE:
+                uid[e.uvid] = r.add_instrument(e.kind, abi.EnvelopeSourceParams(abi.env(*e.params["env"])))
             elif e.kind == abi.INST_DRUMKIT:
                 uid[e.uvid] = r.add_instrument(e.kind, abi.DrumkitParams())
                 for key, name, _ in e.samples:

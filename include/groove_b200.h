@@ -59,6 +59,11 @@ typedef enum {
   GB_INST_SAMPLER = 3,   /* gb_sampler_params   — Sampler         settings/src/instruments.rs:34-36 */
   GB_INST_DRUMKIT = 4,   /* gb_drumkit_params   — Drumkit         settings/src/instruments.rs:34-36 */
   GB_INST_TOY_SOURCE = 5,/* gb_toy_source_params— ToyAudioSource  orchestration/src/orchestrator.rs:1415,1445-1668 */
+  GB_INST_OSCILLATOR = 6,/* gb_oscillator_source_params — a bare Oscillator as a device ("oscillator": 58 of the reference's
+                            project fixtures, e.g. projects/demos/effects/filter-*.json, projects/demos/instruments/oscillator-*.json):
+                            free-running from frame 0 at a fixed frequency, mono on both channels, ignores MIDI */
+  GB_INST_ENVELOPE = 7,  /* gb_envelope_source_params — a bare Envelope as a device (projects/demos/instruments/
+                            envelope-adsr-linear.json): any note-on triggers it, note-off releases; output = its level on both channels */
   /* effects (inner nodes) */
   GB_FX_MIXER = 32,      /* no params           — Mixer (main-mixer is created by gb_create) */
   GB_FX_GAIN = 33,       /* gb_gain_params */
@@ -176,10 +181,20 @@ typedef struct {
   double level_right;
 } gb_toy_source_params;
 
+typedef struct {
+  gb_oscillator_params oscillator;  /* waveform, pulse_width, frequency (Hz, fixed); fixed_frequency / frequency_tune unused */
+} gb_oscillator_source_params;
+
+typedef struct {
+  gb_envelope_params envelope;
+} gb_envelope_source_params;
+
 /* ---- effect params (kebab-case field names of the reference in comments) -- */
 typedef struct { double ceiling; } gb_gain_params;                      /* "ceiling" */
 typedef struct { double min, max; } gb_limiter_params;                  /* "min"/"max" (older: minimum/maximum) */
 typedef struct { double bits; } gb_bitcrusher_params;                   /* "bits" (older: bits-to-crush) */
+/* attack / release are accepted (the reference's CompressorParams carries them, projects/default.json5:56-61) and
+   do not affect the audio: the compressor is a static threshold/ratio curve per sample (docs/ORACLE_SPEC.md §6). */
 typedef struct { double threshold, ratio, attack, release; } gb_compressor_params;
 typedef struct { double seconds; } gb_delay_params;                     /* "delay" (older) / "seconds" */
 typedef struct { double voices, delay_seconds, wet_dry_mix; } gb_chorus_params;

@@ -654,6 +654,67 @@ struct ToySource : Entity {
   }
 };
 
+// A bare Oscillator / Envelope as a device: the "oscillator" and "envelope" instrument types of the
+// reference's older project fixtures (projects/demos/effects/filter-*.json, gain_*.json, bitcrusher_*.json,
+// projects/demos/instruments/oscillator-*.json, envelope-adsr-linear.json; the enum variants are gone from
+// settings/src/instruments.rs:24-39 in this snapshot).  parity unpinned: docs/ORACLE_SPEC.md §3a.
+struct OscillatorSource : Entity {
+  Oscillator osc;
+  uint64_t dq = 0;
+  bool started = false;
+  double out = 0.0;
+  OscillatorSource(const gb_oscillator_source_params& pp, double sr, uint32_t uid_) {
+    uid = uid_;
+    kind = GB_INST_OSCILLATOR;
+    const double top = 1.0 - 1.0 / 9007199254740992.0;
+    osc.waveform = pp.oscillator.waveform;
+    osc.duty_q = cycles_to_q(std::min(clamp01(pp.oscillator.pulse_width), top));
+    osc.seed = splitmix64((uint64_t)uid << 32);
+    dq = cycles_to_q(pp.oscillator.frequency / sr);
+  }
+  bool is_instrument() const override { return true; }
+  void tick(int64_t frame) override {  // free-running from the first rendered frame: phase(n) = n * dq
+    osc.tick(dq, !started);
+    started = true;
+    out = osc.value(frame, 0, false);
+  }
+  Stereo value() const override {
+    Stereo s;
+    s.l = out;
+    s.r = out;
+    return s;
+  }
+};
+struct EnvelopeSource : Entity {
+  EnvShape shape;
+  EnvState st;
+  int64_t n_on = kNever, n_off = kNever;
+  double out = 0.0;
+  EnvelopeSource(const gb_envelope_source_params& pp, double sr, uint32_t uid_) {
+    uid = uid_;
+    kind = GB_INST_ENVELOPE;
+    shape.set(pp.envelope, sr);
+  }
+  bool is_instrument() const override { return true; }
+  void note_on(int64_t f, int, int) override {  // retrigger: the attack starts from the current level
+    st.l_on = env_level(shape, n_on, n_off, st, f);
+    n_on = f;
+    n_off = kHeld;
+  }
+  void note_off(int64_t f, int) override {
+    if (n_off != kHeld) return;
+    st.l_off = env_pre(shape, n_on, st.l_on, f);
+    n_off = f;
+  }
+  void tick(int64_t frame) override { out = env_level(shape, n_on, n_off, st, frame); }
+  Stereo value() const override {
+    Stereo s;
+    s.l = out;
+    s.r = out;
+    return s;
+  }
+};
+
 // -- effects ---------------------------------------------------------------------
 struct Mixer : Entity {};
 // SignalPassthroughController (settings/src/controllers.rs:110-111,181-187; source ABSENT): patched into a
@@ -1073,6 +1134,14 @@ int go_add_instrument(go_engine* e, int32_t kind, const void* params, size_t siz
     case GB_INST_TOY_SOURCE:
       if (!params || size != sizeof(gb_toy_source_params)) return fail(e, GB_EINVAL, "bad toy params size");
       ent = std::make_unique<ToySource>(*(const gb_toy_source_params*)params, id);
+      break;
+    case GB_INST_OSCILLATOR:
+      if (!params || size != sizeof(gb_oscillator_source_params)) return fail(e, GB_EINVAL, "bad oscillator params size");
+      ent = std::make_unique<OscillatorSource>(*(const gb_oscillator_source_params*)params, e->sr, id);
+      break;
+    case GB_INST_ENVELOPE:
+      if (!params || size != sizeof(gb_envelope_source_params)) return fail(e, GB_EINVAL, "bad envelope params size");
+      ent = std::make_unique<EnvelopeSource>(*(const gb_envelope_source_params*)params, e->sr, id);
       break;
     default:
       return fail(e, GB_EINVAL, "unknown instrument kind");

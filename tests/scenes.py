@@ -321,7 +321,40 @@ def scene_cello_held_chord(r: abi.Renderer) -> int:
     return 200000
 
 
+def scene_bare_sources(r: abi.Renderer) -> int:
+    """Bare oscillator / envelope devices (the "oscillator" and "envelope" instrument types of the reference's
+    filter-*, gain_*, bitcrusher_* and oscillator-* demo projects): free-running oscillators of every
+    waveform into filters, and an envelope device retriggered inside its attack and inside its release."""
+    def osc_dev(wave, hz, pw=0.5):
+        return r.add_instrument(abi.INST_OSCILLATOR, abi.OscillatorSourceParams(abi.osc(wave, pw, frequency=hz)))
+    noise = osc_dev(abi.WAVE_NOISE, 0.0)
+    saw = osc_dev(abi.WAVE_SAWTOOTH, 440.0)
+    sine = osc_dev(abi.WAVE_SINE, 1000.0)
+    pulse = osc_dev(abi.WAVE_PULSE_WIDTH, 440.0, 0.1)
+    tri = osc_dev(abi.WAVE_TRIANGLE, 1.0)
+    env = r.add_instrument(abi.INST_ENVELOPE, abi.EnvelopeSourceParams(abi.env(0.1, 0.2, 0.6, 0.3)))
+    lp = r.add_effect(abi.FX_LOW_PASS_12DB, abi.BiquadParams(1000.0, 0.707))
+    bs = r.add_effect(abi.FX_BAND_STOP_12DB, abi.BiquadParams(1000.0, 2.0))
+    crush = r.add_effect(abi.FX_BITCRUSHER, abi.BitcrusherParams(13.0))
+    g1 = r.add_effect(abi.FX_GAIN, abi.GainParams(0.2))
+    g2 = r.add_effect(abi.FX_GAIN, abi.GainParams(0.1))
+    r.patch_chain([noise, lp, g1, abi.MAIN_MIXER])
+    r.patch_chain([saw, crush, g2, abi.MAIN_MIXER])
+    r.patch_chain([sine, bs, g2])
+    r.patch_chain([pulse, g2])
+    r.patch_chain([tri, g1])
+    r.patch_chain([env, g1])
+    r.finalize()
+    ev = [(100, env, abi.EV_NOTE_ON, 60, 127, 0.0), (2000, env, abi.EV_NOTE_ON, 62, 127, 0.0),      # inside the attack
+          (20000, env, abi.EV_NOTE_OFF, 62, 0, 0.0), (25000, env, abi.EV_NOTE_ON, 64, 127, 0.0),   # inside the release
+          (26000, env, abi.EV_NOTE_OFF, 64, 0, 0.0), (26001, env, abi.EV_NOTE_OFF, 64, 0, 0.0),
+          (50, saw, abi.EV_NOTE_ON, 60, 127, 0.0)]                                                  # oscillators ignore MIDI
+    r.push_events(ev)
+    return 45000
+
+
 ALL_SCENES = {
+    "bare_sources": scene_bare_sources,
     "cello_chord": scene_cello_chord,
     "cello_held_chord": scene_cello_held_chord,
     "welsh_variants": scene_welsh_variants,

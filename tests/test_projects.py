@@ -169,3 +169,35 @@ def test_config1_wav_is_within_one_lsb(tmp_path):
     x, sr = project.read_wav(path)
     back = np.round(x * 32768).astype(np.int32)
     assert sr == 44100 and int(np.abs(back - ref.astype(np.int32)).max()) <= 1
+
+
+def test_wav_root_note_metadata(tmp_path):
+    """README.md:82-84: the sampler takes its root frequency from the WAV metadata when it can.  A synthetic
+    file with a `smpl` chunk (MIDI unity note 64), one with an `acid` chunk (root 57, flag bit 1), one whose
+    acid chunk says the root is not valid, and one without metadata."""
+    import struct
+    def wav(chunks):
+        fmt = struct.pack("<HHIIHH", 1, 1, 44100, 88200, 2, 16)
+        data = struct.pack("<4h", 0, 1000, -1000, 0)
+        body = b"WAVE" + b"fmt " + struct.pack("<I", len(fmt)) + fmt + b"data" + struct.pack("<I", len(data)) + data
+        for cid, payload in chunks:
+            body += cid + struct.pack("<I", len(payload)) + payload + (b"\0" if len(payload) & 1 else b"")
+        return b"RIFF" + struct.pack("<I", len(body)) + body
+    smpl = struct.pack("<9I", 0, 0, 22675, 64, 0, 0, 0, 0, 0)
+    acid = lambda flags, note: struct.pack("<IHHfIHHf", flags, note, 0x8000, 0.0, 4, 4, 4, 120.0)
+    cases = {"smpl.wav": ([(b"smpl", smpl)], 64), "acid.wav": ([(b"LIST", b"abc"), (b"acid", acid(2, 57))], 57),
+             "acid-invalid.wav": ([(b"acid", acid(1, 57))], None), "plain.wav": ([], None),
+             "both.wav": ([(b"acid", acid(2, 57)), (b"smpl", smpl)], 64)}
+    for name, (chunks, want) in cases.items():
+        path = tmp_path / name
+        path.write_bytes(wav(chunks))
+        assert project.wav_root_note(str(path)) == want, name
+        x, sr = project.read_wav(str(path))      # the PCM reader is not confused by the extra chunks
+        assert sr == 44100 and x.shape == (4,)
+    loader = project.ProjectLoader(str(tmp_path))
+    assert loader.sample_root_hz("acid.wav") == pytest.approx(220.0)
+    assert loader.sample_root_hz("plain.wav") == 0.0
+    ref = os.path.join(REF, "test-data", "samples", "riff-acidized.wav")
+    if os.path.exists(ref):      # only in the build container
+        assert project.wav_root_note(ref) == 57
+        assert project.wav_root_note(os.path.join(REF, "test-data", "samples", "riff-not-acidized.wav")) is None
