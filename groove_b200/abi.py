@@ -13,7 +13,7 @@ from typing import Iterable, Optional, Sequence
 
 import numpy as np
 
-ABI_VERSION = 2
+ABI_VERSION = 3
 MAIN_MIXER = 1
 
 # --- error codes -------------------------------------------------------------
@@ -143,7 +143,11 @@ class Stats(C.Structure):
                 ("voice_kernel_ms", C.c_double), ("fx_kernel_ms", C.c_double), ("render_ms", C.c_double),
                 ("voice_samples", C.c_uint64), ("h2d_bytes", C.c_uint64), ("d2h_bytes", C.c_uint64),
                 ("rest_kernel_launches", C.c_uint64), ("rest_kernel_ms", C.c_double), ("rest_voice_samples", C.c_uint64),
-                ("sweep_kernel_launches", C.c_uint64), ("sweep_kernel_ms", C.c_double), ("sweep_voice_samples", C.c_uint64)]
+                ("sweep_kernel_launches", C.c_uint64), ("sweep_kernel_ms", C.c_double), ("sweep_voice_samples", C.c_uint64),
+                ("solo_kernel_launches", C.c_uint64), ("solo_kernel_ms", C.c_double), ("solo_voice_samples", C.c_uint64),
+                ("solo_jobs", C.c_uint64), ("solo_class_items", C.c_uint64 * 3),
+                ("fm_kernel_launches", C.c_uint64), ("fm_kernel_ms", C.c_double), ("idle_voice_samples", C.c_uint64),
+                ("rest_ctas", C.c_uint64), ("sweep_ctas", C.c_uint64)]
 
 
 # every symbol include/groove_b200.h declares (suffix after the prefix)

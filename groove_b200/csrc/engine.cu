@@ -23,6 +23,7 @@
 #include <vector>
 
 #include <cuda_runtime.h>
+#include <unistd.h>
 
 #include "../../include/groove_b200.h"
 #include "fx_kernels.cuh"
@@ -35,6 +36,9 @@ namespace {
 constexpr int kVoiceWarps = 8;  // warps per voice CTA
 constexpr int kRestSmemMax = 96 * 1024;  // dynamic shared memory cap of welsh_rest_kernel (tiles + cached voice state)
 constexpr uint32_t kDefaultMaxBlock = 1u << 16;
+// welsh_solo_kernel: row staging tiles + parking columns + one state slot and one instrument record per warp
+constexpr int kSoloSmemBytes = (int)SoloSmem<kVoiceWarps>::kBytes;
+constexpr int kSoloTickets = 64;  // ticket words in front of the per-voice progress counters (one per launch of a chunk)
 
 std::string g_create_err;
 
@@ -396,6 +400,21 @@ struct gb_engine {
   std::vector<Link> links;
   std::vector<Node*> wwork_node;  // instrument of each grouped Welsh CTA
   std::vector<char> wwork_zero;   // ... its output buffer currently holds zeros (idle CTAs are not launched)
+  // solo Welsh items (instruments with fewer voices than a CTA has warps): with enough of them the host
+  // classifies every (voice, sub-chunk) and welsh_solo_kernel walks the resulting job list (voice_kernels.cuh)
+  bool solo_mega = false;
+  std::vector<Node*> witem_node;  // instrument of each solo Welsh item
+  std::vector<int> witem_slot;    // ... and its voice slot in that instrument
+  struct SoloDirty { int lo = 0, hi = 0; };  // frames of the item's output buffer that may hold non-zero audio
+  std::vector<SoloDirty> solo_dirty;
+  DevBuf<SoloItem> sitems;
+  DevBuf<SoloJob> sjobs;
+  DevBuf<ZeroRange> szero;
+  int* d_solo_sync = nullptr;     // [0, kSoloTickets) = job tickets (one per launch), [kSoloTickets + voice] = per-voice progress counter
+  bool solo_waves = false;        // GB_SOLO_WAVES=1: one launch per sub-chunk (stream order instead of the progress counters)
+  int* d_solo_fault = nullptr;    // {flag, job, voice, need, have}: set by the kernel's dependency watchdog
+  bool solo_ran = false;          // a job-list launch happened since the fault words were last checked
+  int min_solo_items = 64;        // GB_SOLO_MIN: fewer solo items than this keep welsh_kernel<.., SOLO> (GB_SOLO_MIN=0: always the job list)
   DevBuf<int> widx;               // per chunk: grouped Welsh CTAs sorted into resting (4 variants) and general
   std::vector<int> widx_on_device;  // what widx.d currently holds (unchanged lists are not uploaded again)
   bool wev_empty_on_device = false, fev_empty_on_device = false;  // the event offset tables on the device are all zero
@@ -594,6 +613,24 @@ void welsh_inst_from_params(const Node& n, double sr, const gb_engine::Options& 
       I->lti.g1b[j][1] = I->lti.g1[j][1] * c2.b0;
     }
     I->lti.inv_b0_2 = 1.0 / c2.b0;
+    {  // released voice, filter envelope run out: cutoff back at cut_a (a fixed filter keeps its one set)
+      SecCoef o1 = I->fixed1, o2 = I->fixed2;
+      if (I->filter_mode == FILTER_ENVELOPE) {
+        double pct = I->cut_a;
+        pct = pct < 0.0 ? 0.0 : (pct > 1.0 ? 1.0 : pct);
+        host_lp24(I->rp, 25.0 * std::exp2(pct * 9.6438561897747243), sr, &o1, &o2);
+      }
+      I->lti_off.c1 = o1; I->lti_off.c2 = o2;
+      I->m1bb_off = scaled(I->m1, o1.b0 * o2.b0);
+      I->m2bb_off = scaled(I->m2, o1.b0 * o2.b0);
+      table(o1, I->lti_off.g1, I->lti_off.mp1);
+      table(o2, I->lti_off.g2, I->lti_off.mp2);
+      for (int j = 0; j < kT; ++j) {
+        I->lti_off.g1b[j][0] = I->lti_off.g1[j][0] * o2.b0;
+        I->lti_off.g1b[j][1] = I->lti_off.g1[j][1] * o2.b0;
+      }
+      I->lti_off.inv_b0_2 = 1.0 / o2.b0;
+    }
     I->lti_ok = opt.lti ? 1 : 0;
     // welsh_rest_kernel variant: same preconditions as welsh_block_lti (see voice_kernels.cuh)
     const bool lin = I->s1.kind == 0 && I->s2.kind == 0 && !I->sync &&
@@ -649,6 +686,8 @@ void resolve_spans(gb_engine* e) {
     if (sp.what == 1) e->stats.voice_kernel_ms += ms;
     else if (sp.what == 3) { e->stats.voice_kernel_ms += ms; e->stats.rest_kernel_ms += ms; }
     else if (sp.what == 4) { e->stats.voice_kernel_ms += ms; e->stats.sweep_kernel_ms += ms; }
+    else if (sp.what == 5) { e->stats.voice_kernel_ms += ms; e->stats.solo_kernel_ms += ms; }
+    else if (sp.what == 6) { e->stats.voice_kernel_ms += ms; e->stats.fm_kernel_ms += ms; }
     else if (sp.what == 0) e->stats.fx_kernel_ms += ms;
     else e->stats.render_ms += ms;
     e->event_pool.push_back({sp.a, sp.b});
@@ -660,12 +699,14 @@ struct Launch {  // per-launch accounting (+ optional CUDA-event timing on the e
   gb_engine* e;
   bool timed;
   size_t index;
-  Launch(gb_engine* e_, bool voice, int special = 0) : e(e_) {  // special: 1 = resting kernel, 2 = sweeping kernel
+  Launch(gb_engine* e_, bool voice, int special = 0) : e(e_) {  // special: 1 = resting, 2 = sweeping, 3 = solo job-list, 4 = FM kernel
     e->stats.kernel_launches++;
     if (voice) e->stats.voice_kernel_launches++;
     if (special == 1) e->stats.rest_kernel_launches++;
     if (special == 2) e->stats.sweep_kernel_launches++;
-    timed = span_begin(e, special == 1 ? 3 : special == 2 ? 4 : voice ? 1 : 0);
+    if (special == 3) e->stats.solo_kernel_launches++;
+    if (special == 4) e->stats.fm_kernel_launches++;
+    timed = span_begin(e, special == 1 ? 3 : special == 2 ? 4 : special == 3 ? 5 : special == 4 ? 6 : voice ? 1 : 0);
     index = e->spans.size() - 1;
   }
   ~Launch() {
@@ -858,6 +899,8 @@ int gb_create(const gb_config* cfg, gb_engine** out) {
   if (const char* v = getenv("GB_REST_KERNEL")) e->opt.rest_kernel = atoi(v) != 0;
   if (const char* v = getenv("GB_SWEEP_KERNEL")) e->opt.sweep_kernel = atoi(v) != 0;
   if (const char* v = getenv("GB_MIN_CUT_VOICES")) e->opt.min_cut_voices = std::max(1, atoi(v));
+  if (const char* v = getenv("GB_SOLO_MIN")) e->min_solo_items = atoi(v);
+  if (const char* v = getenv("GB_SOLO_WAVES")) e->solo_waves = atoi(v) != 0;
   if (const char* v = getenv("GB_FUSED_SUMS")) e->fused_sums_enabled = atoi(v) != 0;
   if (const char* v = getenv("GB_CHUNK_CUTS")) e->chunk_cuts = atoi(v) != 0;
   if (cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking) != cudaSuccess ||
@@ -1266,6 +1309,10 @@ int gb_finalize(gb_engine* e) {
           it.voice = n->voice0 + v;
           it.out = n->partial_count ? n->scratch + (size_t)v * mb : n->buf;
           items.push_back(it);
+          if (kind == GB_INST_WELSH) {
+            e->witem_node.push_back(n);
+            e->witem_slot.push_back(v);
+          }
         }
         continue;
       }
@@ -1312,7 +1359,12 @@ int gb_finalize(gb_engine* e) {
   int rc;
   int fm_grouped = 0;
   e->wwork_node.clear();
+  e->witem_node.clear();
+  e->witem_slot.clear();
   if ((rc = plan_work(GB_INST_WELSH, wv, e->wwork, e->witems, &e->n_wwork, &e->n_wwork_grouped))) return rc;
+  e->solo_mega = !e->witem_node.empty() && (int)e->witem_node.size() >= e->min_solo_items;
+  e->solo_dirty.assign(e->witem_node.size(), gb_engine::SoloDirty());
+  if (e->solo_mega && ((rc = dev_alloc(e, &e->d_solo_sync, (size_t)wv + kSoloTickets)) || (rc = dev_alloc(e, &e->d_solo_fault, 8)))) return rc;
   if ((rc = plan_work(GB_INST_FM, fv, e->fwork, e->fitems, &e->n_fwork, &fm_grouped))) return rc;
   {
     std::vector<PartialDesc> descs;
@@ -1386,6 +1438,7 @@ int gb_finalize(gb_engine* e) {
   CUDA_TRY(e, cudaFuncSetAttribute(welsh_sweep_kernel<8, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kRestSmemMax));
   CUDA_TRY(e, cudaFuncSetAttribute(welsh_sweep_kernel<8, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kRestSmemMax));
   CUDA_TRY(e, cudaFuncSetAttribute(welsh_sweep_kernel<8, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kRestSmemMax));
+  CUDA_TRY(e, cudaFuncSetAttribute(welsh_solo_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSoloSmemBytes));
   CUDA_TRY(e, cudaFuncSetAttribute(fm_kernel<kVoiceWarps>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                    (int)(kVoiceWarps * kTileStride * sizeof(double2))));
   CUDA_TRY(e, cudaStreamSynchronize(e->stream));
@@ -1426,6 +1479,19 @@ int render_chunk(gb_engine* e, int frames, size_t n_ev) {
   if (e->chunk_seq >= (uint64_t)kStageSlots) CUDA_TRY(e, cudaEventSynchronize(e->stage_done[slot]));
   e->widx.use_slot(slot); e->wev.use_slot(slot); e->fev.use_slot(slot); e->wev_off.use_slot(slot);
   e->fev_off.use_slot(slot); e->plays.use_slot(slot); e->segs.use_slot(slot);
+  // solo Welsh voices: note frames as they stand BEFORE this chunk's events (the sub-chunk classification
+  // below replays the chunk's events on top of them)
+  struct SoloPre { int64_t n_on, n_off; };
+  std::vector<SoloPre> solo_pre;
+  if (e->solo_mega) {
+    solo_pre.resize(e->witem_node.size());
+    for (size_t i = 0; i < solo_pre.size(); ++i) {
+      const Node* n = e->witem_node[i];
+      const Slot& sl = n->store.slots[(size_t)e->witem_slot[i]];
+      solo_pre[i].n_on = sl.on_frame;
+      solo_pre[i].n_off = sl.held ? kHeld : sl.idle_at - n->release_frames;
+    }
+  }
   // ---- 1. resolve events ----
   std::vector<std::vector<VoiceEvent>> wlists((size_t)e->n_wvoice), flists((size_t)e->n_fvoice);
   std::map<Node*, std::vector<ControlPoint>> controls;
@@ -1689,6 +1755,7 @@ int render_chunk(gb_engine* e, int frames, size_t n_ev) {
           idle = wlists[(size_t)(w.voice0 + v)].empty() && !sl.held && f0 >= sl.idle_at;
         }
         if (idle) {
+          e->stats.idle_voice_samples += (uint64_t)w.nvoices * (uint64_t)frames;
           if (!e->wwork_zero[(size_t)i]) {
             CUDA_TRY(e, cudaMemsetAsync(w.out, 0, (size_t)e->max_block * sizeof(double2), e->stream));
             e->wwork_zero[(size_t)i] = 1;
@@ -1747,6 +1814,7 @@ int render_chunk(gb_engine* e, int frames, size_t n_ev) {
     welsh_rest_kernel<8, LFO_, FLAT_><<<(int)lists[CLS_].size(), 32 * 8, rest_smem, e->stream>>>(                      \
         e->d_winst, e->d_wvoice, e->wwork.d, e->widx.d + off, f0, frames);                                           \
     off += lists[CLS_].size();                                                                                       \
+    e->stats.rest_ctas += lists[CLS_].size();                                                                        \
   }
       GB_REST_LAUNCH(0, false, false)
       GB_REST_LAUNCH(1, false, true)
@@ -1769,13 +1837,14 @@ int render_chunk(gb_engine* e, int frames, size_t n_ev) {
     welsh_sweep_kernel<8, LFO_, FLAT_><<<(int)lists[5 + CLS_].size(), 32 * 8, sweep_smem, e->stream>>>(                \
         e->d_winst, e->d_wvoice, e->wwork.d, e->widx.d + off, f0, frames);                                           \
     off += lists[5 + CLS_].size();                                                                                   \
+    e->stats.sweep_ctas += lists[5 + CLS_].size();                                                                   \
   }
       GB_SWEEP_LAUNCH(0, false, false)
       GB_SWEEP_LAUNCH(1, false, true)
       GB_SWEEP_LAUNCH(2, true, false)
       GB_SWEEP_LAUNCH(3, true, true)
 #undef GB_SWEEP_LAUNCH
-      if (ns) {
+      if (ns && !e->solo_mega) {
         Launch l(e, true);
         welsh_kernel<8, 2, true><<<ns, 32 * 8, welsh_smem, e->stream>>>(
             e->d_winst, e->d_wvoice, e->wwork.d + ng, e->witems.d, e->wev.d, e->wev_off.d, f0, frames, nullptr);
@@ -1783,6 +1852,234 @@ int render_chunk(gb_engine* e, int frames, size_t n_ev) {
     }
     e->stats.voice_samples += (uint64_t)e->n_wvoice * (uint64_t)frames;
   }
+  // Solo Welsh items through the job list (welsh_solo_kernel).  Prepared AFTER the FM launch below has been
+  // enqueued, so that the host-side classification overlaps with GPU work of the same chunk.
+  auto run_solo = [&]() -> int {
+    if (!e->solo_mega) return 0;
+    const int n_items = (int)e->witem_node.size();
+    const int K = cdiv(frames, kSoloSub);
+    const bool dbg = getenv("GB_DEBUG") != nullptr;
+    if (dbg) { fprintf(stderr, "[solo] f0=%lld frames=%d items=%d K=%d\n", (long long)f0, frames, n_items, K); fflush(stderr); }
+    enum { C_IDLE = 3 };
+    std::vector<int8_t> cls((size_t)n_items * (size_t)K);
+    auto classify = [&](const WelshInst& I, int64_t n_on, int64_t n_off, int64_t s0, int64_t s1, int64_t* valid_until) -> int {
+      // *valid_until: the class holds for every later sub-chunk that ends at or before this frame
+      *valid_until = s1;
+      if (n_on <= kNever) { *valid_until = kHeld; return C_IDLE; }
+      const int64_t idle_at = n_off >= kHeld ? (int64_t)kHeld : n_off + I.amp.nr;
+      if (s0 >= idle_at) { *valid_until = kHeld; return C_IDLE; }
+      if (s1 > idle_at || s0 < n_on || (n_off > s0 && n_off < s1) || (s1 - s0) % kBlockFrames) return SOLO_GENERAL;
+      const bool released = s0 >= n_off;
+      const int64_t base = released ? n_off : n_on;
+      auto stage = [&](const EnvShape& sh, int64_t f, int64_t* next) {  // stage at f and the frame at which it ends
+        const int64_t k = f - base;
+        if (released) {
+          if (k < sh.nr) { *next = base + sh.nr; return 3; }
+          *next = kHeld; return 4;
+        }
+        if (k < sh.na) { *next = base + sh.na; return 0; }
+        if (k - sh.na < sh.nd) { *next = base + sh.na + sh.nd; return 1; }
+        *next = kHeld; return 2;
+      };
+      int64_t na_end, nf_end = kHeld;
+      const int sa = stage(I.amp, s0, &na_end);
+      int64_t until = std::min<int64_t>(std::min<int64_t>(na_end, idle_at), released ? (int64_t)kHeld : n_off);
+      if (s1 > na_end) return SOLO_GENERAL;
+      int result;
+      if (I.filter_mode == FILTER_FIXED) {
+        result = I.rest_class >= 0 ? SOLO_REST : SOLO_GENERAL;
+      } else if (I.filter_mode != FILTER_ENVELOPE) {
+        result = SOLO_GENERAL;
+      } else {
+        const int sf = stage(I.filt, s0, &nf_end);
+        if (s1 > nf_end) return SOLO_GENERAL;
+        until = std::min<int64_t>(until, nf_end);
+        if (sf == 2 || sf == 4) {
+          result = I.rest_class >= 0 ? SOLO_REST : SOLO_GENERAL;
+        } else {
+          const double slope = sf == 0 ? 2.0 * I.filt.inv_na : sf == 1 ? 2.0 * (1.0 - I.filt.sustain) * I.filt.inv_nd
+                                                                       : 2.0 * I.filt.inv_nr;
+          result = I.sweep_class >= 0 && std::fabs(I.cut_b) * slope <= I.knot_max_rate ? SOLO_SWEEP : SOLO_GENERAL;
+        }
+      }
+      (void)sa;
+      *valid_until = until;
+      return result;
+    };
+    int counts[4] = {0, 0, 0, 0};
+    std::vector<int> bucket_n((size_t)K * 3, 0);
+    for (int i = 0; i < n_items; ++i) {
+      const Node* n = e->witem_node[(size_t)i];
+      const WelshInst& I = e->h_winst[(size_t)n->table_index];
+      const auto& evs = wlists[(size_t)(n->voice0 + e->witem_slot[(size_t)i])];
+      int64_t n_on = solo_pre[(size_t)i].n_on, n_off = solo_pre[(size_t)i].n_off;
+      size_t ei = 0;
+      int8_t* c = cls.data() + (size_t)i * (size_t)K;
+      int cur = -1;
+      int64_t valid_until = 0;
+      for (int k = 0; k < K; ++k) {
+        const int64_t s0 = f0 + (int64_t)k * kSoloSub, s1 = std::min<int64_t>(s0 + kSoloSub, f0 + frames);
+        int r;
+        if (ei < evs.size() && evs[ei].frame < s1) {  // note events inside: the general class folds them
+          while (ei < evs.size() && evs[ei].frame < s1) {
+            if (evs[ei].type == VEV_NOTE_ON) { n_on = evs[ei].frame; n_off = kHeld; }
+            else n_off = evs[ei].frame;
+            ++ei;
+          }
+          r = SOLO_GENERAL;
+          cur = -1;
+        } else if (cur >= 0 && s1 <= valid_until) {
+          r = cur;
+        } else {
+          r = classify(I, n_on, n_off, s0, s1, &valid_until);
+          cur = r == SOLO_GENERAL ? -1 : r;
+        }
+        c[k] = (int8_t)r;
+        counts[r]++;
+        if (r != C_IDLE) bucket_n[(size_t)k * 3 + (size_t)r]++;
+      }
+    }
+    // buckets in job order: sub-chunk by sub-chunk; inside one the slowest class first
+    static const int order[3] = {SOLO_GENERAL, SOLO_SWEEP, SOLO_REST};
+    std::vector<int> bucket_off((size_t)K * 3 + 1, 0);
+    {
+      int acc = 0;
+      for (int k = 0; k < K; ++k)
+        for (int o = 0; o < 3; ++o) {
+          bucket_off[(size_t)k * 3 + (size_t)order[o]] = acc;
+          acc += bucket_n[(size_t)k * 3 + (size_t)order[o]];
+        }
+      bucket_off[(size_t)K * 3] = acc;
+    }
+    const int n_sitems = bucket_off[(size_t)K * 3];
+    if (!e->sitems.reserve((size_t)n_sitems + 1)) return fail(e, GB_ENOMEM, "out of memory");
+    e->sitems.use_slot(slot);
+    {
+      std::vector<int> fill(bucket_off.begin(), bucket_off.end() - 1);
+      std::vector<int> done((size_t)n_items, 0);
+      for (int k = 0; k < K; ++k)
+        for (int i = 0; i < n_items; ++i) {
+          const int r = cls[(size_t)i * (size_t)K + (size_t)k];
+          if (r == C_IDLE) continue;
+          SoloItem& si = e->sitems.h[fill[(size_t)k * 3 + (size_t)r]++];
+          si.item = i;
+          si.need = done[(size_t)i]++;
+        }
+    }
+    std::vector<SoloJob> jobs;
+    for (int k = 0; k < K; ++k)
+      for (int o = 0; o < 3; ++o) {
+        const int r = order[o];
+        const int first = bucket_off[(size_t)k * 3 + (size_t)r], cnt = bucket_n[(size_t)k * 3 + (size_t)r];
+        for (int a = 0; a < cnt; a += kVoiceWarps) {
+          SoloJob j;
+          j.cls = r;
+          j.t0 = k * kSoloSub;
+          j.nframes = std::min(kSoloSub, frames - j.t0);
+          j.first = first + a;
+          j.n = std::min(kVoiceWarps, cnt - a);
+          j.pad = 0;
+          jobs.push_back(j);
+        }
+      }
+    // idle stretches: the item's output must read zero there; only stretches that may hold old audio are written
+    std::vector<ZeroRange> zr;
+    for (int i = 0; i < n_items; ++i) {
+      const int8_t* c = cls.data() + (size_t)i * (size_t)K;
+      gb_engine::SoloDirty& d = e->solo_dirty[(size_t)i];
+      int lo = INT32_MAX, hi = 0;
+      for (int k = 0; k < K;) {
+        const bool idle = c[k] == C_IDLE;
+        int k1 = k;
+        while (k1 < K && (c[k1] == C_IDLE) == idle) ++k1;
+        const int a = k * kSoloSub, b = std::min(k1 * kSoloSub, frames);
+        if (idle) {
+          const int za = std::max(a, d.lo), zb = std::min(b, d.hi);
+          if (za < zb) {
+            ZeroRange z;
+            z.p = e->witems.h[i].out + za;
+            z.n = zb - za;
+            zr.push_back(z);
+          }
+        } else {
+          lo = std::min(lo, a);
+          hi = std::max(hi, b);
+        }
+        k = k1;
+      }
+      // after this chunk [0, frames) holds what this chunk wrote; beyond it the old content stays
+      int nlo = lo, nhi = hi;
+      if (d.hi > frames) { nlo = std::min(nlo, std::max(d.lo, frames)); nhi = std::max(nhi, d.hi); }
+      if (nlo >= nhi) { nlo = 0; nhi = 0; }
+      d.lo = nlo; d.hi = nhi;
+    }
+    if (!zr.empty()) {
+      e->szero.use_slot(slot);
+      if (!e->szero.reserve(zr.size())) return fail(e, GB_ENOMEM, "out of memory");
+      memcpy(e->szero.h, zr.data(), zr.size() * sizeof(ZeroRange));
+      CUDA_TRY(e, cudaMemcpyAsync(e->szero.d, e->szero.h, zr.size() * sizeof(ZeroRange), cudaMemcpyHostToDevice, e->stream));
+      e->stats.h2d_bytes += zr.size() * sizeof(ZeroRange);
+      Launch l(e, false);
+      zero_ranges_kernel<<<(int)zr.size(), 256, 0, e->stream>>>(e->szero.d);
+    }
+    e->stats.idle_voice_samples += (uint64_t)counts[C_IDLE] * (uint64_t)kSoloSub;
+    if (jobs.empty()) return 0;
+    e->sjobs.use_slot(slot);
+    if (!e->sjobs.reserve(jobs.size())) return fail(e, GB_ENOMEM, "out of memory");
+    memcpy(e->sjobs.h, jobs.data(), jobs.size() * sizeof(SoloJob));
+    CUDA_TRY(e, cudaMemcpyAsync(e->sitems.d, e->sitems.h, (size_t)n_sitems * sizeof(SoloItem), cudaMemcpyHostToDevice, e->stream));
+    CUDA_TRY(e, cudaMemcpyAsync(e->sjobs.d, e->sjobs.h, jobs.size() * sizeof(SoloJob), cudaMemcpyHostToDevice, e->stream));
+    CUDA_TRY(e, cudaMemsetAsync(e->d_solo_sync, 0, ((size_t)e->n_wvoice + kSoloTickets) * sizeof(int), e->stream));
+    e->stats.h2d_bytes += (size_t)n_sitems * sizeof(SoloItem) + jobs.size() * sizeof(SoloJob);
+    if (dbg) {
+      fprintf(stderr, "[solo] jobs=%zu sitems=%d counts=%d/%d/%d idle=%d zr=%zu\n", jobs.size(), n_sitems, counts[0], counts[1], counts[2], counts[3], zr.size());
+      for (size_t q = 0; q < jobs.size(); ++q) {
+        fprintf(stderr, "  job %zu cls=%d t0=%d n=%d first=%d :", q, jobs[q].cls, jobs[q].t0, jobs[q].n, jobs[q].first);
+        for (int w = 0; w < jobs[q].n; ++w) fprintf(stderr, " (%d,%d)", e->sitems.h[jobs[q].first + w].item, e->sitems.h[jobs[q].first + w].need);
+        fprintf(stderr, "\n");
+      }
+      fflush(stderr);
+    }
+    // one persistent launch walks the whole list; GB_SOLO_WAVES=1 launches once per sub-chunk instead (the
+    // jobs of one sub-chunk are independent, stream order replaces the progress counters)
+    {
+      std::vector<std::pair<int, int>> launches;  // (first job, jobs)
+      if (e->solo_waves && K <= kSoloTickets) {
+        size_t q = 0;
+        while (q < jobs.size()) {
+          size_t q1 = q;
+          while (q1 < jobs.size() && jobs[q1].t0 == jobs[q].t0) ++q1;
+          launches.push_back({(int)q, (int)(q1 - q)});
+          q = q1;
+        }
+      } else {
+        launches.push_back({0, (int)jobs.size()});
+      }
+      int max_grid = 2 * e->num_sms;
+      if (const char* v = getenv("GB_SOLO_GRID")) max_grid = std::max(1, atoi(v));
+      for (size_t li = 0; li < launches.size(); ++li) {
+        Launch l(e, true, 3);
+        const int grid = std::min(launches[li].second, max_grid);
+        welsh_solo_kernel<8><<<grid, 32 * 8, kSoloSmemBytes, e->stream>>>(
+            e->d_winst, e->d_wvoice, e->witems.d, e->sitems.d, e->sjobs.d, launches[li].first, launches[li].second,
+            e->d_solo_sync + li, e->d_solo_sync + kSoloTickets, e->d_solo_fault, e->wev.d, e->wev_off.d, f0, frames);
+      }
+      CUDA_TRY(e, cudaGetLastError());
+      e->solo_ran = true;
+    }
+    if (dbg) {
+      cudaError_t q = cudaErrorNotReady;
+      for (int it = 0; it < 800 && q == cudaErrorNotReady; ++it) { usleep(10000); q = cudaStreamQuery(e->stream); }
+      fprintf(stderr, "[solo] after wait: %s\n", cudaGetErrorString(q)); fflush(stderr);
+      if (q == cudaErrorNotReady) _exit(3);
+    }
+    e->stats.solo_jobs += jobs.size();
+    e->stats.solo_voice_samples += (uint64_t)(counts[0] + counts[1] + counts[2]) * (uint64_t)kSoloSub;
+    e->stats.solo_class_items[0] += (uint64_t)counts[0];
+    e->stats.solo_class_items[1] += (uint64_t)counts[1];
+    e->stats.solo_class_items[2] += (uint64_t)counts[2];
+    return 0;
+  };
   if (e->n_fvoice) {
     if (e->finst_dirty) {
       for (Node* n : e->plan)
@@ -1796,11 +2093,15 @@ int render_chunk(gb_engine* e, int frames, size_t n_ev) {
     int rc = upload_events(flists, e->fev, e->fev_off, any_f, &e->fev_empty_on_device);
     if (rc) return rc;
     {
-      Launch l(e, true);
+      Launch l(e, true, 4);
       fm_kernel<kVoiceWarps><<<e->n_fwork, 32 * kVoiceWarps, tile_bytes, e->stream>>>(
           e->d_finst, e->d_fvoice, e->fwork.d, e->fitems.d, e->fev.d, e->fev_off.d, f0, frames);
     }
     e->stats.voice_samples += (uint64_t)e->n_fvoice * (uint64_t)frames;
+  }
+  if (e->n_wvoice) {
+    int rc = run_solo();
+    if (rc) return rc;
   }
   // samplers / drumkits: one launch per instrument over this chunk's plays (voice order, then time)
   {
@@ -2083,6 +2384,16 @@ int render_impl(gb_engine* e, void* out, size_t frames, size_t* done, OutMode mo
     e->stats.d2h_bytes += frames * sizeof(short2);
   }
   if (call_timed) span_end(e, call_span);
+  if (e->solo_ran) {  // the job-list kernel's dependency watchdog (the stream is drained at this point)
+    int fault[5] = {0, 0, 0, 0, 0};
+    CUDA_TRY(e, cudaMemcpy(fault, e->d_solo_fault, sizeof fault, cudaMemcpyDeviceToHost));
+    e->solo_ran = false;
+    if (fault[0]) {
+      CUDA_TRY(e, cudaMemset(e->d_solo_fault, 0, 8 * sizeof(int)));
+      return fail(e, GB_ECUDA, "welsh_solo_kernel: job %d waited for voice %d to reach %d (stuck at %d)", fault[1], fault[2],
+                  fault[3], fault[4]);
+    }
+  }
   e->full_frames = mode != OUT_F64 ? frames : 0;
   if (done) *done = produced;
   return 0;

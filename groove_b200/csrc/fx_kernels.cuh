@@ -187,6 +187,16 @@ __global__ void __launch_bounds__(256) reduce_partials_kernel(const PartialDesc*
   d.out[t] = make_double2(l, r);
 }
 
+// Zero a list of frame ranges (idle stretches of solo voices' output buffers): one CTA per range.
+struct ZeroRange {
+  double2* p;
+  int n;
+  int pad;
+};
+__global__ void __launch_bounds__(256) zero_ranges_kernel(const ZeroRange* __restrict__ ranges) {
+  const ZeroRange r = ranges[blockIdx.x];
+  for (int t = threadIdx.x; t < r.n; t += blockDim.x) r.p[t] = make_double2(0.0, 0.0);
+}
 __global__ void __launch_bounds__(256) fill_kernel(double2* __restrict__ out, int n, double l, double r) {
   int t = blockIdx.x * blockDim.x + threadIdx.x;
   if (t < n) out[t] = make_double2(l, r);

@@ -174,6 +174,10 @@ struct WelshInst {
   i64 steady_after;                 // frames after note-on from which both envelopes rest at their sustain levels
   double amp_rest;                  // 0.5 * amp.sustain: the DCA input level of a resting voice (without LFO)
   int lti_ok, osc_flat;             // osc_flat: both oscillators piecewise constant (OscMix slopes are 0); lti holds this instrument's resting coefficient sets (GB_LTI=0 disables the path)
+  // the same tables for a RELEASED voice whose filter envelope has run out (cutoff back at cut_a) while the
+  // amplitude envelope still releases; equal to lti / m1bb / m2bb for a fixed filter (welsh_solo_kernel)
+  LtiTable lti_off;
+  OscMix m1bb_off, m2bb_off;
 };
 enum { FILTER_FIXED = 0, FILTER_ENVELOPE = 1, FILTER_LFO = 2 };
 
@@ -1358,10 +1362,10 @@ struct alignas(16) RestState {
 // directly.  NV voices of one instrument are scanned together: they share the span maps, so each step
 // loads its matrix once.  sec = 0 / 1 picks the cached state words (s[2 sec], s[2 sec + 1]): lane 0 reads
 // them as the span's entry state, lane 31 replaces them by the state after the span.
-template <int NV>
-__device__ __forceinline__ void lti_scan_entry(const double (&v0)[NV], const double (&v1)[NV], const double (*mp)[4],
-                                               int lane, RestState* const (&rs)[NV], int sec, double (&e0)[NV],
-                                               double (&e1)[NV]) {
+template <int NV, typename State>
+__device__ __forceinline__ void lti_scan_entry_t(const double (&v0)[NV], const double (&v1)[NV], const double (*mp)[4],
+                                                 int lane, State* const (&rs)[NV], int sec, double (&e0)[NV],
+                                                 double (&e1)[NV]) {
   double u0[NV], u1[NV];
 #pragma unroll
   for (int v = 0; v < NV; ++v) {
@@ -1394,6 +1398,12 @@ __device__ __forceinline__ void lti_scan_entry(const double (&v0)[NV], const dou
       *reinterpret_cast<double2*>(&rs[v]->s[2 * sec]) = make_double2(x0, x1);
     }
   }
+}
+template <int NV>
+__device__ __forceinline__ void lti_scan_entry(const double (&v0)[NV], const double (&v1)[NV], const double (*mp)[4],
+                                               int lane, RestState* const (&rs)[NV], int sec, double (&e0)[NV],
+                                               double (&e1)[NV]) {
+  lti_scan_entry_t<NV, RestState>(v0, v1, mp, lane, rs, sec, e0, e1);
 }
 
 template <bool LFO_AMP, bool ZERO_A, int NV, bool ACC>
@@ -1809,6 +1819,444 @@ __global__ void __launch_bounds__(32 * W, 2) welsh_sweep_kernel(const WelshInst*
   }
 }
 
+// ---- the solo-voice kernel -------------------------------------------------------------------------
+// Instruments with fewer voices than a CTA has warps contribute one (instrument, voice, output buffer)
+// item per voice (a batch of one-voice patch variants — BASELINE config 5 — is 4096 such items per GPU).
+// Every warp is then a different patch at a different stage of its note.  Left to classify its blocks on
+// the device (welsh_kernel<.., SOLO>), the warps of an SM spread over all of the kernel's code paths at
+// once: ncu showed 52 % of the stall samples as instruction-cache misses and another 22 % on the global
+// voice records (profiles/r2_cfg5_before_*).  Here the HOST does the classification, as it already does
+// for grouped CTAs: note frames and envelope stage lengths are integers, so for every sub-chunk of
+// kSoloSub frames it knows whether a voice is idle, rests (cutoff constant: welsh_solo_rest), sweeps
+// inside one envelope stage slowly enough for coefficient knots (welsh_sweep_block), or needs the
+// per-block general machinery (note events, stage boundaries, fast sweeps, non-linear oscillators).
+// Items of one class and one sub-chunk are packed W to a job; ONE persistent launch walks the job list
+// in order (ticket counter), so the warps of a CTA always run the same code, voice state lives in shared
+// memory for the length of an item, and a voice's consecutive items are ordered by a per-voice progress
+// counter in global memory (a job only ever waits for jobs earlier in the list, which are already
+// running: no deadlock).
+constexpr int kSoloSub = 8 * kBlockFrames;  // frames per sub-chunk (classification granularity)
+enum { SOLO_REST = 0, SOLO_SWEEP = 1, SOLO_GENERAL = 2 };
+
+struct SoloItem {
+  int item;  // index into the WarpItem table
+  int need;  // value of progress[voice] this item waits for (= the voice's earlier non-idle items of the chunk)
+};
+struct SoloJob {
+  int cls;      // SOLO_*
+  int t0;       // first frame of the sub-chunk, relative to the chunk start
+  int nframes;  // frames (REST / SWEEP: a multiple of kBlockFrames)
+  int first;    // first SoloItem
+  int n;        // items (<= W)
+  int pad;
+};
+
+struct alignas(16) SoloRestState {
+  u64 p1, p2;     // oscillator phases at the frame before the current block
+  u64 d1, d2;
+  double s[4];    // filter state at the start of the current block
+  double ls, lc;  // depth * (sin, cos) of the LFO angle at the first frame of the current block
+  double aq0, aq1, aq2, aw, adw;  // amplitude stage (0.5 folded in): level = q0 + w (q1 + q2 w), w = aw + t adw, t = frame - item start
+};
+
+// Stage parameters of an envelope that stays inside ONE stage from frame f on: attack / decay / sustain
+// of a held note (as env_stage_held), or release / silence after the note-off.
+__device__ __forceinline__ void env_stage_any(const EnvShape& sh, i64 n_on, i64 n_off, double l_on, double l_off, i64 f,
+                                              double& q0, double& q1, double& q2, double& w0, double& dw) {
+  if (f < n_off) {
+    env_stage_held(sh, n_on, l_on, f, q0, q1, q2, w0, dw);
+    return;
+  }
+  const i64 k = f - n_off;
+  q0 = 0.0; q1 = 0.0; q2 = 0.0; w0 = 0.0; dw = 0.0;
+  if (k < sh.nr) {  // release: l_off * u^2
+    w0 = 1.0 - (double)k * sh.inv_nr; dw = -sh.inv_nr;
+    q2 = l_off;
+  }
+}
+
+// One block of a voice whose cutoff is constant (welsh_rest_block for one voice, with the amplitude
+// envelope inside one stage instead of resting).  L / o1 / o2: the instrument's resting tables (lti,
+// m1bb, m2bb) or those of a released voice (lti_off, ...).  t0 = the block's first frame relative to
+// the item start.
+template <bool LFO_AMP>
+__device__ __forceinline__ void welsh_solo_rest_block(SoloRestState* rs, const WelshInst& I, const LtiTable& L,
+                                                      const OscMix& o1, const OscMix& o2, int lane, int t0,
+                                                      double2* tile_row) {
+  double yp[kT];
+  double ps0 = 0.0, ps1 = 0.0;
+  {
+    const ulonglong2 pp = *reinterpret_cast<const ulonglong2*>(&rs->p1);
+    const ulonglong2 dd = *reinterpret_cast<const ulonglong2*>(&rs->d1);
+    const u64 k = (u64)(lane * kT);
+    u64 p1 = pp.x + k * dd.x, p2 = pp.y + k * dd.y;
+    __syncwarp();  // every lane has read the block's base phases
+    if (lane == 0)
+      *reinterpret_cast<ulonglong2*>(&rs->p1) =
+          make_ulonglong2(p1 + (u64)kBlockFrames * dd.x, p2 + (u64)kBlockFrames * dd.y);
+    const u64 t1 = I.s1.thresh, t2 = I.s2.thresh;
+    const double a1 = L.c1.a1, a2 = L.c1.a2;
+#pragma unroll
+    for (int j = 0; j < kT; ++j) {
+      p1 += dd.x;
+      p2 += dd.y;
+      yp[j] = lp_step_bx(osc_mix_eval<false>(o1, t1, p1, o2, t2, p2), a1, a2, ps0, ps1);
+    }
+    ps0 *= L.inv_b0_2; ps1 *= L.inv_b0_2;
+  }
+  double e0, e1;
+  {
+    const double v0[1] = {ps0}, v1[1] = {ps1};
+    double x0[1], x1[1];
+    SoloRestState* const one[1] = {rs};
+    lti_scan_entry_t<1, SoloRestState>(v0, v1, L.mp1, lane, one, 0, x0, x1);
+    e0 = x0[0]; e1 = x1[0];
+  }
+  {
+    const double a1 = L.c2.a1, a2 = L.c2.a2;
+    ps0 = 0.0; ps1 = 0.0;
+#pragma unroll
+    for (int j = 0; j < kT; ++j) {
+      const double2 g = *reinterpret_cast<const double2*>(L.g1b[j]);
+      yp[j] = lp_step_bx(fma(g.y, e1, fma(g.x, e0, yp[j])), a1, a2, ps0, ps1);
+    }
+  }
+  {
+    const double v0[1] = {ps0}, v1[1] = {ps1};
+    double x0[1], x1[1];
+    SoloRestState* const one[1] = {rs};
+    lti_scan_entry_t<1, SoloRestState>(v0, v1, L.mp2, lane, one, 1, x0, x1);
+    e0 = x0[0]; e1 = x1[0];
+  }
+  double lsd = 0.0, lcd = 0.0;
+  if (LFO_AMP) {
+    const double2 ph = *reinterpret_cast<const double2*>(&rs->ls);
+    const double2 r = I.lane_rot[lane];
+    lsd = fma(ph.x, r.x, ph.y * r.y);
+    lcd = fma(ph.y, r.x, -(ph.x * r.y));
+    __syncwarp();
+    if (lane == 0) {
+      const double2 br = I.block_rot;
+      *reinterpret_cast<double2*>(&rs->ls) = make_double2(fma(lsd, br.x, lcd * br.y), fma(lcd, br.x, -(lsd * br.y)));
+    }
+  }
+  const double aq0 = rs->aq0, aq1 = rs->aq1, aq2 = rs->aq2, aw = rs->aw, adw = rs->adw;
+  const double gl = I.gl, gr = I.gr;
+  const int tl = t0 + lane * kT;
+  double2* row = tile_row + lane * (kT + 1);
+#pragma unroll
+  for (int j = 0; j < kT; ++j) {
+    const double2 g = *reinterpret_cast<const double2*>(L.g2[j]);
+    const double w = fma((double)(tl + j), adw, aw);
+    double amp = fma(w, fma(aq2, w, aq1), aq0);
+    if (LFO_AMP) {
+      const double2 rot = I.lfo_rot[j];
+      amp *= fma(lsd, rot.x, fma(lcd, rot.y, 1.0));
+    }
+    const double m = fma(g.y, e1, fma(g.x, e0, yp[j])) * amp;
+    row[j] = make_double2(m * gl, m * gr);
+  }
+  __syncwarp();
+}
+
+// One 256-frame block of one solo voice through the per-block classified paths of welsh_kernel (its
+// SOLO = true body): time-invariant / fast / general.  Returns false when the voice is idle for the block.
+__device__ __forceinline__ bool welsh_solo_general_block(const WelshInst& I, const WelshInst* gI, WelshVoice* voices,
+                                                         int vi, const VoiceEvent* __restrict__ events,
+                                                         const int* __restrict__ ev_off, i64 fb, i64 f_end, int lane,
+                                                         double2* tile_row, double* park) {
+  const bool pitch = I.routing == LFO_PITCH;
+  const bool lin_inst = I.s1.kind == 0 && I.s2.kind == 0 && !I.sync &&
+                        (I.routing == LFO_NONE || (I.routing == LFO_AMPLITUDE && I.wl == W_SINE));
+  const bool simple_inst = lin_inst && I.filter_mode == FILTER_ENVELOPE;
+  const bool lti_inst = lin_inst && I.lti_ok && (I.filter_mode == FILTER_FIXED || I.filter_mode == FILTER_ENVELOPE);
+  WelshVoice* vp = voices + vi;
+  NoteWords st;
+  st.n_on = vp->n_on; st.n_off = vp->n_off;
+  st.la_on = vp->la_on; st.la_off = vp->la_off; st.lf_on = vp->lf_on; st.lf_off = vp->lf_off;
+  int ei = ev_off[vi];
+  const int e_end = ev_off[vi + 1];
+  while (ei < e_end && events[ei].frame < fb) ++ei;  // already folded into the record by earlier blocks
+  const bool idle = fb >= st.n_off + I.amp.nr;
+  const bool ev_here = ei < e_end && events[ei].frame < fb + kBlockFrames;
+  if (idle && !ev_here) return false;
+  const int local = vi - I.voice0;
+  auto seed_of = [&](u64 salt) { return splitmix64(((u64)(unsigned)I.uid << 32) ^ salt); };
+  bool fast = false;
+  EnvSeg aseg, fseg;
+  int cls = 0;
+  if (!pitch && !ev_here) {
+    cls = welsh_lane_class(st, I, fb + (i64)lane * kT, f_end, aseg, fseg);
+    fast = __all_sync(0xffffffffu, cls != 0);
+  }
+  bool lti = false;
+  if (fast && lti_inst) {
+    const bool rest = cls == 2 && (I.filter_mode == FILTER_FIXED ||
+                                   (fseg.q1 == 0.0 && fseg.q2 == 0.0 && fseg.q0 == I.filt.sustain));
+    lti = __all_sync(0xffffffffu, rest);
+  }
+  if (lti || fast) {  // the specialised blocks accumulate into the warp's tile row
+    double2* row = tile_row + lane * (kT + 1);
+#pragma unroll
+    for (int j = 0; j < kT; ++j) row[j] = make_double2(0.0, 0.0);
+  }
+  if (lti) {
+    if (I.routing == LFO_NONE) welsh_block_lti_ool<false, false, false>(vp, &I, fb, lane, &aseg, tile_row);
+    else welsh_block_lti_ool<true, false, false>(vp, &I, fb, lane, &aseg, tile_row);
+  } else if (fast) {
+    const WelshInst* Ip = &I;
+    if (I.filter_mode == FILTER_FIXED) {
+      if (__all_sync(0xffffffffu, cls == 2))
+        welsh_fast_call<COEF_FIXED, true>(vp, Ip, fb, lane, cls, aseg, fseg, seed_of((u64)(2 * local)), seed_of((u64)(2 * local + 1)), seed_of(0x4C464F00ull ^ (u64)local), tile_row, true);
+      else
+        welsh_fast_call<COEF_FIXED, false>(vp, Ip, fb, lane, cls, aseg, fseg, seed_of((u64)(2 * local)), seed_of((u64)(2 * local + 1)), seed_of(0x4C464F00ull ^ (u64)local), tile_row, false);
+    } else {
+      bool smooth = false;
+      if (I.filter_mode == FILTER_ENVELOPE && cls == 2) {
+        const double w8 = fma((double)kT, fseg.dw, fseg.w0);
+        const double r0 = fabs(fma(2.0 * fseg.q2, fseg.w0, fseg.q1)), r8 = fabs(fma(2.0 * fseg.q2, w8, fseg.q1));
+        smooth = fabs(I.cut_b * fseg.dw) * fmax(r0, r8) <= I.knot_max_rate && I.knot_max_rate > 0.0;
+      }
+      if (__all_sync(0xffffffffu, smooth)) {
+        if (simple_inst) {
+          if (I.routing == LFO_NONE) welsh_block_simple_ool<false, false>(vp, Ip, fb, lane, &aseg, &fseg, tile_row, park);
+          else welsh_block_simple_ool<true, false>(vp, Ip, fb, lane, &aseg, &fseg, tile_row, park);
+        } else {
+          welsh_fast_call<COEF_KNOTS, true>(vp, Ip, fb, lane, cls, aseg, fseg, seed_of((u64)(2 * local)), seed_of((u64)(2 * local + 1)), seed_of(0x4C464F00ull ^ (u64)local), tile_row, false);
+        }
+      } else {
+        welsh_fast_call<COEF_EXACT, false>(vp, Ip, fb, lane, cls, aseg, fseg, seed_of((u64)(2 * local)), seed_of((u64)(2 * local + 1)), seed_of(0x4C464F00ull ^ (u64)local), tile_row, false);
+      }
+    }
+  } else {
+    welsh_block_general((pitch ? 2 : 0) + (ev_here ? 1 : 0), vp, gI, events, ei, e_end, fb, f_end, lane,
+                        seed_of((u64)(2 * local)), seed_of((u64)(2 * local + 1)), seed_of(0x4C464F00ull ^ (u64)local), tile_row, false);
+  }
+  return true;
+}
+
+__device__ __forceinline__ int ld_acquire_i32(const int* p) {
+  int v;
+  asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_release_i32(int* p, int v) {
+  asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+
+// Shared-memory layout of welsh_solo_kernel (all dynamic, so that the out-of-line class bodies below address
+// it as shared memory): W tile rows | kParkWords x 32 W parking doubles | W state slots | W instrument records.
+constexpr int kSoloStateBytes = 256;  // per-warp slot for SoloRestState / SweepState
+template <int W>
+struct SoloSmem {
+  static constexpr size_t kPark = (size_t)W * kTileStride * sizeof(double2);
+  static constexpr size_t kSlots = kPark + (size_t)kParkWords * 32 * W * sizeof(double);
+  static constexpr size_t kInsts = kSlots + (size_t)W * kSoloStateBytes;
+  static constexpr size_t kBytes = kInsts + (size_t)W * sizeof(WelshInst);
+  static __device__ __forceinline__ unsigned char* base() {
+    extern __shared__ double2 smem_tiles[];
+    return reinterpret_cast<unsigned char*>(smem_tiles);
+  }
+  static __device__ __forceinline__ double2* tile_row(int warp) {
+    return reinterpret_cast<double2*>(base()) + warp * kTileStride;
+  }
+  static __device__ __forceinline__ double* park() { return reinterpret_cast<double*>(base() + kPark) + threadIdx.x; }
+  static __device__ __forceinline__ unsigned char* slot(int warp) { return base() + kSlots + (size_t)warp * kSoloStateBytes; }
+  static __device__ __forceinline__ WelshInst* inst(int warp) { return reinterpret_cast<WelshInst*>(base() + kInsts) + warp; }
+};
+
+// Phases, filter state, LFO phasor and amplitude stage of a voice at the first frame fs of an item
+// (the common head of SoloRestState and SweepState), written by lane 0 straight into the warp's slot.
+template <typename State>
+__device__ __forceinline__ void solo_state_head(State* rs, const WelshInst& I, const WelshVoice* vp, i64 fs) {
+  const u64 k = (u64)(fs - 1 - vp->anchor);
+  const u64 d1 = vp->d1, d2 = vp->d2;
+  rs->d1 = d1; rs->d2 = d2;
+  rs->p1 = vp->p1 + k * d1; rs->p2 = vp->p2 + k * d2;
+  rs->s[0] = vp->s[0]; rs->s[1] = vp->s[1]; rs->s[2] = vp->s[2]; rs->s[3] = vp->s[3];
+  double ls = 0.0, lc = 0.0;
+  if (I.routing == LFO_AMPLITUDE) {
+    sincos_phase(vp->pl + (k + 1) * I.lfo_dq, &ls, &lc);
+    ls *= I.depth; lc *= I.depth;
+  }
+  rs->ls = ls; rs->lc = lc;
+  double q0, q1, q2, w, dw;
+  env_stage_any(I.amp, vp->n_on, vp->n_off, vp->la_on, vp->la_off, fs, q0, q1, q2, w, dw);
+  rs->aq0 = 0.5 * q0; rs->aq1 = 0.5 * q1; rs->aq2 = 0.5 * q2; rs->aw = w; rs->adw = dw;
+}
+
+// The three class bodies are out-of-line: each gets its own register allocation and the dispatcher stays
+// a few dozen instructions.  They find their warp's tile row, state slot and instrument record in the
+// kernel's dynamic shared memory.
+template <int W>
+__device__ __noinline__ void solo_rest_item(WelshVoice* vp, i64 fs, int nframes, double2* out) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const WelshInst& I = *SoloSmem<W>::inst(warp);
+  double2* tile_row = SoloSmem<W>::tile_row(warp);
+  SoloRestState* rs = reinterpret_cast<SoloRestState*>(SoloSmem<W>::slot(warp));
+  const bool released = fs >= vp->n_off;
+  if (lane == 0) solo_state_head(rs, I, vp, fs);
+  __syncwarp();
+  const LtiTable& L = released ? I.lti_off : I.lti;
+  const OscMix& o1 = released ? I.m1bb_off : I.m1bb;
+  const OscMix& o2 = released ? I.m2bb_off : I.m2bb;
+  const bool lfo = I.routing == LFO_AMPLITUDE;
+  const i64 fe = fs + nframes;
+  int t0 = 0;
+#pragma unroll 1
+  for (i64 fb = fs; fb < fe; fb += kBlockFrames, t0 += kBlockFrames) {
+    if (lfo) welsh_solo_rest_block<true>(rs, I, L, o1, o2, lane, t0, tile_row);
+    else welsh_solo_rest_block<false>(rs, I, L, o1, o2, lane, t0, tile_row);
+    warp_store_row(tile_row, true, out, fb, fs, fe, lane);
+    __syncwarp();
+  }
+  if (lane == 0) {
+    vp->s[0] = rs->s[0]; vp->s[1] = rs->s[1]; vp->s[2] = rs->s[2]; vp->s[3] = rs->s[3];
+    vp->knot_frame = kNever;
+  }
+  __syncwarp();
+}
+
+template <int W>
+__device__ __noinline__ void solo_sweep_item(WelshVoice* vp, i64 fs, int nframes, double2* out) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const WelshInst& I = *SoloSmem<W>::inst(warp);
+  double2* tile_row = SoloSmem<W>::tile_row(warp);
+  SweepState* rs = reinterpret_cast<SweepState*>(SoloSmem<W>::slot(warp));
+  if (lane == 0) {
+    solo_state_head(rs, I, vp, fs);
+    double q0, q1, q2, w0, dw;
+    env_stage_any(I.filt, vp->n_on, vp->n_off, vp->lf_on, vp->lf_off, fs, q0, q1, q2, w0, dw);
+    rs->fq0 = q0; rs->fq1 = q1; rs->fq2 = q2; rs->fw = w0; rs->fdw = dw;
+#pragma unroll
+    for (int q = 0; q < 2; ++q) {  // knots at fs - kT and fs: the stage's formula, continued backwards
+      const double w = fma((double)((q - 1) * kT), dw, w0);
+      welsh_knot(I, fma(I.cut_b, fma(w, fma(q2, w, q1), q0), I.cut_a), rs->kn[q]);
+    }
+  }
+  __syncwarp();
+  const bool lfo = I.routing == LFO_AMPLITUDE;
+  const i64 fe = fs + nframes;
+  int t0 = 0;
+#pragma unroll 1
+  for (i64 fb = fs; fb < fe; fb += kBlockFrames, t0 += kBlockFrames) {
+    if (lfo) welsh_sweep_block<true, false, false>(rs, I, lane, t0, tile_row);
+    else welsh_sweep_block<false, false, false>(rs, I, lane, t0, tile_row);
+    warp_store_row(tile_row, true, out, fb, fs, fe, lane);
+    __syncwarp();
+  }
+  if (lane == 0) {
+    vp->s[0] = rs->s[0]; vp->s[1] = rs->s[1]; vp->s[2] = rs->s[2]; vp->s[3] = rs->s[3];
+    vp->knot_frame = kNever;
+  }
+  __syncwarp();
+}
+
+template <int W>
+__device__ __noinline__ void solo_general_item(const WelshInst* gI, WelshVoice* voices, int vi,
+                                               const VoiceEvent* __restrict__ events, const int* __restrict__ ev_off,
+                                               i64 fs, int nframes, i64 f_end, double2* out) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const WelshInst& I = *SoloSmem<W>::inst(warp);
+  double2* tile_row = SoloSmem<W>::tile_row(warp);
+  double* park = SoloSmem<W>::park();
+  const i64 fe = fs + nframes;
+#pragma unroll 1
+  for (i64 fb = fs; fb < fe; fb += kBlockFrames) {
+    const bool any = welsh_solo_general_block(I, gI, voices, vi, events, ev_off, fb, f_end, lane, tile_row, park);
+    __syncwarp();
+    warp_store_row(tile_row, any, out, fb, fs, fe, lane);
+    __syncwarp();
+  }
+}
+
+// One item of a job: wait for the voice's previous item, make the instrument record resident, run the
+// class body, publish the voice's progress.  The wait is executed by all 32 lanes in step (same address,
+// the value taken from lane 0), so the warp never diverges around the spin.
+template <int W>
+__device__ __noinline__ void solo_run_item(int j, SoloJob job, const WelshInst* __restrict__ insts,
+                                           WelshVoice* __restrict__ voices, const WarpItem* __restrict__ items,
+                                           const SoloItem* __restrict__ sitems, int* __restrict__ progress,
+                                           int* __restrict__ fault, int* s_inst, const VoiceEvent* __restrict__ events,
+                                           const int* __restrict__ ev_off, i64 f0, i64 f_chunk_end) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const SoloItem si = sitems[job.first + warp];
+  const WarpItem item = items[si.item];
+  {
+    // watchdog: a dependency that does not resolve within ~0.5 s of SM clocks is a scheduling bug; report it
+    // (job, voice, need, have) through `fault` and carry on, so that the host fails loudly instead of hanging
+    const int* pp = progress + item.voice;
+    const long long t_wait = clock64();
+    for (;;) {
+      const int have = __shfl_sync(0xffffffffu, ld_acquire_i32(pp), 0);
+      if (have >= si.need) break;
+      __nanosleep(200);
+      const int late = __shfl_sync(0xffffffffu, (int)(clock64() - t_wait > 1000000000ll), 0);
+      if (late) {
+        if (lane == 0 && atomicCAS(fault, 0, 1) == 0) { fault[1] = j; fault[2] = item.voice; fault[3] = si.need; fault[4] = have; }
+        break;
+      }
+    }
+  }
+  if (s_inst[warp] != item.inst) {  // instrument record -> shared memory (kept while the warp stays on the instrument)
+    const int* src = reinterpret_cast<const int*>(insts + item.inst);
+    int* dst = reinterpret_cast<int*>(SoloSmem<W>::inst(warp));
+    for (int i = lane; i < (int)(sizeof(WelshInst) / sizeof(int)); i += 32) dst[i] = src[i];
+    __syncwarp();
+    if (lane == 0) s_inst[warp] = item.inst;
+  }
+  __syncwarp();
+  WelshVoice* vp = voices + item.voice;
+  const i64 fs = f0 + job.t0;        // first frame of the item
+  double2* out = item.out + job.t0;  // the voice's output for this sub-chunk
+  if (job.cls == SOLO_REST) {
+    solo_rest_item<W>(vp, fs, job.nframes, out);
+  } else if (job.cls == SOLO_SWEEP) {
+    solo_sweep_item<W>(vp, fs, job.nframes, out);
+  } else {
+    const i64 fe = fs + job.nframes;
+    solo_general_item<W>(insts + item.inst, voices, item.voice, events, ev_off, fs, job.nframes,
+                         fe < f_chunk_end ? fe : f_chunk_end, out);
+  }
+  __syncwarp();
+  if (lane == 0) {
+    __threadfence();
+    st_release_i32(progress + item.voice, si.need + 1);
+  }
+  __syncwarp();
+}
+
+// grid = min(jobs, resident CTAs); block = 32 * W threads; dynamic smem = SoloSmem<W>::kBytes.
+// Jobs [job0, job0 + n_jobs) are handed out through *ticket (zero at launch).
+template <int W>
+__global__ void __launch_bounds__(32 * W, 2) welsh_solo_kernel(const WelshInst* __restrict__ insts,
+                                                             WelshVoice* __restrict__ voices,
+                                                             const WarpItem* __restrict__ items,
+                                                             const SoloItem* __restrict__ sitems,
+                                                             const SoloJob* __restrict__ jobs, int job0, int n_jobs,
+                                                             int* __restrict__ ticket, int* __restrict__ progress,
+                                                             int* __restrict__ fault,
+                                                             const VoiceEvent* __restrict__ events,
+                                                             const int* __restrict__ ev_off, i64 f0, int chunk_frames) {
+  static_assert(sizeof(SoloRestState) <= kSoloStateBytes && sizeof(SweepState) <= kSoloStateBytes, "state slot too small");
+  static_assert(sizeof(WelshInst) % 16 == 0, "instrument records are copied and aligned as 16-byte words");
+  __shared__ int s_inst[W];
+  __shared__ int s_job;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (lane == 0) s_inst[warp] = -1;
+  const i64 f_chunk_end = f0 + chunk_frames;
+  for (;;) {
+    __syncthreads();  // every warp is done with the previous job (and has read s_job)
+    if (threadIdx.x == 0) s_job = atomicAdd(ticket, 1);
+    __syncthreads();
+    const int j = s_job;
+    if (j >= n_jobs) break;
+    const SoloJob job = jobs[job0 + j];
+    if (warp < job.n)
+      solo_run_item<W>(job0 + j, job, insts, voices, items, sitems, progress, fault, s_inst, events, ev_off, f0, f_chunk_end);
+  }
+}
+
 // --------------------------------------------------------------------------- FM ---
 struct FmInst {
   EnvShape car, mod;
@@ -1916,7 +2364,7 @@ __device__ __forceinline__ void fm_block(FmVoice& st, const FmInst& I, const Voi
     if (play_bits & (1u << j)) {
       if (reset_bits & (1u << j)) pc = 0;
       else pc += dc[j];
-      m = sinpi(2.0 * pos_of(pc)) * cenv[j];
+      m = sin_phase(pc) * cenv[j];
     }
     int t = lane * kT + j;
     double2 o = make_double2(m * I.gl, m * I.gr);
@@ -1988,7 +2436,7 @@ __device__ __forceinline__ void fm_block_fast(FmVoice& st, const FmInst& I, i64 
     double m = 0.0;
     if (on) {
       pc += dc[j];
-      m = sinpi(2.0 * pos_of(pc)) * env_seg_at(cseg, j);
+      m = sin_phase(pc) * env_seg_at(cseg, j);
     }
     const int t = lane * kT + j;
     double2 o = make_double2(m * I.gl, m * I.gr);
@@ -2020,15 +2468,28 @@ __global__ void __launch_bounds__(32 * W, 2) fm_kernel(const FmInst* __restrict_
   const i64 f_end = f0 + nframes;
   const int g_begin = solo ? 0 : warp;
   const int g_end = solo ? (mine ? 1 : 0) : wk.nvoices;
+  // one voice per warp at most (solo items, instruments of up to W voices): the voice record and the event
+  // cursor stay in registers for the whole chunk instead of going through global memory every block
+  const bool resident = solo || wk.nvoices <= W;
+  FmVoice st;
+  int ei = 0, e_end = 0;
+  if (resident && g_begin < g_end) {
+    const int vi = solo ? item.voice : wk.voice0 + g_begin;
+    st = voices[vi];
+    ei = ev_off[vi];
+    e_end = ev_off[vi + 1];
+  }
 #pragma unroll 1
   for (i64 fb = f0; fb < f_end; fb += kBlockFrames) {
     bool any = false;
 #pragma unroll 1
     for (int g = g_begin; g < g_end; g += W) {
       const int vi = solo ? item.voice : wk.voice0 + g;
-      FmVoice st = voices[vi];
-      int ei = ev_off[vi];
-      const int e_end = ev_off[vi + 1];
+      if (!resident) {
+        st = voices[vi];
+        ei = ev_off[vi];
+        e_end = ev_off[vi + 1];
+      }
       while (ei < e_end && events[ei].frame < fb) ++ei;
       bool idle = fb >= st.n_off + I.car.nr;
       bool ev_here = ei < e_end && events[ei].frame < fb + kBlockFrames;
@@ -2042,9 +2503,11 @@ __global__ void __launch_bounds__(32 * W, 2) fm_kernel(const FmInst* __restrict_
         else fm_block<false>(st, I, events, ei, e_end, fb, f_end, lane, tile_row, any);
       }
       any = true;
-      __syncwarp();
-      if (lane == 0) voices[vi] = st;
-      __syncwarp();
+      if (!resident) {
+        __syncwarp();
+        if (lane == 0) voices[vi] = st;
+        __syncwarp();
+      }
     }
     if (solo) {
       __syncwarp();
@@ -2057,6 +2520,7 @@ __global__ void __launch_bounds__(32 * W, 2) fm_kernel(const FmInst* __restrict_
       __syncthreads();
     }
   }
+  if (resident && g_begin < g_end && lane == 0) voices[solo ? item.voice : wk.voice0 + g_begin] = st;
 }
 
 // ------------------------------------------------------------ sampler / drumkit ---

@@ -48,6 +48,30 @@ def cello_params(voices: int, gain: float, pan: float, filter_decay: float = 3.2
     return p
 
 
+def piano_params(voices: int, gain: float, pan: float) -> abi.WelshParams:
+    """assets/patches/welsh/piano.json through derive_welsh_synth_params (settings/src/patches.rs:87-170):
+    sawtooth + 15 % pulse an octave and two semitones up, HARD SYNC, no LFO, amplitude A0/D0.67/S0.25,
+    filter envelope A0/D5.22/S0 with weight 0.75 from 40 Hz (release := decay).  bench.py's `general` leg."""
+    p = abi.WelshParams()
+    p.oscillator_1 = abi.osc(abi.WAVE_SAWTOOTH)
+    p.oscillator_2 = abi.osc(abi.WAVE_PULSE_WIDTH, 0.15, tune=2.244924096618746)
+    p.oscillator_2_sync = 1
+    p.oscillator_mix = 3.0 / 7.0
+    p.amp_envelope = abi.env(0.0, 0.67, 0.25, 0.67)
+    p.lfo = abi.osc(abi.WAVE_NONE, frequency=0.0)
+    p.lfo_routing = abi.LFO_NONE
+    p.lfo_depth = 0.0
+    p.filter_cutoff_hz = 40.0
+    p.filter_passband_ripple = 0.707
+    p.filter_cutoff_start = hz_to_pct(40.0)
+    p.filter_cutoff_end = 0.75
+    p.filter_envelope = abi.env(0.0, 5.22, 0.0, 5.22)
+    p.voice_dca = abi.DcaParams(1.0, 0.0)
+    p.dca = abi.DcaParams(gain, pan)
+    p.voices = voices
+    return p
+
+
 @dataclass
 class Cfg4:
     sample_rate: float = 48000.0
@@ -64,18 +88,33 @@ class Cfg4:
         return self.total_voices * self.frames
 
 
-def build_cfg4(r: abi.Renderer, cfg: Cfg4) -> int:
+def build_cfg4(r: abi.Renderer, cfg: Cfg4, params=None) -> int:
     """Build config 4 (or a truncated slice of it) on ``r``; returns the frame count to render."""
+    uids = build_cfg4_graph(r, cfg, params)
+    r.push_events(cfg4_events(cfg, uids))
+    return cfg.frames
+
+
+def build_cfg4_graph(r: abi.Renderer, cfg: Cfg4, params=None):
+    """The instruments and patch cables of config 4, finalized; returns the instrument uids.
+    `params(voices, gain, pan)` replaces the cello recipe (bench.py's `general` leg: another patch)."""
     assert cfg.total_voices % cfg.groups == 0
     per = cfg.total_voices // cfg.groups
     uids = []
     for q in range(cfg.groups):
         i0 = cfg.voice_offset + q
         pan = -1.0 + 2.0 * (i0 % 64) / 63.0
-        u = r.add_instrument(abi.INST_WELSH, cello_params(per, 1.0 / 4096.0, pan, cfg.filter_decay))
+        p = params(per, 1.0 / 4096.0, pan) if params else cello_params(per, 1.0 / 4096.0, pan, cfg.filter_decay)
+        u = r.add_instrument(abi.INST_WELSH, p)
         r.patch(u, abi.MAIN_MIXER)
         uids.append(u)
     r.finalize()
+    return uids
+
+
+def cfg4_events(cfg: Cfg4, uids) -> np.ndarray:
+    """Config 4's note events (frame-sorted) for the instruments `uids` of build_cfg4_graph."""
+    per = cfg.total_voices // cfg.groups
     ev = np.zeros(2 * cfg.total_voices, dtype=abi.EVENT_DTYPE)
     k = 0
     for j in range(per):
@@ -87,9 +126,7 @@ def build_cfg4(r: abi.Renderer, cfg: Cfg4) -> int:
             ev[k] = (on, uids[q], abi.EV_NOTE_ON, key, 127, 0.0)
             ev[k + 1] = (off, uids[q], abi.EV_NOTE_OFF, key, 0, 0.0)
             k += 2
-    ev = ev[np.argsort(ev["frame"], kind="stable")]
-    r.push_events(ev)
-    return cfg.frames
+    return ev[np.argsort(ev["frame"], kind="stable")]
 
 
 def cfg4_slice(voices: int, frames: int, voice_offset: int = 0) -> Cfg4:
@@ -171,13 +208,15 @@ def cfg5_variant(j: int, gain: float = 1.0 / 256.0):
 
 
 def build_cfg5(r: abi.Renderer, n_variants: int, first: int = 0, frames: int = CFG5_FRAMES,
-               note_off: int = CFG5_NOTE_OFF):
+               note_off: int = CFG5_NOTE_OFF, variants=None, push: bool = True):
     """Variants first .. first+n-1, each its own one-voice instrument patched into the main mixer
-    (its node buffer is the per-variant stereo output; the mixer's is the summed bus)."""
+    (its node buffer is the per-variant stereo output; the mixer's is the summed bus).
+    `variants` = precomputed [cfg5_variant(j)] (bench.py draws them once); push=False returns the events
+    instead of pushing them (bench.py pushes them inside its end-to-end span)."""
     uids = []
     ev = np.zeros(2 * n_variants, dtype=abi.EVENT_DTYPE)
     for i in range(n_variants):
-        kind, p, key = cfg5_variant(first + i)
+        kind, p, key = variants[i] if variants is not None else cfg5_variant(first + i)
         u = r.add_instrument(kind, p)
         r.patch(u, abi.MAIN_MIXER)
         uids.append(u)
@@ -185,5 +224,7 @@ def build_cfg5(r: abi.Renderer, n_variants: int, first: int = 0, frames: int = C
         ev[2 * i + 1] = (note_off, u, abi.EV_NOTE_OFF, key, 0, 0.0)
     r.finalize()
     ev = ev[np.argsort(ev["frame"], kind="stable")]
+    if not push:
+        return frames, uids, ev
     r.push_events(ev)
     return frames, uids

@@ -37,7 +37,8 @@
 extern "C" {
 #endif
 
-#define GB_ABI_VERSION 2 /* 2: gb_link_control, GB_FX_SIGNAL_PASSTHROUGH, gb_stats grew (rest_kernel_*) */
+#define GB_ABI_VERSION 3 /* 2: gb_link_control, GB_FX_SIGNAL_PASSTHROUGH, gb_stats grew (rest_kernel_*);
+                            3: GB_INST_OSCILLATOR / GB_INST_ENVELOPE, gb_stats grew (solo_*, fm_*, idle_*, *_ctas) */
 
 /* ---- error codes --------------------------------------------------------- */
 enum {
@@ -300,6 +301,15 @@ typedef struct {
   uint64_t sweep_kernel_launches; /* likewise for the sweeping-voice kernel (one moving envelope stage per chunk) */
   double sweep_kernel_ms;
   uint64_t sweep_voice_samples;
+  uint64_t solo_kernel_launches;  /* the job-list kernel of solo voices (instruments with fewer voices than a CTA has warps) */
+  double solo_kernel_ms;
+  uint64_t solo_voice_samples;    /* non-idle (voice, sub-chunk) items x sub-chunk frames */
+  uint64_t solo_jobs;
+  uint64_t solo_class_items[3];   /* items by class: resting / sweeping / general */
+  uint64_t fm_kernel_launches;
+  double fm_kernel_ms;
+  uint64_t idle_voice_samples;    /* of voice_samples: voices the host knew to be silent (never launched) */
+  uint64_t rest_ctas, sweep_ctas; /* CTAs of the resting / sweeping kernel launches, summed */
 } gb_stats;
 int gb_get_stats(gb_engine* e, gb_stats* out);
 int gb_reset_stats(gb_engine* e);

@@ -33,7 +33,8 @@ _lib = None
 def oracle_lib() -> C.CDLL:
     global _lib
     if _lib is None:
-        _lib = C.CDLL(build_oracle())
+        # GROOVE_ORACLE_SO: bench.py's CPU legs point this at their -O3 -march=native build of the same source
+        _lib = C.CDLL(os.environ.get("GROOVE_ORACLE_SO") or build_oracle())
         _lib.go_tune_ratio.restype = C.c_double
         _lib.go_tune_ratio.argtypes = [C.c_int, C.c_double]
         _lib.go_note_hz.restype = C.c_double

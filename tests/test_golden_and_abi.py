@@ -109,3 +109,37 @@ def test_run_length_formula():
     assert song_frames(4, 240.0, 24000.0) == 24000
     assert song_frames(8, 128.0, 44100.0) == 165375
     assert song_frames(4, 1024.0, 44100.0) == 10336
+
+
+def test_rust_sys_crate_matches_header():
+    """groove-b200-sys/ (source only: no Rust toolchain in this image) must not drift from the header: every
+    entry point, every entity kind and every field of every params struct, in order."""
+    hdr = open(os.path.join(ROOT, "include", "groove_b200.h")).read()
+    rs = open(os.path.join(ROOT, "groove-b200-sys", "src", "lib.rs")).read()
+    for sym in _header_symbols():
+        assert re.search(r"pub fn %s\(" % sym, rs), sym
+    m = re.search(r"#define GB_ABI_VERSION (\d+)", hdr)
+    assert re.search(r"GB_ABI_VERSION: u32 = %s;" % m.group(1), rs)
+    for name, value in re.findall(r"\b(GB_(?:INST|FX)_[A-Z0-9_]+) = (\d+)", hdr):
+        assert re.search(r"pub const %s: i32 = %s;" % (name, value), rs), name
+    ctype = {"int32_t": "i32", "uint32_t": "u32", "double": "f64", "int64_t": "i64", "uint64_t": "u64"}
+    for body, name in re.findall(r"typedef struct \{(.*?)\} (gb_[a-z0-9_]+);", hdr, flags=re.S):
+        body = re.sub(r"/\*.*?\*/", "", body, flags=re.S)
+        fields = []
+        for decl in body.split(";"):
+            decl = decl.strip()
+            if not decl:
+                continue
+            typ, rest = decl.split(None, 1)
+            for f in rest.split(","):
+                f = f.strip()
+                arr = re.match(r"(\w+)\[(\d+)\]", f)
+                fields.append((arr.group(1) if arr else f, typ, int(arr.group(2)) if arr else 0))
+        rm = re.search(r"pub struct %s \{(.*?)\n    \}" % name, rs, flags=re.S)
+        assert rm, name
+        rfields = re.findall(r"pub (\w+): ([^,\n]+),", rm.group(1))
+        assert len(rfields) == len(fields), (name, fields, rfields)
+        for (fname, typ, n), (rname, rtyp) in zip(fields, rfields):
+            assert rname == (fname + "_" if fname == "type" else fname), (name, fname, rname)
+            want = ctype.get(typ, typ)
+            assert rtyp == (f"[{want}; {n}]" if n else want), (name, fname, rtyp)

@@ -184,9 +184,13 @@ def test_cfg4_slice_parity_and_linearity():
     assert np.abs(whole).max() > 1e-3
 
 
-def test_cfg5_variant_batch_parity():
+@pytest.mark.parametrize("solo_min", [None, "0"])
+def test_cfg5_variant_batch_parity(solo_min, monkeypatch):
     """BASELINE config 5 on a batch the oracle finishes in seconds: 96 randomised one-voice
-    subtractive / FM variants (solo-warp work items, short envelopes -> exact and general paths)."""
+    subtractive / FM variants (solo-warp work items, short envelopes -> exact and general paths).
+    GB_SOLO_MIN=0 forces the job-list kernel (welsh_solo_kernel) that larger batches take by themselves."""
+    if solo_min is not None:
+        monkeypatch.setenv("GB_SOLO_MIN", solo_min)
     frames, note_off = 24000, 12000
     o = OracleEngine(48000.0)
     workloads.build_cfg5(o, 96, first=1000, frames=frames, note_off=note_off)
@@ -194,9 +198,69 @@ def test_cfg5_variant_batch_parity():
     g = gpu_engine(48000.0, max_block=frames)
     workloads.build_cfg5(g, 96, first=1000, frames=frames, note_off=note_off)
     out = g.render(frames)
+    st = g.stats()
     g.close()
+    assert (st.solo_kernel_launches > 0) == (solo_min == "0")
     assert np.abs(ref).max() > 1e-3
     check(out, ref)
+
+
+def test_solo_job_list_classes(monkeypatch):
+    """welsh_solo_kernel: the host sorts every (solo voice, 2048-frame sub-chunk) into idle / resting /
+    sweeping / general.  Instruments of 1-3 voices with envelopes slow enough for the sweeping class in
+    attack, decay AND release, a released voice whose filter envelope runs out before its amplitude
+    envelope (released resting tables), amplitude LFOs, a fixed filter, sine / noise oscillators and hard
+    sync (general class), a retrigger, several render chunks with a ragged tail and idle stretches whose
+    buffers held audio in the chunk before."""
+    monkeypatch.setenv("GB_SOLO_MIN", "0")
+    slow = dict(filt=(1.6, 1.0, 0.5, 1.6), amp=(0.3, 0.4, 0.7, 1.9), cutoff_start=0.3, cutoff_end=0.5)
+    cfgs = [
+        (1, dict(w1=abi.WAVE_SAWTOOTH, w2=abi.WAVE_TRIANGLE, tune2=1.0029, **slow)),
+        (2, dict(w1=abi.WAVE_PULSE_WIDTH, pw1=0.2, w2=abi.WAVE_SQUARE, routing=abi.LFO_AMPLITUDE, depth=0.3, lfo_hz=6.0, **slow)),
+        (3, dict(w1=abi.WAVE_TRIANGLE, w2=abi.WAVE_SAWTOOTH, mix=0.3, filt=(0.002, 0.03, 0.4, 0.05), amp=(0.01, 0.02, 0.8, 1.2),
+                 cutoff_start=0.25, cutoff_end=0.7)),                                   # filter release ends long before the amp's
+        (1, dict(w1=abi.WAVE_SQUARE, w2=abi.WAVE_PULSE_WIDTH, pw2=0.3, cutoff_end=0.0, cutoff_hz=1200.0, amp=(0.2, 0.3, 0.6, 0.8),
+                 routing=abi.LFO_AMPLITUDE, depth=0.2, lfo_hz=9.0)),                    # fixed filter
+        (1, dict(w1=abi.WAVE_SINE, w2=abi.WAVE_NOISE, **slow)),                          # general class throughout
+        (2, dict(w1=abi.WAVE_SAWTOOTH, w2=abi.WAVE_SQUARE, sync=1, tune2=1.5, **slow)),
+        (1, dict(w1=abi.WAVE_SAWTOOTH, w2=abi.WAVE_SAWTOOTH, tune2=0.5, filt=(0.01, 0.05, 0.3, 0.1), amp=(0.001, 0.05, 0.5, 0.05),
+                 cutoff_start=0.2, cutoff_end=0.9)),                                   # fast sweeps: exact coefficients
+    ]
+    frames = 230_000
+
+    def scene(r):
+        uids = []
+        for rep in range(3):
+            for i, (nv, c) in enumerate(cfgs):
+                u = r.add_instrument(abi.INST_WELSH, scenes.generic_welsh(voices=nv, gain=0.04, pan=-0.8 + 0.2 * i + 0.05 * rep, **c))
+                r.patch(u, abi.MAIN_MIXER)
+                uids.append((u, nv, rep))
+        r.finalize()
+        for k, (u, nv, rep) in enumerate(uids):
+            for v in range(nv):
+                on = 300 + 977 * rep + 131 * k + 4000 * v
+                r.note_on(on, u, 40 + 5 * v + k % 7)
+                r.note_off(on + 140_000 - 9000 * rep, u, 40 + 5 * v + k % 7)
+            if rep == 1:
+                r.note_on(60_000 + k, u, 40 + k % 7)        # retrigger of voice 0 inside its decay / sustain
+        return frames
+
+    o = OracleEngine(48000.0)
+    scene(o)
+    ref = o.render(frames)
+    for max_block, chunk in ((65536, None), (10_000, None), (65536, 33_333)):
+        g = gpu_engine(48000.0, max_block=max_block)
+        scene(g)
+        if chunk is None:
+            out = g.render(frames)
+        else:
+            out = np.concatenate([g.render(min(chunk, frames - a)).copy() for a in range(0, frames, chunk)])
+        st = g.stats()
+        g.close()
+        assert st.solo_kernel_launches > 0
+        assert all(c > 0 for c in st.solo_class_items), list(st.solo_class_items)
+        assert st.idle_voice_samples > 0
+        check(out, ref)
 
 
 def test_cfg5_batch_is_sum_of_its_variants():
