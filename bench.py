@@ -234,11 +234,11 @@ STAT_SUMS = ("render_ms", "voice_kernel_ms", "fx_kernel_ms", "kernel_launches", 
 class Acc(dict):
     """Sums of engine stats over the timed steps of one leg."""
 
-    def add(self, st, wall: float, reduce_ms: float = 0.0):
+    def add(self, wall: float, st, reduce_ms: float = 0.0):
         for k in STAT_SUMS:
             self[k] = self.get(k, 0) + getattr(st, k)
         cls = list(st.solo_class_items)
-        self["solo_class_items"] = [x + y for x, y in zip(self.get("solo_class_items", [0, 0, 0]), cls)]
+        self["solo_class_items"] = [x + y for x, y in zip(self.get("solo_class_items", [0, 0, 0, 0]), cls)]
         self["wall"] = self.get("wall", 0.0) + wall
         self["reduce_ms"] = self.get("reduce_ms", 0.0) + reduce_ms
         self["steps"] = self.get("steps", 0) + 1
@@ -285,12 +285,14 @@ def run_ours(a) -> None:
             self.pinned_out = (torch.empty((frames, 2), dtype=torch.float64, pin_memory=True)
                                if world > 1 and rank == 0 and reduce else None)
 
-        def step(self, mode: str, block: int = 0):
+        def step(self, mode: str, block: int = 0, lookahead: int = 0):
             """Engine construction (allocation, plan) is setup and stays outside the timed span; pushing the
             step's events from host memory, the per-chunk uploads and the result download are inside."""
             eng = Engine(SR, device=local, max_block=self.max_block)
             eng.set_timing(True)
             ev = self.graph(eng)
+            if lookahead:
+                eng.set_lookahead(lookahead)
             flush.zero_()
             barrier()
             t0 = time.perf_counter()
@@ -324,13 +326,13 @@ def run_ours(a) -> None:
             eng.close()
             return wall, st, reduce_ms
 
-        def run(self, mode: str, steps: int, warmup: int, block: int = 0) -> Acc:
+        def run(self, mode: str, steps: int, warmup: int, block: int = 0, lookahead: int = 0) -> Acc:
             for _ in range(warmup):
-                self.step(mode, block)
+                self.step(mode, block, lookahead)
             barrier()
             acc = Acc()
             for _ in range(steps):
-                acc.add(*self.step(mode, block))
+                acc.add(*self.step(mode, block, lookahead))
             barrier()
             return acc
 
@@ -423,7 +425,7 @@ def run_ours(a) -> None:
                                      acc["solo_kernel_ms"], acc["solo_kernel_launches"],
                                      n_w * workloads.CFG5_FRAMES * steps, WV,
                                      {"sounding_voice_samples_per_launch": wvs / max(acc["solo_kernel_launches"], 1),
-                                      "items_by_class": dict(zip(("resting", "sweeping", "general"),
+                                      "items_by_class": dict(zip(("resting", "sweeping", "general", "exact"),
                                                                  [int(x // steps) for x in acc["solo_class_items"]])),
                                       "jobs_per_launch": acc["solo_jobs"] / max(acc["solo_kernel_launches"], 1)}),
             "fm": kernel_roofline("fm_kernel<8>", acc["fm_kernel_ms"], acc["fm_kernel_launches"],
@@ -632,13 +634,18 @@ def run_ours(a) -> None:
             sb_cfg = replace(weak_cfg, frames=sb_frames, note_off_base=int(sb_frames * 2_400_000 / 2_880_000))
             wsb = cfg4_workload("small_blocks", sb_cfg)
             big = wsb.run("e2e", 2, 1)
-            small = wsb.run("blocks", 2, 1, block=64)
+            small = wsb.run("blocks", 2, 1, block=64, lookahead=a.max_block)
+            plain = wsb.run("blocks", 1, 0, block=64)
             put("small_blocks", {
                 "what": f"config-4 recipe, {sb_frames / SR:g} s, rendered through gb_render_block in 64-frame caller buffers "
-                        "(the reference's own call size: orchestrator.rs:1696, audio_panel.rs:69) against one big call",
+                        "(the reference's own call size: orchestrator.rs:1696, audio_panel.rs:69) with "
+                        f"gb_set_lookahead({a.max_block}), against one big call; `without_lookahead` = the same calls "
+                        "each going to the device",
                 "value": sb_cfg.voice_samples / (small["wall"] / 2), "unit": UNIT, "ms_per_step": small["wall"] / 2 * 1e3,
                 "big_buffer_ms_per_step": big["wall"] / 2 * 1e3, "fraction_of_big_buffer_e2e": big["wall"] / small["wall"],
-                "calls_per_step": -(-sb_frames // 64), "gpu_launches": int(small["kernel_launches"] // 2)})
+                "calls_per_step": -(-sb_frames // 64), "gpu_launches": int(small["kernel_launches"] // 2),
+                "without_lookahead": {"ms_per_step": plain["wall"] * 1e3, "gpu_launches": int(plain["kernel_launches"]),
+                                      "fraction_of_big_buffer_e2e": big["wall"] / 2 / plain["wall"]}})
 
     if rank == 0:
         if not a.no_cpu_baseline:

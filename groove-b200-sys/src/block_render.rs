@@ -135,6 +135,12 @@ impl Engine {
         let rc = unsafe { ffi::gb_render_pcm16(self.raw, out_interleaved_lr.as_mut_ptr(), frames, &mut done) };
         self.check(rc).map(|_| done)
     }
+    /// Serve the Orchestrator's 64-frame `tick` buffers (orchestrator.rs:1696) from one big device render
+    /// every `frames` frames; the sequencer knows its events that far ahead (include/groove_b200.h).
+    pub fn set_lookahead(&mut self, frames: usize) -> Result<()> {
+        let rc = unsafe { ffi::gb_set_lookahead(self.raw, frames) };
+        self.check(rc)
+    }
     pub fn position(&self) -> i64 {
         unsafe { ffi::gb_position(self.raw) }
     }

@@ -260,7 +260,7 @@ pub mod ffi {
         pub solo_kernel_ms: f64,
         pub solo_voice_samples: u64,
         pub solo_jobs: u64,
-        pub solo_class_items: [u64; 3],
+        pub solo_class_items: [u64; 4],
         pub fm_kernel_launches: u64,
         pub fm_kernel_ms: f64,
         pub idle_voice_samples: u64,
@@ -285,6 +285,7 @@ pub mod ffi {
         pub fn gb_last_device_buffer(e: *mut gb_engine, device_ptr: *mut *mut c_void, frames: *mut usize) -> c_int;
         pub fn gb_read_last(e: *mut gb_engine, out_interleaved_lr: *mut f64, frames: usize) -> c_int;
         pub fn gb_position(e: *const gb_engine) -> i64;
+        pub fn gb_set_lookahead(e: *mut gb_engine, frames: usize) -> c_int;
         pub fn gb_link_control(e: *mut gb_engine, source_uid: u32, target_uid: u32, control_index: i32) -> c_int;
         pub fn gb_save_state(e: *mut gb_engine, buf: *mut c_void, size: *mut usize) -> c_int;
         pub fn gb_restore_state(e: *mut gb_engine, buf: *const c_void, size: usize) -> c_int;

@@ -145,7 +145,7 @@ class Stats(C.Structure):
                 ("rest_kernel_launches", C.c_uint64), ("rest_kernel_ms", C.c_double), ("rest_voice_samples", C.c_uint64),
                 ("sweep_kernel_launches", C.c_uint64), ("sweep_kernel_ms", C.c_double), ("sweep_voice_samples", C.c_uint64),
                 ("solo_kernel_launches", C.c_uint64), ("solo_kernel_ms", C.c_double), ("solo_voice_samples", C.c_uint64),
-                ("solo_jobs", C.c_uint64), ("solo_class_items", C.c_uint64 * 3),
+                ("solo_jobs", C.c_uint64), ("solo_class_items", C.c_uint64 * 4),
                 ("fm_kernel_launches", C.c_uint64), ("fm_kernel_ms", C.c_double), ("idle_voice_samples", C.c_uint64),
                 ("rest_ctas", C.c_uint64), ("sweep_ctas", C.c_uint64)]
 
@@ -155,7 +155,7 @@ ABI_SYMBOLS = (
     "create", "destroy", "last_error", "add_instrument", "add_effect", "load_sample", "patch", "finalize",
     "push_events", "render_block", "render_pcm16", "render_device", "last_device_buffer", "read_last", "position",
     "save_state",
-    "restore_state", "get_stats", "reset_stats", "set_timing", "measure_fma_peak", "link_control",
+    "restore_state", "get_stats", "reset_stats", "set_timing", "measure_fma_peak", "link_control", "set_lookahead",
 )
 
 
@@ -217,6 +217,8 @@ class Renderer:
             "reset_stats": (C.c_int, [vp]),
             "set_timing": (C.c_int, [vp, C.c_int32]),
             "measure_fma_peak": (C.c_int, [vp, C.c_int32, C.POINTER(C.c_double)]),
+            "link_control": (C.c_int, [vp, C.c_uint32, C.c_uint32, C.c_int32]),
+            "set_lookahead": (C.c_int, [vp, C.c_size_t]),
         }
         for name, (res, args) in sig.items():
             fn = getattr(self._lib, self._p + name, None)
@@ -339,6 +341,10 @@ class Renderer:
         n = C.c_size_t()
         self._check(self._f("last_device_buffer")(self._h, C.byref(ptr), C.byref(n)))
         return ptr.value, n.value
+
+    def set_lookahead(self, frames: int):
+        """Serve small render() calls from one big render every ``frames`` frames (include/groove_b200.h)."""
+        self._check(self._f("set_lookahead")(self._h, frames))
 
     @property
     def position(self) -> int:

@@ -22,6 +22,8 @@
 #include <string>
 #include <vector>
 
+#include <chrono>
+
 #include <cuda_runtime.h>
 #include <unistd.h>
 
@@ -359,6 +361,10 @@ struct gb_engine {
   uint64_t chunk_seq = 0;
   bool finalized = false;
   int64_t pos = 0;
+  // gb_set_lookahead: frames rendered ahead of what gb_render_block has handed out (host buffer)
+  size_t lookahead = 0;
+  std::vector<double> ahead;       // interleaved L,R
+  size_t ahead_n = 0, ahead_off = 0;
   uint32_t next_uid = 2;
   int num_sms = 148;
   // Developer switches (A/B measurements, path-agreement tests): read from the environment ONCE, in
@@ -411,6 +417,8 @@ struct gb_engine {
   DevBuf<SoloJob> sjobs;
   DevBuf<ZeroRange> szero;
   int* d_solo_sync = nullptr;     // [0, kSoloTickets) = job tickets (one per launch), [kSoloTickets + voice] = per-voice progress counter
+  int solo_sub = kSoloSubDefault; // GB_SOLO_SUB: frames per sub-chunk (a multiple of kBlockFrames)
+  int solo_lockstep = 1;          // GB_SOLO_LOCKSTEP: bit 0 = rest / sweep / exact jobs run their blocks in lockstep, bit 1 = general jobs too
   bool solo_waves = false;        // GB_SOLO_WAVES=1: one launch per sub-chunk (stream order instead of the progress counters)
   int* d_solo_fault = nullptr;    // {flag, job, voice, need, have}: set by the kernel's dependency watchdog
   bool solo_ran = false;          // a job-list launch happened since the fault words were last checked
@@ -429,7 +437,9 @@ struct gb_engine {
   bool fused_sums = false;          // this chunk: consumers read partial buffers directly
   bool fused_sums_enabled = true;   // GB_FUSED_SUMS=0 switches the shortcut off (A/B measurements)
   bool chunk_cuts = true;           // GB_CHUNK_CUTS=0: chunks of max_block regardless of voice transitions
-  std::vector<void*> allocations;  // everything cudaMalloc'ed at finalize/load time
+  std::vector<void*> allocations;  // everything cudaMalloc'ed at finalize/load time (slabs of dev_alloc, samples)
+  char* slab_ptr = nullptr;        // bump pointer into the current slab
+  size_t slab_left = 0, slab_next = 0;
 
   double2* last_out = nullptr;  // main mixer buffer of the last chunk
   size_t last_frames = 0;
@@ -468,13 +478,24 @@ int fail(gb_engine* e, int code, const char* fmt, ...) {
       return fail(e, GB_ECUDA, "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_rc), __FILE__, __LINE__); \
   } while (0)
 
+// Plan-time device memory comes out of slabs (a batch of 8192 one-voice instruments would otherwise be 8192
+// cudaMalloc / cudaFree pairs per engine): bump allocation, 256-byte aligned, freed with the engine.
 template <typename T>
 int dev_alloc(gb_engine* e, T** out, size_t count, bool zero = true) {
-  void* p = nullptr;
-  size_t bytes = std::max<size_t>(count, 1) * sizeof(T);
-  CUDA_TRY(e, cudaMalloc(&p, bytes));
+  const size_t bytes = (std::max<size_t>(count, 1) * sizeof(T) + 255) & ~(size_t)255;
+  if (bytes > e->slab_left) {
+    e->slab_next = std::min<size_t>(std::max<size_t>(2 * e->slab_next, (size_t)32 << 20), (size_t)1 << 30);  // 32 MB, doubling up to 1 GB
+    const size_t slab = std::max(bytes, e->slab_next);
+    void* p = nullptr;
+    CUDA_TRY(e, cudaMalloc(&p, slab));
+    e->allocations.push_back(p);
+    e->slab_ptr = (char*)p;
+    e->slab_left = slab;
+  }
+  void* p = e->slab_ptr;
+  e->slab_ptr += bytes;
+  e->slab_left -= bytes;
   if (zero) CUDA_TRY(e, cudaMemsetAsync(p, 0, bytes, e->stream));
-  e->allocations.push_back(p);
   *out = (T*)p;
   return 0;
 }
@@ -645,6 +666,8 @@ void welsh_inst_from_params(const Node& n, double sr, const gb_engine::Options& 
     if (lin && I->filter_mode == FILTER_ENVELOPE && I->knot_max_rate > 0.0 && 0.49 * sr >= 20000.0)
       I->sweep_class = (I->routing == LFO_AMPLITUDE ? 2 : 0) + (I->osc_flat ? 1 : 0);
     if (!opt.sweep_kernel) I->sweep_class = -1;
+    // welsh_exact_block (solo items): as above with exact coefficient sets at every frame, so no smoothness needed
+    I->exact_class = lin && I->filter_mode == FILTER_ENVELOPE ? (I->routing == LFO_AMPLITUDE ? 1 : 0) : -1;
   }
 }
 void fm_inst_from_params(const Node& n, double sr, FmInst* I) {
@@ -901,6 +924,8 @@ int gb_create(const gb_config* cfg, gb_engine** out) {
   if (const char* v = getenv("GB_MIN_CUT_VOICES")) e->opt.min_cut_voices = std::max(1, atoi(v));
   if (const char* v = getenv("GB_SOLO_MIN")) e->min_solo_items = atoi(v);
   if (const char* v = getenv("GB_SOLO_WAVES")) e->solo_waves = atoi(v) != 0;
+  if (const char* v = getenv("GB_SOLO_LOCKSTEP")) e->solo_lockstep = atoi(v);
+  if (const char* v = getenv("GB_SOLO_SUB")) e->solo_sub = std::max(1, atoi(v) / kBlockFrames) * kBlockFrames;
   if (const char* v = getenv("GB_FUSED_SUMS")) e->fused_sums_enabled = atoi(v) != 0;
   if (const char* v = getenv("GB_CHUNK_CUTS")) e->chunk_cuts = atoi(v) != 0;
   if (cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking) != cudaSuccess ||
@@ -1148,6 +1173,30 @@ int gb_link_control(gb_engine* e, uint32_t src, uint32_t dst, int32_t index) {
   gb_engine::Link l;
   l.src = src; l.dst = dst; l.index = index;
   e->links.push_back(l);
+  return 0;
+}
+
+// The instrument tables (coefficient sets, scan maps, rotation tables: welsh_inst_from_params) are part of the
+// plan: built and uploaded by gb_finalize, and again before the next chunk whenever a parameter changed.
+int upload_inst_tables(gb_engine* e) {
+  if (e->winst_dirty && !e->h_winst.empty()) {
+    for (Node* n : e->plan)
+      if (n->kind == GB_INST_WELSH) welsh_inst_from_params(*n, e->sr, e->opt, &e->h_winst[(size_t)n->table_index]);
+    CUDA_TRY(e, cudaMemcpyAsync(e->d_winst, e->h_winst.data(), e->h_winst.size() * sizeof(WelshInst),
+                                cudaMemcpyHostToDevice, e->stream));
+    CUDA_TRY(e, cudaStreamSynchronize(e->stream));  // h_winst is pageable
+    e->stats.h2d_bytes += e->h_winst.size() * sizeof(WelshInst);
+  }
+  e->winst_dirty = false;
+  if (e->finst_dirty && !e->h_finst.empty()) {
+    for (Node* n : e->plan)
+      if (n->kind == GB_INST_FM) fm_inst_from_params(*n, e->sr, &e->h_finst[(size_t)n->table_index]);
+    CUDA_TRY(e, cudaMemcpyAsync(e->d_finst, e->h_finst.data(), e->h_finst.size() * sizeof(FmInst),
+                                cudaMemcpyHostToDevice, e->stream));
+    CUDA_TRY(e, cudaStreamSynchronize(e->stream));
+    e->stats.h2d_bytes += e->h_finst.size() * sizeof(FmInst);
+  }
+  e->finst_dirty = false;
   return 0;
 }
 
@@ -1441,10 +1490,23 @@ int gb_finalize(gb_engine* e) {
   CUDA_TRY(e, cudaFuncSetAttribute(welsh_solo_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSoloSmemBytes));
   CUDA_TRY(e, cudaFuncSetAttribute(fm_kernel<kVoiceWarps>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                    (int)(kVoiceWarps * kTileStride * sizeof(double2))));
+  {
+    // staging buffers sized for a full chunk now: growing one inside a render call costs a device
+    // synchronisation and fresh pinned host mirrors
+    bool ok = e->wev_off.reserve((size_t)e->n_wvoice + 1) && e->fev_off.reserve((size_t)e->n_fvoice + 1) &&
+              e->wev.reserve(4 * (size_t)e->n_wvoice + 64) && e->fev.reserve(4 * (size_t)e->n_fvoice + 64) &&
+              e->widx.reserve((size_t)e->n_wwork_grouped + 1);
+    if (ok && e->solo_mega) {
+      const size_t kmax = (size_t)cdiv((int)e->max_block, e->solo_sub), n = e->witem_node.size();
+      ok = e->sitems.reserve(n * kmax + 1) && e->sjobs.reserve(n * kmax / kVoiceWarps + kmax * SOLO_CLASSES + 1) &&
+           e->szero.reserve(4 * n + 16);
+    }
+    if (!ok) return fail(e, GB_ENOMEM, "out of memory");
+  }
   CUDA_TRY(e, cudaStreamSynchronize(e->stream));
   e->finalized = true;
   e->winst_dirty = e->finst_dirty = true;
-  return 0;
+  return upload_inst_tables(e);
 }
 
 int gb_push_events(gb_engine* e, const gb_event* ev, size_t n) {
@@ -1472,8 +1534,25 @@ struct ControlPoint {
 
 // Render one chunk of `frames` (<= max_block) frames starting at e->pos.  Events for the chunk are
 // e->events[0 .. n_ev).
+struct HostProfile {  // GB_HOST_PROFILE=1: wall time of render_chunk's host sections, to stderr
+  bool on;
+  std::chrono::steady_clock::time_point t;
+  std::string line;
+  HostProfile() : on(getenv("GB_HOST_PROFILE") != nullptr), t(std::chrono::steady_clock::now()) {}
+  void mark(const char* what) {
+    if (!on) return;
+    auto n = std::chrono::steady_clock::now();
+    char b[64];
+    snprintf(b, sizeof b, " %s %.3f", what, std::chrono::duration<double, std::milli>(n - t).count());
+    line += b;
+    t = n;
+  }
+  ~HostProfile() { if (on) fprintf(stderr, "[host]%s\n", line.c_str()); }
+};
+
 int render_chunk(gb_engine* e, int frames, size_t n_ev) {
   const int64_t f0 = e->pos;
+  HostProfile hp;
   // staging slot of this chunk: wait until the chunk that used it kStageSlots chunks ago has been consumed
   const int slot = (int)(e->chunk_seq % kStageSlots);
   if (e->chunk_seq >= (uint64_t)kStageSlots) CUDA_TRY(e, cudaEventSynchronize(e->stage_done[slot]));
@@ -1492,6 +1571,7 @@ int render_chunk(gb_engine* e, int frames, size_t n_ev) {
       solo_pre[i].n_off = sl.held ? kHeld : sl.idle_at - n->release_frames;
     }
   }
+  hp.mark("pre");
   // ---- 1. resolve events ----
   std::vector<std::vector<VoiceEvent>> wlists((size_t)e->n_wvoice), flists((size_t)e->n_fvoice);
   std::map<Node*, std::vector<ControlPoint>> controls;
@@ -1714,16 +1794,9 @@ int render_chunk(gb_engine* e, int frames, size_t n_ev) {
     return 0;
   };
   const size_t tile_bytes = (size_t)kVoiceWarps * kTileStride * sizeof(double2);
+  hp.mark("events");
   if (e->n_wvoice) {
-    if (e->winst_dirty) {
-      for (Node* n : e->plan)
-        if (n->kind == GB_INST_WELSH) welsh_inst_from_params(*n, e->sr, e->opt, &e->h_winst[(size_t)n->table_index]);
-      CUDA_TRY(e, cudaMemcpyAsync(e->d_winst, e->h_winst.data(), e->h_winst.size() * sizeof(WelshInst),
-                                  cudaMemcpyHostToDevice, e->stream));
-      CUDA_TRY(e, cudaStreamSynchronize(e->stream));  // h_winst is pageable
-      e->stats.h2d_bytes += e->h_winst.size() * sizeof(WelshInst);
-      e->winst_dirty = false;
-    }
+    if (e->winst_dirty) { int rc0 = upload_inst_tables(e); if (rc0) return rc0; }
     int rc = upload_events(wlists, e->wev, e->wev_off, any_w, &e->wev_empty_on_device);
     if (rc) return rc;
     {
@@ -1857,10 +1930,11 @@ int render_chunk(gb_engine* e, int frames, size_t n_ev) {
   auto run_solo = [&]() -> int {
     if (!e->solo_mega) return 0;
     const int n_items = (int)e->witem_node.size();
+    const int kSoloSub = e->solo_sub;  // frames per sub-chunk (classification granularity)
     const int K = cdiv(frames, kSoloSub);
     const bool dbg = getenv("GB_DEBUG") != nullptr;
     if (dbg) { fprintf(stderr, "[solo] f0=%lld frames=%d items=%d K=%d\n", (long long)f0, frames, n_items, K); fflush(stderr); }
-    enum { C_IDLE = 3 };
+    enum { C_IDLE = SOLO_CLASSES, NC = SOLO_CLASSES };
     std::vector<int8_t> cls((size_t)n_items * (size_t)K);
     auto classify = [&](const WelshInst& I, int64_t n_on, int64_t n_off, int64_t s0, int64_t s1, int64_t* valid_until) -> int {
       // *valid_until: the class holds for every later sub-chunk that ends at or before this frame
@@ -1899,15 +1973,16 @@ int render_chunk(gb_engine* e, int frames, size_t n_ev) {
         } else {
           const double slope = sf == 0 ? 2.0 * I.filt.inv_na : sf == 1 ? 2.0 * (1.0 - I.filt.sustain) * I.filt.inv_nd
                                                                        : 2.0 * I.filt.inv_nr;
-          result = I.sweep_class >= 0 && std::fabs(I.cut_b) * slope <= I.knot_max_rate ? SOLO_SWEEP : SOLO_GENERAL;
+          result = I.sweep_class >= 0 && std::fabs(I.cut_b) * slope <= I.knot_max_rate ? SOLO_SWEEP
+                   : I.exact_class >= 0 ? SOLO_EXACT : SOLO_GENERAL;
         }
       }
       (void)sa;
       *valid_until = until;
       return result;
     };
-    int counts[4] = {0, 0, 0, 0};
-    std::vector<int> bucket_n((size_t)K * 3, 0);
+    int counts[NC + 1] = {0, 0, 0, 0, 0};
+    std::vector<int> bucket_n((size_t)K * NC, 0);
     for (int i = 0; i < n_items; ++i) {
       const Node* n = e->witem_node[(size_t)i];
       const WelshInst& I = e->h_winst[(size_t)n->table_index];
@@ -1936,22 +2011,22 @@ int render_chunk(gb_engine* e, int frames, size_t n_ev) {
         }
         c[k] = (int8_t)r;
         counts[r]++;
-        if (r != C_IDLE) bucket_n[(size_t)k * 3 + (size_t)r]++;
+        if (r != C_IDLE) bucket_n[(size_t)k * NC + (size_t)r]++;
       }
     }
     // buckets in job order: sub-chunk by sub-chunk; inside one the slowest class first
-    static const int order[3] = {SOLO_GENERAL, SOLO_SWEEP, SOLO_REST};
-    std::vector<int> bucket_off((size_t)K * 3 + 1, 0);
+    static const int order[NC] = {SOLO_GENERAL, SOLO_EXACT, SOLO_SWEEP, SOLO_REST};
+    std::vector<int> bucket_off((size_t)K * NC + 1, 0);
     {
       int acc = 0;
       for (int k = 0; k < K; ++k)
-        for (int o = 0; o < 3; ++o) {
-          bucket_off[(size_t)k * 3 + (size_t)order[o]] = acc;
-          acc += bucket_n[(size_t)k * 3 + (size_t)order[o]];
+        for (int o = 0; o < NC; ++o) {
+          bucket_off[(size_t)k * NC + (size_t)order[o]] = acc;
+          acc += bucket_n[(size_t)k * NC + (size_t)order[o]];
         }
-      bucket_off[(size_t)K * 3] = acc;
+      bucket_off[(size_t)K * NC] = acc;
     }
-    const int n_sitems = bucket_off[(size_t)K * 3];
+    const int n_sitems = bucket_off[(size_t)K * NC];
     if (!e->sitems.reserve((size_t)n_sitems + 1)) return fail(e, GB_ENOMEM, "out of memory");
     e->sitems.use_slot(slot);
     {
@@ -1961,16 +2036,18 @@ int render_chunk(gb_engine* e, int frames, size_t n_ev) {
         for (int i = 0; i < n_items; ++i) {
           const int r = cls[(size_t)i * (size_t)K + (size_t)k];
           if (r == C_IDLE) continue;
-          SoloItem& si = e->sitems.h[fill[(size_t)k * 3 + (size_t)r]++];
+          SoloItem& si = e->sitems.h[fill[(size_t)k * NC + (size_t)r]++];
           si.item = i;
           si.need = done[(size_t)i]++;
         }
     }
     std::vector<SoloJob> jobs;
-    for (int k = 0; k < K; ++k)
-      for (int o = 0; o < 3; ++o) {
+    std::vector<int> wave_first;  // first job of each sub-chunk (GB_SOLO_WAVES)
+    for (int k = 0; k < K; ++k) {
+      wave_first.push_back((int)jobs.size());
+      for (int o = 0; o < NC; ++o) {
         const int r = order[o];
-        const int first = bucket_off[(size_t)k * 3 + (size_t)r], cnt = bucket_n[(size_t)k * 3 + (size_t)r];
+        const int first = bucket_off[(size_t)k * NC + (size_t)r], cnt = bucket_n[(size_t)k * NC + (size_t)r];
         for (int a = 0; a < cnt; a += kVoiceWarps) {
           SoloJob j;
           j.cls = r;
@@ -1978,10 +2055,12 @@ int render_chunk(gb_engine* e, int frames, size_t n_ev) {
           j.nframes = std::min(kSoloSub, frames - j.t0);
           j.first = first + a;
           j.n = std::min(kVoiceWarps, cnt - a);
-          j.pad = 0;
+          j.lockstep = e->solo_lockstep >> (r == SOLO_GENERAL ? 1 : 0) & 1;
           jobs.push_back(j);
         }
       }
+    }
+    wave_first.push_back((int)jobs.size());
     // idle stretches: the item's output must read zero there; only stretches that may hold old audio are written
     std::vector<ZeroRange> zr;
     for (int i = 0; i < n_items; ++i) {
@@ -2032,12 +2111,8 @@ int render_chunk(gb_engine* e, int frames, size_t n_ev) {
     CUDA_TRY(e, cudaMemsetAsync(e->d_solo_sync, 0, ((size_t)e->n_wvoice + kSoloTickets) * sizeof(int), e->stream));
     e->stats.h2d_bytes += (size_t)n_sitems * sizeof(SoloItem) + jobs.size() * sizeof(SoloJob);
     if (dbg) {
-      fprintf(stderr, "[solo] jobs=%zu sitems=%d counts=%d/%d/%d idle=%d zr=%zu\n", jobs.size(), n_sitems, counts[0], counts[1], counts[2], counts[3], zr.size());
-      for (size_t q = 0; q < jobs.size(); ++q) {
-        fprintf(stderr, "  job %zu cls=%d t0=%d n=%d first=%d :", q, jobs[q].cls, jobs[q].t0, jobs[q].n, jobs[q].first);
-        for (int w = 0; w < jobs[q].n; ++w) fprintf(stderr, " (%d,%d)", e->sitems.h[jobs[q].first + w].item, e->sitems.h[jobs[q].first + w].need);
-        fprintf(stderr, "\n");
-      }
+      fprintf(stderr, "[solo] jobs=%zu sitems=%d counts=%d/%d/%d/%d idle=%d zr=%zu\n", jobs.size(), n_sitems, counts[0], counts[1],
+              counts[2], counts[3], counts[C_IDLE], zr.size());
       fflush(stderr);
     }
     // one persistent launch walks the whole list; GB_SOLO_WAVES=1 launches once per sub-chunk instead (the
@@ -2045,13 +2120,9 @@ int render_chunk(gb_engine* e, int frames, size_t n_ev) {
     {
       std::vector<std::pair<int, int>> launches;  // (first job, jobs)
       if (e->solo_waves && K <= kSoloTickets) {
-        size_t q = 0;
-        while (q < jobs.size()) {
-          size_t q1 = q;
-          while (q1 < jobs.size() && jobs[q1].t0 == jobs[q].t0) ++q1;
-          launches.push_back({(int)q, (int)(q1 - q)});
-          q = q1;
-        }
+        for (int k = 0; k < K; ++k)
+          if (wave_first[(size_t)k + 1] > wave_first[(size_t)k])
+            launches.push_back({wave_first[(size_t)k], wave_first[(size_t)k + 1] - wave_first[(size_t)k]});
       } else {
         launches.push_back({0, (int)jobs.size()});
       }
@@ -2066,30 +2137,21 @@ int render_chunk(gb_engine* e, int frames, size_t n_ev) {
       }
       CUDA_TRY(e, cudaGetLastError());
       e->solo_ran = true;
-    }
-    if (dbg) {
-      cudaError_t q = cudaErrorNotReady;
-      for (int it = 0; it < 800 && q == cudaErrorNotReady; ++it) { usleep(10000); q = cudaStreamQuery(e->stream); }
-      fprintf(stderr, "[solo] after wait: %s\n", cudaGetErrorString(q)); fflush(stderr);
-      if (q == cudaErrorNotReady) _exit(3);
+      if (dbg) {
+        cudaError_t q = cudaErrorNotReady;
+        for (int it = 0; it < 800 && q == cudaErrorNotReady; ++it) { usleep(10000); q = cudaStreamQuery(e->stream); }
+        fprintf(stderr, "[solo] f0=%lld frames=%d after wait: %s\n", (long long)f0, frames, cudaGetErrorString(q)); fflush(stderr);
+        if (q == cudaErrorNotReady) _exit(3);
+      }
     }
     e->stats.solo_jobs += jobs.size();
-    e->stats.solo_voice_samples += (uint64_t)(counts[0] + counts[1] + counts[2]) * (uint64_t)kSoloSub;
-    e->stats.solo_class_items[0] += (uint64_t)counts[0];
-    e->stats.solo_class_items[1] += (uint64_t)counts[1];
-    e->stats.solo_class_items[2] += (uint64_t)counts[2];
+    e->stats.solo_voice_samples += (uint64_t)n_sitems * (uint64_t)kSoloSub;
+    for (int c = 0; c < NC; ++c) e->stats.solo_class_items[c] += (uint64_t)counts[c];
     return 0;
   };
+  hp.mark("welsh");
   if (e->n_fvoice) {
-    if (e->finst_dirty) {
-      for (Node* n : e->plan)
-        if (n->kind == GB_INST_FM) fm_inst_from_params(*n, e->sr, &e->h_finst[(size_t)n->table_index]);
-      CUDA_TRY(e, cudaMemcpyAsync(e->d_finst, e->h_finst.data(), e->h_finst.size() * sizeof(FmInst),
-                                  cudaMemcpyHostToDevice, e->stream));
-      CUDA_TRY(e, cudaStreamSynchronize(e->stream));
-      e->stats.h2d_bytes += e->h_finst.size() * sizeof(FmInst);
-      e->finst_dirty = false;
-    }
+    if (e->finst_dirty) { int rc0 = upload_inst_tables(e); if (rc0) return rc0; }
     int rc = upload_events(flists, e->fev, e->fev_off, any_f, &e->fev_empty_on_device);
     if (rc) return rc;
     {
@@ -2099,10 +2161,12 @@ int render_chunk(gb_engine* e, int frames, size_t n_ev) {
     }
     e->stats.voice_samples += (uint64_t)e->n_fvoice * (uint64_t)frames;
   }
+  hp.mark("fm");
   if (e->n_wvoice) {
     int rc = run_solo();
     if (rc) return rc;
   }
+  hp.mark("solo");
   // samplers / drumkits: one launch per instrument over this chunk's plays (voice order, then time)
   {
     std::vector<SamplePlay> plays_h;
@@ -2241,6 +2305,7 @@ int render_chunk(gb_engine* e, int frames, size_t n_ev) {
   e->last_out = root->buf;
   e->last_frames = (size_t)frames;
   CUDA_TRY(e, cudaEventRecord(e->stage_done[slot], e->stream));
+  hp.mark("fx");
   e->chunk_seq++;
   e->pos += frames;
   return 0;
@@ -2404,7 +2469,41 @@ int render_impl(gb_engine* e, void* out, size_t frames, size_t* done, OutMode mo
 extern "C" {
 
 int gb_render_block(gb_engine* e, double* out, size_t frames, size_t* done) {
-  return render_impl(e, out, frames, done, OUT_F64);
+  if (!e || !e->lookahead) return render_impl(e, out, frames, done, OUT_F64);
+  if (frames && !out) return fail(e, GB_EINVAL, "null output buffer");
+  // look-ahead mode: small caller buffers (the reference calls with 64 frames, orchestrator.rs:1696) are served
+  // from a host buffer that one big render fills every `lookahead` frames
+  size_t got = 0;
+  while (got < frames) {
+    if (e->ahead_off == e->ahead_n) {
+      if (frames - got >= e->lookahead) {  // a big request goes straight through
+        size_t d = 0;
+        int rc = render_impl(e, out + 2 * got, frames - got, &d, OUT_F64);
+        if (rc) return rc;
+        got += d;
+        break;
+      }
+      e->ahead_n = e->ahead_off = 0;
+      size_t d = 0;
+      int rc = render_impl(e, e->ahead.data(), e->lookahead, &d, OUT_F64);
+      if (rc) return rc;
+      e->ahead_n = d;
+    }
+    const size_t k = std::min(frames - got, e->ahead_n - e->ahead_off);
+    memcpy(out + 2 * got, e->ahead.data() + 2 * e->ahead_off, k * 2 * sizeof(double));
+    e->ahead_off += k;
+    got += k;
+  }
+  if (done) *done = got;
+  return 0;
+}
+int gb_set_lookahead(gb_engine* e, size_t frames) {
+  if (!e) return GB_EINVAL;
+  if (e->ahead_off != e->ahead_n) return fail(e, GB_ESTATE, "frames rendered ahead are still pending");
+  e->lookahead = frames;
+  e->ahead.assign(2 * frames, 0.0);
+  e->ahead_n = e->ahead_off = 0;
+  return 0;
 }
 int gb_render_pcm16(gb_engine* e, int16_t* out, size_t frames, size_t* done) {
   return render_impl(e, out, frames, done, OUT_PCM16);
@@ -2427,7 +2526,7 @@ int gb_last_device_buffer(gb_engine* e, void** device_ptr, size_t* frames) {
   *frames = e->full_frames;
   return 0;
 }
-int64_t gb_position(const gb_engine* e) { return e ? e->pos : -1; }
+int64_t gb_position(const gb_engine* e) { return e ? e->pos - (int64_t)(e->ahead_n - e->ahead_off) : -1; }
 
 // ---- state save / restore -------------------------------------------------------------------
 // Layout: header {magic, pos, n_wvoice, n_fvoice, n_nodes} then device voice tables, then per plan
@@ -2500,6 +2599,7 @@ extern "C" {
 int gb_save_state(gb_engine* e, void* buf, size_t* size) {
   if (!e || !size) return GB_EINVAL;
   if (!e->finalized) return fail(e, GB_ESTATE, "engine is not finalized");
+  if (e->ahead_off != e->ahead_n) return fail(e, GB_ESTATE, "look-ahead mode: frames rendered ahead have not been handed out yet");
   cudaSetDevice(e->device);
   CUDA_TRY(e, cudaStreamSynchronize(e->stream));
   Blob b;
@@ -2574,6 +2674,7 @@ int gb_restore_state(gb_engine* e, const void* buf, size_t size) {
   int rc = for_each_state_region(e, [&](void* d, size_t bytes) { return blob_to_dev(e, r, d, bytes); });
   if (rc) return rc;
   e->pos = pos;
+  e->ahead_n = e->ahead_off = 0;  // frames rendered ahead of the restored position are dropped
   e->winst_dirty = e->finst_dirty = true;
   return 0;
 }

@@ -173,6 +173,7 @@ struct WelshInst {
   int rest_class, sweep_class;      // welsh_rest_kernel / welsh_sweep_kernel variant (2*lfo_amp + zero_a), -1 = does not qualify
   i64 steady_after;                 // frames after note-on from which both envelopes rest at their sustain levels
   double amp_rest;                  // 0.5 * amp.sustain: the DCA input level of a resting voice (without LFO)
+  int exact_class, pad_exact;       // welsh_exact_block applies (piecewise-linear oscillators, filter envelope): 0 / 1, else -1
   int lti_ok, osc_flat;             // osc_flat: both oscillators piecewise constant (OscMix slopes are 0); lti holds this instrument's resting coefficient sets (GB_LTI=0 disables the path)
   // the same tables for a RELEASED voice whose filter envelope has run out (cutoff back at cut_a) while the
   // amplitude envelope still releases; equal to lti / m1bb / m2bb for a fixed filter (welsh_solo_kernel)
@@ -815,7 +816,7 @@ __device__ __forceinline__ void cta_reduce_store(const double2* tiles, const int
 // the filter envelope and moving <= kKnotMaxRate per frame, every lane sounding inside single
 // envelope stages.  Everything the general fast path decides per frame is a compile-time constant
 // here; the arithmetic is identical to welsh_block_fast<COEF_KNOTS, true>.
-constexpr int kParkWords = 14;  // doubles parked per thread by welsh_block_simple (see below)
+constexpr int kParkWords = 16;  // doubles parked per thread by welsh_block_simple (14) / welsh_exact_block (16)
 
 // 1 + pos_of(q): the top 52 phase bits as the mantissa of a double in [1,2)
 __device__ __forceinline__ double pos1_of(u64 q) {
@@ -1751,6 +1752,106 @@ __device__ __forceinline__ void welsh_sweep_block(SweepState* rs, const WelshIns
   __syncwarp();
 }
 
+// welsh_sweep_block with the coefficient sets of BOTH sections evaluated exactly at every frame
+// (welsh_coef_exact, as the general path does) instead of interpolated between knots: for filter-envelope
+// stages whose cutoff moves faster than the knot threshold allows (short attacks, decays and releases).
+// Section 2's a1, a2 of the lane's kT frames wait in the thread's parking column of shared memory
+// (`park`, stride `pstride` doubles) while section 1 is scanned; b0 of section 2 follows from the unity
+// DC gain, 4 b0 = 1 - a1 - a2 (an identity of lp24_from_u's forms).
+template <bool LFO_AMP>
+__device__ __forceinline__ void welsh_exact_block(SweepState* rs, const WelshInst& I, int lane, int t0, double2* tile_row,
+                                                  double* park, int pstride) {
+  const int tl = t0 + lane * kT;  // the lane's first frame, relative to the item start
+  double yp[kT], g0[kT], g1[kT];
+  double ps0 = 0.0, ps1 = 0.0, h00 = 1.0, h01 = 0.0, h10 = 0.0, h11 = 1.0;
+  {
+    const ulonglong2 pp = *reinterpret_cast<const ulonglong2*>(&rs->p1);
+    const ulonglong2 dd = *reinterpret_cast<const ulonglong2*>(&rs->d1);
+    const u64 k = (u64)(lane * kT);
+    u64 p1 = pp.x + k * dd.x, p2 = pp.y + k * dd.y;
+    __syncwarp();  // every lane has read the block's base phases
+    if (lane == 0)
+      *reinterpret_cast<ulonglong2*>(&rs->p1) =
+          make_ulonglong2(p1 + (u64)kBlockFrames * dd.x, p2 + (u64)kBlockFrames * dd.y);
+    const OscMix o1 = I.m1, o2 = I.m2;
+    const u64 t1 = I.s1.thresh, t2 = I.s2.thresh;
+    const double fq0 = rs->fq0, fq1 = rs->fq1, fq2 = rs->fq2, fw = rs->fw, fdw = rs->fdw;
+    const double cut_a = I.cut_a, cut_b = I.cut_b;
+#pragma unroll
+    for (int j = 0; j < kT; ++j) {
+      p1 += dd.x;
+      p2 += dd.y;
+      const double x = osc_mix_eval<false>(o1, t1, p1, o2, t2, p2);
+      const double w = fma((double)(tl + j), fdw, fw);
+      SecCoef c1, c2;
+      welsh_coef_exact(I, fma(cut_b, fma(w, fma(fq2, w, fq1), fq0), cut_a), c1, c2);
+      park[(2 * j) * pstride] = c2.a1;
+      park[(2 * j + 1) * pstride] = c2.a2;
+      g0[j] = h00; g1[j] = h01;
+      yp[j] = lp_step(c1.b0, c1.a1, c1.a2, x, ps0, ps1);
+      const double t00 = fma(c1.a1, h00, h10), t01 = fma(c1.a1, h01, h11);
+      h10 = c1.a2 * h00; h11 = c1.a2 * h01;
+      h00 = t00; h01 = t01;
+    }
+  }
+  double e0, e1, end0, end1;
+  {
+    Affine2 a;
+    a.m00 = h00; a.m01 = h01; a.m10 = h10; a.m11 = h11; a.v0 = ps0; a.v1 = ps1;
+    const double2 st = *reinterpret_cast<const double2*>(&rs->s[0]);  // only lane 0 uses it
+    affine_scan_states(a, lane, st.x, st.y, e0, e1, end0, end1);
+    __syncwarp();
+    if (lane == 0) *reinterpret_cast<double2*>(&rs->s[0]) = make_double2(end0, end1);
+  }
+  ps0 = 0.0; ps1 = 0.0; h00 = 1.0; h01 = 0.0; h10 = 0.0; h11 = 1.0;
+#pragma unroll
+  for (int j = 0; j < kT; ++j) {
+    const double a1 = park[(2 * j) * pstride], a2 = park[(2 * j + 1) * pstride];
+    const double b0 = fma(-0.25, a1 + a2, 0.25);
+    const double x = fma(g1[j], e1, fma(g0[j], e0, yp[j]));
+    g0[j] = h00; g1[j] = h01;
+    yp[j] = lp_step(b0, a1, a2, x, ps0, ps1);
+    const double t00 = fma(a1, h00, h10), t01 = fma(a1, h01, h11);
+    h10 = a2 * h00; h11 = a2 * h01;
+    h00 = t00; h01 = t01;
+  }
+  {
+    Affine2 a;
+    a.m00 = h00; a.m01 = h01; a.m10 = h10; a.m11 = h11; a.v0 = ps0; a.v1 = ps1;
+    const double2 st = *reinterpret_cast<const double2*>(&rs->s[2]);
+    affine_scan_states(a, lane, st.x, st.y, e0, e1, end0, end1);
+    __syncwarp();
+    if (lane == 0) *reinterpret_cast<double2*>(&rs->s[2]) = make_double2(end0, end1);
+  }
+  double lsd = 0.0, lcd = 0.0;
+  if (LFO_AMP) {
+    const double2 ph = *reinterpret_cast<const double2*>(&rs->ls);
+    const double2 r = I.lane_rot[lane];
+    lsd = fma(ph.x, r.x, ph.y * r.y);
+    lcd = fma(ph.y, r.x, -(ph.x * r.y));
+    __syncwarp();
+    if (lane == 0) {
+      const double2 br = I.block_rot;
+      *reinterpret_cast<double2*>(&rs->ls) = make_double2(fma(lsd, br.x, lcd * br.y), fma(lcd, br.x, -(lsd * br.y)));
+    }
+  }
+  const double aq0 = rs->aq0, aq1 = rs->aq1, aq2 = rs->aq2, aw = rs->aw, adw = rs->adw;
+  const double gl = I.gl, gr = I.gr;
+  double2* row = tile_row + lane * (kT + 1);
+#pragma unroll
+  for (int j = 0; j < kT; ++j) {
+    const double w = fma((double)(tl + j), adw, aw);
+    double amp = fma(w, fma(aq2, w, aq1), aq0);
+    if (LFO_AMP) {
+      const double2 rot = I.lfo_rot[j];
+      amp *= fma(lsd, rot.x, fma(lcd, rot.y, 1.0));
+    }
+    const double m = fma(g1[j], e1, fma(g0[j], e0, yp[j])) * amp;
+    row[j] = make_double2(m * gl, m * gr);
+  }
+  __syncwarp();
+}
+
 // grid = number of sweeping CTAs of this variant; block = 32 * W threads;
 // dynamic smem = W * kTileStride double2 (tiles) + max_voices SweepState.  nframes is a multiple of kBlockFrames.
 template <int W, bool LFO_AMP, bool ZERO_A>
@@ -1827,28 +1928,30 @@ __global__ void __launch_bounds__(32 * W, 2) welsh_sweep_kernel(const WelshInst*
 // once: ncu showed 52 % of the stall samples as instruction-cache misses and another 22 % on the global
 // voice records (profiles/r2_cfg5_before_*).  Here the HOST does the classification, as it already does
 // for grouped CTAs: note frames and envelope stage lengths are integers, so for every sub-chunk of
-// kSoloSub frames it knows whether a voice is idle, rests (cutoff constant: welsh_solo_rest), sweeps
+// kSoloSubDefault frames it knows whether a voice is idle, rests (cutoff constant: welsh_solo_rest), sweeps
 // inside one envelope stage slowly enough for coefficient knots (welsh_sweep_block), or needs the
 // per-block general machinery (note events, stage boundaries, fast sweeps, non-linear oscillators).
-// Items of one class and one sub-chunk are packed W to a job; ONE persistent launch walks the job list
-// in order (ticket counter), so the warps of a CTA always run the same code, voice state lives in shared
-// memory for the length of an item, and a voice's consecutive items are ordered by a per-voice progress
-// counter in global memory (a job only ever waits for jobs earlier in the list, which are already
-// running: no deadlock).
-constexpr int kSoloSub = 8 * kBlockFrames;  // frames per sub-chunk (classification granularity)
-enum { SOLO_REST = 0, SOLO_SWEEP = 1, SOLO_GENERAL = 2 };
+// Items of one class and one sub-chunk are packed W to a job; ONE persistent launch hands the jobs out in
+// list order (ticket counter), one per CTA.  The W warps of a job run the same class body and meet at a
+// CTA barrier after every 256-frame block, so they stay within a block of each other and share their
+// instruction fetches (the instruction cache holds one block body, not several).  Voice state lives in
+// shared memory for the length of an item, and a voice's consecutive items are ordered by a per-voice
+// progress counter in global memory (a job only ever waits for jobs earlier in the list, which running
+// CTAs already hold: no deadlock).
+constexpr int kSoloSubDefault = 8 * kBlockFrames;  // frames per sub-chunk (classification granularity; GB_SOLO_SUB overrides)
+enum { SOLO_REST = 0, SOLO_SWEEP = 1, SOLO_GENERAL = 2, SOLO_EXACT = 3, SOLO_CLASSES = 4 };
 
 struct SoloItem {
   int item;  // index into the WarpItem table
   int need;  // value of progress[voice] this item waits for (= the voice's earlier non-idle items of the chunk)
 };
-struct SoloJob {
+struct SoloJob {  // up to W items of one class and one sub-chunk: one per warp of a CTA, run in step
   int cls;      // SOLO_*
   int t0;       // first frame of the sub-chunk, relative to the chunk start
-  int nframes;  // frames (REST / SWEEP: a multiple of kBlockFrames)
+  int nframes;  // frames (REST / SWEEP / EXACT: a multiple of kBlockFrames)
   int first;    // first SoloItem
   int n;        // items (<= W)
-  int pad;
+  int lockstep; // the job's warps meet at a CTA barrier after every block
 };
 
 struct alignas(16) SoloRestState {
@@ -2085,11 +2188,24 @@ __device__ __forceinline__ void solo_state_head(State* rs, const WelshInst& I, c
   rs->aq0 = 0.5 * q0; rs->aq1 = 0.5 * q1; rs->aq2 = 0.5 * q2; rs->aw = w; rs->adw = dw;
 }
 
+// CTA barrier of a job's block loop: a named barrier (id 1), so that warps without an item can arrive from
+// their own loop (solo_idle_item) while the others arrive from inside a class body.
+template <int W>
+__device__ __forceinline__ void solo_job_bar(bool lockstep) {
+  if (lockstep) asm volatile("barrier.sync 1, %0;" ::"n"(32 * W) : "memory");
+  else __syncwarp();
+}
+template <int W>
+__device__ __noinline__ void solo_idle_item(int nframes) {
+#pragma unroll 1
+  for (int t = 0; t < nframes; t += kBlockFrames) solo_job_bar<W>(true);
+}
+
 // The three class bodies are out-of-line: each gets its own register allocation and the dispatcher stays
 // a few dozen instructions.  They find their warp's tile row, state slot and instrument record in the
 // kernel's dynamic shared memory.
 template <int W>
-__device__ __noinline__ void solo_rest_item(WelshVoice* vp, i64 fs, int nframes, double2* out) {
+__device__ __noinline__ void solo_rest_item(WelshVoice* vp, i64 fs, int nframes, double2* out, bool lockstep) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const WelshInst& I = *SoloSmem<W>::inst(warp);
   double2* tile_row = SoloSmem<W>::tile_row(warp);
@@ -2108,7 +2224,7 @@ __device__ __noinline__ void solo_rest_item(WelshVoice* vp, i64 fs, int nframes,
     if (lfo) welsh_solo_rest_block<true>(rs, I, L, o1, o2, lane, t0, tile_row);
     else welsh_solo_rest_block<false>(rs, I, L, o1, o2, lane, t0, tile_row);
     warp_store_row(tile_row, true, out, fb, fs, fe, lane);
-    __syncwarp();
+    solo_job_bar<W>(lockstep);
   }
   if (lane == 0) {
     vp->s[0] = rs->s[0]; vp->s[1] = rs->s[1]; vp->s[2] = rs->s[2]; vp->s[3] = rs->s[3];
@@ -2117,8 +2233,8 @@ __device__ __noinline__ void solo_rest_item(WelshVoice* vp, i64 fs, int nframes,
   __syncwarp();
 }
 
-template <int W>
-__device__ __noinline__ void solo_sweep_item(WelshVoice* vp, i64 fs, int nframes, double2* out) {
+template <int W, bool EXACT>
+__device__ __noinline__ void solo_sweep_item(WelshVoice* vp, i64 fs, int nframes, double2* out, bool lockstep) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const WelshInst& I = *SoloSmem<W>::inst(warp);
   double2* tile_row = SoloSmem<W>::tile_row(warp);
@@ -2128,22 +2244,28 @@ __device__ __noinline__ void solo_sweep_item(WelshVoice* vp, i64 fs, int nframes
     double q0, q1, q2, w0, dw;
     env_stage_any(I.filt, vp->n_on, vp->n_off, vp->lf_on, vp->lf_off, fs, q0, q1, q2, w0, dw);
     rs->fq0 = q0; rs->fq1 = q1; rs->fq2 = q2; rs->fw = w0; rs->fdw = dw;
+    if (!EXACT) {
 #pragma unroll
-    for (int q = 0; q < 2; ++q) {  // knots at fs - kT and fs: the stage's formula, continued backwards
-      const double w = fma((double)((q - 1) * kT), dw, w0);
-      welsh_knot(I, fma(I.cut_b, fma(w, fma(q2, w, q1), q0), I.cut_a), rs->kn[q]);
+      for (int q = 0; q < 2; ++q) {  // knots at fs - kT and fs: the stage's formula, continued backwards
+        const double w = fma((double)((q - 1) * kT), dw, w0);
+        welsh_knot(I, fma(I.cut_b, fma(w, fma(q2, w, q1), q0), I.cut_a), rs->kn[q]);
+      }
     }
   }
   __syncwarp();
   const bool lfo = I.routing == LFO_AMPLITUDE;
   const i64 fe = fs + nframes;
+  double* park = SoloSmem<W>::park();
   int t0 = 0;
 #pragma unroll 1
   for (i64 fb = fs; fb < fe; fb += kBlockFrames, t0 += kBlockFrames) {
-    if (lfo) welsh_sweep_block<true, false, false>(rs, I, lane, t0, tile_row);
+    if (EXACT) {
+      if (lfo) welsh_exact_block<true>(rs, I, lane, t0, tile_row, park, 32 * W);
+      else welsh_exact_block<false>(rs, I, lane, t0, tile_row, park, 32 * W);
+    } else if (lfo) welsh_sweep_block<true, false, false>(rs, I, lane, t0, tile_row);
     else welsh_sweep_block<false, false, false>(rs, I, lane, t0, tile_row);
     warp_store_row(tile_row, true, out, fb, fs, fe, lane);
-    __syncwarp();
+    solo_job_bar<W>(lockstep);
   }
   if (lane == 0) {
     vp->s[0] = rs->s[0]; vp->s[1] = rs->s[1]; vp->s[2] = rs->s[2]; vp->s[3] = rs->s[3];
@@ -2155,7 +2277,7 @@ __device__ __noinline__ void solo_sweep_item(WelshVoice* vp, i64 fs, int nframes
 template <int W>
 __device__ __noinline__ void solo_general_item(const WelshInst* gI, WelshVoice* voices, int vi,
                                                const VoiceEvent* __restrict__ events, const int* __restrict__ ev_off,
-                                               i64 fs, int nframes, i64 f_end, double2* out) {
+                                               i64 fs, int nframes, i64 f_end, double2* out, bool lockstep) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const WelshInst& I = *SoloSmem<W>::inst(warp);
   double2* tile_row = SoloSmem<W>::tile_row(warp);
@@ -2166,57 +2288,66 @@ __device__ __noinline__ void solo_general_item(const WelshInst* gI, WelshVoice* 
     const bool any = welsh_solo_general_block(I, gI, voices, vi, events, ev_off, fb, f_end, lane, tile_row, park);
     __syncwarp();
     warp_store_row(tile_row, any, out, fb, fs, fe, lane);
-    __syncwarp();
+    solo_job_bar<W>(lockstep);
   }
 }
 
-// One item of a job: wait for the voice's previous item, make the instrument record resident, run the
-// class body, publish the voice's progress.  The wait is executed by all 32 lanes in step (same address,
-// the value taken from lane 0), so the warp never diverges around the spin.
+__device__ __forceinline__ int ld_relaxed_i32(const int* p) {
+  int v;
+  asm volatile("ld.relaxed.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+
+// One item of a job: make the instrument record resident, wait for the voice's previous item, run the class
+// body, publish the voice's progress.  The wait is executed by all 32 lanes in step (same address, the value
+// taken from lane 0), so the warp never diverges around the spin; it polls with relaxed loads and takes
+// one acquire load at the end (an acquire invalidates the SM's L1: once per item, not once per poll).
+// Returns the resident instrument.
 template <int W>
-__device__ __noinline__ void solo_run_item(int j, SoloJob job, const WelshInst* __restrict__ insts,
-                                           WelshVoice* __restrict__ voices, const WarpItem* __restrict__ items,
-                                           const SoloItem* __restrict__ sitems, int* __restrict__ progress,
-                                           int* __restrict__ fault, int* s_inst, const VoiceEvent* __restrict__ events,
-                                           const int* __restrict__ ev_off, i64 f0, i64 f_chunk_end) {
+__device__ __noinline__ int solo_run_item(int j, SoloJob job, int cur_inst, const WelshInst* __restrict__ insts,
+                                          WelshVoice* __restrict__ voices, const WarpItem* __restrict__ items,
+                                          const SoloItem* __restrict__ sitems, int* __restrict__ progress,
+                                          int* __restrict__ fault, const VoiceEvent* __restrict__ events,
+                                          const int* __restrict__ ev_off, i64 f0, i64 f_chunk_end) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const SoloItem si = sitems[job.first + warp];
   const WarpItem item = items[si.item];
+  if (cur_inst != item.inst) {  // instrument record -> shared memory (kept while the warp stays on the instrument)
+    const int4* src = reinterpret_cast<const int4*>(insts + item.inst);
+    int4* dst = reinterpret_cast<int4*>(SoloSmem<W>::inst(warp));
+    for (int i = lane; i < (int)(sizeof(WelshInst) / sizeof(int4)); i += 32) dst[i] = src[i];
+  }
   {
     // watchdog: a dependency that does not resolve within ~0.5 s of SM clocks is a scheduling bug; report it
     // (job, voice, need, have) through `fault` and carry on, so that the host fails loudly instead of hanging
     const int* pp = progress + item.voice;
     const long long t_wait = clock64();
     for (;;) {
-      const int have = __shfl_sync(0xffffffffu, ld_acquire_i32(pp), 0);
+      const int have = __shfl_sync(0xffffffffu, ld_relaxed_i32(pp), 0);
       if (have >= si.need) break;
-      __nanosleep(200);
+      __nanosleep(250);
       const int late = __shfl_sync(0xffffffffu, (int)(clock64() - t_wait > 1000000000ll), 0);
       if (late) {
         if (lane == 0 && atomicCAS(fault, 0, 1) == 0) { fault[1] = j; fault[2] = item.voice; fault[3] = si.need; fault[4] = have; }
         break;
       }
     }
-  }
-  if (s_inst[warp] != item.inst) {  // instrument record -> shared memory (kept while the warp stays on the instrument)
-    const int* src = reinterpret_cast<const int*>(insts + item.inst);
-    int* dst = reinterpret_cast<int*>(SoloSmem<W>::inst(warp));
-    for (int i = lane; i < (int)(sizeof(WelshInst) / sizeof(int)); i += 32) dst[i] = src[i];
-    __syncwarp();
-    if (lane == 0) s_inst[warp] = item.inst;
+    (void)ld_acquire_i32(pp);
   }
   __syncwarp();
   WelshVoice* vp = voices + item.voice;
   const i64 fs = f0 + job.t0;        // first frame of the item
   double2* out = item.out + job.t0;  // the voice's output for this sub-chunk
   if (job.cls == SOLO_REST) {
-    solo_rest_item<W>(vp, fs, job.nframes, out);
+    solo_rest_item<W>(vp, fs, job.nframes, out, job.lockstep != 0);
   } else if (job.cls == SOLO_SWEEP) {
-    solo_sweep_item<W>(vp, fs, job.nframes, out);
+    solo_sweep_item<W, false>(vp, fs, job.nframes, out, job.lockstep != 0);
+  } else if (job.cls == SOLO_EXACT) {
+    solo_sweep_item<W, true>(vp, fs, job.nframes, out, job.lockstep != 0);
   } else {
     const i64 fe = fs + job.nframes;
     solo_general_item<W>(insts + item.inst, voices, item.voice, events, ev_off, fs, job.nframes,
-                         fe < f_chunk_end ? fe : f_chunk_end, out);
+                         fe < f_chunk_end ? fe : f_chunk_end, out, job.lockstep != 0);
   }
   __syncwarp();
   if (lane == 0) {
@@ -2224,6 +2355,7 @@ __device__ __noinline__ void solo_run_item(int j, SoloJob job, const WelshInst* 
     st_release_i32(progress + item.voice, si.need + 1);
   }
   __syncwarp();
+  return item.inst;
 }
 
 // grid = min(jobs, resident CTAs); block = 32 * W threads; dynamic smem = SoloSmem<W>::kBytes.
@@ -2240,11 +2372,10 @@ __global__ void __launch_bounds__(32 * W, 2) welsh_solo_kernel(const WelshInst* 
                                                              const int* __restrict__ ev_off, i64 f0, int chunk_frames) {
   static_assert(sizeof(SoloRestState) <= kSoloStateBytes && sizeof(SweepState) <= kSoloStateBytes, "state slot too small");
   static_assert(sizeof(WelshInst) % 16 == 0, "instrument records are copied and aligned as 16-byte words");
-  __shared__ int s_inst[W];
   __shared__ int s_job;
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  if (lane == 0) s_inst[warp] = -1;
+  const int warp = threadIdx.x >> 5;
   const i64 f_chunk_end = f0 + chunk_frames;
+  int cur_inst = -1;
   for (;;) {
     __syncthreads();  // every warp is done with the previous job (and has read s_job)
     if (threadIdx.x == 0) s_job = atomicAdd(ticket, 1);
@@ -2253,7 +2384,10 @@ __global__ void __launch_bounds__(32 * W, 2) welsh_solo_kernel(const WelshInst* 
     if (j >= n_jobs) break;
     const SoloJob job = jobs[job0 + j];
     if (warp < job.n)
-      solo_run_item<W>(job0 + j, job, insts, voices, items, sitems, progress, fault, s_inst, events, ev_off, f0, f_chunk_end);
+      cur_inst = solo_run_item<W>(job0 + j, job, cur_inst, insts, voices, items, sitems, progress, fault, events, ev_off, f0,
+                                  f_chunk_end);
+    else if (job.lockstep)
+      solo_idle_item<W>(job.nframes);
   }
 }
 

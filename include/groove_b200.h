@@ -38,7 +38,8 @@ extern "C" {
 #endif
 
 #define GB_ABI_VERSION 3 /* 2: gb_link_control, GB_FX_SIGNAL_PASSTHROUGH, gb_stats grew (rest_kernel_*);
-                            3: GB_INST_OSCILLATOR / GB_INST_ENVELOPE, gb_stats grew (solo_*, fm_*, idle_*, *_ctas) */
+                            3: GB_INST_OSCILLATOR / GB_INST_ENVELOPE, gb_stats grew (solo_*, fm_*, idle_*, *_ctas),
+                               gb_set_lookahead */
 
 /* ---- error codes --------------------------------------------------------- */
 enum {
@@ -269,7 +270,17 @@ int gb_render_device(gb_engine* e, size_t frames, size_t* frames_done);
 int gb_last_device_buffer(gb_engine* e, void** device_ptr, size_t* frames);
 /* Copy the most recent device-resident render (<= frames of it) to the host. */
 int gb_read_last(gb_engine* e, double* out_interleaved_lr, size_t frames);
-int64_t gb_position(const gb_engine* e);         /* frames rendered so far */
+int64_t gb_position(const gb_engine* e);         /* frames handed out so far */
+/* Look-ahead for small caller buffers.  Orchestrator::tick is called with 64-frame buffers
+   (orchestrator.rs:1696, audio_panel.rs:69); at that size a GPU call is all launch latency.  With a
+   look-ahead of L frames gb_render_block renders L frames in one go whenever its host buffer runs dry and
+   serves requests shorter than L from that buffer, so the device sees the same large chunks as an offline
+   render.  The caller's side of the contract: every event with a frame below gb_position() + L has been
+   pushed before the call (offline renders and the sequencer-driven Orchestrator know their events ahead;
+   a live MIDI input accepts L frames of latency: later events apply from the next refill on).  The audio is
+   the same as without look-ahead.  0 switches it off; changing it or gb_save_state needs an empty buffer
+   (GB_ESTATE otherwise).  Only gb_render_block looks ahead. */
+int gb_set_lookahead(gb_engine* e, size_t frames);
 
 /* Control link from an audio-rate source: replaces Orchestrator::link_control_by_name
  * (orchestration/src/orchestrator.rs:207-234) for a SignalPassthroughController source.  Controllers do
@@ -305,7 +316,7 @@ typedef struct {
   double solo_kernel_ms;
   uint64_t solo_voice_samples;    /* non-idle (voice, sub-chunk) items x sub-chunk frames */
   uint64_t solo_jobs;
-  uint64_t solo_class_items[3];   /* items by class: resting / sweeping / general */
+  uint64_t solo_class_items[4];   /* items by class: resting / sweeping (knots) / general / sweeping (exact per frame) */
   uint64_t fm_kernel_launches;
   double fm_kernel_ms;
   uint64_t idle_voice_samples;    /* of voice_samples: voices the host knew to be silent (never launched) */

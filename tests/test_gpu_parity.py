@@ -68,6 +68,46 @@ def test_caller_buffer_size_does_not_change_audio(chunk):
     check(out, ref)
 
 
+@pytest.mark.parametrize("lookahead", [64, 4096])
+def test_lookahead_serves_small_buffers_with_the_same_audio(lookahead):
+    """gb_set_lookahead (include/groove_b200.h): the Orchestrator's 64-frame tick buffers (orchestrator.rs:1696)
+    are served from one big device render per `lookahead` frames; audio and position as without it."""
+    for scene in (scenes.scene_welsh_variants, scenes.scene_effects_rack):
+        o = OracleEngine()
+        n = scene(o)
+        ref = o.render(n)
+        g = gpu_engine()
+        scene(g)
+        g.set_lookahead(lookahead)
+        parts, done = [], 0
+        sizes = [64, 64, 17, 64, 3 * lookahead + 5]   # small calls, a ragged one, one larger than the look-ahead
+        i = 0
+        while done < n:
+            k = min(sizes[i % len(sizes)], n - done)
+            parts.append(g.render(k).copy())
+            done += k
+            i += 1
+            assert g.position == done
+            if i == 3:                              # 145 frames handed out: frames rendered ahead are pending
+                with pytest.raises(abi.GrooveError):
+                    g.set_lookahead(0)
+                with pytest.raises(abi.GrooveError):
+                    g.save_state()
+        launches = g.stats().kernel_launches
+        g.close()
+        check(np.concatenate(parts), ref)
+        g2 = gpu_engine()
+        scene(g2)
+        done = 0
+        while done < n:
+            k = min(64, n - done)
+            g2.render(k)
+            done += k
+        if lookahead > 64:
+            assert launches < g2.stats().kernel_launches / 4
+        g2.close()
+
+
 def test_graph_semantics_on_gpu():
     """orchestrator.rs:1444-1668 restated on the GPU engine: silence, sums, gain chains, branch."""
     g = gpu_engine()
@@ -258,7 +298,7 @@ def test_solo_job_list_classes(monkeypatch):
         st = g.stats()
         g.close()
         assert st.solo_kernel_launches > 0
-        assert all(c > 0 for c in st.solo_class_items), list(st.solo_class_items)
+        assert all(c > 0 for c in st.solo_class_items), list(st.solo_class_items)   # rest / sweep / general / exact
         assert st.idle_voice_samples > 0
         check(out, ref)
 

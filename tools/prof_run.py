@@ -36,5 +36,5 @@ for _ in range(a.reps):
         workloads.build_cfg4(e, cfg)
     e.render_device(frames)
     st = e.stats()
-    print(json.dumps({k: getattr(st, k) for k, _ in st._fields_}))
+    print(json.dumps({k: (list(getattr(st, k)) if k == "solo_class_items" else getattr(st, k)) for k, _ in st._fields_}))
     e.close()
