@@ -266,6 +266,7 @@ pub mod ffi {
         pub idle_voice_samples: u64,
         pub rest_ctas: u64,
         pub sweep_ctas: u64,
+        pub fx_batched_nodes: u64,
     }
 
     extern "C" {

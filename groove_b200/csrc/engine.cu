@@ -306,6 +306,9 @@ struct Node {
   bool is_inst = false;
   std::vector<uint32_t> sources;  // uids, patch order
   int order = -1;                 // position in the plan (-1 = unreachable)
+  int level = 0;                  // longest path from a leaf (sources and control-link sources are lower)
+  Node* post = nullptr;           // IIR stage: the memoryless effect fused behind it (writes that node's buffer)
+  bool fused_away = false;        // memoryless effect that runs as some IIR stage's post-op
   double2* buf = nullptr;         // chunk output (max_block frames)
   double2* scratch = nullptr;     // pre-reduction when > kMaxSources inputs / partial sums
   const double2** d_src_table = nullptr;  // device table of source buffers (> kMaxSources inputs)
@@ -419,6 +422,9 @@ struct gb_engine {
   int* d_solo_sync = nullptr;     // [0, kSoloTickets) = job tickets (one per launch), [kSoloTickets + voice] = per-voice progress counter
   int solo_sub = kSoloSubDefault; // GB_SOLO_SUB: frames per sub-chunk (a multiple of kBlockFrames)
   int solo_lockstep = 1;          // GB_SOLO_LOCKSTEP: bit 0 = rest / sweep / exact jobs run their blocks in lockstep, bit 1 = general jobs too
+  bool fuse_post_ops = true;      // GB_FX_FUSE
+  bool batch_fx = true;           // GB_FX_BATCH: independent effects of one kind and level share a launch
+  DevBuf<FxDesc> fxdescs;
   bool solo_waves = false;        // GB_SOLO_WAVES=1: one launch per sub-chunk (stream order instead of the progress counters)
   int* d_solo_fault = nullptr;    // {flag, job, voice, need, have}: set by the kernel's dependency watchdog
   bool solo_ran = false;          // a job-list launch happened since the fault words were last checked
@@ -838,9 +844,24 @@ void seg_values(gb_engine* e, const Node* n, double* v) {
   }
 }
 
+// Effects that can share a launch with other nodes of their level: 1 = memoryless (pointwise_batch_kernel),
+// 2 = 24 dB low-pass, 3 = the biquad family; 0 = launched on their own.
+int batch_class(const Node* n) {
+  if (n->is_inst) return 0;
+  switch (n->kind) {
+    case GB_FX_GAIN: case GB_FX_LIMITER: case GB_FX_BITCRUSHER: case GB_FX_COMPRESSOR: return 1;
+    case GB_FX_LOW_PASS_24DB: return 2;
+    default: return n->kind >= GB_FX_LOW_PASS_12DB && n->kind <= GB_FX_HIGH_SHELF_12DB ? 3 : 0;
+  }
+}
+int pointwise_op(const Node* n) {
+  return n->kind == GB_FX_GAIN ? OP_GAIN : n->kind == GB_FX_LIMITER ? OP_LIMITER
+       : n->kind == GB_FX_BITCRUSHER ? OP_BITCRUSHER : OP_COMPRESSOR;
+}
+
 // Run one effect node over the whole chunk; `segs`/`nseg` = its parameter segment table (device).
 int run_effect(gb_engine* e, Node* n, const SourceList& src, int frames, const SegParam* segs, int nseg,
-               int64_t chunk_pos) {
+               int64_t chunk_pos, const PostOp* post = nullptr) {
   switch (n->kind) {
     case GB_FX_MIXER: case GB_FX_SIGNAL_PASSTHROUGH: {
       Launch l(e, false);
@@ -854,7 +875,14 @@ int run_effect(gb_engine* e, Node* n, const SourceList& src, int frames, const S
     } break;
     case GB_FX_LOW_PASS_24DB: {
       Launch l(e, false);
-      lp24_kernel<<<1, 32 * kFxWarps, 0, e->stream>>>(src, n->buf, frames, segs, nseg, n->d_lp);
+      if (post) {
+        FxDesc d;
+        memset(&d, 0, sizeof d);
+        d.src = src; d.out = n->post->buf; d.segs = segs; d.nseg = nseg; d.state = n->d_lp; d.post = *post;
+        lp24_single_kernel<<<1, 32 * kFxWarps, 0, e->stream>>>(d, frames);
+      } else {
+        lp24_kernel<<<1, 32 * kFxWarps, 0, e->stream>>>(src, n->buf, frames, segs, nseg, n->d_lp);
+      }
     } break;
     case GB_FX_CHORUS: {
       Launch l(e, false);
@@ -884,7 +912,14 @@ int run_effect(gb_engine* e, Node* n, const SourceList& src, int frames, const S
     default:
       if (n->kind >= GB_FX_LOW_PASS_12DB && n->kind <= GB_FX_HIGH_SHELF_12DB) {
         Launch l(e, false);
-        biquad_df1_kernel<<<1, 32 * kFxWarps, 0, e->stream>>>(src, n->buf, frames, segs, nseg, n->d_bq);
+        if (post) {
+          FxDesc d;
+          memset(&d, 0, sizeof d);
+          d.src = src; d.out = n->post->buf; d.segs = segs; d.nseg = nseg; d.state = n->d_bq; d.post = *post;
+          biquad_single_kernel<<<1, 32 * kFxWarps, 0, e->stream>>>(d, frames);
+        } else {
+          biquad_df1_kernel<<<1, 32 * kFxWarps, 0, e->stream>>>(src, n->buf, frames, segs, nseg, n->d_bq);
+        }
       }
       break;
   }
@@ -924,6 +959,8 @@ int gb_create(const gb_config* cfg, gb_engine** out) {
   if (const char* v = getenv("GB_MIN_CUT_VOICES")) e->opt.min_cut_voices = std::max(1, atoi(v));
   if (const char* v = getenv("GB_SOLO_MIN")) e->min_solo_items = atoi(v);
   if (const char* v = getenv("GB_SOLO_WAVES")) e->solo_waves = atoi(v) != 0;
+  if (const char* v = getenv("GB_FX_FUSE")) e->fuse_post_ops = atoi(v) != 0;
+  if (const char* v = getenv("GB_FX_BATCH")) e->batch_fx = atoi(v) != 0;
   if (const char* v = getenv("GB_SOLO_LOCKSTEP")) e->solo_lockstep = atoi(v);
   if (const char* v = getenv("GB_SOLO_SUB")) e->solo_sub = std::max(1, atoi(v) / kBlockFrames) * kBlockFrames;
   if (const char* v = getenv("GB_FUSED_SUMS")) e->fused_sums_enabled = atoi(v) != 0;
@@ -1262,6 +1299,22 @@ int gb_finalize(gb_engine* e) {
       st.push_back({c, 0});
     }
   }
+  // Levels: a node's sources (and control-link sources) sit on lower levels, so level order is a valid
+  // execution order in which independent nodes of one kind are neighbours — render_chunk turns such runs
+  // into ONE batched launch (parallel chains of a song, a batch of songs).
+  for (Node* n : e->plan) {
+    n->level = 0;
+    n->post = nullptr;
+    n->fused_away = false;
+    for (uint32_t c : children[n->uid]) {
+      Node* cn = find(e, c);
+      if (cn && cn->order >= 0) n->level = std::max(n->level, cn->level + 1);
+    }
+  }
+  std::stable_sort(e->plan.begin(), e->plan.end(), [](const Node* a, const Node* b) {
+    return a->level != b->level ? a->level < b->level : (a->level > 0 && batch_class(a) < batch_class(b));
+  });
+  for (size_t i = 0; i < e->plan.size(); ++i) e->plan[i]->order = (int)i;
   const size_t mb = e->max_block;
   int wv = 0, fv = 0;
   for (Node* n : e->plan) {
@@ -1435,6 +1488,19 @@ int gb_finalize(gb_engine* e) {
           Node* sn = find(e, su);
           if (sn && sn->order >= 0) sn->consumers++;
         }
+    // A memoryless effect whose only source is an IIR stage that nothing else reads runs as that stage's
+    // post-op: one read and one write per frame for the pair (GB_FX_FUSE=0 keeps them apart).
+    if (e->fuse_post_ops)
+      for (Node* n : e->plan) {
+        if (batch_class(n) != 1 || n->sources.size() != 1) continue;
+        Node* a = find(e, n->sources[0]);
+        if (!a || a->order < 0 || batch_class(a) < 2 || a->consumers != 1 || a->post) continue;
+        bool linked = false;
+        for (auto& l : e->links) linked = linked || l.dst == n->uid || l.src == a->uid || l.dst == a->uid;
+        if (linked) continue;
+        a->post = n;
+        n->fused_away = true;
+      }
     for (Node* n : e->plan) {
       if (n->is_inst || (int)n->sources.size() <= kMaxSources) continue;
       std::vector<const double2*> ptrs, fused;
@@ -1495,7 +1561,7 @@ int gb_finalize(gb_engine* e) {
     // synchronisation and fresh pinned host mirrors
     bool ok = e->wev_off.reserve((size_t)e->n_wvoice + 1) && e->fev_off.reserve((size_t)e->n_fvoice + 1) &&
               e->wev.reserve(4 * (size_t)e->n_wvoice + 64) && e->fev.reserve(4 * (size_t)e->n_fvoice + 64) &&
-              e->widx.reserve((size_t)e->n_wwork_grouped + 1);
+              e->widx.reserve((size_t)e->n_wwork_grouped + 1) && e->fxdescs.reserve(e->plan.size() + 1);
     if (ok && e->solo_mega) {
       const size_t kmax = (size_t)cdiv((int)e->max_block, e->solo_sub), n = e->witem_node.size();
       ok = e->sitems.reserve(n * kmax + 1) && e->sjobs.reserve(n * kmax / kVoiceWarps + kmax * SOLO_CLASSES + 1) &&
@@ -1557,7 +1623,7 @@ int render_chunk(gb_engine* e, int frames, size_t n_ev) {
   const int slot = (int)(e->chunk_seq % kStageSlots);
   if (e->chunk_seq >= (uint64_t)kStageSlots) CUDA_TRY(e, cudaEventSynchronize(e->stage_done[slot]));
   e->widx.use_slot(slot); e->wev.use_slot(slot); e->fev.use_slot(slot); e->wev_off.use_slot(slot);
-  e->fev_off.use_slot(slot); e->plays.use_slot(slot); e->segs.use_slot(slot);
+  e->fev_off.use_slot(slot); e->plays.use_slot(slot); e->segs.use_slot(slot); e->fxdescs.use_slot(slot);
   // solo Welsh voices: note frames as they stand BEFORE this chunk's events (the sub-chunk classification
   // below replays the chunk's events on top of them)
   struct SoloPre { int64_t n_on, n_off; };
@@ -2217,11 +2283,87 @@ int render_chunk(gb_engine* e, int frames, size_t n_ev) {
     dim3 grid(cdiv(frames, 256), n_red);
     reduce_partials_kernel<<<grid, 256, 0, e->stream>>>(e->fused_sums ? e->partials_nf.d : e->partials.d, frames);
   }
-  // ---- 5. plan walk: toy sources, instrument DCA automation, effects (one launch per node) ----
-  for (Node* n : e->plan) {
+  // ---- 5. plan walk: toy sources, instrument DCA automation, effects ----
+  // One launch per node, except runs of independent effects of one batch class on one level: those share
+  // a launch (batch_class), and a memoryless effect fused behind an IIR stage has no launch of its own.
+  auto seg_table = [&](Node* n, const SegParam** segs, int* nseg) {
     auto sr = seg_of.find(n);
-    const SegParam* segs = sr != seg_of.end() ? e->segs.d + sr->second.off : nullptr;
-    const int nseg = sr != seg_of.end() ? sr->second.n : 0;
+    *segs = sr != seg_of.end() ? e->segs.d + sr->second.off : nullptr;
+    *nseg = sr != seg_of.end() ? sr->second.n : 0;
+  };
+  auto batchable = [&](Node* n) {
+    if (!e->batch_fx || batch_class(n) == 0 || n->fused_away) return false;
+    int live = 0;
+    for (uint32_t s : n->sources) {
+      Node* sn = find(e, s);
+      if (sn && sn->order >= 0 && sn->buf) ++live;
+    }
+    if (live > kMaxSources) return false;
+    for (auto& l : e->links)
+      if (l.dst == n->uid && l.d_table) return false;
+    return true;
+  };
+  auto post_of = [&](Node* n) {
+    PostOp po;
+    po.segs = nullptr; po.nseg = 0; po.op = -1;
+    if (n->post) {
+      seg_table(n->post, &po.segs, &po.nseg);
+      po.op = pointwise_op(n->post);
+    }
+    return po;
+  };
+  size_t fx_used = 0;
+  for (size_t pi = 0; pi < e->plan.size(); ++pi) {
+    Node* n = e->plan[pi];
+    if (n->fused_away) continue;  // rendered by its source's launch
+    if (batchable(n)) {
+      size_t pj = pi + 1;
+      while (pj < e->plan.size() && e->plan[pj]->level == n->level && batch_class(e->plan[pj]) == batch_class(n) &&
+             (e->plan[pj]->fused_away || batchable(e->plan[pj])))
+        ++pj;
+      size_t cnt = 0;
+      for (size_t q = pi; q < pj; ++q) cnt += e->plan[q]->fused_away ? 0 : 1;
+      if (cnt >= 2) {
+        if (!e->fxdescs.reserve(fx_used + cnt)) return fail(e, GB_ENOMEM, "out of memory");
+        FxDesc* d0 = e->fxdescs.h + fx_used;
+        size_t k = 0;
+        for (size_t q = pi; q < pj; ++q) {
+          Node* m = e->plan[q];
+          if (m->fused_away) continue;
+          FxDesc& d = d0[k++];
+          memset(&d, 0, sizeof d);
+          bool summed = false;
+          int rc = gather_sources(e, m, frames, &d.src, &summed);
+          if (rc) return rc;
+          d.out = m->post ? m->post->buf : m->buf;
+          seg_table(m, &d.segs, &d.nseg);
+          d.state = m->d_lp ? (void*)m->d_lp : (void*)m->d_bq;
+          d.post = post_of(m);
+          d.op = batch_class(m) == 1 ? pointwise_op(m) : 0;
+        }
+        CUDA_TRY(e, cudaMemcpyAsync(e->fxdescs.d + fx_used, d0, cnt * sizeof(FxDesc), cudaMemcpyHostToDevice, e->stream));
+        e->stats.h2d_bytes += cnt * sizeof(FxDesc);
+        {
+          Launch l(e, false);
+          const FxDesc* dd = e->fxdescs.d + fx_used;
+          if (batch_class(n) == 1) {
+            dim3 grid(cdiv(frames, 256), (unsigned)cnt);
+            pointwise_batch_kernel<<<grid, 256, 0, e->stream>>>(dd, frames);
+          } else if (batch_class(n) == 2) {
+            lp24_batch_kernel<<<(int)cnt, 32 * kFxWarps, 0, e->stream>>>(dd, frames);
+          } else {
+            biquad_batch_kernel<<<(int)cnt, 32 * kFxWarps, 0, e->stream>>>(dd, frames);
+          }
+        }
+        fx_used += cnt;
+        e->stats.fx_batched_nodes += cnt;
+        pi = pj - 1;
+        continue;
+      }
+    }
+    const SegParam* segs;
+    int nseg;
+    seg_table(n, &segs, &nseg);
     if (n->is_inst) {
       if (n->kind == GB_INST_TOY_SOURCE) {
         Launch l(e, false);
@@ -2291,7 +2433,8 @@ int render_chunk(gb_engine* e, int frames, size_t n_ev) {
       use_segs = l.d_table;
       use_nseg = std::max(ns, 1);
     }
-    rc = run_effect(e, n, src, frames, use_segs, use_nseg, f0);
+    const PostOp po = post_of(n);
+    rc = run_effect(e, n, src, frames, use_segs, use_nseg, f0, n->post ? &po : nullptr);
     if (rc) return rc;
     if (n->kind == GB_FX_CHORUS && n->delay_frames > 0) {
       Launch l(e, false);

@@ -273,24 +273,39 @@ __device__ __forceinline__ void cta_entry_state(const Affine2& warp_total, Affin
   __syncthreads();
 }
 
-// One launch = one biquad effect over the whole chunk; coefficients (v[0..4] = b0,b1,b2,a1,a2) follow
-// the segment table frame by frame.  One CTA of kFxWarps warps; both channels per thread.
-__global__ void __launch_bounds__(32 * kFxWarps) biquad_df1_kernel(SourceList src, double2* __restrict__ out,
-                                                                    int frames, const SegParam* __restrict__ segs,
-                                                                    int nseg, BiquadState* __restrict__ state) {
+// A memoryless effect (gain, limiter, bitcrusher, compressor) fused behind an IIR stage: applied to the
+// stage's output on its way to memory, with its own parameter segment table.  op < 0: none.
+struct PostOp {
+  const SegParam* segs;
+  int nseg;
+  int op;
+};
+__device__ __forceinline__ double2 post_apply(const PostOp& po, double2 v, int t) {
+  if (po.op < 0) return v;
+  const SegParam& sp = po.segs[po.nseg > 1 ? seg_find(po.segs, po.nseg, t) : 0];
+  return make_double2(op_apply(po.op, v.x, sp.v[0], sp.v[1]), op_apply(po.op, v.y, sp.v[0], sp.v[1]));
+}
+
+// One CTA = one biquad effect over the whole chunk; coefficients (v[0..4] = b0,b1,b2,a1,a2) follow the
+// segment table frame by frame.  kFxWarps warps; both channels per thread.  Input and output go through
+// shared memory, so global loads and stores are coalesced 16-byte accesses.
+__device__ __forceinline__ void biquad_df1_body(const SourceList& src, double2* __restrict__ out, int frames,
+                                                const SegParam* __restrict__ segs, int nseg,
+                                                BiquadState* __restrict__ state, const PostOp& po) {
   __shared__ Affine2 sh[2][kFxWarps];
-  __shared__ double2 sx[kFxRound + 2];
+  __shared__ double2 sx[kFxRound + 2 + (kFxRound + 2) / kFxT + 1];  // slot P(k) = k + k / kFxT: conflict-free per-lane runs
+  auto P = [](int k) { return k + k / kFxT; };
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   BiquadState st = *state;
   for (int r0 = 0; r0 < frames; r0 += kFxRound) {
     // stage the round's input (coalesced), with the two history frames in front
     for (int i = threadIdx.x; i < kFxRound; i += blockDim.x) {
       int t = r0 + i;
-      sx[i + 2] = t < frames ? sum_sources(src, t) : make_double2(0.0, 0.0);
+      sx[P(i + 2)] = t < frames ? sum_sources(src, t) : make_double2(0.0, 0.0);
     }
     if (threadIdx.x == 0) {
-      sx[0] = make_double2(st.x2[0], st.x2[1]);
-      sx[1] = make_double2(st.x1[0], st.x1[1]);
+      sx[P(0)] = make_double2(st.x2[0], st.x2[1]);
+      sx[P(1)] = make_double2(st.x1[0], st.x1[1]);
     }
     __syncthreads();
     const int base = (warp * 32 + lane) * kFxT;  // round-relative first frame of this lane
@@ -309,7 +324,7 @@ __global__ void __launch_bounds__(32 * kFxWarps) biquad_df1_kernel(SourceList sr
           next_t0 = k + 1 < nseg ? segs[k + 1].t0 : 0x7fffffff;
           b0 = segs[k].v[0]; b1 = segs[k].v[1]; b2 = segs[k].v[2]; a1 = segs[k].v[3]; a2 = segs[k].v[4];
         }
-        double2 x0 = sx[base + j + 2], xm1 = sx[base + j + 1], xm2 = sx[base + j];
+        double2 x0 = sx[P(base + j + 2)], xm1 = sx[P(base + j + 1)], xm2 = sx[P(base + j)];
         double v[2] = {b0 * x0.x + b1 * xm1.x + b2 * xm2.x, b0 * x0.y + b1 * xm1.y + b2 * xm2.y};
 #pragma unroll
         for (int ch = 0; ch < 2; ++ch) {
@@ -339,17 +354,18 @@ __global__ void __launch_bounds__(32 * kFxWarps) biquad_df1_kernel(SourceList sr
       affine_lane_entry(inc, lane, w0, w1, e0[ch], e1[ch], d0, d1);
       endv0[ch] = ce0; endv1[ch] = ce1;
     }
-#pragma unroll
-    for (int j = 0; j < kFxT; ++j) {
-      if (j < nvalid) {
-        double l = yp[0][j] + g0[j] * e0[0] + g1[j] * e1[0];
-        double r = yp[1][j] + g0[j] * e0[1] + g1[j] * e1[1];
-        out[r0 + base + j] = make_double2(l, r);
-      }
-    }
     // carry state to the next round
     int last = min(kFxRound, frames - r0);  // frames in this round
-    double2 xl1 = sx[last + 1], xl2 = sx[last];
+    double2 xl1 = sx[P(last + 1)], xl2 = sx[P(last)];
+    __syncthreads();  // every thread has read its inputs: the staging buffer now takes the round's output
+#pragma unroll
+    for (int j = 0; j < kFxT; ++j) {
+      double l = yp[0][j] + g0[j] * e0[0] + g1[j] * e1[0];
+      double r = yp[1][j] + g0[j] * e0[1] + g1[j] * e1[1];
+      sx[P(base + j + 2)] = make_double2(l, r);
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < last; i += blockDim.x) out[r0 + i] = post_apply(po, sx[P(i + 2)], r0 + i);
     __syncthreads();
     st.x1[0] = xl1.x; st.x1[1] = xl1.y;
     st.x2[0] = xl2.x; st.x2[1] = xl2.y;
@@ -358,25 +374,40 @@ __global__ void __launch_bounds__(32 * kFxWarps) biquad_df1_kernel(SourceList sr
   }
   if (threadIdx.x == 0) *state = st;
 }
+__global__ void __launch_bounds__(32 * kFxWarps) biquad_df1_kernel(SourceList src, double2* __restrict__ out,
+                                                                    int frames, const SegParam* __restrict__ segs,
+                                                                    int nseg, BiquadState* __restrict__ state) {
+  PostOp none;
+  none.segs = nullptr; none.nseg = 0; none.op = -1;
+  biquad_df1_body(src, out, frames, segs, nseg, state, none);
+}
 
 // 24 dB low-pass effect: two transposed-DF2 sections; coefficients (v[0..5] = b0,a1,a2 of section 1
 // then of section 2) follow the segment table frame by frame.
 struct Lp24State {
   double s[2][4];
 };
-__global__ void __launch_bounds__(32 * kFxWarps) lp24_kernel(SourceList src, double2* __restrict__ out, int frames,
-                                                              const SegParam* __restrict__ segs, int nseg,
-                                                              Lp24State* __restrict__ state) {
+__device__ __forceinline__ void lp24_body(const SourceList& src, double2* __restrict__ out, int frames,
+                                          const SegParam* __restrict__ segs, int nseg, Lp24State* __restrict__ state,
+                                          const PostOp& po) {
   __shared__ Affine2 sh[2][kFxWarps];
+  __shared__ double2 sx[kFxRound + kFxRound / kFxT];  // a lane's kFxT frames sit kFxT + 1 slots from its neighbour's
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   Lp24State st = *state;
   for (int r0 = 0; r0 < frames; r0 += kFxRound) {
-    const int base = r0 + (warp * 32 + lane) * kFxT;
+    // stage the round's input: coalesced global loads, then each lane takes its kFxT consecutive frames
+    for (int i = threadIdx.x; i < kFxRound; i += blockDim.x) {
+      const int t = r0 + i;
+      sx[i + i / kFxT] = t < frames ? sum_sources(src, t) : make_double2(0.0, 0.0);
+    }
+    __syncthreads();
+    const int lbase = (warp * 32 + lane) * kFxT;
+    const int base = r0 + lbase;
     const int nvalid = frames - base;
     double sig[2][kFxT];
 #pragma unroll
     for (int j = 0; j < kFxT; ++j) {
-      double2 v = j < nvalid ? sum_sources(src, base + j) : make_double2(0.0, 0.0);
+      const double2 v = sx[lbase + lbase / kFxT + j];
       sig[0][j] = v.x; sig[1][j] = v.y;
     }
     const int k0 = nvalid > 0 ? seg_find(segs, nseg, base) : 0;
@@ -425,12 +456,65 @@ __global__ void __launch_bounds__(32 * kFxWarps) lp24_kernel(SourceList src, dou
         for (int j = 0; j < kFxT; ++j) sig[ch][j] += g0[j] * e0 + g1[j] * e1;
       }
     }
+    // (the barriers of cta_entry_state lie between the last input read and this write)
 #pragma unroll
-    for (int j = 0; j < kFxT; ++j)
-      if (j < nvalid) out[base + j] = make_double2(sig[0][j], sig[1][j]);
+    for (int j = 0; j < kFxT; ++j) sx[lbase + lbase / kFxT + j] = make_double2(sig[0][j], sig[1][j]);
+    __syncthreads();
+    const int last = min(kFxRound, frames - r0);
+    for (int i = threadIdx.x; i < last; i += blockDim.x) out[r0 + i] = post_apply(po, sx[i + i / kFxT], r0 + i);
+    __syncthreads();
   }
   if (threadIdx.x == 0) *state = st;
 }
+__global__ void __launch_bounds__(32 * kFxWarps) lp24_kernel(SourceList src, double2* __restrict__ out, int frames,
+                                                              const SegParam* __restrict__ segs, int nseg,
+                                                              Lp24State* __restrict__ state) {
+  PostOp none;
+  none.segs = nullptr; none.nseg = 0; none.op = -1;
+  lp24_body(src, out, frames, segs, nseg, state, none);
+}
+
+// ---- batched launches: independent effect nodes of one kind and one graph level in ONE launch ----------
+// (a batch of songs, or the parallel chains of one song: config 1's chain copied 1024 times is 1024 CTAs
+// here instead of 1024 one-CTA launches).  blockIdx.x (IIR stages) / blockIdx.y (pointwise) picks the node.
+struct FxDesc {
+  SourceList src;
+  double2* out;
+  const SegParam* segs;
+  void* state;     // Lp24State / BiquadState of an IIR stage
+  PostOp post;     // IIR stages: a memoryless effect fused behind the stage
+  int nseg;
+  int op;          // pointwise nodes: OP_*
+};
+__global__ void __launch_bounds__(32 * kFxWarps) lp24_batch_kernel(const FxDesc* __restrict__ descs, int frames) {
+  const FxDesc& d = descs[blockIdx.x];
+  lp24_body(d.src, d.out, frames, d.segs, d.nseg, static_cast<Lp24State*>(d.state), d.post);
+}
+__global__ void __launch_bounds__(32 * kFxWarps) biquad_batch_kernel(const FxDesc* __restrict__ descs, int frames) {
+  const FxDesc& d = descs[blockIdx.x];
+  biquad_df1_body(d.src, d.out, frames, d.segs, d.nseg, static_cast<BiquadState*>(d.state), d.post);
+}
+// a single IIR stage with a fused post-op (descriptor by value)
+__global__ void __launch_bounds__(32 * kFxWarps) lp24_single_kernel(FxDesc d, int frames) {
+  lp24_body(d.src, d.out, frames, d.segs, d.nseg, static_cast<Lp24State*>(d.state), d.post);
+}
+__global__ void __launch_bounds__(32 * kFxWarps) biquad_single_kernel(FxDesc d, int frames) {
+  biquad_df1_body(d.src, d.out, frames, d.segs, d.nseg, static_cast<BiquadState*>(d.state), d.post);
+}
+__global__ void __launch_bounds__(256) pointwise_batch_kernel(const FxDesc* __restrict__ descs, int frames) {
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= frames) return;
+  const FxDesc& d = descs[blockIdx.y];
+  const double2 v = sum_sources(d.src, t);
+  if (d.op == OP_SUM) {
+    d.out[t] = v;
+    return;
+  }
+  const SegParam& sp = d.segs[d.nseg > 1 ? seg_find(d.segs, d.nseg, t) : 0];
+  d.out[t] = make_double2(op_apply(d.op, v.x, sp.v[0], sp.v[1]), op_apply(d.op, v.y, sp.v[0], sp.v[1]));
+}
+
+
 
 // ------------------------------------------------------------- delay-line effects ---
 // `hist` holds the last `len` input frames before the chunk: hist[len-1] = x[chunk_start-1].

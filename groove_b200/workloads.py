@@ -228,3 +228,31 @@ def build_cfg5(r: abi.Renderer, n_variants: int, first: int = 0, frames: int = C
         return frames, uids, ev
     r.push_events(ev)
     return frames, uids
+
+
+# ---------------------------------------------------------------------------------------------------
+# Stream-effect batch: N copies of BASELINE config 1's effect chain (a source through a 24 dB low-pass whose
+# cutoff a control trip moves, projects/demos/effects/drums-filtered-24db.json) plus a gain, each chain its
+# own patch-cable path into the main mixer.  The sources are bare oscillator devices (resident buffers after
+# one cheap launch each); what the leg measures is the effect side: HBM-bound, 16 B read + 16 B written per
+# frame per chain.
+def build_fx_chains(r: abi.Renderer, n_chains: int, frames: int = 1 << 16, step: int = 4096) -> np.ndarray:
+    """Returns the (frame-sorted) cutoff automation events; the graph is finalized."""
+    shapes = (abi.WAVE_SAWTOOTH, abi.WAVE_SQUARE, abi.WAVE_TRIANGLE, abi.WAVE_PULSE_WIDTH)
+    filters = []
+    for i in range(n_chains):
+        o = r.add_instrument(abi.INST_OSCILLATOR,
+                             abi.OscillatorSourceParams(abi.osc(shapes[i % 4], 0.25, frequency=55.0 * (1 + i % 16))))
+        f = r.add_effect(abi.FX_LOW_PASS_24DB, abi.Lowpass24Params(300.0 + 7.0 * (i % 256), 0.8))
+        g = r.add_effect(abi.FX_GAIN, abi.GainParams(1.0 / n_chains))
+        r.patch_chain([o, f, g, abi.MAIN_MIXER])
+        filters.append(f)
+    r.finalize()
+    points = list(range(step, frames, step))
+    ev = np.zeros(len(points) * n_chains, dtype=abi.EVENT_DTYPE)
+    k = 0
+    for j, t in enumerate(points):          # the trip: cutoff rising, one control step per `step` frames
+        for i, f in enumerate(filters):
+            ev[k] = (t, f, abi.EV_CONTROL, 0, 0, 0.3 + 0.6 * (j + 1) / (len(points) + 1))
+            k += 1
+    return ev

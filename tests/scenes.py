@@ -353,8 +353,56 @@ def scene_bare_sources(r: abi.Renderer) -> int:
     return 45000
 
 
+def scene_fx_chains(r: abi.Renderer) -> int:
+    """Parallel effect chains (the shape of a batch of songs, or of config 1's chain copied): each an IIR
+    stage followed by a memoryless effect, all automated.  On the GPU the IIR stages of one kind share a launch
+    and the memoryless effect runs as the stage's post-op; chain 6's filter feeds TWO consumers (no fusion),
+    chain 7's gain has a second source (no fusion either)."""
+    def osc_dev(wave, hz, pw=0.5):
+        return r.add_instrument(abi.INST_OSCILLATOR, abi.OscillatorSourceParams(abi.osc(wave, pw, frequency=hz)))
+    chains = [
+        (abi.WAVE_SAWTOOTH, 110.0, (abi.FX_LOW_PASS_24DB, abi.Lowpass24Params(700.0, 0.8)), (abi.FX_GAIN, abi.GainParams(0.4))),
+        (abi.WAVE_SQUARE, 220.0, (abi.FX_LOW_PASS_24DB, abi.Lowpass24Params(1500.0, 2.5)), (abi.FX_LIMITER, abi.LimiterParams(0.0, 0.3))),
+        (abi.WAVE_NOISE, 0.0, (abi.FX_LOW_PASS_24DB, abi.Lowpass24Params(300.0, 1.2)), (abi.FX_COMPRESSOR, abi.CompressorParams(0.1, 0.5, 0, 0))),
+        (abi.WAVE_TRIANGLE, 330.0, (abi.FX_BAND_PASS_12DB, abi.BiquadParams(900.0, 1.5)), (abi.FX_BITCRUSHER, abi.BitcrusherParams(9))),
+        (abi.WAVE_PULSE_WIDTH, 82.0, (abi.FX_HIGH_PASS_12DB, abi.BiquadParams(400.0, 3.0)), (abi.FX_GAIN, abi.GainParams(0.3))),
+        (abi.WAVE_SINE, 660.0, (abi.FX_PEAKING_EQ_12DB, abi.BiquadParams(660.0, 9.0)), (abi.FX_GAIN, abi.GainParams(0.2))),
+    ]
+    stages, posts = [], []
+    for wave, hz, (fk, fp), (pk, pp) in chains:
+        o = osc_dev(wave, hz, 0.3)
+        f = r.add_effect(fk, fp)
+        g = r.add_effect(pk, pp)
+        r.patch_chain([o, f, g, abi.MAIN_MIXER])
+        stages.append(f)
+        posts.append(g)
+    o6 = osc_dev(abi.WAVE_SAWTOOTH, 55.0)
+    f6 = r.add_effect(abi.FX_LOW_PASS_24DB, abi.Lowpass24Params(2000.0, 1.0))
+    g6a = r.add_effect(abi.FX_GAIN, abi.GainParams(0.1))
+    g6b = r.add_effect(abi.FX_LIMITER, abi.LimiterParams(0.0, 0.05))
+    r.patch_chain([o6, f6, g6a, abi.MAIN_MIXER])
+    r.patch_chain([f6, g6b, abi.MAIN_MIXER])
+    o7 = osc_dev(abi.WAVE_SQUARE, 98.0)
+    f7 = r.add_effect(abi.FX_LOW_SHELF_12DB, abi.BiquadParams(200.0, 5.0))
+    g7 = r.add_effect(abi.FX_GAIN, abi.GainParams(0.15))
+    r.patch_chain([o7, f7, g7, abi.MAIN_MIXER])
+    r.patch(o6, g7)
+    r.finalize()
+    ev = []
+    for k, f in enumerate(range(100, 20000, 1777)):
+        ev.append((f, stages[0], abi.EV_SET_PARAM, 0, 0, 500.0 + 150.0 * k))     # lpf24 cutoff (Hz)
+        ev.append((f + 64, stages[1], abi.EV_CONTROL, 0, 0, 0.2 + 0.05 * k))     # lpf24 cutoff (control value)
+        ev.append((f + 128, stages[3], abi.EV_CONTROL, 0, 0, 0.3 + 0.03 * k))    # band-pass cutoff
+        ev.append((f + 200, posts[0], abi.EV_CONTROL, 0, 0, 0.9 - 0.06 * k))     # fused gain's ceiling
+        ev.append((f + 300, posts[3], abi.EV_CONTROL, 0, 0, (4 + k % 9) / 16.0))  # fused bitcrusher's bits
+        ev.append((f + 400, g6b, abi.EV_CONTROL, 1, 0, 0.02 + 0.01 * k))         # unfused limiter's max
+    r.push_events(sorted(ev, key=lambda e: e[0]))
+    return 21000
+
+
 ALL_SCENES = {
     "bare_sources": scene_bare_sources,
+    "fx_chains": scene_fx_chains,
     "cello_chord": scene_cello_chord,
     "cello_held_chord": scene_cello_held_chord,
     "welsh_variants": scene_welsh_variants,

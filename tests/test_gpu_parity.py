@@ -108,6 +108,28 @@ def test_lookahead_serves_small_buffers_with_the_same_audio(lookahead):
         g2.close()
 
 
+def test_effect_batching_and_fusion(monkeypatch):
+    """Independent effects of one kind and graph level share a launch, and a memoryless effect behind an IIR
+    stage runs as its post-op: same audio as one launch per node (GB_FX_BATCH=0 GB_FX_FUSE=0), fewer launches."""
+    out, ref = both(scenes.scene_fx_chains, max_block=4096)
+    check(out, ref)
+    def run():
+        g = gpu_engine(max_block=4096)
+        n = scenes.scene_fx_chains(g)
+        y = g.render(n).copy()
+        st = g.stats()
+        g.close()
+        return y, st.kernel_launches, st.fx_batched_nodes
+    y1, l1, b1 = run()
+    monkeypatch.setenv("GB_FX_BATCH", "0")
+    monkeypatch.setenv("GB_FX_FUSE", "0")
+    y0, l0, b0 = run()
+    assert b0 == 0 and b1 > 0
+    assert l1 < l0 - 5 * 6            # per chunk: 4 lp24 + 4 biquad stages in 2 launches, 6 fused post-ops
+    assert float(np.abs(y1 - y0).max()) <= 1e-15
+    check(y1, ref)
+
+
 def test_graph_semantics_on_gpu():
     """orchestrator.rs:1444-1668 restated on the GPU engine: silence, sums, gain chains, branch."""
     g = gpu_engine()
