@@ -379,6 +379,7 @@ struct gb_engine {
     bool lti = true;              // GB_LTI=0: no time-invariant blocks
     bool rest_kernel = true;      // GB_REST_KERNEL=0
     bool sweep_kernel = true;     // GB_SWEEP_KERNEL=0
+    bool sync_kernels = true;     // GB_SYNC_KERNELS=0: hard-sync patches stay on the general kernel
     int min_cut_voices = 256;     // GB_MIN_CUT_VOICES: chunk cuts only for engines with at least this many Welsh voices
   } opt;
   std::map<uint32_t, std::unique_ptr<Node>> nodes;
@@ -421,7 +422,8 @@ struct gb_engine {
   DevBuf<ZeroRange> szero;
   int* d_solo_sync = nullptr;     // [0, kSoloTickets) = job tickets (one per launch), [kSoloTickets + voice] = per-voice progress counter
   int solo_sub = kSoloSubDefault; // GB_SOLO_SUB: frames per sub-chunk (a multiple of kBlockFrames)
-  int solo_lockstep = 1;          // GB_SOLO_LOCKSTEP: bit 0 = rest / sweep / exact jobs run their blocks in lockstep, bit 1 = general jobs too
+  int solo_lockstep = 0;          // GB_SOLO_LOCKSTEP: bit 0 = rest / sweep / exact jobs run their blocks in lockstep, bit 1 = general jobs too
+                                  // (measured on config 5: 6.47 ms free-running, 6.68 / 7.84 ms with bit 0 / bits 0+1: profiles/r2_cfg5_scheduler_sweep.txt)
   bool fuse_post_ops = true;      // GB_FX_FUSE
   bool batch_fx = true;           // GB_FX_BATCH: independent effects of one kind and level share a launch
   DevBuf<FxDesc> fxdescs;
@@ -662,15 +664,22 @@ void welsh_inst_from_params(const Node& n, double sr, const gb_engine::Options& 
     // welsh_rest_kernel variant: same preconditions as welsh_block_lti (see voice_kernels.cuh)
     const bool lin = I->s1.kind == 0 && I->s2.kind == 0 && !I->sync &&
                      (I->routing == LFO_NONE || (I->routing == LFO_AMPLITUDE && I->wl == W_SINE));
+    // hard-sync patches take the same kernels in their SYNC instantiation (variants 4 / 5: general oscillator form)
+    const bool lin_sync = I->s1.kind == 0 && I->s2.kind == 0 && I->sync && opt.sync_kernels &&
+                          (I->routing == LFO_NONE || (I->routing == LFO_AMPLITUDE && I->wl == W_SINE));
     I->rest_class = -1;
     if (lin && I->lti_ok && (I->filter_mode == FILTER_FIXED || I->filter_mode == FILTER_ENVELOPE))
       I->rest_class = (I->routing == LFO_AMPLITUDE ? 2 : 0) + (I->osc_flat ? 1 : 0);
+    else if (lin_sync && I->lti_ok && (I->filter_mode == FILTER_FIXED || I->filter_mode == FILTER_ENVELOPE))
+      I->rest_class = 4 + (I->routing == LFO_AMPLITUDE ? 1 : 0);
     if (!opt.rest_kernel) I->rest_class = -1;
     // welsh_sweep_kernel: the knot path of a moving filter envelope; the frequency clamp must stay out of
     // reach (0.49 sr >= 20 kHz) so that the coefficient trajectory of a stage is smooth
     I->sweep_class = -1;
     if (lin && I->filter_mode == FILTER_ENVELOPE && I->knot_max_rate > 0.0 && 0.49 * sr >= 20000.0)
       I->sweep_class = (I->routing == LFO_AMPLITUDE ? 2 : 0) + (I->osc_flat ? 1 : 0);
+    else if (lin_sync && I->filter_mode == FILTER_ENVELOPE && I->knot_max_rate > 0.0 && 0.49 * sr >= 20000.0)
+      I->sweep_class = 4 + (I->routing == LFO_AMPLITUDE ? 1 : 0);
     if (!opt.sweep_kernel) I->sweep_class = -1;
     // welsh_exact_block (solo items): as above with exact coefficient sets at every frame, so no smoothness needed
     I->exact_class = lin && I->filter_mode == FILTER_ENVELOPE ? (I->routing == LFO_AMPLITUDE ? 1 : 0) : -1;
@@ -956,6 +965,7 @@ int gb_create(const gb_config* cfg, gb_engine** out) {
   if (const char* v = getenv("GB_LTI")) e->opt.lti = atoi(v) != 0;
   if (const char* v = getenv("GB_REST_KERNEL")) e->opt.rest_kernel = atoi(v) != 0;
   if (const char* v = getenv("GB_SWEEP_KERNEL")) e->opt.sweep_kernel = atoi(v) != 0;
+  if (const char* v = getenv("GB_SYNC_KERNELS")) e->opt.sync_kernels = atoi(v) != 0;
   if (const char* v = getenv("GB_MIN_CUT_VOICES")) e->opt.min_cut_voices = std::max(1, atoi(v));
   if (const char* v = getenv("GB_SOLO_MIN")) e->min_solo_items = atoi(v);
   if (const char* v = getenv("GB_SOLO_WAVES")) e->solo_waves = atoi(v) != 0;
@@ -1549,6 +1559,10 @@ int gb_finalize(gb_engine* e) {
   CUDA_TRY(e, cudaFuncSetAttribute(welsh_rest_kernel<8, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kRestSmemMax));
   CUDA_TRY(e, cudaFuncSetAttribute(welsh_rest_kernel<8, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kRestSmemMax));
   CUDA_TRY(e, cudaFuncSetAttribute(welsh_rest_kernel<8, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kRestSmemMax));
+  CUDA_TRY(e, cudaFuncSetAttribute(welsh_rest_kernel<8, false, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kRestSmemMax));
+  CUDA_TRY(e, cudaFuncSetAttribute(welsh_rest_kernel<8, true, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kRestSmemMax));
+  CUDA_TRY(e, cudaFuncSetAttribute(welsh_sweep_kernel<8, false, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kRestSmemMax));
+  CUDA_TRY(e, cudaFuncSetAttribute(welsh_sweep_kernel<8, true, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kRestSmemMax));
   CUDA_TRY(e, cudaFuncSetAttribute(welsh_sweep_kernel<8, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kRestSmemMax));
   CUDA_TRY(e, cudaFuncSetAttribute(welsh_sweep_kernel<8, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kRestSmemMax));
   CUDA_TRY(e, cudaFuncSetAttribute(welsh_sweep_kernel<8, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kRestSmemMax));
@@ -1871,7 +1885,8 @@ int render_chunk(gb_engine* e, int frames, size_t n_ev) {
       // goes to welsh_rest_kernel, the others to welsh_kernel.  Host knowledge only: note frames are
       // integers tracked by the slot stores.
       const int ng = e->n_wwork_grouped, ns = e->n_wwork - e->n_wwork_grouped;
-      std::vector<int> lists[9];  // 0..3 = resting variants, 4 = general, 5..8 = sweeping variants (idle CTAs are not launched)
+      constexpr int kVar = 6, kGen = kVar, kSw = kVar + 1;  // kernel variants: 0..3 = (lfo, flat oscillators), 4..5 = hard sync (lfo)
+      std::vector<int> lists[2 * kVar + 1];  // 0..5 = resting variants, 6 = general, 7..12 = sweeping variants (idle CTAs are not launched)
       e->wwork_zero.resize((size_t)ng, 0);
       const bool chunk_ok = frames % kBlockFrames == 0;
       size_t rest_voices_max = 0, sweep_voices_max = 0;
@@ -1921,12 +1936,12 @@ int render_chunk(gb_engine* e, int frames, size_t n_ev) {
           }
         }
         if (sweep) {
-          lists[5 + I.sweep_class].push_back(i);
+          lists[kSw + I.sweep_class].push_back(i);
           sweep_voices_max = std::max(sweep_voices_max, (size_t)w.nvoices);
           sweep_voices += (uint64_t)w.nvoices;
           continue;
         }
-        lists[rest ? I.rest_class : 4].push_back(i);
+        lists[rest ? I.rest_class : kGen].push_back(i);
         if (rest) {
           rest_voices_max = std::max(rest_voices_max, (size_t)w.nvoices);
           rest_voices += (uint64_t)w.nvoices;
@@ -1947,41 +1962,45 @@ int render_chunk(gb_engine* e, int frames, size_t n_ev) {
       }
       const size_t rest_smem = (size_t)kVoiceWarps * kTileStride * sizeof(double2) + rest_voices_max * sizeof(RestState);
       size_t off = 0;
-#define GB_REST_LAUNCH(CLS_, LFO_, FLAT_)                                                                            \
+#define GB_REST_LAUNCH(CLS_, LFO_, FLAT_, SYNC_)                                                                     \
   if (!lists[CLS_].empty()) {                                                                                        \
     Launch l(e, true, 1);                                                                                            \
-    welsh_rest_kernel<8, LFO_, FLAT_><<<(int)lists[CLS_].size(), 32 * 8, rest_smem, e->stream>>>(                      \
+    welsh_rest_kernel<8, LFO_, FLAT_, SYNC_><<<(int)lists[CLS_].size(), 32 * 8, rest_smem, e->stream>>>(               \
         e->d_winst, e->d_wvoice, e->wwork.d, e->widx.d + off, f0, frames);                                           \
     off += lists[CLS_].size();                                                                                       \
     e->stats.rest_ctas += lists[CLS_].size();                                                                        \
   }
-      GB_REST_LAUNCH(0, false, false)
-      GB_REST_LAUNCH(1, false, true)
-      GB_REST_LAUNCH(2, true, false)
-      GB_REST_LAUNCH(3, true, true)
+      GB_REST_LAUNCH(0, false, false, false)
+      GB_REST_LAUNCH(1, false, true, false)
+      GB_REST_LAUNCH(2, true, false, false)
+      GB_REST_LAUNCH(3, true, true, false)
+      GB_REST_LAUNCH(4, false, false, true)
+      GB_REST_LAUNCH(5, true, false, true)
 #undef GB_REST_LAUNCH
       e->stats.rest_voice_samples += rest_voices * (uint64_t)frames;
       e->stats.sweep_voice_samples += sweep_voices * (uint64_t)frames;
       const size_t welsh_smem = (size_t)kVoiceWarps * kTileStride * sizeof(double2) + (size_t)kParkWords * 32 * kVoiceWarps * sizeof(double);
-      if (!lists[4].empty()) {
+      if (!lists[kGen].empty()) {
         Launch l(e, true);
-        welsh_kernel<8, 2, false><<<(int)lists[4].size(), 32 * 8, welsh_smem, e->stream>>>(
+        welsh_kernel<8, 2, false><<<(int)lists[kGen].size(), 32 * 8, welsh_smem, e->stream>>>(
             e->d_winst, e->d_wvoice, e->wwork.d, e->witems.d, e->wev.d, e->wev_off.d, f0, frames, e->widx.d + off);
       }
-      off += lists[4].size();
+      off += lists[kGen].size();
       const size_t sweep_smem = (size_t)kVoiceWarps * kTileStride * sizeof(double2) + sweep_voices_max * sizeof(SweepState);
-#define GB_SWEEP_LAUNCH(CLS_, LFO_, FLAT_)                                                                           \
-  if (!lists[5 + CLS_].empty()) {                                                                                    \
+#define GB_SWEEP_LAUNCH(CLS_, LFO_, FLAT_, SYNC_)                                                                    \
+  if (!lists[kSw + CLS_].empty()) {                                                                                  \
     Launch l(e, true, 2);                                                                                            \
-    welsh_sweep_kernel<8, LFO_, FLAT_><<<(int)lists[5 + CLS_].size(), 32 * 8, sweep_smem, e->stream>>>(                \
+    welsh_sweep_kernel<8, LFO_, FLAT_, SYNC_><<<(int)lists[kSw + CLS_].size(), 32 * 8, sweep_smem, e->stream>>>(       \
         e->d_winst, e->d_wvoice, e->wwork.d, e->widx.d + off, f0, frames);                                           \
-    off += lists[5 + CLS_].size();                                                                                   \
-    e->stats.sweep_ctas += lists[5 + CLS_].size();                                                                   \
+    off += lists[kSw + CLS_].size();                                                                                 \
+    e->stats.sweep_ctas += lists[kSw + CLS_].size();                                                                 \
   }
-      GB_SWEEP_LAUNCH(0, false, false)
-      GB_SWEEP_LAUNCH(1, false, true)
-      GB_SWEEP_LAUNCH(2, true, false)
-      GB_SWEEP_LAUNCH(3, true, true)
+      GB_SWEEP_LAUNCH(0, false, false, false)
+      GB_SWEEP_LAUNCH(1, false, true, false)
+      GB_SWEEP_LAUNCH(2, true, false, false)
+      GB_SWEEP_LAUNCH(3, true, true, false)
+      GB_SWEEP_LAUNCH(4, false, false, true)
+      GB_SWEEP_LAUNCH(5, true, false, true)
 #undef GB_SWEEP_LAUNCH
       if (ns && !e->solo_mega) {
         Launch l(e, true);
@@ -2027,7 +2046,7 @@ int render_chunk(gb_engine* e, int frames, size_t n_ev) {
       if (s1 > na_end) return SOLO_GENERAL;
       int result;
       if (I.filter_mode == FILTER_FIXED) {
-        result = I.rest_class >= 0 ? SOLO_REST : SOLO_GENERAL;
+        result = I.rest_class >= 0 && !I.sync ? SOLO_REST : SOLO_GENERAL;
       } else if (I.filter_mode != FILTER_ENVELOPE) {
         result = SOLO_GENERAL;
       } else {
@@ -2035,11 +2054,11 @@ int render_chunk(gb_engine* e, int frames, size_t n_ev) {
         if (s1 > nf_end) return SOLO_GENERAL;
         until = std::min<int64_t>(until, nf_end);
         if (sf == 2 || sf == 4) {
-          result = I.rest_class >= 0 ? SOLO_REST : SOLO_GENERAL;
+          result = I.rest_class >= 0 && !I.sync ? SOLO_REST : SOLO_GENERAL;
         } else {
           const double slope = sf == 0 ? 2.0 * I.filt.inv_na : sf == 1 ? 2.0 * (1.0 - I.filt.sustain) * I.filt.inv_nd
                                                                        : 2.0 * I.filt.inv_nr;
-          result = I.sweep_class >= 0 && std::fabs(I.cut_b) * slope <= I.knot_max_rate ? SOLO_SWEEP
+          result = I.sweep_class >= 0 && !I.sync && std::fabs(I.cut_b) * slope <= I.knot_max_rate ? SOLO_SWEEP
                    : I.exact_class >= 0 ? SOLO_EXACT : SOLO_GENERAL;
         }
       }

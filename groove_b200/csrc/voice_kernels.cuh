@@ -1343,6 +1343,31 @@ __global__ void __launch_bounds__(32 * W, MINB) welsh_kernel(const WelshInst* __
   }
 }
 
+// Oscillator phases of a lane inside a 256-frame block whose base phases (P1, P2) are those of the frame
+// before the block.  With hard sync oscillator 2 restarts on every frame at which oscillator 1 wraps
+// (welsh_block / welsh_phases_at): a lane's start phase follows from j = floor(p1 / d1), the frames since the
+// last wrap (if that is inside the block so far, p2 = j d2), taken from a double-precision estimate with a
+// one-step correction instead of a 64-bit division.
+template <bool SYNC>
+__device__ __forceinline__ void osc_lane_start(u64 P1, u64 P2, u64 d1, u64 d2, int lane, u64& p1, u64& p2) {
+  const u64 k = (u64)(lane * kT);
+  p1 = P1 + k * d1;
+  p2 = P2 + k * d2;
+  if (SYNC && d1 != 0) {
+    u64 j = (u64)__double2ull_rz(__ull2double_rn(p1) * rcp_ranged(__ull2double_rn(d1)));
+    const u64 r = p1 - j * d1;
+    if ((i64)r < 0) --j;          // estimate one too high (d1 < 2^63: a negative remainder is unambiguous)
+    else if (r >= d1) ++j;        // ... or one too low
+    if (j < k) p2 = j * d2;
+  }
+}
+template <bool SYNC>
+__device__ __forceinline__ void osc_advance(u64& p1, u64& p2, u64 d1, u64 d2) {
+  p1 += d1;
+  if (SYNC) p2 = p1 < d1 ? 0 : p2 + d2;
+  else p2 += d2;
+}
+
 // ---- the resting-voice kernel ----------------------------------------------------------------------
 // The host knows every voice's note frames, so per chunk it sorts the grouped CTAs: those whose voices
 // all rest for the WHOLE chunk (note held since before the chunk, both envelopes at their sustain
@@ -1407,7 +1432,7 @@ __device__ __forceinline__ void lti_scan_entry(const double (&v0)[NV], const dou
   lti_scan_entry_t<NV, RestState>(v0, v1, mp, lane, rs, sec, e0, e1);
 }
 
-template <bool LFO_AMP, bool ZERO_A, int NV, bool ACC>
+template <bool LFO_AMP, bool ZERO_A, int NV, bool ACC, bool SYNC = false>
 __device__ __forceinline__ void welsh_rest_block(RestState* const (&rs)[NV], const WelshInst& I, int lane,
                                                  double2* tile_row) {
   // Cached state is read where it is needed and written back as soon as its new value exists, so that
@@ -1423,12 +1448,11 @@ __device__ __forceinline__ void welsh_rest_block(RestState* const (&rs)[NV], con
       const ulonglong2 pp = *reinterpret_cast<const ulonglong2*>(&rs[v]->p1);
       const ulonglong2 dd = *reinterpret_cast<const ulonglong2*>(&rs[v]->d1);
       d1[v] = dd.x; d2[v] = dd.y;
-      const u64 k = (u64)(lane * kT);
-      p1[v] = pp.x + k * dd.x; p2[v] = pp.y + k * dd.y;
+      osc_lane_start<SYNC>(pp.x, pp.y, dd.x, dd.y, lane, p1[v], p2[v]);
       ps0[v] = 0.0; ps1[v] = 0.0;
     }
     __syncwarp();  // every lane has read the block's base phases
-    if (lane == 0) {
+    if (!SYNC && lane == 0) {
 #pragma unroll
       for (int v = 0; v < NV; ++v)
         *reinterpret_cast<ulonglong2*>(&rs[v]->p1) =
@@ -1445,10 +1469,13 @@ __device__ __forceinline__ void welsh_rest_block(RestState* const (&rs)[NV], con
     for (int j = 0; j < kT; ++j) {
 #pragma unroll
       for (int v = 0; v < NV; ++v) {
-        p1[v] += d1[v];
-        p2[v] += d2[v];
+        osc_advance<SYNC>(p1[v], p2[v], d1[v], d2[v]);
         yp[v][j] = lp_step_bx(osc_mix_eval<ZERO_A>(o1, t1, p1[v], o2, t2, p2[v]), a1, a2, ps0[v], ps1[v]);
       }
+    }
+    if (SYNC && lane == 31) {  // the last lane ends on the block's last frame: the next block's base phases
+#pragma unroll
+      for (int v = 0; v < NV; ++v) *reinterpret_cast<ulonglong2*>(&rs[v]->p1) = make_ulonglong2(p1[v], p2[v]);
     }
     const double inv = L.inv_b0_2;
 #pragma unroll
@@ -1520,7 +1547,7 @@ __device__ __forceinline__ void welsh_rest_block(RestState* const (&rs)[NV], con
 
 // grid = number of resting CTAs of this variant; block = 32 * W threads;
 // dynamic smem = W * kTileStride double2 (tiles) + max_voices RestState.  nframes is a multiple of kBlockFrames.
-template <int W, bool LFO_AMP, bool ZERO_A>
+template <int W, bool LFO_AMP, bool ZERO_A, bool SYNC = false>
 __global__ void __launch_bounds__(32 * W, 2) welsh_rest_kernel(const WelshInst* __restrict__ insts,
                                                              WelshVoice* __restrict__ voices,
                                                              const CtaWork* __restrict__ work,
@@ -1544,6 +1571,7 @@ __global__ void __launch_bounds__(32 * W, 2) welsh_rest_kernel(const WelshInst* 
     const u64 k = (u64)(f0 - 1 - vp->anchor);
     r.d1 = vp->d1; r.d2 = vp->d2;
     r.p1 = vp->p1 + k * r.d1; r.p2 = vp->p2 + k * r.d2;
+    if (SYNC) r.p2 = welsh_phases_at(*vp, I, f0 - 1).p2;  // oscillator 2 restarted at oscillator 1's last wrap
     r.s[0] = vp->s[0]; r.s[1] = vp->s[1]; r.s[2] = vp->s[2]; r.s[3] = vp->s[3];
     r.ls = 0.0; r.lc = 0.0;
     if (LFO_AMP) {
@@ -1565,12 +1593,12 @@ __global__ void __launch_bounds__(32 * W, 2) welsh_rest_kernel(const WelshInst* 
     for (int g = warp; g < wk.nvoices; g += 2 * W) {
       if (g + W < wk.nvoices) {
         RestState* const two[2] = {cache + g, cache + g + W};
-        if (first) welsh_rest_block<LFO_AMP, ZERO_A, 2, false>(two, I, lane, tile_row);
-        else welsh_rest_block<LFO_AMP, ZERO_A, 2, true>(two, I, lane, tile_row);
+        if (first) welsh_rest_block<LFO_AMP, ZERO_A, 2, false, SYNC>(two, I, lane, tile_row);
+        else welsh_rest_block<LFO_AMP, ZERO_A, 2, true, SYNC>(two, I, lane, tile_row);
       } else {
         RestState* const one[1] = {cache + g};
-        if (first) welsh_rest_block<LFO_AMP, ZERO_A, 1, false>(one, I, lane, tile_row);
-        else welsh_rest_block<LFO_AMP, ZERO_A, 1, true>(one, I, lane, tile_row);
+        if (first) welsh_rest_block<LFO_AMP, ZERO_A, 1, false, SYNC>(one, I, lane, tile_row);
+        else welsh_rest_block<LFO_AMP, ZERO_A, 1, true, SYNC>(one, I, lane, tile_row);
       }
       first = false;
     }
@@ -1632,7 +1660,7 @@ __device__ __forceinline__ void welsh_knot(const WelshInst& I, double pct, doubl
   k[0] = c1.a1; k[1] = c1.a2; k[2] = c2.a1; k[3] = c2.a2;
 }
 
-template <bool LFO_AMP, bool ZERO_A, bool ACC>
+template <bool LFO_AMP, bool ZERO_A, bool ACC, bool SYNC = false>
 __device__ __forceinline__ void welsh_sweep_block(SweepState* rs, const WelshInst& I, int lane, int t0,
                                                   double2* tile_row) {
   // t0 = first frame of the block relative to the chunk start
@@ -1664,18 +1692,17 @@ __device__ __forceinline__ void welsh_sweep_block(SweepState* rs, const WelshIns
   {
     const ulonglong2 pp = *reinterpret_cast<const ulonglong2*>(&rs->p1);
     const ulonglong2 dd = *reinterpret_cast<const ulonglong2*>(&rs->d1);
-    const u64 k = (u64)(lane * kT);
-    u64 p1 = pp.x + k * dd.x, p2 = pp.y + k * dd.y;
+    u64 p1, p2;
+    osc_lane_start<SYNC>(pp.x, pp.y, dd.x, dd.y, lane, p1, p2);
     __syncwarp();  // every lane has read the block's base phases
-    if (lane == 0)
+    if (!SYNC && lane == 0)
       *reinterpret_cast<ulonglong2*>(&rs->p1) =
           make_ulonglong2(p1 + (u64)kBlockFrames * dd.x, p2 + (u64)kBlockFrames * dd.y);
     const OscMix o1 = I.m1, o2 = I.m2;
     const u64 t1 = I.s1.thresh, t2 = I.s2.thresh;
 #pragma unroll
     for (int j = 0; j < kT; ++j) {
-      p1 += dd.x;
-      p2 += dd.y;
+      osc_advance<SYNC>(p1, p2, dd.x, dd.y);
       const double x = osc_mix_eval<ZERO_A>(o1, t1, p1, o2, t2, p2);
       const double a1 = coef(0, j), a2 = coef(1, j);
       const double b0 = fma(-0.25, a1 + a2, 0.25);
@@ -1685,6 +1712,7 @@ __device__ __forceinline__ void welsh_sweep_block(SweepState* rs, const WelshIns
       h10 = a2 * h00; h11 = a2 * h01;
       h00 = t00; h01 = t01;
     }
+    if (SYNC && lane == 31) *reinterpret_cast<ulonglong2*>(&rs->p1) = make_ulonglong2(p1, p2);
   }
   double e0, e1, end0, end1;
   {
@@ -1854,7 +1882,7 @@ __device__ __forceinline__ void welsh_exact_block(SweepState* rs, const WelshIns
 
 // grid = number of sweeping CTAs of this variant; block = 32 * W threads;
 // dynamic smem = W * kTileStride double2 (tiles) + max_voices SweepState.  nframes is a multiple of kBlockFrames.
-template <int W, bool LFO_AMP, bool ZERO_A>
+template <int W, bool LFO_AMP, bool ZERO_A, bool SYNC = false>
 __global__ void __launch_bounds__(32 * W, 2) welsh_sweep_kernel(const WelshInst* __restrict__ insts,
                                                               WelshVoice* __restrict__ voices,
                                                               const CtaWork* __restrict__ work,
@@ -1878,6 +1906,7 @@ __global__ void __launch_bounds__(32 * W, 2) welsh_sweep_kernel(const WelshInst*
     const u64 k = (u64)(f0 - 1 - vp->anchor);
     r.d1 = vp->d1; r.d2 = vp->d2;
     r.p1 = vp->p1 + k * r.d1; r.p2 = vp->p2 + k * r.d2;
+    if (SYNC) r.p2 = welsh_phases_at(*vp, I, f0 - 1).p2;  // oscillator 2 restarted at oscillator 1's last wrap
     r.s[0] = vp->s[0]; r.s[1] = vp->s[1]; r.s[2] = vp->s[2]; r.s[3] = vp->s[3];
     r.ls = 0.0; r.lc = 0.0;
     if (LFO_AMP) {
@@ -1905,8 +1934,8 @@ __global__ void __launch_bounds__(32 * W, 2) welsh_sweep_kernel(const WelshInst*
     bool first = true;
 #pragma unroll 1
     for (int g = warp; g < wk.nvoices; g += W) {
-      if (first) welsh_sweep_block<LFO_AMP, ZERO_A, false>(cache + g, I, lane, t0, tile_row);
-      else welsh_sweep_block<LFO_AMP, ZERO_A, true>(cache + g, I, lane, t0, tile_row);
+      if (first) welsh_sweep_block<LFO_AMP, ZERO_A, false, SYNC>(cache + g, I, lane, t0, tile_row);
+      else welsh_sweep_block<LFO_AMP, ZERO_A, true, SYNC>(cache + g, I, lane, t0, tile_row);
       first = false;
     }
     __syncthreads();

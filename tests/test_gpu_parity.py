@@ -625,6 +625,51 @@ def test_held_chord_scene_uses_rest_and_sweep_kernels():
     check(out, ref)
 
 
+@pytest.mark.parametrize("lfo", [False, True])
+def test_hard_sync_patch_takes_the_sync_kernels(lfo, monkeypatch):
+    """Hard-sync patches (settings/src/patches.rs:122; `piano`, 18 of the 106 Welsh patches) in grouped CTAs:
+    the filter decay runs in welsh_sweep_kernel<.., SYNC>, the sustain in welsh_rest_kernel<.., SYNC> —
+    oscillator 2 restarting at every wrap of oscillator 1 — and must match the general kernel's render
+    (GB_SYNC_KERNELS=0) and the oracle.  Held 5.8 s so that both stages and the release are covered."""
+    frames = 330_000
+
+    def scene(r):
+        p = workloads.piano_params(16, 1.0 / 16.0, 0.2)
+        if lfo:
+            p.lfo = abi.osc(abi.WAVE_SINE, frequency=5.5)
+            p.lfo_routing = abi.LFO_AMPLITUDE
+            p.lfo_depth = 0.3
+        u = r.add_instrument(abi.INST_WELSH, p)
+        r.patch(u, abi.MAIN_MIXER)
+        r.finalize()
+        ev = []
+        for i in range(16):
+            ev.append((100 + 37 * i, u, abi.EV_NOTE_ON, 30 + 3 * i, 127, 0.0))
+            ev.append((280_000 + 64 * i, u, abi.EV_NOTE_OFF, 30 + 3 * i, 0, 0.0))
+        r.push_events(ev)
+        return frames
+
+    o = OracleEngine(48000.0)
+    scene(o)
+    ref = o.render(frames)
+
+    def run():
+        g = gpu_engine(48000.0, max_block=8192)
+        scene(g)
+        y = g.render(frames).copy()
+        st = g.stats()
+        g.close()
+        return y, st
+    out, st = run()
+    assert st.rest_kernel_launches > 0 and st.sweep_kernel_launches > 0
+    check(out, ref)
+    monkeypatch.setenv("GB_SYNC_KERNELS", "0")
+    gen, st0 = run()
+    assert st0.rest_kernel_launches == 0 and st0.sweep_kernel_launches == 0
+    check(gen, ref)
+    assert float(np.abs(out - gen).max()) <= 1e-10
+
+
 def test_two_gpu_bus_reduce_matches_single_gpu_render(tmp_path):
     """N > 1 on real GPUs: two ranks (torchrun, NCCL) each render their shard of a config-4 slice, the
     stereo buses are summed onto rank 0 with one NCCL f64 reduce, and rank 0 compares the result with its
