@@ -64,6 +64,7 @@ def parse_args():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--voices", type=int, default=4096, help="voices per GPU (config 4: 4096)")
     ap.add_argument("--seconds", type=float, default=60.0, help="audio seconds per step (config 4: 60)")
+    ap.add_argument("--groups", type=int, default=0, help="instruments per GPU (config 4: 128; 0 = min(128, voices))")
     ap.add_argument("--max-block", type=int, default=1 << 16)
     ap.add_argument("--workload", default="cfg4", choices=["cfg4", "cfg5"],
                     help="headline workload: cfg4 = BASELINE config 4; cfg5 = batch of one-shot patch variants")
@@ -279,8 +280,11 @@ def run_ours(a) -> None:
     class Workload:
         """One benchmark workload: `graph(eng)` builds the (finalized) engine and returns the events to push."""
 
-        def __init__(self, name, frames, max_block, graph, reduce=True):
-            self.name, self.frames, self.max_block, self.graph, self.reduce = name, frames, max_block, graph, reduce
+        def __init__(self, name, frames, max_block, graph, reduce=True, collective=True):
+            # collective=False: a workload that ONE rank runs on its own (no barrier, no bus reduce)
+            self.name, self.frames, self.max_block, self.graph = name, frames, max_block, graph
+            self.reduce = reduce and collective
+            self.collective = collective
             self.host_out = np.empty((frames, 2), dtype=np.float64)
             self.pinned_out = (torch.empty((frames, 2), dtype=torch.float64, pin_memory=True)
                                if world > 1 and rank == 0 and reduce else None)
@@ -294,7 +298,10 @@ def run_ours(a) -> None:
             if lookahead:
                 eng.set_lookahead(lookahead)
             flush.zero_()
-            barrier()
+            if self.collective:
+                barrier()
+            else:
+                torch.cuda.synchronize()
             t0 = time.perf_counter()
             reduce_ms = 0.0
             eng.push_events(ev)
@@ -327,13 +334,14 @@ def run_ours(a) -> None:
             return wall, st, reduce_ms
 
         def run(self, mode: str, steps: int, warmup: int, block: int = 0, lookahead: int = 0) -> Acc:
+            sync = barrier if self.collective else torch.cuda.synchronize
             for _ in range(warmup):
                 self.step(mode, block, lookahead)
-            barrier()
+            sync()
             acc = Acc()
             for _ in range(steps):
                 acc.add(*self.step(mode, block, lookahead))
-            barrier()
+            sync()
             return acc
 
     def max_over_ranks(*vals):
@@ -346,13 +354,13 @@ def run_ours(a) -> None:
     frames4 = int(round(a.seconds * SR))
     off4 = int(frames4 * 2_400_000 / 2_880_000)
 
-    def cfg4_workload(name, cfg, params=None, reduce=True):
+    def cfg4_workload(name, cfg, params=None, reduce=True, collective=True):
         def graph(eng):
             return workloads.cfg4_events(cfg, workloads.build_cfg4_graph(eng, cfg, params))
-        return Workload(name, cfg.frames, a.max_block, graph, reduce)
+        return Workload(name, cfg.frames, a.max_block, graph, reduce, collective)
 
     weak_cfg = parallel.shard_cfg4(workloads.Cfg4(total_voices=a.voices, frames=frames4, note_off_base=off4,
-                                                  groups=min(128, a.voices)), rank, world, weak=True)
+                                                  groups=a.groups or min(128, a.voices)), rank, world, weak=True)
     cfg5_variants = None
 
     def cfg5_workload():
@@ -558,7 +566,7 @@ def run_ours(a) -> None:
             })
 
     if "strong" in legs and not headline5 and world > 1:
-        whole = workloads.Cfg4(total_voices=a.voices, frames=frames4, note_off_base=off4, groups=min(128, a.voices))
+        whole = workloads.Cfg4(total_voices=a.voices, frames=frames4, note_off_base=off4, groups=a.groups or min(128, a.voices))
         ws = cfg4_workload("strong", parallel.shard_cfg4(whole, rank, world, weak=False))
         acc = ws.run("device", 3, 1)
         (ms_n,) = max_over_ranks(acc["render_ms"] + acc["reduce_ms"])
@@ -566,7 +574,7 @@ def run_ours(a) -> None:
         # the single-GPU time of the same total work, in the same run: rank 0 alone renders all the voices
         ms_1 = 0.0
         if rank == 0:
-            w1 = cfg4_workload("strong-n1", whole, reduce=False)
+            w1 = cfg4_workload("strong-n1", whole, reduce=False, collective=False)
             for _ in range(2):
                 _, st, _ = w1.step("device")
             ms_1 = st.render_ms
@@ -622,11 +630,13 @@ def run_ours(a) -> None:
             ms = acc["fx_kernel_ms"] / 3
             by = 32.0 * fx_frames * n_chains
             put("stream_fx", {
-                "what": f"{n_chains} copies of config 1's effect chain (24 dB low-pass -> gain) over {fx_frames} frames, one "
-                        "launch for all the chains: 16 B read + 16 B written per frame per chain (SURVEY.md 8(d))",
+                "what": f"{n_chains} copies of config 1's effect chain (24 dB low-pass with a stepped cutoff trip -> gain) over "
+                        f"{fx_frames} frames: ONE launch for all the chains (the gain runs as the filter's post-op), then the "
+                        "mixer's table sum; counted 16 B read + 16 B written per frame per chain (SURVEY.md 8(d)) over the "
+                        "effect kernels' CUDA-event time (the mixer's own 16 B read per chain is not counted)",
                 "value": n_chains * fx_frames / (ms * 1e-3), "unit": "chain-frames/s", "ms_per_step": ms,
                 "render_ms": acc["render_ms"] / 3,
-                "roofline": {"bound": "hbm", "kernel": "fx_chain_kernel", "achieved": by / (ms * 1e-3) / 1e9, "peak": hbm_peak,
+                "roofline": {"bound": "hbm", "kernel": "lp24_batch_kernel<2> (gain fused as post-op) + sum_table_kernel", "achieved": by / (ms * 1e-3) / 1e9, "peak": hbm_peak,
                              "unit": "GB/s", "frac": by / (ms * 1e-3) / 1e9 / hbm_peak, "peak_source": hbm_src,
                              "algorithmic_bytes_per_launch": by, "traffic": None}})
         if "small_blocks" in legs:
@@ -656,6 +666,8 @@ def run_ours(a) -> None:
 
 
 def main():
+    import faulthandler
+    faulthandler.dump_traceback_later(1500, exit=True)   # a hung collective must not hang the caller: trace and exit
     a = parse_args()
     if a._cpu_child:
         cpu_child(a._cpu_child)

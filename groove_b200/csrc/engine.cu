@@ -425,6 +425,7 @@ struct gb_engine {
   int solo_lockstep = 0;          // GB_SOLO_LOCKSTEP: bit 0 = rest / sweep / exact jobs run their blocks in lockstep, bit 1 = general jobs too
                                   // (measured on config 5: 6.47 ms free-running, 6.68 / 7.84 ms with bit 0 / bits 0+1: profiles/r2_cfg5_scheduler_sweep.txt)
   bool fuse_post_ops = true;      // GB_FX_FUSE
+  int fx_minb = 2;                // GB_FX_MINB: resident CTAs per SM the batched IIR kernels are compiled for (1: 174 registers, 2: 128, 3: 80)
   bool batch_fx = true;           // GB_FX_BATCH: independent effects of one kind and level share a launch
   DevBuf<FxDesc> fxdescs;
   bool solo_waves = false;        // GB_SOLO_WAVES=1: one launch per sub-chunk (stream order instead of the progress counters)
@@ -970,6 +971,7 @@ int gb_create(const gb_config* cfg, gb_engine** out) {
   if (const char* v = getenv("GB_SOLO_MIN")) e->min_solo_items = atoi(v);
   if (const char* v = getenv("GB_SOLO_WAVES")) e->solo_waves = atoi(v) != 0;
   if (const char* v = getenv("GB_FX_FUSE")) e->fuse_post_ops = atoi(v) != 0;
+  if (const char* v = getenv("GB_FX_MINB")) e->fx_minb = atoi(v);
   if (const char* v = getenv("GB_FX_BATCH")) e->batch_fx = atoi(v) != 0;
   if (const char* v = getenv("GB_SOLO_LOCKSTEP")) e->solo_lockstep = atoi(v);
   if (const char* v = getenv("GB_SOLO_SUB")) e->solo_sub = std::max(1, atoi(v) / kBlockFrames) * kBlockFrames;
@@ -1405,6 +1407,10 @@ int gb_finalize(gb_engine* e) {
     const int wpc = kVoiceWarps;  // warps per CTA (4-warp CTAs with tighter register caps measured slower)
     int vpc = std::max(wpc, cdiv(total_voices, target));
     vpc = cdiv(vpc, wpc) * wpc;
+    // Two voices per warp (lockstep pairs) beat twice the CTAs with one voice per warp as long as the pairs
+    // still give about one CTA per SM: 2048 voices render in 28.6 ms as 128 CTAs of 16 against 30.5 ms as 256
+    // CTAs of 8; 1024 voices in 20.0 ms as 128 CTAs of 8 against 27.5 ms as 64 of 16 (profiles/r2_strong_probe.txt).
+    if (vpc == wpc && 20 * total_voices >= 17 * 2 * wpc * e->num_sms) vpc = 2 * wpc;
     if (e->opt.vpc > 0) vpc = e->opt.vpc;  // tests: force the voices-per-CTA split
     for (Node* n : e->plan) {
       if (n->kind != kind) continue;
@@ -2369,9 +2375,13 @@ int render_chunk(gb_engine* e, int frames, size_t n_ev) {
             dim3 grid(cdiv(frames, 256), (unsigned)cnt);
             pointwise_batch_kernel<<<grid, 256, 0, e->stream>>>(dd, frames);
           } else if (batch_class(n) == 2) {
-            lp24_batch_kernel<<<(int)cnt, 32 * kFxWarps, 0, e->stream>>>(dd, frames);
+            if (e->fx_minb == 1) lp24_batch_kernel<1><<<(int)cnt, 32 * kFxWarps, 0, e->stream>>>(dd, frames);
+            else if (e->fx_minb == 2) lp24_batch_kernel<2><<<(int)cnt, 32 * kFxWarps, 0, e->stream>>>(dd, frames);
+            else lp24_batch_kernel<3><<<(int)cnt, 32 * kFxWarps, 0, e->stream>>>(dd, frames);
           } else {
-            biquad_batch_kernel<<<(int)cnt, 32 * kFxWarps, 0, e->stream>>>(dd, frames);
+            if (e->fx_minb == 1) biquad_batch_kernel<1><<<(int)cnt, 32 * kFxWarps, 0, e->stream>>>(dd, frames);
+            else if (e->fx_minb == 2) biquad_batch_kernel<2><<<(int)cnt, 32 * kFxWarps, 0, e->stream>>>(dd, frames);
+            else biquad_batch_kernel<3><<<(int)cnt, 32 * kFxWarps, 0, e->stream>>>(dd, frames);
           }
         }
         fx_used += cnt;

@@ -486,11 +486,13 @@ struct FxDesc {
   int nseg;
   int op;          // pointwise nodes: OP_*
 };
-__global__ void __launch_bounds__(32 * kFxWarps) lp24_batch_kernel(const FxDesc* __restrict__ descs, int frames) {
+template <int MINB>
+__global__ void __launch_bounds__(32 * kFxWarps, MINB) lp24_batch_kernel(const FxDesc* __restrict__ descs, int frames) {
   const FxDesc& d = descs[blockIdx.x];
   lp24_body(d.src, d.out, frames, d.segs, d.nseg, static_cast<Lp24State*>(d.state), d.post);
 }
-__global__ void __launch_bounds__(32 * kFxWarps) biquad_batch_kernel(const FxDesc* __restrict__ descs, int frames) {
+template <int MINB>
+__global__ void __launch_bounds__(32 * kFxWarps, MINB) biquad_batch_kernel(const FxDesc* __restrict__ descs, int frames) {
   const FxDesc& d = descs[blockIdx.x];
   biquad_df1_body(d.src, d.out, frames, d.segs, d.nseg, static_cast<BiquadState*>(d.state), d.post);
 }

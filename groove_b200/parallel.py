@@ -17,13 +17,18 @@ def shard_cfg4(cfg: workloads.Cfg4, rank: int, world: int, weak: bool = True) ->
     """Rank-local slice of config 4.
 
     weak scaling (bench.py): every rank renders `cfg.total_voices` voices of a `world`-times larger
-    ensemble.  strong scaling: the `cfg.total_voices` voices are split evenly (voice i belongs to the
-    rank i // (total/world)); groups shrink accordingly.
+    ensemble.  strong scaling: the `cfg.total_voices` voices are split evenly.  When the instruments divide
+    evenly they are dealt out WHOLE (rank r renders instruments r G/world .. (r+1) G/world - 1 with all their
+    voices: independent tracks, SURVEY.md 8(e)), so every rank keeps full voice groups for its CTAs;
+    otherwise the voices are cut by index (voice i belongs to rank i // (total/world)) and the groups shrink.
     """
     if weak:
         return replace(cfg, voice_offset=cfg.voice_offset + rank * cfg.total_voices)
     assert cfg.total_voices % world == 0
     per = cfg.total_voices // world
+    if cfg.groups % world == 0 and not cfg.group_total:
+        g = cfg.groups // world
+        return replace(cfg, total_voices=per, groups=g, group_first=rank * g, group_total=cfg.groups)
     groups = min(cfg.groups, per)
     while per % groups:
         groups -= 1

@@ -80,6 +80,8 @@ class Cfg4:
     note_off_base: int = 2_400_000
     groups: int = 128          # instruments; voice i belongs to instrument i mod groups
     voice_offset: int = 0      # first global voice index (multi-GPU shards use rank * total_voices)
+    group_first: int = 0       # strong-scaling shards: this slice holds instruments group_first .. group_first + groups - 1
+    group_total: int = 0       # ... of an ensemble of group_total instruments (0 = groups: the whole ensemble)
     filter_decay: float = 3.29 # cello.json's filter-envelope decay (s); bench.py's "time_varying" leg stretches it
                                # past the note length so that the cutoff never rests
 
@@ -102,7 +104,7 @@ def build_cfg4_graph(r: abi.Renderer, cfg: Cfg4, params=None):
     per = cfg.total_voices // cfg.groups
     uids = []
     for q in range(cfg.groups):
-        i0 = cfg.voice_offset + q
+        i0 = cfg.voice_offset + cfg.group_first + q
         pan = -1.0 + 2.0 * (i0 % 64) / 63.0
         p = params(per, 1.0 / 4096.0, pan) if params else cello_params(per, 1.0 / 4096.0, pan, cfg.filter_decay)
         u = r.add_instrument(abi.INST_WELSH, p)
@@ -115,11 +117,12 @@ def build_cfg4_graph(r: abi.Renderer, cfg: Cfg4, params=None):
 def cfg4_events(cfg: Cfg4, uids) -> np.ndarray:
     """Config 4's note events (frame-sorted) for the instruments `uids` of build_cfg4_graph."""
     per = cfg.total_voices // cfg.groups
+    stride = cfg.group_total or cfg.groups
     ev = np.zeros(2 * cfg.total_voices, dtype=abi.EVENT_DTYPE)
     k = 0
     for j in range(per):
         for q in range(cfg.groups):
-            i = cfg.voice_offset + q + cfg.groups * j
+            i = cfg.voice_offset + cfg.group_first + q + stride * j
             on = 64 * (i % 128)
             off = cfg.note_off_base + 64 * (i % 128)
             key = 36 + (i % 49)

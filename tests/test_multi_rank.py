@@ -67,4 +67,12 @@ def test_shard_helpers():
     w = [parallel.shard_cfg4(cfg, r, 8) for r in range(8)]
     assert [c.voice_offset for c in w] == [4096 * r for r in range(8)] and all(c.total_voices == 4096 for c in w)
     s = [parallel.shard_cfg4(cfg, r, 8, weak=False) for r in range(8)]
-    assert sum(c.total_voices for c in s) == 4096 and [c.voice_offset for c in s] == [512 * r for r in range(8)]
+    assert sum(c.total_voices for c in s) == 4096 and [c.group_first for c in s] == [16 * r for r in range(8)]
+    assert all(c.groups == 16 and c.group_total == 128 and c.voice_offset == 0 for c in s)
+    # the shards' voices partition the whole ensemble's (same events, instrument by instrument)
+    whole = workloads.cfg4_events(cfg, list(range(100, 228)))
+    parts = [workloads.cfg4_events(c, list(range(100 + c.group_first, 100 + c.group_first + 16))) for c in s]
+    key = lambda ev: sorted(map(tuple, ev.tolist()))
+    assert key(whole) == key(np.concatenate(parts))
+    odd = [parallel.shard_cfg4(workloads.Cfg4(total_voices=96, groups=3), r, 2, weak=False) for r in range(2)]
+    assert [c.voice_offset for c in odd] == [0, 48] and all(c.total_voices == 48 for c in odd)
