@@ -315,10 +315,13 @@ def run_ours(a) -> None:
                     torch.cuda.synchronize()
                     reduce_ms = ev0.elapsed_time(ev1)
             elif mode == "blocks":               # the reference's call pattern: fixed small caller buffers
-                done = 0
+                import ctypes
+                fn, h, base = eng._f("render_block"), eng._h, self.host_out.ctypes.data   # the bare C ABI call per buffer
+                got, done = ctypes.c_size_t(), 0
                 while done < self.frames:
                     k = min(block, self.frames - done)
-                    eng.render(k, self.host_out[done:done + k])
+                    if fn(h, base + 16 * done, k, ctypes.byref(got)) != 0:
+                        raise RuntimeError(eng._f("last_error")(h))
                     done += k
             elif world == 1 or not self.reduce:
                 eng.render(self.frames, self.host_out)

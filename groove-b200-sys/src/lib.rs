@@ -267,6 +267,7 @@ pub mod ffi {
         pub rest_ctas: u64,
         pub sweep_ctas: u64,
         pub fx_batched_nodes: u64,
+        pub rest_tp_launches: u64,
     }
 
     extern "C" {

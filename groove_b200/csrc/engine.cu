@@ -380,6 +380,7 @@ struct gb_engine {
     bool rest_kernel = true;      // GB_REST_KERNEL=0
     bool sweep_kernel = true;     // GB_SWEEP_KERNEL=0
     bool sync_kernels = true;     // GB_SYNC_KERNELS=0: hard-sync patches stay on the general kernel
+    bool rest_tp = true;          // GB_REST_TP=0: no time-parallel resting kernel (and no CTAs below 8 voices)
     int min_cut_voices = 256;     // GB_MIN_CUT_VOICES: chunk cuts only for engines with at least this many Welsh voices
   } opt;
   std::map<uint32_t, std::unique_ptr<Node>> nodes;
@@ -638,6 +639,12 @@ void welsh_inst_from_params(const Node& n, double sr, const gb_engine::Options& 
     I->m2bb = scaled(I->m2, c1.b0 * c2.b0);
     table(c1, I->lti.g1, I->lti.mp1);
     table(c2, I->lti.g2, I->lti.mp2);
+    auto square = [](const double* m, double* o) {
+      o[0] = m[0] * m[0] + m[1] * m[2]; o[1] = m[0] * m[1] + m[1] * m[3];
+      o[2] = m[2] * m[0] + m[3] * m[2]; o[3] = m[2] * m[1] + m[3] * m[3];
+    };
+    square(I->lti.mp1[4], I->mp32_1);  // the lane map to the 32nd power: one 256-frame block
+    square(I->lti.mp2[4], I->mp32_2);
     for (int j = 0; j < kT; ++j) {
       I->lti.g1b[j][0] = I->lti.g1[j][0] * c2.b0;
       I->lti.g1b[j][1] = I->lti.g1[j][1] * c2.b0;
@@ -967,6 +974,7 @@ int gb_create(const gb_config* cfg, gb_engine** out) {
   if (const char* v = getenv("GB_REST_KERNEL")) e->opt.rest_kernel = atoi(v) != 0;
   if (const char* v = getenv("GB_SWEEP_KERNEL")) e->opt.sweep_kernel = atoi(v) != 0;
   if (const char* v = getenv("GB_SYNC_KERNELS")) e->opt.sync_kernels = atoi(v) != 0;
+  if (const char* v = getenv("GB_REST_TP")) e->opt.rest_tp = atoi(v) != 0;
   if (const char* v = getenv("GB_MIN_CUT_VOICES")) e->opt.min_cut_voices = std::max(1, atoi(v));
   if (const char* v = getenv("GB_SOLO_MIN")) e->min_solo_items = atoi(v);
   if (const char* v = getenv("GB_SOLO_WAVES")) e->solo_waves = atoi(v) != 0;
@@ -1411,6 +1419,16 @@ int gb_finalize(gb_engine* e) {
     // still give about one CTA per SM: 2048 voices render in 28.6 ms as 128 CTAs of 16 against 30.5 ms as 256
     // CTAs of 8; 1024 voices in 20.0 ms as 128 CTAs of 8 against 27.5 ms as 64 of 16 (profiles/r2_strong_probe.txt).
     if (vpc == wpc && 20 * total_voices >= 17 * 2 * wpc * e->num_sms) vpc = 2 * wpc;
+    // Few voices for the machine (a strong-scaling shard of 1/8): CTAs of one voice pair, enough of them to cover
+    // the SMs; their resting stretches go to welsh_rest_tp_kernel, whose warps share the pair along time.
+    // Small songs (< 256 voices) keep whole-instrument CTAs: there launches, not SM coverage, are the cost.
+    // Measured (profiles/r2_strong_probe.txt, resting launch of 65 536 frames): 512 voices as 256 CTAs of one
+    // pair 0.223 ms against 0.436 ms as 64 CTAs of 8; with two pairs per CTA (1024 voices) 0.413 against 0.438
+    // and a slower step, with four (2048) 0.788 against 0.624 — a round costs 6.5 us per pair against 2.4 us of
+    // a warp's own block, so only the one-pair split is taken.
+    if (kind == GB_INST_WELSH && e->opt.rest_tp && e->opt.rest_kernel && total_voices >= 256 &&
+        cdiv(total_voices, target) <= 2)
+      vpc = 2;
     if (e->opt.vpc > 0) vpc = e->opt.vpc;  // tests: force the voices-per-CTA split
     for (Node* n : e->plan) {
       if (n->kind != kind) continue;
@@ -1565,6 +1583,12 @@ int gb_finalize(gb_engine* e) {
   CUDA_TRY(e, cudaFuncSetAttribute(welsh_rest_kernel<8, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kRestSmemMax));
   CUDA_TRY(e, cudaFuncSetAttribute(welsh_rest_kernel<8, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kRestSmemMax));
   CUDA_TRY(e, cudaFuncSetAttribute(welsh_rest_kernel<8, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kRestSmemMax));
+  CUDA_TRY(e, cudaFuncSetAttribute(welsh_rest_tp_kernel<8, false, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kRestSmemMax));
+  CUDA_TRY(e, cudaFuncSetAttribute(welsh_rest_tp_kernel<8, false, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kRestSmemMax));
+  CUDA_TRY(e, cudaFuncSetAttribute(welsh_rest_tp_kernel<8, true, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kRestSmemMax));
+  CUDA_TRY(e, cudaFuncSetAttribute(welsh_rest_tp_kernel<8, true, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kRestSmemMax));
+  CUDA_TRY(e, cudaFuncSetAttribute(welsh_rest_tp_kernel<8, false, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kRestSmemMax));
+  CUDA_TRY(e, cudaFuncSetAttribute(welsh_rest_tp_kernel<8, true, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kRestSmemMax));
   CUDA_TRY(e, cudaFuncSetAttribute(welsh_rest_kernel<8, false, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kRestSmemMax));
   CUDA_TRY(e, cudaFuncSetAttribute(welsh_rest_kernel<8, true, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kRestSmemMax));
   CUDA_TRY(e, cudaFuncSetAttribute(welsh_sweep_kernel<8, false, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kRestSmemMax));
@@ -1891,8 +1915,9 @@ int render_chunk(gb_engine* e, int frames, size_t n_ev) {
       // goes to welsh_rest_kernel, the others to welsh_kernel.  Host knowledge only: note frames are
       // integers tracked by the slot stores.
       const int ng = e->n_wwork_grouped, ns = e->n_wwork - e->n_wwork_grouped;
-      constexpr int kVar = 6, kGen = kVar, kSw = kVar + 1;  // kernel variants: 0..3 = (lfo, flat oscillators), 4..5 = hard sync (lfo)
-      std::vector<int> lists[2 * kVar + 1];  // 0..5 = resting variants, 6 = general, 7..12 = sweeping variants (idle CTAs are not launched)
+      constexpr int kVar = 6, kTp = kVar, kGen = 2 * kVar, kSw = 2 * kVar + 1;  // kernel variants: 0..3 = (lfo, flat oscillators), 4..5 = hard sync (lfo)
+      std::vector<int> lists[3 * kVar + 1];  // 0..5 = resting variants, 6..11 = resting, time-parallel, 12 = general, 13..18 = sweeping (idle CTAs are not launched)
+      size_t tp_voices_max = 0;
       e->wwork_zero.resize((size_t)ng, 0);
       const bool chunk_ok = frames % kBlockFrames == 0;
       size_t rest_voices_max = 0, sweep_voices_max = 0;
@@ -1947,9 +1972,11 @@ int render_chunk(gb_engine* e, int frames, size_t n_ev) {
           sweep_voices += (uint64_t)w.nvoices;
           continue;
         }
-        lists[rest ? I.rest_class : kGen].push_back(i);
+        const bool tp = rest && e->opt.rest_tp && w.nvoices <= kTpMaxVoices;
+        lists[rest ? (tp ? kTp : 0) + I.rest_class : kGen].push_back(i);
         if (rest) {
-          rest_voices_max = std::max(rest_voices_max, (size_t)w.nvoices);
+          if (tp) tp_voices_max = std::max(tp_voices_max, (size_t)w.nvoices);
+          else rest_voices_max = std::max(rest_voices_max, (size_t)w.nvoices);
           rest_voices += (uint64_t)w.nvoices;
         }
       }
@@ -1983,6 +2010,24 @@ int render_chunk(gb_engine* e, int frames, size_t n_ev) {
       GB_REST_LAUNCH(4, false, false, true)
       GB_REST_LAUNCH(5, true, false, true)
 #undef GB_REST_LAUNCH
+      const size_t tp_smem = (size_t)kVoiceWarps * kTileStride * sizeof(double2) +
+                             tp_voices_max * (sizeof(TpState) + kVoiceWarps * sizeof(TpPriv));
+#define GB_REST_TP_LAUNCH(CLS_, LFO_, FLAT_, SYNC_)                                                                  \
+  if (!lists[kTp + CLS_].empty()) {                                                                                  \
+    Launch l(e, true, 1);                                                                                            \
+    welsh_rest_tp_kernel<8, LFO_, FLAT_, SYNC_><<<(int)lists[kTp + CLS_].size(), 32 * 8, tp_smem, e->stream>>>(        \
+        e->d_winst, e->d_wvoice, e->wwork.d, e->widx.d + off, f0, frames, (int)tp_voices_max);                       \
+    off += lists[kTp + CLS_].size();                                                                                 \
+    e->stats.rest_ctas += lists[kTp + CLS_].size();                                                                  \
+    e->stats.rest_tp_launches++;                                                                                     \
+  }
+      GB_REST_TP_LAUNCH(0, false, false, false)
+      GB_REST_TP_LAUNCH(1, false, true, false)
+      GB_REST_TP_LAUNCH(2, true, false, false)
+      GB_REST_TP_LAUNCH(3, true, true, false)
+      GB_REST_TP_LAUNCH(4, false, false, true)
+      GB_REST_TP_LAUNCH(5, true, false, true)
+#undef GB_REST_TP_LAUNCH
       e->stats.rest_voice_samples += rest_voices * (uint64_t)frames;
       e->stats.sweep_voice_samples += sweep_voices * (uint64_t)frames;
       const size_t welsh_smem = (size_t)kVoiceWarps * kTileStride * sizeof(double2) + (size_t)kParkWords * 32 * kVoiceWarps * sizeof(double);

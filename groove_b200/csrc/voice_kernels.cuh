@@ -179,6 +179,9 @@ struct WelshInst {
   // amplitude envelope still releases; equal to lti / m1bb / m2bb for a fixed filter (welsh_solo_kernel)
   LtiTable lti_off;
   OscMix m1bb_off, m2bb_off;
+  // lti.mp1[4]^2, lti.mp2[4]^2: the homogeneous map of a whole 256-frame block (welsh_rest_tp_kernel carries the
+  // filter state from one warp's block to the next with it)
+  double mp32_1[4], mp32_2[4];
 };
 enum { FILTER_FIXED = 0, FILTER_ENVELOPE = 1, FILTER_LFO = 2 };
 
@@ -1349,8 +1352,14 @@ __global__ void __launch_bounds__(32 * W, MINB) welsh_kernel(const WelshInst* __
 // last wrap (if that is inside the block so far, p2 = j d2), taken from a double-precision estimate with a
 // one-step correction instead of a 64-bit division.
 template <bool SYNC>
+__device__ __forceinline__ void osc_start_at(u64 P1, u64 P2, u64 d1, u64 d2, u64 k, u64& p1, u64& p2);
+template <bool SYNC>
 __device__ __forceinline__ void osc_lane_start(u64 P1, u64 P2, u64 d1, u64 d2, int lane, u64& p1, u64& p2) {
-  const u64 k = (u64)(lane * kT);
+  osc_start_at<SYNC>(P1, P2, d1, d2, (u64)(lane * kT), p1, p2);
+}
+// ... the same k frames after the base frame (k = 0: the base phases themselves)
+template <bool SYNC>
+__device__ __forceinline__ void osc_start_at(u64 P1, u64 P2, u64 d1, u64 d2, u64 k, u64& p1, u64& p2) {
   p1 = P1 + k * d1;
   p2 = P2 + k * d2;
   if (SYNC && d1 != 0) {
@@ -1390,7 +1399,7 @@ struct alignas(16) RestState {
 // them as the span's entry state, lane 31 replaces them by the state after the span.
 template <int NV, typename State>
 __device__ __forceinline__ void lti_scan_entry_t(const double (&v0)[NV], const double (&v1)[NV], const double (*mp)[4],
-                                                 int lane, State* const (&rs)[NV], int sec, double (&e0)[NV],
+                                                 int lane, State* const* rs, int sec, double (&e0)[NV],
                                                  double (&e1)[NV]) {
   double u0[NV], u1[NV];
 #pragma unroll
@@ -1609,6 +1618,264 @@ __global__ void __launch_bounds__(32 * W, 2) welsh_rest_kernel(const WelshInst* 
   for (int t = threadIdx.x; t < wk.nvoices; t += 32 * W) {
     WelshVoice* vp = voices + wk.voice0 + t;
     vp->s[0] = cache[t].s[0]; vp->s[1] = cache[t].s[1]; vp->s[2] = cache[t].s[2]; vp->s[3] = cache[t].s[3];
+    vp->knot_frame = kNever;
+  }
+}
+
+// ---- the resting-voice kernel, time-parallel ---------------------------------------------------------
+// welsh_rest_kernel gives every warp its own voices and walks them through the chunk block by block: the
+// chunk's 256 blocks are a serial chain per warp (1.7 us per block), so a shard of a few hundred voices —
+// config 4 split over 8 GPUs — is latency-bound on a fraction of the SMs (profiles/r2_strong_probe.txt).
+// Here the W warps of a CTA take W CONSECUTIVE blocks of the SAME voice pair instead: a resting voice is a
+// time-invariant recurrence, so every warp runs its block from a zero entry state (the scan of
+// welsh_rest_block, unchanged), publishes the block's end vector z_w, and after one CTA barrier each warp
+// obtains its true block entry by the W-step recurrence E_{w+1} = M^32 E_w + z_w (M^32: per-instrument
+// constant) and adds M^(lane) E_w to its lanes' entry states (binary powers mp[k]).  Two barriers per pair
+// and round (one per filter section); a chain of 256 blocks becomes 32 rounds.  CTAs hold 2..8 voices
+// (pairs in sequence), so 512 voices are 256 CTAs.
+struct alignas(16) TpState {
+  u64 d1, d2;
+  double s[2][4];  // filter state at the start of the round, double-buffered by round parity
+};
+struct alignas(16) TpPriv {  // a warp's own copy of the round-start phases and LFO phasor (advanced in step by all warps)
+  u64 p1, p2;
+  double ls, lc;
+};
+struct alignas(16) TpScratch {
+  double s[4];    // zero-entry block end vectors of the two sections (written by the scan)
+};
+
+template <bool LFO_AMP, bool ZERO_A, int NV, bool ACC, bool SYNC, int W>
+__device__ __forceinline__ void welsh_rest_block_tp(TpState* const (&ts)[NV], TpPriv* const (&pv)[NV], const WelshInst& I,
+                                                    int warp, int lane, int nb, int par, TpScratch (*zs)[W],
+                                                    const double2* brot, double2* tile_row) {
+  const LtiTable& L = I.lti;
+  double yp[NV][kT];
+  double ps0[NV], ps1[NV];
+  TpScratch* zr[NV];
+#pragma unroll
+  for (int v = 0; v < NV; ++v) zr[v] = &zs[v][warp];
+  // ---- pass 1: oscillators + section 1 from a zero state ----
+  {
+    u64 p1[NV], p2[NV], d1[NV], d2[NV];
+    const u64 koff = (u64)(warp * kBlockFrames + lane * kT);
+#pragma unroll
+    for (int v = 0; v < NV; ++v) {
+      const ulonglong2 pp = *reinterpret_cast<const ulonglong2*>(&pv[v]->p1);
+      const ulonglong2 dd = *reinterpret_cast<const ulonglong2*>(&ts[v]->d1);
+      d1[v] = dd.x; d2[v] = dd.y;
+      osc_start_at<SYNC>(pp.x, pp.y, dd.x, dd.y, koff, p1[v], p2[v]);
+      ps0[v] = 0.0; ps1[v] = 0.0;
+    }
+    const OscMix o1 = I.m1bb, o2 = I.m2bb;
+    const u64 t1 = I.s1.thresh, t2 = I.s2.thresh;
+    const double a1 = L.c1.a1, a2 = L.c1.a2;
+#pragma unroll
+    for (int j = 0; j < kT; ++j) {
+#pragma unroll
+      for (int v = 0; v < NV; ++v) {
+        osc_advance<SYNC>(p1[v], p2[v], d1[v], d2[v]);
+        yp[v][j] = lp_step_bx(osc_mix_eval<ZERO_A>(o1, t1, p1[v], o2, t2, p2[v]), a1, a2, ps0[v], ps1[v]);
+      }
+    }
+    const double inv = L.inv_b0_2;
+#pragma unroll
+    for (int v = 0; v < NV; ++v) { ps0[v] *= inv; ps1[v] *= inv; }
+  }
+  double e0[NV], e1[NV];
+  // one filter section: zero-entry scan, publish, barrier, block entry by the W-step recurrence, lane correction;
+  // warp 0 leaves the state after the round's nb blocks in the other parity's slot
+  auto section = [&](const double (*mp)[4], const double* m32, int sec) {
+    if (lane == 0) {
+#pragma unroll
+      for (int v = 0; v < NV; ++v) { zr[v]->s[2 * sec] = 0.0; zr[v]->s[2 * sec + 1] = 0.0; }
+    }
+    __syncwarp();
+    lti_scan_entry_t<NV, TpScratch>(ps0, ps1, mp, lane, zr, sec, e0, e1);
+    __syncthreads();
+    const double2 r0 = *reinterpret_cast<const double2*>(m32), r1 = *reinterpret_cast<const double2*>(m32 + 2);
+#pragma unroll
+    for (int v = 0; v < NV; ++v) {
+      const double2 st = *reinterpret_cast<const double2*>(&ts[v]->s[par][2 * sec]);
+      double x0 = st.x, x1 = st.y, c0 = 0.0, c1 = 0.0;
+#pragma unroll
+      for (int i = 0; i < W; ++i) {
+        if (i == warp) { c0 = x0; c1 = x1; }
+        if (i < nb) {
+          const double2 z = *reinterpret_cast<const double2*>(&zs[v][i].s[2 * sec]);
+          double n0 = z.x, n1 = z.y;
+          affine_vec_step(n0, n1, r0.x, r0.y, r1.x, r1.y, x0, x1);
+          x0 = n0; x1 = n1;
+        }
+      }
+      if (warp == 0 && lane == 0) *reinterpret_cast<double2*>(&ts[v]->s[par ^ 1][2 * sec]) = make_double2(x0, x1);
+#pragma unroll
+      for (int k = 0; k < 5; ++k) {  // M^lane applied to the block entry: binary powers of the lane map
+        const double2 q0 = *reinterpret_cast<const double2*>(mp[k]), q1 = *reinterpret_cast<const double2*>(mp[k] + 2);
+        double n0 = 0.0, n1 = 0.0;
+        affine_vec_step(n0, n1, q0.x, q0.y, q1.x, q1.y, c0, c1);
+        const bool bit = (lane >> k) & 1;
+        c0 = bit ? n0 : c0;
+        c1 = bit ? n1 : c1;
+      }
+      e0[v] += c0; e1[v] += c1;
+    }
+  };
+  section(L.mp1, I.mp32_1, 0);
+  // ---- pass 2: section 2 on the fixed-up section-1 output ----
+  {
+    const double a1 = L.c2.a1, a2 = L.c2.a2;
+#pragma unroll
+    for (int v = 0; v < NV; ++v) { ps0[v] = 0.0; ps1[v] = 0.0; }
+#pragma unroll
+    for (int j = 0; j < kT; ++j) {
+      const double2 g = *reinterpret_cast<const double2*>(L.g1b[j]);
+#pragma unroll
+      for (int v = 0; v < NV; ++v)
+        yp[v][j] = lp_step_bx(fma(g.y, e1[v], fma(g.x, e0[v], yp[v][j])), a1, a2, ps0[v], ps1[v]);
+    }
+  }
+  section(L.mp2, I.mp32_2, 1);
+  // ---- LFO phasor of this lane: the round's phasor turned by `warp` blocks and the lane's offset ----
+  double lsd[NV], lcd[NV];
+#pragma unroll
+  for (int v = 0; v < NV; ++v) {
+    lsd[v] = 0.0; lcd[v] = 0.0;
+    if (LFO_AMP) {
+      const double2 ph = *reinterpret_cast<const double2*>(&pv[v]->ls);
+      const double2 b = brot[warp], r = I.lane_rot[lane];
+      const double bs = fma(ph.x, b.x, ph.y * b.y), bc = fma(ph.y, b.x, -(ph.x * b.y));
+      lsd[v] = fma(bs, r.x, bc * r.y);
+      lcd[v] = fma(bc, r.x, -(bs * r.y));
+    }
+  }
+  // ---- amplitude, DCA, into the warp's tile row ----
+  const double arest = I.amp_rest;
+  const double gl = I.gl, gr = I.gr;
+  double2* row = tile_row + lane * (kT + 1);
+#pragma unroll
+  for (int j = 0; j < kT; ++j) {
+    const double2 g = *reinterpret_cast<const double2*>(L.g2[j]);
+    double2 rot = make_double2(0.0, 0.0);
+    if (LFO_AMP) rot = I.lfo_rot[j];
+    double m = 0.0;
+#pragma unroll
+    for (int v = 0; v < NV; ++v) {
+      const double amp = LFO_AMP ? fma(lsd[v], rot.x, fma(lcd[v], rot.y, arest)) : arest;
+      const double y = fma(g.y, e1[v], fma(g.x, e0[v], yp[v][j]));
+      m = v == 0 ? y * amp : fma(y, amp, m);
+    }
+    if (ACC) {
+      const double2 p = row[j];
+      row[j] = make_double2(fma(m, gl, p.x), fma(m, gr, p.y));
+    } else {
+      row[j] = make_double2(m * gl, m * gr);
+    }
+  }
+  __syncwarp();  // every lane has read the warp's round-start copies
+  if (lane == 0) {  // ... which advance by the round's nb blocks
+#pragma unroll
+    for (int v = 0; v < NV; ++v) {
+      u64 n1, n2;
+      osc_start_at<SYNC>(pv[v]->p1, pv[v]->p2, ts[v]->d1, ts[v]->d2, (u64)(nb * kBlockFrames), n1, n2);
+      pv[v]->p1 = n1; pv[v]->p2 = n2;
+      if (LFO_AMP) {
+        const double2 ph = *reinterpret_cast<const double2*>(&pv[v]->ls);
+        const double2 b = brot[nb];
+        *reinterpret_cast<double2*>(&pv[v]->ls) = make_double2(fma(ph.x, b.x, ph.y * b.y), fma(ph.y, b.x, -(ph.x * b.y)));
+      }
+    }
+  }
+  __syncwarp();
+}
+
+// grid = number of resting CTAs of this variant with at most kTpMaxVoices voices; block = 32 * W threads;
+// dynamic smem = W tile rows + max_voices TpState + W * max_voices TpPriv.  nframes is a multiple of kBlockFrames.
+constexpr int kTpMaxVoices = 8;
+template <int W, bool LFO_AMP, bool ZERO_A, bool SYNC = false>
+__global__ void __launch_bounds__(32 * W, 2) welsh_rest_tp_kernel(const WelshInst* __restrict__ insts,
+                                                                WelshVoice* __restrict__ voices,
+                                                                const CtaWork* __restrict__ work,
+                                                                const int* __restrict__ idx, i64 f0, int nframes,
+                                                                int max_voices) {
+  extern __shared__ double2 smem_tiles[];
+  __shared__ WelshInst sI;
+  __shared__ TpScratch zs[2][2][W];  // [pair parity][voice of the pair][warp]
+  __shared__ double2 brot[W + 1];    // the LFO's block rotation to the k-th power
+  const CtaWork wk = work[idx[blockIdx.x]];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  {
+    const int* src = reinterpret_cast<const int*>(insts + wk.inst);
+    int* dst = reinterpret_cast<int*>(&sI);
+    for (int i = threadIdx.x; i < (int)(sizeof(WelshInst) / sizeof(int)); i += 32 * W) dst[i] = src[i];
+  }
+  __syncthreads();
+  const WelshInst& I = sI;
+  TpState* cache = reinterpret_cast<TpState*>(smem_tiles + W * kTileStride);
+  TpPriv* priv = reinterpret_cast<TpPriv*>(cache + max_voices) + warp * max_voices;
+  for (int t = threadIdx.x; t < wk.nvoices * (W + 1); t += 32 * W) {
+    const int v = t % wk.nvoices, who = t / wk.nvoices;  // who < W: that warp's private copy; who == W: the shared state
+    const WelshVoice* vp = voices + wk.voice0 + v;
+    const u64 k = (u64)(f0 - 1 - vp->anchor);
+    if (who == W) {
+      TpState r;
+      r.d1 = vp->d1; r.d2 = vp->d2;
+      r.s[0][0] = vp->s[0]; r.s[0][1] = vp->s[1]; r.s[0][2] = vp->s[2]; r.s[0][3] = vp->s[3];
+      r.s[1][0] = 0.0; r.s[1][1] = 0.0; r.s[1][2] = 0.0; r.s[1][3] = 0.0;
+      cache[v] = r;
+    } else {
+      TpPriv q;
+      q.p1 = vp->p1 + k * vp->d1; q.p2 = vp->p2 + k * vp->d2;
+      if (SYNC) q.p2 = welsh_phases_at(*vp, I, f0 - 1).p2;
+      q.ls = 0.0; q.lc = 0.0;
+      if (LFO_AMP) {
+        double ls, lc;
+        sincos_phase(vp->pl + (k + 1) * I.lfo_dq, &ls, &lc);
+        const double dl = I.depth * I.amp_rest;
+        q.ls = ls * dl; q.lc = lc * dl;
+      }
+      reinterpret_cast<TpPriv*>(cache + max_voices)[who * max_voices + v] = q;
+    }
+  }
+  if (threadIdx.x <= W) {
+    double c = 1.0, sn = 0.0;  // (cos, sin) of k block rotations
+    for (int k = 0; k < (int)threadIdx.x; ++k) {
+      const double nc = c * I.block_rot.x - sn * I.block_rot.y, ns = sn * I.block_rot.x + c * I.block_rot.y;
+      c = nc; sn = ns;
+    }
+    brot[threadIdx.x] = make_double2(c, sn);
+  }
+  __syncthreads();
+  double2* tile_row = smem_tiles + warp * kTileStride;
+  const i64 f_end = f0 + nframes;
+  int par = 0, pairs = 0;
+#pragma unroll 1
+  for (int r0 = 0; r0 < nframes; r0 += W * kBlockFrames, par ^= 1) {
+    const int nb = min(W, (nframes - r0) / kBlockFrames);
+    bool first = true;
+#pragma unroll 1
+    for (int g = 0; g < wk.nvoices; g += 2, ++pairs) {
+      TpScratch (*z)[W] = zs[pairs & 1];
+      if (g + 1 < wk.nvoices) {
+        TpState* const two[2] = {cache + g, cache + g + 1};
+        TpPriv* const pq[2] = {priv + g, priv + g + 1};
+        if (first) welsh_rest_block_tp<LFO_AMP, ZERO_A, 2, false, SYNC, W>(two, pq, I, warp, lane, nb, par, z, brot, tile_row);
+        else welsh_rest_block_tp<LFO_AMP, ZERO_A, 2, true, SYNC, W>(two, pq, I, warp, lane, nb, par, z, brot, tile_row);
+      } else {
+        TpState* const one[1] = {cache + g};
+        TpPriv* const pq[1] = {priv + g};
+        if (first) welsh_rest_block_tp<LFO_AMP, ZERO_A, 1, false, SYNC, W>(one, pq, I, warp, lane, nb, par, z, brot, tile_row);
+        else welsh_rest_block_tp<LFO_AMP, ZERO_A, 1, true, SYNC, W>(one, pq, I, warp, lane, nb, par, z, brot, tile_row);
+      }
+      first = false;
+    }
+    if (warp < nb) warp_store_row(tile_row, true, wk.out, f0 + r0 + (i64)warp * kBlockFrames, f0, f_end, lane);
+    __syncwarp();
+  }
+  __syncthreads();  // warp 0's last state write
+  for (int t = threadIdx.x; t < wk.nvoices; t += 32 * W) {
+    WelshVoice* vp = voices + wk.voice0 + t;
+    vp->s[0] = cache[t].s[par][0]; vp->s[1] = cache[t].s[par][1]; vp->s[2] = cache[t].s[par][2]; vp->s[3] = cache[t].s[par][3];
     vp->knot_frame = kNever;
   }
 }

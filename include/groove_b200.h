@@ -322,6 +322,7 @@ typedef struct {
   uint64_t idle_voice_samples;    /* of voice_samples: voices the host knew to be silent (never launched) */
   uint64_t rest_ctas, sweep_ctas; /* CTAs of the resting / sweeping kernel launches, summed */
   uint64_t fx_batched_nodes;      /* effect nodes that shared a launch with others of their kind and graph level */
+  uint64_t rest_tp_launches;      /* of rest_kernel_launches: the time-parallel variant (CTAs of <= 8 voices) */
 } gb_stats;
 int gb_get_stats(gb_engine* e, gb_stats* out);
 int gb_reset_stats(gb_engine* e);

@@ -670,6 +670,63 @@ def test_hard_sync_patch_takes_the_sync_kernels(lfo, monkeypatch):
     assert float(np.abs(out - gen).max()) <= 1e-10
 
 
+@pytest.mark.parametrize("vpc,max_block", [(2, 8192), (3, 4352), (8, 65536), (4, 2048)])
+def test_time_parallel_resting_kernel(vpc, max_block, monkeypatch):
+    """welsh_rest_tp_kernel: CTAs of 2..8 voices whose 8 warps take consecutive 256-frame blocks of the same
+    voice pair (a strong-scaling shard's shape).  Forced here with GB_VPC on the 16-voice held chord; chunk
+    sizes cover full rounds (8 blocks), partial rounds (4352 = 17 blocks) and single-round chunks; vpc 3 gives
+    CTAs with a pair and a single voice.  Must match the oracle and the per-warp kernel (GB_REST_TP=0)."""
+    monkeypatch.setenv("GB_VPC", str(vpc))
+    monkeypatch.setenv("GB_MIN_CUT_VOICES", "1")
+    o = OracleEngine(44100.0)
+    n = scenes.scene_cello_held_chord(o)
+    ref = o.render(n)
+
+    def run():
+        g = gpu_engine(44100.0, max_block=max_block)
+        scenes.scene_cello_held_chord(g)
+        y = g.render(n).copy()
+        st = g.stats()
+        g.close()
+        return y, st
+    out, st = run()
+    assert st.rest_tp_launches > 0
+    check(out, ref)
+    monkeypatch.setenv("GB_REST_TP", "0")
+    base, st0 = run()
+    assert st0.rest_tp_launches == 0 and st0.rest_kernel_launches > 0
+    assert float(np.abs(out - base).max()) <= 1e-12
+
+
+def test_time_parallel_resting_kernel_hard_sync(monkeypatch):
+    """The SYNC instantiation of the time-parallel kernel (oscillator 2's restarts seen from a block offset)."""
+    monkeypatch.setenv("GB_VPC", "2")
+    frames = 330_000
+
+    def scene(r):
+        p = workloads.piano_params(16, 1.0 / 16.0, -0.4)
+        u = r.add_instrument(abi.INST_WELSH, p)
+        r.patch(u, abi.MAIN_MIXER)
+        r.finalize()
+        ev = []
+        for i in range(16):
+            ev.append((50 + 41 * i, u, abi.EV_NOTE_ON, 33 + 2 * i, 127, 0.0))
+            ev.append((300_000 + 64 * i, u, abi.EV_NOTE_OFF, 33 + 2 * i, 0, 0.0))
+        r.push_events(ev)
+        return frames
+
+    o = OracleEngine(48000.0)
+    scene(o)
+    ref = o.render(frames)
+    g = gpu_engine(48000.0, max_block=16384)
+    scene(g)
+    out = g.render(frames)
+    st = g.stats()
+    g.close()
+    assert st.rest_tp_launches > 0
+    check(out, ref)
+
+
 def test_two_gpu_bus_reduce_matches_single_gpu_render(tmp_path):
     """N > 1 on real GPUs: two ranks (torchrun, NCCL) each render their shard of a config-4 slice, the
     stereo buses are summed onto rank 0 with one NCCL f64 reduce, and rank 0 compares the result with its
