@@ -384,6 +384,7 @@ struct gb_engine {
     int min_cut_voices = 256;     // GB_MIN_CUT_VOICES: chunk cuts only for engines with at least this many Welsh voices
   } opt;
   std::map<uint32_t, std::unique_ptr<Node>> nodes;
+  std::vector<Node*> by_uid;      // nodes[uid].get(), O(1): every event of a chunk looks its target up
   std::vector<Node*> plan;  // reachable nodes, sources before consumers
   std::vector<gb_event> events;
   std::string err;
@@ -510,9 +511,12 @@ int dev_alloc(gb_engine* e, T** out, size_t count, bool zero = true) {
   return 0;
 }
 
-Node* find(gb_engine* e, uint32_t uid) {
-  auto it = e->nodes.find(uid);
-  return it == e->nodes.end() ? nullptr : it->second.get();
+Node* find(gb_engine* e, uint32_t uid) {  // uids are dense (1 = main mixer, then in order of creation)
+  return uid < e->by_uid.size() ? e->by_uid[uid] : nullptr;
+}
+void index_node(gb_engine* e, Node* n) {
+  if (n->uid >= e->by_uid.size()) e->by_uid.resize((size_t)n->uid + 1, nullptr);
+  e->by_uid[n->uid] = n;
 }
 
 void welsh_inst_from_params(const Node& n, double sr, const gb_engine::Options& opt, WelshInst* I) {
@@ -997,6 +1001,7 @@ int gb_create(const gb_config* cfg, gb_engine** out) {
   auto mixer = std::make_unique<Node>();
   mixer->uid = GB_MAIN_MIXER;
   mixer->kind = GB_FX_MIXER;
+  index_node(e.get(), mixer.get());
   e->nodes[GB_MAIN_MIXER] = std::move(mixer);
   *out = e.release();
   return 0;
@@ -1073,6 +1078,7 @@ int gb_add_instrument(gb_engine* e, int32_t kind, const void* params, size_t siz
       return fail(e, GB_EINVAL, "unknown instrument kind %d", kind);
   }
   *uid = n->uid;
+  index_node(e, n.get());
   e->nodes[n->uid] = std::move(n);
   e->next_uid++;
   return 0;
@@ -1148,6 +1154,7 @@ int gb_add_effect(gb_engine* e, int32_t kind, const void* params, size_t size, u
   }
 #undef NEED
   *uid = n->uid;
+  index_node(e, n.get());
   e->nodes[n->uid] = std::move(n);
   e->next_uid++;
   return 0;
