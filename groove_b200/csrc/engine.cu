@@ -1426,16 +1426,15 @@ int gb_finalize(gb_engine* e) {
     // still give about one CTA per SM: 2048 voices render in 28.6 ms as 128 CTAs of 16 against 30.5 ms as 256
     // CTAs of 8; 1024 voices in 20.0 ms as 128 CTAs of 8 against 27.5 ms as 64 of 16 (profiles/r2_strong_probe.txt).
     if (vpc == wpc && 20 * total_voices >= 17 * 2 * wpc * e->num_sms) vpc = 2 * wpc;
-    // Few voices for the machine (a strong-scaling shard of 1/8): CTAs of one voice pair, enough of them to cover
-    // the SMs; their resting stretches go to welsh_rest_tp_kernel, whose warps share the pair along time.
+    // Few voices for the machine (a strong-scaling shard of 1/4 or 1/8): CTAs of two voice pairs whose resting
+    // stretches go to welsh_rest_tp_kernel (its warps share a pair along time).  Measured per shard
+    // (profiles/r2_strong_probe.txt): 1024 voices 17.9 ms as 256 such CTAs against 20.0 ms as 128 CTAs of 8 on the
+    // per-warp kernel; 512 voices 11.5 ms as 128 CTAs of 4 (12.4 ms as 256 CTAs of 2: twice the partials to mix)
+    // against 19.1 ms; 2048 voices stay with 16-voice CTAs (28.6 ms against 29.9 ms).
     // Small songs (< 256 voices) keep whole-instrument CTAs: there launches, not SM coverage, are the cost.
-    // Measured (profiles/r2_strong_probe.txt, resting launch of 65 536 frames): 512 voices as 256 CTAs of one
-    // pair 0.223 ms against 0.436 ms as 64 CTAs of 8; with two pairs per CTA (1024 voices) 0.413 against 0.438
-    // and a slower step, with four (2048) 0.788 against 0.624 — a round costs 6.5 us per pair against 2.4 us of
-    // a warp's own block, so only the one-pair split is taken.
     if (kind == GB_INST_WELSH && e->opt.rest_tp && e->opt.rest_kernel && total_voices >= 256 &&
-        cdiv(total_voices, target) <= 2)
-      vpc = 2;
+        cdiv(total_voices, target) <= 4)
+      vpc = 4;
     if (e->opt.vpc > 0) vpc = e->opt.vpc;  // tests: force the voices-per-CTA split
     for (Node* n : e->plan) {
       if (n->kind != kind) continue;

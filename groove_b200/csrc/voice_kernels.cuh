@@ -1629,8 +1629,8 @@ __global__ void __launch_bounds__(32 * W, 2) welsh_rest_kernel(const WelshInst* 
 // Here the W warps of a CTA take W CONSECUTIVE blocks of the SAME voice pair instead: a resting voice is a
 // time-invariant recurrence, so every warp runs its block from a zero entry state (the scan of
 // welsh_rest_block, unchanged), publishes the block's end vector z_w, and after one CTA barrier each warp
-// obtains its true block entry by the W-step recurrence E_{w+1} = M^32 E_w + z_w (M^32: per-instrument
-// constant) and adds M^(lane) E_w to its lanes' entry states (binary powers mp[k]).  Two barriers per pair
+// obtains its true block entry by the recurrence E_{w+1} = M^32 E_w + z_w (M^32: per-instrument constant, w
+// steps for warp w) and adds M^lane E_w to its lanes' entry states (a 64-entry table built at kernel start).  Two barriers per pair
 // and round (one per filter section); a chain of 256 blocks becomes 32 rounds.  CTAs hold 2..8 voices
 // (pairs in sequence), so 512 voices are 256 CTAs.
 struct alignas(16) TpState {
@@ -1648,7 +1648,7 @@ struct alignas(16) TpScratch {
 template <bool LFO_AMP, bool ZERO_A, int NV, bool ACC, bool SYNC, int W>
 __device__ __forceinline__ void welsh_rest_block_tp(TpState* const (&ts)[NV], TpPriv* const (&pv)[NV], const WelshInst& I,
                                                     int warp, int lane, int nb, int par, TpScratch (*zs)[W],
-                                                    const double2* brot, double2* tile_row) {
+                                                    const double2* brot, const double4* mlane, double2* tile_row) {
   const LtiTable& L = I.lti;
   double yp[NV][kT];
   double ps0[NV], ps1[NV];
@@ -1694,14 +1694,17 @@ __device__ __forceinline__ void welsh_rest_block_tp(TpState* const (&ts)[NV], Tp
     lti_scan_entry_t<NV, TpScratch>(ps0, ps1, mp, lane, zr, sec, e0, e1);
     __syncthreads();
     const double2 r0 = *reinterpret_cast<const double2*>(m32), r1 = *reinterpret_cast<const double2*>(m32 + 2);
+    // warp w needs the state after w blocks; warp 0 (whose own entry is the round's) runs all nb steps for the
+    // state after the round
+    const int steps = warp == 0 ? nb : warp;
+    const double4 ml = mlane[sec * 32 + lane];  // M^lane of this section, row-major
 #pragma unroll
     for (int v = 0; v < NV; ++v) {
       const double2 st = *reinterpret_cast<const double2*>(&ts[v]->s[par][2 * sec]);
-      double x0 = st.x, x1 = st.y, c0 = 0.0, c1 = 0.0;
+      double x0 = st.x, x1 = st.y;
 #pragma unroll
       for (int i = 0; i < W; ++i) {
-        if (i == warp) { c0 = x0; c1 = x1; }
-        if (i < nb) {
+        if (i < steps) {
           const double2 z = *reinterpret_cast<const double2*>(&zs[v][i].s[2 * sec]);
           double n0 = z.x, n1 = z.y;
           affine_vec_step(n0, n1, r0.x, r0.y, r1.x, r1.y, x0, x1);
@@ -1709,16 +1712,9 @@ __device__ __forceinline__ void welsh_rest_block_tp(TpState* const (&ts)[NV], Tp
         }
       }
       if (warp == 0 && lane == 0) *reinterpret_cast<double2*>(&ts[v]->s[par ^ 1][2 * sec]) = make_double2(x0, x1);
-#pragma unroll
-      for (int k = 0; k < 5; ++k) {  // M^lane applied to the block entry: binary powers of the lane map
-        const double2 q0 = *reinterpret_cast<const double2*>(mp[k]), q1 = *reinterpret_cast<const double2*>(mp[k] + 2);
-        double n0 = 0.0, n1 = 0.0;
-        affine_vec_step(n0, n1, q0.x, q0.y, q1.x, q1.y, c0, c1);
-        const bool bit = (lane >> k) & 1;
-        c0 = bit ? n0 : c0;
-        c1 = bit ? n1 : c1;
-      }
-      e0[v] += c0; e1[v] += c1;
+      const double c0 = warp == 0 ? st.x : x0, c1 = warp == 0 ? st.y : x1;  // this warp's block entry
+      e0[v] = fma(ml.y, c1, fma(ml.x, c0, e0[v]));                           // + M^lane applied to it
+      e1[v] = fma(ml.w, c1, fma(ml.z, c0, e1[v]));
     }
   };
   section(L.mp1, I.mp32_1, 0);
@@ -1802,6 +1798,7 @@ __global__ void __launch_bounds__(32 * W, 2) welsh_rest_tp_kernel(const WelshIns
   __shared__ WelshInst sI;
   __shared__ TpScratch zs[2][2][W];  // [pair parity][voice of the pair][warp]
   __shared__ double2 brot[W + 1];    // the LFO's block rotation to the k-th power
+  __shared__ double4 mlane[64];      // [section][lane]: M^lane
   const CtaWork wk = work[idx[blockIdx.x]];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   {
@@ -1837,6 +1834,19 @@ __global__ void __launch_bounds__(32 * W, 2) welsh_rest_tp_kernel(const WelshIns
       reinterpret_cast<TpPriv*>(cache + max_voices)[who * max_voices + v] = q;
     }
   }
+  if (threadIdx.x < 64) {  // M^lane of both sections: the lane map to the lane's power, by its binary digits
+    const int sec = threadIdx.x >> 5, l = threadIdx.x & 31;
+    const double (*mp)[4] = sec ? I.lti.mp2 : I.lti.mp1;
+    double a00 = 1.0, a01 = 0.0, a10 = 0.0, a11 = 1.0;
+    for (int k = 0; k < 5; ++k)
+      if ((l >> k) & 1) {
+        const double* m = mp[k];
+        const double b00 = m[0] * a00 + m[1] * a10, b01 = m[0] * a01 + m[1] * a11;
+        const double b10 = m[2] * a00 + m[3] * a10, b11 = m[2] * a01 + m[3] * a11;
+        a00 = b00; a01 = b01; a10 = b10; a11 = b11;
+      }
+    mlane[threadIdx.x] = make_double4(a00, a01, a10, a11);
+  }
   if (threadIdx.x <= W) {
     double c = 1.0, sn = 0.0;  // (cos, sin) of k block rotations
     for (int k = 0; k < (int)threadIdx.x; ++k) {
@@ -1859,13 +1869,13 @@ __global__ void __launch_bounds__(32 * W, 2) welsh_rest_tp_kernel(const WelshIns
       if (g + 1 < wk.nvoices) {
         TpState* const two[2] = {cache + g, cache + g + 1};
         TpPriv* const pq[2] = {priv + g, priv + g + 1};
-        if (first) welsh_rest_block_tp<LFO_AMP, ZERO_A, 2, false, SYNC, W>(two, pq, I, warp, lane, nb, par, z, brot, tile_row);
-        else welsh_rest_block_tp<LFO_AMP, ZERO_A, 2, true, SYNC, W>(two, pq, I, warp, lane, nb, par, z, brot, tile_row);
+        if (first) welsh_rest_block_tp<LFO_AMP, ZERO_A, 2, false, SYNC, W>(two, pq, I, warp, lane, nb, par, z, brot, mlane, tile_row);
+        else welsh_rest_block_tp<LFO_AMP, ZERO_A, 2, true, SYNC, W>(two, pq, I, warp, lane, nb, par, z, brot, mlane, tile_row);
       } else {
         TpState* const one[1] = {cache + g};
         TpPriv* const pq[1] = {priv + g};
-        if (first) welsh_rest_block_tp<LFO_AMP, ZERO_A, 1, false, SYNC, W>(one, pq, I, warp, lane, nb, par, z, brot, tile_row);
-        else welsh_rest_block_tp<LFO_AMP, ZERO_A, 1, true, SYNC, W>(one, pq, I, warp, lane, nb, par, z, brot, tile_row);
+        if (first) welsh_rest_block_tp<LFO_AMP, ZERO_A, 1, false, SYNC, W>(one, pq, I, warp, lane, nb, par, z, brot, mlane, tile_row);
+        else welsh_rest_block_tp<LFO_AMP, ZERO_A, 1, true, SYNC, W>(one, pq, I, warp, lane, nb, par, z, brot, mlane, tile_row);
       }
       first = false;
     }

@@ -19,6 +19,7 @@ ap.add_argument("workload", choices=["cfg4", "cfg5", "tv", "strong", "fx", "pian
 ap.add_argument("--variants", type=int, default=8192)
 ap.add_argument("--voices", type=int, default=4096)
 ap.add_argument("--seconds", type=float, default=6.0)
+ap.add_argument("--groups", type=int, default=0)
 ap.add_argument("--reps", type=int, default=2)
 a = ap.parse_args()
 for _ in range(a.reps):
@@ -35,7 +36,7 @@ for _ in range(a.reps):
     else:
         frames = int(round(a.seconds * 48000))
         cfg = workloads.Cfg4(total_voices=a.voices, frames=frames, note_off_base=int(frames * 2_400_000 / 2_880_000),
-                             groups=min(128, a.voices), filter_decay=120.0 if a.workload == "tv" else 3.29)
+                             groups=a.groups or min(128, a.voices), filter_decay=120.0 if a.workload == "tv" else 3.29)
         e = Engine(48000.0, device=0)
         e.set_timing(True)
         workloads.build_cfg4(e, cfg, params=workloads.piano_params if a.workload == "piano" else None)
