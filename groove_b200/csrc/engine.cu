@@ -313,6 +313,8 @@ struct Node {
   double2* scratch = nullptr;     // pre-reduction when > kMaxSources inputs / partial sums
   const double2** d_src_table = nullptr;  // device table of source buffers (> kMaxSources inputs)
   const double2** d_src_table_fused = nullptr;  // the same with split instruments replaced by their partial buffers
+  const double2** d_src_table_fused_alt = nullptr;  // ... by their partial buffers of odd chunks (gb_engine::overlap)
+  double2* scratch_alt = nullptr;  // split Welsh instrument: the partial buffers of odd chunks (gb_engine::overlap)
   int n_src_fused = 0;
   int consumers = 0;           // plan nodes that read this node's buffer
   bool fuse_partials = false;  // split instrument whose only consumer sums its partials itself (no reduce pass)
@@ -360,6 +362,17 @@ struct gb_engine {
   cudaStream_t copy_stream = nullptr;               // device -> host result copies, overlapped with the next chunks
   cudaEvent_t stage_done[kStageSlots] = {};          // chunk i's work enqueued on `stream` (guards staging slot i % kStageSlots)
   cudaEvent_t d2d_done[kStageSlots] = {}, d2h_done[kStageSlots] = {};
+  // Overlapped mixdown (engines whose instruments are all split Welsh instruments summed by their consumer, e.g.
+  // BASELINE config 4): the grouped voice kernels run on `vstream` and write partial buffers that alternate
+  // with the chunk's parity, while `stream` still sums / mixes / copies out the previous chunk — the HBM-bound
+  // table sum then runs on the SM slots the voice kernels leave free instead of between them.
+  cudaStream_t vstream = nullptr;
+  cudaEvent_t v_done[2] = {}, p_done[2] = {}, call_start = nullptr;
+  bool overlap = false;          // decided by gb_finalize
+  bool overlap_enabled = true;   // GB_OVERLAP=0
+  CtaWork* d_wwork_alt = nullptr;        // the grouped CTA list with the odd-chunk output buffers
+  PartialDesc* d_partials_alt = nullptr; // e->partials with the odd-chunk buffers
+  int parity = 0;                        // partial-buffer set of the chunk being enqueued
   double2* ring = nullptr;                           // pinned: kStageSlots x max_block frames (host-buffer renders)
   uint64_t chunk_seq = 0;
   bool finalized = false;
@@ -380,6 +393,7 @@ struct gb_engine {
     bool rest_kernel = true;      // GB_REST_KERNEL=0
     bool sweep_kernel = true;     // GB_SWEEP_KERNEL=0
     bool sync_kernels = true;     // GB_SYNC_KERNELS=0: hard-sync patches stay on the general kernel
+    int rest_nv = 2;              // GB_REST_NV=4: welsh_rest_kernel with four voices in lockstep per warp (one CTA per SM)
     bool rest_tp = true;          // GB_REST_TP=0: no time-parallel resting kernel (and no CTAs below 8 voices)
     int min_cut_voices = 256;     // GB_MIN_CUT_VOICES: chunk cuts only for engines with at least this many Welsh voices
   } opt;
@@ -412,6 +426,7 @@ struct gb_engine {
   std::vector<Link> links;
   std::vector<Node*> wwork_node;  // instrument of each grouped Welsh CTA
   std::vector<char> wwork_zero;   // ... its output buffer currently holds zeros (idle CTAs are not launched)
+  std::vector<char> wwork_zero_alt;  // ... the odd-chunk buffer (gb_engine::overlap)
   // solo Welsh items (instruments with fewer voices than a CTA has warps): with enough of them the host
   // classifies every (voice, sub-chunk) and welsh_solo_kernel walks the resulting job list (voice_kernels.cuh)
   bool solo_mega = false;
@@ -465,7 +480,7 @@ struct gb_engine {
   bool timing = false;
   // CUDA-event pairs recorded around launches / render calls on the engine stream; resolved
   // lazily (gb_get_stats) so that timing never serialises the stream.
-  struct TimedSpan { cudaEvent_t a, b; int what; bool closed; };  // what: 0 = fx kernel, 1 = voice kernel, 2 = render call
+  struct TimedSpan { cudaEvent_t a, b; int what; bool closed; cudaStream_t st; };  // what: 0 = fx kernel, 1 = voice kernel, 2 = render call
   std::vector<TimedSpan> spans;
   std::vector<std::pair<cudaEvent_t, cudaEvent_t>> event_pool;
 };
@@ -499,6 +514,10 @@ int dev_alloc(gb_engine* e, T** out, size_t count, bool zero = true) {
     const size_t slab = std::max(bytes, e->slab_next);
     void* p = nullptr;
     CUDA_TRY(e, cudaMalloc(&p, slab));
+    // Zeroed once, here, and drained: a per-allocation memset on the engine stream is not ordered against the
+    // synchronous table copies (legacy stream) that follow most allocations and could land after them.
+    CUDA_TRY(e, cudaMemset(p, 0, slab));
+    CUDA_TRY(e, cudaDeviceSynchronize());
     e->allocations.push_back(p);
     e->slab_ptr = (char*)p;
     e->slab_left = slab;
@@ -506,7 +525,7 @@ int dev_alloc(gb_engine* e, T** out, size_t count, bool zero = true) {
   void* p = e->slab_ptr;
   e->slab_ptr += bytes;
   e->slab_left -= bytes;
-  if (zero) CUDA_TRY(e, cudaMemsetAsync(p, 0, bytes, e->stream));
+  (void)zero;  // slabs are zeroed when they are created and never handed out twice
   *out = (T*)p;
   return 0;
 }
@@ -709,8 +728,9 @@ void fm_inst_from_params(const Node& n, double sr, FmInst* I) {
   I->voice0 = n.voice0;
 }
 
-bool span_begin(gb_engine* e, int what) {
+bool span_begin(gb_engine* e, int what, cudaStream_t st = nullptr) {
   if (!e->timing) return false;
+  if (!st) st = e->stream;
   std::pair<cudaEvent_t, cudaEvent_t> ev;
   if (!e->event_pool.empty()) {
     ev = e->event_pool.back();
@@ -718,15 +738,15 @@ bool span_begin(gb_engine* e, int what) {
   } else {
     if (cudaEventCreate(&ev.first) != cudaSuccess || cudaEventCreate(&ev.second) != cudaSuccess) return false;
   }
-  if (cudaEventRecord(ev.first, e->stream) != cudaSuccess) {  // timing is best effort: an untimed launch, not a failed one
+  if (cudaEventRecord(ev.first, st) != cudaSuccess) {  // timing is best effort: an untimed launch, not a failed one
     e->event_pool.push_back(ev);
     return false;
   }
-  e->spans.push_back({ev.first, ev.second, what, false});
+  e->spans.push_back({ev.first, ev.second, what, false, st});
   return true;
 }
 void span_end(gb_engine* e, size_t index) {
-  e->spans[index].closed = cudaEventRecord(e->spans[index].b, e->stream) == cudaSuccess;
+  e->spans[index].closed = cudaEventRecord(e->spans[index].b, e->spans[index].st) == cudaSuccess;
 }
 void resolve_spans(gb_engine* e) {
   for (auto& sp : e->spans) {
@@ -749,14 +769,14 @@ struct Launch {  // per-launch accounting (+ optional CUDA-event timing on the e
   gb_engine* e;
   bool timed;
   size_t index;
-  Launch(gb_engine* e_, bool voice, int special = 0) : e(e_) {  // special: 1 = resting, 2 = sweeping, 3 = solo job-list, 4 = FM kernel
+  Launch(gb_engine* e_, bool voice, int special = 0, cudaStream_t st = nullptr) : e(e_) {  // special: 1 = resting, 2 = sweeping, 3 = solo job-list, 4 = FM kernel
     e->stats.kernel_launches++;
     if (voice) e->stats.voice_kernel_launches++;
     if (special == 1) e->stats.rest_kernel_launches++;
     if (special == 2) e->stats.sweep_kernel_launches++;
     if (special == 3) e->stats.solo_kernel_launches++;
     if (special == 4) e->stats.fm_kernel_launches++;
-    timed = span_begin(e, special == 1 ? 3 : special == 2 ? 4 : special == 3 ? 5 : special == 4 ? 6 : voice ? 1 : 0);
+    timed = span_begin(e, special == 1 ? 3 : special == 2 ? 4 : special == 3 ? 5 : special == 4 ? 6 : voice ? 1 : 0, st);
     index = e->spans.size() - 1;
   }
   ~Launch() {
@@ -788,7 +808,8 @@ int gather_sources(gb_engine* e, Node* n, int frames, SourceList* out, bool* don
     const bool plain = done && (n->kind == GB_FX_MIXER || n->kind == GB_FX_SIGNAL_PASSTHROUGH);
     double2* dst = plain ? n->buf : n->scratch;
     if (e->fused_sums && n->d_src_table_fused)
-      sum_table_kernel<<<cdiv(frames, kSumFrames), kSumRows * kSumFrames, 0, e->stream>>>(n->d_src_table_fused, n->n_src_fused, dst, frames);
+      sum_table_kernel<<<cdiv(frames, kSumFrames), kSumRows * kSumFrames, 0, e->stream>>>(
+          e->parity && n->d_src_table_fused_alt ? n->d_src_table_fused_alt : n->d_src_table_fused, n->n_src_fused, dst, frames);
     else
       sum_table_kernel<<<cdiv(frames, kSumFrames), kSumRows * kSumFrames, 0, e->stream>>>(n->d_src_table, (int)ptrs.size(), dst, frames);
     if (plain) *done = true;
@@ -979,6 +1000,8 @@ int gb_create(const gb_config* cfg, gb_engine** out) {
   if (const char* v = getenv("GB_SWEEP_KERNEL")) e->opt.sweep_kernel = atoi(v) != 0;
   if (const char* v = getenv("GB_SYNC_KERNELS")) e->opt.sync_kernels = atoi(v) != 0;
   if (const char* v = getenv("GB_REST_TP")) e->opt.rest_tp = atoi(v) != 0;
+  if (const char* v = getenv("GB_REST_NV")) e->opt.rest_nv = atoi(v) == 4 ? 4 : 2;
+  if (const char* v = getenv("GB_OVERLAP")) e->overlap_enabled = atoi(v) != 0;
   if (const char* v = getenv("GB_MIN_CUT_VOICES")) e->opt.min_cut_voices = std::max(1, atoi(v));
   if (const char* v = getenv("GB_SOLO_MIN")) e->min_solo_items = atoi(v);
   if (const char* v = getenv("GB_SOLO_WAVES")) e->solo_waves = atoi(v) != 0;
@@ -990,7 +1013,8 @@ int gb_create(const gb_config* cfg, gb_engine** out) {
   if (const char* v = getenv("GB_FUSED_SUMS")) e->fused_sums_enabled = atoi(v) != 0;
   if (const char* v = getenv("GB_CHUNK_CUTS")) e->chunk_cuts = atoi(v) != 0;
   if (cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking) != cudaSuccess ||
-      cudaStreamCreateWithFlags(&e->copy_stream, cudaStreamNonBlocking) != cudaSuccess)
+      cudaStreamCreateWithFlags(&e->copy_stream, cudaStreamNonBlocking) != cudaSuccess ||
+      cudaStreamCreateWithFlags(&e->vstream, cudaStreamNonBlocking) != cudaSuccess)
     return fail(nullptr, GB_ECUDA, "cudaStreamCreate failed");
   for (int i = 0; i < kStageSlots; ++i) {
     if (cudaEventCreateWithFlags(&e->stage_done[i], cudaEventDisableTiming) != cudaSuccess ||
@@ -998,6 +1022,12 @@ int gb_create(const gb_config* cfg, gb_engine** out) {
         cudaEventCreateWithFlags(&e->d2h_done[i], cudaEventDisableTiming) != cudaSuccess)
       return fail(nullptr, GB_ECUDA, "cudaEventCreate failed");
   }
+  for (int i = 0; i < 2; ++i)
+    if (cudaEventCreateWithFlags(&e->v_done[i], cudaEventDisableTiming) != cudaSuccess ||
+        cudaEventCreateWithFlags(&e->p_done[i], cudaEventDisableTiming) != cudaSuccess)
+      return fail(nullptr, GB_ECUDA, "cudaEventCreate failed");
+  if (cudaEventCreateWithFlags(&e->call_start, cudaEventDisableTiming) != cudaSuccess)
+    return fail(nullptr, GB_ECUDA, "cudaEventCreate failed");
   auto mixer = std::make_unique<Node>();
   mixer->uid = GB_MAIN_MIXER;
   mixer->kind = GB_FX_MIXER;
@@ -1019,6 +1049,12 @@ void gb_destroy(gb_engine* e) {
   }
   if (e->ring) cudaFreeHost(e->ring);
   if (e->copy_stream) cudaStreamDestroy(e->copy_stream);
+  if (e->vstream) cudaStreamDestroy(e->vstream);
+  for (int i = 0; i < 2; ++i) {
+    if (e->v_done[i]) cudaEventDestroy(e->v_done[i]);
+    if (e->p_done[i]) cudaEventDestroy(e->p_done[i]);
+  }
+  if (e->call_start) cudaEventDestroy(e->call_start);
   for (void* p : e->allocations) cudaFree(p);
   if (e->d_full) cudaFree(e->d_full);
   if (e->d_pcm) cudaFree(e->d_pcm);
@@ -1582,6 +1618,53 @@ int gb_finalize(gb_engine* e) {
       }
     }
   }
+  // Overlapped mixdown: possible when every voice kernel output is a partial buffer that only a consumer's table
+  // sum (or reduce_partials) reads — all instruments split Welsh instruments, no solo items, no control links.
+  // Those buffers, the CTA list that points at them, and the consumers' tables then exist twice (chunk parity).
+  e->overlap = false;
+  if (e->overlap_enabled && e->n_wwork_grouped > 0 && e->n_wwork == e->n_wwork_grouped && e->links.empty()) {
+    bool ok = true;
+    for (Node* n : e->plan)
+      if (n->is_inst) ok = ok && n->kind == GB_INST_WELSH && n->partial_count > 0 && n->fuse_partials;
+    if (ok) {
+      int rc2;
+      for (Node* n : e->plan)
+        if (n->is_inst && (rc2 = dev_alloc(e, &n->scratch_alt, (size_t)n->partial_count * mb))) return rc2;
+      std::vector<CtaWork> alt(e->wwork.h, e->wwork.h + e->n_wwork);
+      for (int i = 0; i < e->n_wwork; ++i) {
+        const Node* n = e->wwork_node[(size_t)i];
+        alt[(size_t)i].out = n->scratch_alt + (alt[(size_t)i].out - n->scratch);
+      }
+      if ((rc2 = dev_alloc(e, &e->d_wwork_alt, alt.size(), false))) return rc2;
+      CUDA_TRY(e, cudaMemcpy(e->d_wwork_alt, alt.data(), alt.size() * sizeof(CtaWork), cudaMemcpyHostToDevice));
+      std::vector<PartialDesc> pd(e->partials.h, e->partials.h + e->n_partials);
+      {
+        size_t k = 0;
+        for (Node* n : e->plan) {
+          if (!(n->kind == GB_INST_WELSH || n->kind == GB_INST_FM) || n->partial_count == 0) continue;
+          pd[k++].base = n->scratch_alt;
+        }
+      }
+      if ((rc2 = dev_alloc(e, &e->d_partials_alt, pd.size(), false))) return rc2;
+      CUDA_TRY(e, cudaMemcpy(e->d_partials_alt, pd.data(), pd.size() * sizeof(PartialDesc), cudaMemcpyHostToDevice));
+      for (Node* n : e->plan) {
+        if (n->is_inst || !n->d_src_table_fused) continue;
+        std::vector<const double2*> fused;
+        for (uint32_t su : n->sources) {
+          Node* sn = find(e, su);
+          if (!(sn && sn->order >= 0 && sn->buf)) continue;
+          if (sn->fuse_partials)
+            for (int k = 0; k < sn->partial_count; ++k) fused.push_back(sn->scratch_alt + (size_t)k * mb);
+          else
+            fused.push_back(sn->buf);
+        }
+        if ((rc2 = dev_alloc(e, &n->d_src_table_fused_alt, fused.size(), false))) return rc2;
+        CUDA_TRY(e, cudaMemcpy((void*)n->d_src_table_fused_alt, fused.data(), fused.size() * sizeof(double2*), cudaMemcpyHostToDevice));
+      }
+      e->overlap = true;
+    }
+  }
+  e->parity = 0;
   const int welsh_smem_bytes = (int)(kVoiceWarps * kTileStride * sizeof(double2) + kParkWords * 32 * kVoiceWarps * sizeof(double));
   CUDA_TRY(e, cudaFuncSetAttribute(welsh_kernel<8, 2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, welsh_smem_bytes));
   CUDA_TRY(e, cudaFuncSetAttribute(welsh_kernel<8, 2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, welsh_smem_bytes));
@@ -1597,6 +1680,12 @@ int gb_finalize(gb_engine* e) {
   CUDA_TRY(e, cudaFuncSetAttribute(welsh_rest_tp_kernel<8, true, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kRestSmemMax));
   CUDA_TRY(e, cudaFuncSetAttribute(welsh_rest_kernel<8, false, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kRestSmemMax));
   CUDA_TRY(e, cudaFuncSetAttribute(welsh_rest_kernel<8, true, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kRestSmemMax));
+  CUDA_TRY(e, cudaFuncSetAttribute(welsh_rest_kernel<8, false, false, false, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, kRestSmemMax));
+  CUDA_TRY(e, cudaFuncSetAttribute(welsh_rest_kernel<8, false, true, false, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, kRestSmemMax));
+  CUDA_TRY(e, cudaFuncSetAttribute(welsh_rest_kernel<8, true, false, false, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, kRestSmemMax));
+  CUDA_TRY(e, cudaFuncSetAttribute(welsh_rest_kernel<8, true, true, false, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, kRestSmemMax));
+  CUDA_TRY(e, cudaFuncSetAttribute(welsh_rest_kernel<8, false, false, true, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, kRestSmemMax));
+  CUDA_TRY(e, cudaFuncSetAttribute(welsh_rest_kernel<8, true, false, true, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, kRestSmemMax));
   CUDA_TRY(e, cudaFuncSetAttribute(welsh_sweep_kernel<8, false, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kRestSmemMax));
   CUDA_TRY(e, cudaFuncSetAttribute(welsh_sweep_kernel<8, true, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kRestSmemMax));
   CUDA_TRY(e, cudaFuncSetAttribute(welsh_sweep_kernel<8, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kRestSmemMax));
@@ -1884,7 +1973,7 @@ int render_chunk(gb_engine* e, int frames, size_t n_ev) {
 
   // ---- 3. voices ----
   auto upload_events = [&](std::vector<std::vector<VoiceEvent>>& lists, DevBuf<VoiceEvent>& evb, DevBuf<int>& offb,
-                           bool any, bool* empty_on_device) -> int {
+                           bool any, bool* empty_on_device, cudaStream_t st) -> int {
     size_t nv = lists.size(), total = 0;
     // a chunk without note events needs the all-zero offset table: if that is what the device already
     // holds, nothing is uploaded (every small copy costs the stream several microseconds)
@@ -1901,19 +1990,32 @@ int render_chunk(gb_engine* e, int frames, size_t n_ev) {
         for (auto& x : lists[v]) evb.h[k++] = x;
     }
     offb.h[nv] = (int)k;
-    CUDA_TRY(e, cudaMemcpyAsync(offb.d, offb.h, (nv + 1) * sizeof(int), cudaMemcpyHostToDevice, e->stream));
+    CUDA_TRY(e, cudaMemcpyAsync(offb.d, offb.h, (nv + 1) * sizeof(int), cudaMemcpyHostToDevice, st));
     e->stats.h2d_bytes += (nv + 1) * sizeof(int);
     if (k) {
-      CUDA_TRY(e, cudaMemcpyAsync(evb.d, evb.h, k * sizeof(VoiceEvent), cudaMemcpyHostToDevice, e->stream));
+      CUDA_TRY(e, cudaMemcpyAsync(evb.d, evb.h, k * sizeof(VoiceEvent), cudaMemcpyHostToDevice, st));
       e->stats.h2d_bytes += k * sizeof(VoiceEvent);
     }
     return 0;
   };
   const size_t tile_bytes = (size_t)kVoiceWarps * kTileStride * sizeof(double2);
   hp.mark("events");
+  // Overlapped mixdown: this chunk's grouped voice kernels go to vstream and write the partial buffers of the
+  // chunk's parity; they wait for the table sum that read those buffers two chunks ago.
+  const int par = e->overlap ? (int)(e->chunk_seq & 1) : 0;
+  e->parity = par;
+  cudaStream_t vs = e->overlap ? e->vstream : e->stream;
+  if (e->overlap) {
+    CUDA_TRY(e, cudaStreamWaitEvent(vs, e->call_start, 0));
+    CUDA_TRY(e, cudaStreamWaitEvent(vs, e->p_done[par], 0));
+  }
   if (e->n_wvoice) {
-    if (e->winst_dirty) { int rc0 = upload_inst_tables(e); if (rc0) return rc0; }
-    int rc = upload_events(wlists, e->wev, e->wev_off, any_w, &e->wev_empty_on_device);
+    if (e->winst_dirty) {
+      if (e->overlap) CUDA_TRY(e, cudaStreamSynchronize(e->vstream));  // earlier chunks' kernels still read the table
+      int rc0 = upload_inst_tables(e);
+      if (rc0) return rc0;
+    }
+    int rc = upload_events(wlists, e->wev, e->wev_off, any_w, &e->wev_empty_on_device, vs);
     if (rc) return rc;
     {
       // Sort the grouped CTAs of this chunk: a CTA whose voices all rest for the whole chunk (note held
@@ -1925,6 +2027,9 @@ int render_chunk(gb_engine* e, int frames, size_t n_ev) {
       std::vector<int> lists[3 * kVar + 1];  // 0..5 = resting variants, 6..11 = resting, time-parallel, 12 = general, 13..18 = sweeping (idle CTAs are not launched)
       size_t tp_voices_max = 0;
       e->wwork_zero.resize((size_t)ng, 0);
+      e->wwork_zero_alt.resize((size_t)ng, 0);
+      std::vector<char>& wzero = par ? e->wwork_zero_alt : e->wwork_zero;
+      const CtaWork* wwd = par ? e->d_wwork_alt : e->wwork.d;
       const bool chunk_ok = frames % kBlockFrames == 0;
       size_t rest_voices_max = 0, sweep_voices_max = 0;
       uint64_t rest_voices = 0, sweep_voices = 0;
@@ -1947,13 +2052,14 @@ int render_chunk(gb_engine* e, int frames, size_t n_ev) {
         }
         if (idle) {
           e->stats.idle_voice_samples += (uint64_t)w.nvoices * (uint64_t)frames;
-          if (!e->wwork_zero[(size_t)i]) {
-            CUDA_TRY(e, cudaMemsetAsync(w.out, 0, (size_t)e->max_block * sizeof(double2), e->stream));
-            e->wwork_zero[(size_t)i] = 1;
+          if (!wzero[(size_t)i]) {
+            double2* zout = par ? n->scratch_alt + (w.out - n->scratch) : w.out;
+            CUDA_TRY(e, cudaMemsetAsync(zout, 0, (size_t)e->max_block * sizeof(double2), vs));
+            wzero[(size_t)i] = 1;
           }
           continue;
         }
-        e->wwork_zero[(size_t)i] = 0;
+        wzero[(size_t)i] = 0;
         // sweeping: every voice held since before the chunk, no note event in it, the filter envelope inside one
         // moving stage and the amplitude envelope inside one stage for the whole chunk, the cutoff slow enough
         // for coefficient knots (the bound uses the stage's steepest slope)
@@ -1994,7 +2100,7 @@ int render_chunk(gb_engine* e, int frames, size_t n_ev) {
         const size_t k = flat.size();
         if (k && flat != e->widx_on_device) {
           memcpy(e->widx.h, flat.data(), k * sizeof(int));
-          CUDA_TRY(e, cudaMemcpyAsync(e->widx.d, e->widx.h, k * sizeof(int), cudaMemcpyHostToDevice, e->stream));
+          CUDA_TRY(e, cudaMemcpyAsync(e->widx.d, e->widx.h, k * sizeof(int), cudaMemcpyHostToDevice, vs));
           e->stats.h2d_bytes += k * sizeof(int);
           e->widx_on_device = flat;
         }
@@ -2003,9 +2109,13 @@ int render_chunk(gb_engine* e, int frames, size_t n_ev) {
       size_t off = 0;
 #define GB_REST_LAUNCH(CLS_, LFO_, FLAT_, SYNC_)                                                                     \
   if (!lists[CLS_].empty()) {                                                                                        \
-    Launch l(e, true, 1);                                                                                            \
-    welsh_rest_kernel<8, LFO_, FLAT_, SYNC_><<<(int)lists[CLS_].size(), 32 * 8, rest_smem, e->stream>>>(               \
-        e->d_winst, e->d_wvoice, e->wwork.d, e->widx.d + off, f0, frames);                                           \
+    Launch l(e, true, 1, vs);                                                                                        \
+    if (e->opt.rest_nv == 4)                                                                                         \
+      welsh_rest_kernel<8, LFO_, FLAT_, SYNC_, 4><<<(int)lists[CLS_].size(), 32 * 8, rest_smem, vs>>>(                 \
+          e->d_winst, e->d_wvoice, wwd, e->widx.d + off, f0, frames);                                                \
+    else                                                                                                             \
+      welsh_rest_kernel<8, LFO_, FLAT_, SYNC_><<<(int)lists[CLS_].size(), 32 * 8, rest_smem, vs>>>(                    \
+          e->d_winst, e->d_wvoice, wwd, e->widx.d + off, f0, frames);                                                \
     off += lists[CLS_].size();                                                                                       \
     e->stats.rest_ctas += lists[CLS_].size();                                                                        \
   }
@@ -2020,9 +2130,9 @@ int render_chunk(gb_engine* e, int frames, size_t n_ev) {
                              tp_voices_max * (sizeof(TpState) + kVoiceWarps * sizeof(TpPriv));
 #define GB_REST_TP_LAUNCH(CLS_, LFO_, FLAT_, SYNC_)                                                                  \
   if (!lists[kTp + CLS_].empty()) {                                                                                  \
-    Launch l(e, true, 1);                                                                                            \
-    welsh_rest_tp_kernel<8, LFO_, FLAT_, SYNC_><<<(int)lists[kTp + CLS_].size(), 32 * 8, tp_smem, e->stream>>>(        \
-        e->d_winst, e->d_wvoice, e->wwork.d, e->widx.d + off, f0, frames, (int)tp_voices_max);                       \
+    Launch l(e, true, 1, vs);                                                                                        \
+    welsh_rest_tp_kernel<8, LFO_, FLAT_, SYNC_><<<(int)lists[kTp + CLS_].size(), 32 * 8, tp_smem, vs>>>(               \
+        e->d_winst, e->d_wvoice, wwd, e->widx.d + off, f0, frames, (int)tp_voices_max);                              \
     off += lists[kTp + CLS_].size();                                                                                 \
     e->stats.rest_ctas += lists[kTp + CLS_].size();                                                                  \
     e->stats.rest_tp_launches++;                                                                                     \
@@ -2038,17 +2148,17 @@ int render_chunk(gb_engine* e, int frames, size_t n_ev) {
       e->stats.sweep_voice_samples += sweep_voices * (uint64_t)frames;
       const size_t welsh_smem = (size_t)kVoiceWarps * kTileStride * sizeof(double2) + (size_t)kParkWords * 32 * kVoiceWarps * sizeof(double);
       if (!lists[kGen].empty()) {
-        Launch l(e, true);
-        welsh_kernel<8, 2, false><<<(int)lists[kGen].size(), 32 * 8, welsh_smem, e->stream>>>(
-            e->d_winst, e->d_wvoice, e->wwork.d, e->witems.d, e->wev.d, e->wev_off.d, f0, frames, e->widx.d + off);
+        Launch l(e, true, 0, vs);
+        welsh_kernel<8, 2, false><<<(int)lists[kGen].size(), 32 * 8, welsh_smem, vs>>>(
+            e->d_winst, e->d_wvoice, wwd, e->witems.d, e->wev.d, e->wev_off.d, f0, frames, e->widx.d + off);
       }
       off += lists[kGen].size();
       const size_t sweep_smem = (size_t)kVoiceWarps * kTileStride * sizeof(double2) + sweep_voices_max * sizeof(SweepState);
 #define GB_SWEEP_LAUNCH(CLS_, LFO_, FLAT_, SYNC_)                                                                    \
   if (!lists[kSw + CLS_].empty()) {                                                                                  \
-    Launch l(e, true, 2);                                                                                            \
-    welsh_sweep_kernel<8, LFO_, FLAT_, SYNC_><<<(int)lists[kSw + CLS_].size(), 32 * 8, sweep_smem, e->stream>>>(       \
-        e->d_winst, e->d_wvoice, e->wwork.d, e->widx.d + off, f0, frames);                                           \
+    Launch l(e, true, 2, vs);                                                                                        \
+    welsh_sweep_kernel<8, LFO_, FLAT_, SYNC_><<<(int)lists[kSw + CLS_].size(), 32 * 8, sweep_smem, vs>>>(              \
+        e->d_winst, e->d_wvoice, wwd, e->widx.d + off, f0, frames);                                                  \
     off += lists[kSw + CLS_].size();                                                                                 \
     e->stats.sweep_ctas += lists[kSw + CLS_].size();                                                                 \
   }
@@ -2066,6 +2176,10 @@ int render_chunk(gb_engine* e, int frames, size_t n_ev) {
       }
     }
     e->stats.voice_samples += (uint64_t)e->n_wvoice * (uint64_t)frames;
+  }
+  if (e->overlap) {  // the rest of the chunk (table sums, effects, copy-out) follows this chunk's voice kernels
+    CUDA_TRY(e, cudaEventRecord(e->v_done[par], vs));
+    CUDA_TRY(e, cudaStreamWaitEvent(e->stream, e->v_done[par], 0));
   }
   // Solo Welsh items through the job list (welsh_solo_kernel).  Prepared AFTER the FM launch below has been
   // enqueued, so that the host-side classification overlaps with GPU work of the same chunk.
@@ -2294,7 +2408,7 @@ int render_chunk(gb_engine* e, int frames, size_t n_ev) {
   hp.mark("welsh");
   if (e->n_fvoice) {
     if (e->finst_dirty) { int rc0 = upload_inst_tables(e); if (rc0) return rc0; }
-    int rc = upload_events(flists, e->fev, e->fev_off, any_f, &e->fev_empty_on_device);
+    int rc = upload_events(flists, e->fev, e->fev_off, any_f, &e->fev_empty_on_device, e->stream);
     if (rc) return rc;
     {
       Launch l(e, true, 4);
@@ -2357,7 +2471,8 @@ int render_chunk(gb_engine* e, int frames, size_t n_ev) {
   if (n_red) {
     Launch l(e, false);
     dim3 grid(cdiv(frames, 256), n_red);
-    reduce_partials_kernel<<<grid, 256, 0, e->stream>>>(e->fused_sums ? e->partials_nf.d : e->partials.d, frames);
+    reduce_partials_kernel<<<grid, 256, 0, e->stream>>>(
+        e->fused_sums ? e->partials_nf.d : (e->parity ? e->d_partials_alt : e->partials.d), frames);
   }
   // ---- 5. plan walk: toy sources, instrument DCA automation, effects ----
   // One launch per node, except runs of independent effects of one batch class on one level: those share
@@ -2528,6 +2643,7 @@ int render_chunk(gb_engine* e, int frames, size_t n_ev) {
   e->last_out = root->buf;
   e->last_frames = (size_t)frames;
   CUDA_TRY(e, cudaEventRecord(e->stage_done[slot], e->stream));
+  if (e->overlap) CUDA_TRY(e, cudaEventRecord(e->p_done[par], e->stream));
   hp.mark("fx");
   e->chunk_seq++;
   e->pos += frames;
@@ -2607,6 +2723,7 @@ int render_impl(gb_engine* e, void* out, size_t frames, size_t* done, OutMode mo
     CUDA_TRY(e, cudaMallocHost(&e->ring, (size_t)kStageSlots * e->max_block * sizeof(double2)));
   size_t produced = 0;
   const bool call_timed = span_begin(e, 2);
+  if (e->overlap) CUDA_TRY(e, cudaEventRecord(e->call_start, e->stream));  // vstream starts after whatever precedes this call
   const size_t call_span = e->spans.size() - 1;
   // Chunks are enqueued without waiting for each other.  For host-buffer renders chunk i's result goes
   // d_full -> pinned ring slot on the copy stream while chunks i+1.. compute, and the host moves a ring

@@ -1556,8 +1556,10 @@ __device__ __forceinline__ void welsh_rest_block(RestState* const (&rs)[NV], con
 
 // grid = number of resting CTAs of this variant; block = 32 * W threads;
 // dynamic smem = W * kTileStride double2 (tiles) + max_voices RestState.  nframes is a multiple of kBlockFrames.
-template <int W, bool LFO_AMP, bool ZERO_A, bool SYNC = false>
-__global__ void __launch_bounds__(32 * W, 2) welsh_rest_kernel(const WelshInst* __restrict__ insts,
+// NVW = 4: four voices in lockstep per warp, one CTA per SM (255 registers): CTAs of 32 voices, half the CTA
+// partials for the mixdown at the same number of voices in flight per SM.
+template <int W, bool LFO_AMP, bool ZERO_A, bool SYNC = false, int NVW = 2>
+__global__ void __launch_bounds__(32 * W, NVW == 4 ? 1 : 2) welsh_rest_kernel(const WelshInst* __restrict__ insts,
                                                              WelshVoice* __restrict__ voices,
                                                              const CtaWork* __restrict__ work,
                                                              const int* __restrict__ idx, i64 f0, int nframes) {
@@ -1600,7 +1602,18 @@ __global__ void __launch_bounds__(32 * W, 2) welsh_rest_kernel(const WelshInst* 
     bool first = true;
 #pragma unroll 1
     for (int g = warp; g < wk.nvoices; g += 2 * W) {
-      if (g + W < wk.nvoices) {
+      bool took4 = false;
+      if constexpr (NVW == 4) {
+        if (g + 3 * W < wk.nvoices) {
+          RestState* const four[4] = {cache + g, cache + g + W, cache + g + 2 * W, cache + g + 3 * W};
+          if (first) welsh_rest_block<LFO_AMP, ZERO_A, 4, false, SYNC>(four, I, lane, tile_row);
+          else welsh_rest_block<LFO_AMP, ZERO_A, 4, true, SYNC>(four, I, lane, tile_row);
+          g += 2 * W;
+          took4 = true;
+        }
+      }
+      if (took4) {
+      } else if (g + W < wk.nvoices) {
         RestState* const two[2] = {cache + g, cache + g + W};
         if (first) welsh_rest_block<LFO_AMP, ZERO_A, 2, false, SYNC>(two, I, lane, tile_row);
         else welsh_rest_block<LFO_AMP, ZERO_A, 2, true, SYNC>(two, I, lane, tile_row);

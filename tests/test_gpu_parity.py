@@ -341,15 +341,18 @@ def test_cfg5_batch_is_sum_of_its_variants():
     assert np.abs(whole - parts).max() < 1e-12
 
 
-@pytest.mark.parametrize("vpc", [None, "24", "16"])
+@pytest.mark.parametrize("vpc", [None, "24", "16", "41/4", "32/4"])
 def test_resting_voices_kernel(vpc, monkeypatch):
     """Chunks in which every voice of a CTA rests (note held, both envelopes at sustain, no events in the
     chunk) go to welsh_rest_kernel: voice state cached in shared memory across the chunk, two voices per
     warp.  Instruments with 41 / 16 / 9 voices and forced voices-per-CTA splits cover the paired, the
     single and the accumulate variants, all four (LFO, flat-oscillator) classes, and the hand-over to and
-    from the general kernel at note-on / note-off chunks."""
+    from the general kernel at note-on / note-off chunks.  "vpc/4": the four-voices-per-warp instantiation
+    (GB_REST_NV=4; quads, then a pair or a single voice for the remainder of a CTA)."""
     if vpc:
-        monkeypatch.setenv("GB_VPC", vpc)
+        monkeypatch.setenv("GB_VPC", vpc.split("/")[0])
+        if vpc.endswith("/4"):
+            monkeypatch.setenv("GB_REST_NV", "4")
     fast_filt = (0.0, 0.01, 0.6, 0.05)
     cfgs = [
         (41, dict(w1=abi.WAVE_PULSE_WIDTH, pw1=0.1, w2=abi.WAVE_SQUARE, mix=0.5, routing=abi.LFO_AMPLITUDE, depth=0.05,
