@@ -315,6 +315,8 @@ struct Node {
   const double2** d_src_table_fused = nullptr;  // the same with split instruments replaced by their partial buffers
   const double2** d_src_table_fused_alt = nullptr;  // ... by their partial buffers of odd chunks (gb_engine::overlap)
   double2* scratch_alt = nullptr;  // split Welsh instrument: the partial buffers of odd chunks (gb_engine::overlap)
+  const double2** d_src_table_vr[2] = {nullptr, nullptr};  // consumer of a voice-range engine: its other sources + the range partials, per chunk parity
+  int n_src_vr = 0;
   int n_src_fused = 0;
   int consumers = 0;           // plan nodes that read this node's buffer
   bool fuse_partials = false;  // split instrument whose only consumer sums its partials itself (no reduce pass)
@@ -373,6 +375,13 @@ struct gb_engine {
   CtaWork* d_wwork_alt = nullptr;        // the grouped CTA list with the odd-chunk output buffers
   PartialDesc* d_partials_alt = nullptr; // e->partials with the odd-chunk buffers
   int parity = 0;                        // partial-buffer set of the chunk being enqueued
+  // Voice-range resting chunks (welsh_rest_vr_kernel): when every grouped CTA rests, the voices are cut into
+  // ranges of 14 regardless of instrument boundaries so that all SMs carry the same load.
+  bool vr_ok = false;                    // decided by gb_finalize (needs `overlap`)
+  int vr_class = -1;                     // the instruments' common rest class
+  int vr_count = 0;                      // ranges (CTAs)
+  VrWork* d_vr_work[2] = {nullptr, nullptr};
+  bool chunk_vr = false;                 // this chunk's resting voices went through the ranges
   double2* ring = nullptr;                           // pinned: kStageSlots x max_block frames (host-buffer renders)
   uint64_t chunk_seq = 0;
   bool finalized = false;
@@ -393,6 +402,7 @@ struct gb_engine {
     bool rest_kernel = true;      // GB_REST_KERNEL=0
     bool sweep_kernel = true;     // GB_SWEEP_KERNEL=0
     bool sync_kernels = true;     // GB_SYNC_KERNELS=0: hard-sync patches stay on the general kernel
+    int rest_vr = -1;             // GB_REST_VR: 1 = voice-range resting chunks whenever possible, 0 = never, -1 = when they even out the SM load
     int rest_nv = 2;              // GB_REST_NV=4: welsh_rest_kernel with four voices in lockstep per warp (one CTA per SM)
     bool rest_tp = true;          // GB_REST_TP=0: no time-parallel resting kernel (and no CTAs below 8 voices)
     int min_cut_voices = 256;     // GB_MIN_CUT_VOICES: chunk cuts only for engines with at least this many Welsh voices
@@ -807,7 +817,9 @@ int gather_sources(gb_engine* e, Node* n, int frames, SourceList* out, bool* don
     Launch l(e, false);
     const bool plain = done && (n->kind == GB_FX_MIXER || n->kind == GB_FX_SIGNAL_PASSTHROUGH);
     double2* dst = plain ? n->buf : n->scratch;
-    if (e->fused_sums && n->d_src_table_fused)
+    if (e->fused_sums && e->chunk_vr && n->d_src_table_vr[e->parity])
+      sum_table_kernel<<<cdiv(frames, kSumFrames), kSumRows * kSumFrames, 0, e->stream>>>(n->d_src_table_vr[e->parity], n->n_src_vr, dst, frames);
+    else if (e->fused_sums && n->d_src_table_fused)
       sum_table_kernel<<<cdiv(frames, kSumFrames), kSumRows * kSumFrames, 0, e->stream>>>(
           e->parity && n->d_src_table_fused_alt ? n->d_src_table_fused_alt : n->d_src_table_fused, n->n_src_fused, dst, frames);
     else
@@ -1002,6 +1014,7 @@ int gb_create(const gb_config* cfg, gb_engine** out) {
   if (const char* v = getenv("GB_REST_TP")) e->opt.rest_tp = atoi(v) != 0;
   if (const char* v = getenv("GB_REST_NV")) e->opt.rest_nv = atoi(v) == 4 ? 4 : 2;
   if (const char* v = getenv("GB_OVERLAP")) e->overlap_enabled = atoi(v) != 0;
+  if (const char* v = getenv("GB_REST_VR")) e->opt.rest_vr = atoi(v);
   if (const char* v = getenv("GB_MIN_CUT_VOICES")) e->opt.min_cut_voices = std::max(1, atoi(v));
   if (const char* v = getenv("GB_SOLO_MIN")) e->min_solo_items = atoi(v);
   if (const char* v = getenv("GB_SOLO_WAVES")) e->solo_waves = atoi(v) != 0;
@@ -1299,6 +1312,89 @@ int upload_inst_tables(gb_engine* e) {
   e->finst_dirty = false;
   return 0;
 }
+
+// Voice ranges for all-resting chunks (welsh_rest_vr_kernel).  Called by gb_finalize once the instrument tables
+// exist (the rest classes are part of them).  Needs the overlapped-mixdown layout plus: one consumer for all
+// instruments, instruments with even voice counts of at least one range, laid out back to back in the voice
+// table, one common non-sync rest class.
+int plan_voice_ranges(gb_engine* e) {
+  e->vr_ok = false;
+  if (!e->overlap) return 0;
+  const size_t mb = e->max_block;
+  int rc2;
+  constexpr int kVrVoices = 14;
+  Node* consumer = nullptr;
+  int n_cons = 0, n_inst = 0, n_fused_src = 0, next_voice = 0, cls = -2;
+  bool vr = e->opt.rest_vr != 0 && e->opt.rest_kernel;
+  for (Node* n : e->plan) {
+    if (!n->is_inst) {
+      if (n->d_src_table_fused) { consumer = n; ++n_cons; }
+      continue;
+    }
+    ++n_inst;
+    const WelshInst& I = e->h_winst[(size_t)n->table_index];
+    vr = vr && n->nvoices % 2 == 0 && n->nvoices >= kVrVoices && n->voice0 == next_voice && I.rest_class >= 0 &&
+         I.rest_class < 4 && (cls == -2 || cls == I.rest_class);
+    cls = I.rest_class;
+    next_voice = n->voice0 + n->nvoices;
+  }
+  if (vr && n_cons == 1) {
+    for (uint32_t su : consumer->sources) {
+      Node* sn = find(e, su);
+      if (sn && sn->order >= 0 && sn->is_inst) ++n_fused_src;
+    }
+  }
+  vr = vr && n_cons == 1 && n_fused_src == n_inst && next_voice == e->n_wvoice;
+  const int slots = 2 * e->num_sms;
+  const int ranges = (e->n_wvoice + kVrVoices - 1) / kVrVoices;
+  // automatic: only where the ranges lower the voices on the fullest SM (4096 voices: 293 ranges of 14 put 28
+  // voices on every SM, the 256 instrument CTAs of 16 put 32 on 108 SMs and 16 on the other 40)
+  if (e->opt.rest_vr < 0) {
+    int vpc_max = 0;
+    for (int i = 0; i < e->n_wwork_grouped; ++i) vpc_max = std::max(vpc_max, e->wwork.h[i].nvoices);
+    vr = vr && ranges <= slots &&
+         cdiv(ranges, e->num_sms) * kVrVoices < cdiv(e->n_wwork_grouped, e->num_sms) * vpc_max && vpc_max > kTpMaxVoices;
+  }
+  if (vr) {
+    std::vector<const Node*> inst_of((size_t)e->n_wvoice, nullptr);
+    for (Node* n : e->plan)
+      if (n->is_inst)
+        for (int v = 0; v < n->nvoices; ++v) inst_of[(size_t)(n->voice0 + v)] = n;
+    for (int par2 = 0; par2 < 2; ++par2) {
+      double2* outs = nullptr;
+      if ((rc2 = dev_alloc(e, &outs, (size_t)ranges * mb))) return rc2;
+      std::vector<VrWork> vw((size_t)ranges);
+      for (int r = 0; r < ranges; ++r) {
+        VrWork& w = vw[(size_t)r];
+        w.voice0 = r * kVrVoices;
+        w.nvoices = std::min(kVrVoices, e->n_wvoice - w.voice0);
+        const Node* a = inst_of[(size_t)w.voice0];
+        const Node* b = inst_of[(size_t)(w.voice0 + w.nvoices - 1)];
+        w.inst_a = a->table_index;
+        w.inst_b = b->table_index;
+        w.split = a == b ? w.nvoices : a->voice0 + a->nvoices - w.voice0;
+        w.pad = 0;
+        w.out = outs + (size_t)r * mb;
+      }
+      if ((rc2 = dev_alloc(e, &e->d_vr_work[par2], vw.size(), false))) return rc2;
+      CUDA_TRY(e, cudaMemcpy(e->d_vr_work[par2], vw.data(), vw.size() * sizeof(VrWork), cudaMemcpyHostToDevice));
+      std::vector<const double2*> tab;
+      for (uint32_t su : consumer->sources) {
+        Node* sn = find(e, su);
+        if (sn && sn->order >= 0 && sn->buf && !sn->is_inst) tab.push_back(sn->buf);
+      }
+      for (int r = 0; r < ranges; ++r) tab.push_back(vw[(size_t)r].out);
+      if ((rc2 = dev_alloc(e, &consumer->d_src_table_vr[par2], tab.size(), false))) return rc2;
+      CUDA_TRY(e, cudaMemcpy((void*)consumer->d_src_table_vr[par2], tab.data(), tab.size() * sizeof(double2*), cudaMemcpyHostToDevice));
+      consumer->n_src_vr = (int)tab.size();
+    }
+    e->vr_ok = true;
+    e->vr_class = cls;
+    e->vr_count = ranges;
+  }
+  return 0;
+}
+
 
 int gb_finalize(gb_engine* e) {
   if (!e) return GB_EINVAL;
@@ -1711,7 +1807,11 @@ int gb_finalize(gb_engine* e) {
   CUDA_TRY(e, cudaStreamSynchronize(e->stream));
   e->finalized = true;
   e->winst_dirty = e->finst_dirty = true;
-  return upload_inst_tables(e);
+  {
+    const int rc_up = upload_inst_tables(e);
+    if (rc_up) return rc_up;
+  }
+  return plan_voice_ranges(e);
 }
 
 int gb_push_events(gb_engine* e, const gb_event* ev, size_t n) {
@@ -2004,6 +2104,7 @@ int render_chunk(gb_engine* e, int frames, size_t n_ev) {
   // chunk's parity; they wait for the table sum that read those buffers two chunks ago.
   const int par = e->overlap ? (int)(e->chunk_seq & 1) : 0;
   e->parity = par;
+  e->chunk_vr = false;
   cudaStream_t vs = e->overlap ? e->vstream : e->stream;
   if (e->overlap) {
     CUDA_TRY(e, cudaStreamWaitEvent(vs, e->call_start, 0));
@@ -2107,6 +2208,26 @@ int render_chunk(gb_engine* e, int frames, size_t n_ev) {
       }
       const size_t rest_smem = (size_t)kVoiceWarps * kTileStride * sizeof(double2) + rest_voices_max * sizeof(RestState);
       size_t off = 0;
+      // every grouped CTA rests in this chunk: the voice ranges take it (the consumer then sums the range partials)
+      if (e->vr_ok && ng > 0 && lists[e->vr_class].size() + lists[kTp + e->vr_class].size() == (size_t)ng && e->fused_sums_enabled) {
+        bool plain = true;
+        for (Node* n : e->plan) plain = plain && !n->unit_gain;
+        if (plain) {
+          constexpr int kVrW = 7;
+          const size_t vr_smem = (size_t)kVrW * kTileStride * sizeof(double2) + 2 * kVrW * sizeof(RestState);
+          Launch l(e, true, 1, vs);
+          switch (e->vr_class) {
+            case 0: welsh_rest_vr_kernel<kVrW, false, false><<<e->vr_count, 32 * kVrW, vr_smem, vs>>>(e->d_winst, e->d_wvoice, e->d_vr_work[par], f0, frames); break;
+            case 1: welsh_rest_vr_kernel<kVrW, false, true><<<e->vr_count, 32 * kVrW, vr_smem, vs>>>(e->d_winst, e->d_wvoice, e->d_vr_work[par], f0, frames); break;
+            case 2: welsh_rest_vr_kernel<kVrW, true, false><<<e->vr_count, 32 * kVrW, vr_smem, vs>>>(e->d_winst, e->d_wvoice, e->d_vr_work[par], f0, frames); break;
+            default: welsh_rest_vr_kernel<kVrW, true, true><<<e->vr_count, 32 * kVrW, vr_smem, vs>>>(e->d_winst, e->d_wvoice, e->d_vr_work[par], f0, frames); break;
+          }
+          e->stats.rest_ctas += (uint64_t)e->vr_count;
+          e->chunk_vr = true;
+          lists[e->vr_class].clear();
+          lists[kTp + e->vr_class].clear();
+        }
+      }
 #define GB_REST_LAUNCH(CLS_, LFO_, FLAT_, SYNC_)                                                                     \
   if (!lists[CLS_].empty()) {                                                                                        \
     Launch l(e, true, 1, vs);                                                                                        \

@@ -1635,6 +1635,84 @@ __global__ void __launch_bounds__(32 * W, NVW == 4 ? 1 : 2) welsh_rest_kernel(co
   }
 }
 
+// ---- the resting-voice kernel over voice ranges ------------------------------------------------------
+// welsh_rest_kernel's CTAs belong to one instrument each (16 of its voices), so 4096 voices are 256 CTAs on the
+// 296 CTA slots of 148 SMs: 108 SMs carry 32 voices, 40 carry 16, and the launch lasts as long as the full ones.
+// When EVERY grouped CTA of an engine rests for a chunk (and all instruments mix into one consumer that sums
+// the CTA partials itself), the chunk runs here instead: the engine's voices, in voice-table order, are cut
+// into ranges of 2 W voices regardless of instrument boundaries (W = 7: 293 CTAs for 4096 voices, 28 voices on
+// every SM).  A warp holds two consecutive voices — of one instrument, since instruments have even voice counts
+// — and takes its instrument record from one of the CTA's two copies; the tile rows are already panned per
+// warp, so the CTA sum mixes both instruments into the range's partial buffer.
+struct alignas(16) VrWork {
+  int inst_a, inst_b;  // instrument of the first voices / of the voices from `split` on (== inst_a if the range has one instrument)
+  int split;           // voices of inst_a in this range (even)
+  int voice0, nvoices; // global voice range
+  int pad;
+  double2* out;
+};
+
+template <int W, bool LFO_AMP, bool ZERO_A>
+__global__ void __launch_bounds__(32 * W, 2) welsh_rest_vr_kernel(const WelshInst* __restrict__ insts,
+                                                                WelshVoice* __restrict__ voices,
+                                                                const VrWork* __restrict__ work, i64 f0, int nframes) {
+  extern __shared__ double2 smem_tiles[];
+  __shared__ int s_active[W];
+  __shared__ WelshInst sI[2];
+  const VrWork wk = work[blockIdx.x];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  {
+    const int* a = reinterpret_cast<const int*>(insts + wk.inst_a);
+    const int* b = reinterpret_cast<const int*>(insts + wk.inst_b);
+    int* dst = reinterpret_cast<int*>(&sI[0]);
+    constexpr int kWords = (int)(sizeof(WelshInst) / sizeof(int));
+    for (int i = threadIdx.x; i < 2 * kWords; i += 32 * W) dst[i] = i < kWords ? a[i] : b[i - kWords];
+  }
+  __syncthreads();
+  RestState* cache = reinterpret_cast<RestState*>(smem_tiles + W * kTileStride);
+  for (int t = threadIdx.x; t < wk.nvoices; t += 32 * W) {
+    const WelshInst& I = sI[t >= wk.split ? 1 : 0];
+    const WelshVoice* vp = voices + wk.voice0 + t;
+    RestState r;
+    const u64 k = (u64)(f0 - 1 - vp->anchor);
+    r.d1 = vp->d1; r.d2 = vp->d2;
+    r.p1 = vp->p1 + k * r.d1; r.p2 = vp->p2 + k * r.d2;
+    r.s[0] = vp->s[0]; r.s[1] = vp->s[1]; r.s[2] = vp->s[2]; r.s[3] = vp->s[3];
+    r.ls = 0.0; r.lc = 0.0;
+    if (LFO_AMP) {
+      double ls, lc;
+      sincos_phase(vp->pl + (k + 1) * I.lfo_dq, &ls, &lc);
+      const double dl = I.depth * I.amp_rest;
+      r.ls = ls * dl; r.lc = lc * dl;
+    }
+    cache[t] = r;
+  }
+  if (lane == 0) s_active[warp] = 2 * warp < wk.nvoices ? 1 : 0;
+  __syncthreads();
+  const WelshInst& I = sI[2 * warp >= wk.split ? 1 : 0];
+  double2* tile_row = smem_tiles + warp * kTileStride;
+  const i64 f_end = f0 + nframes;
+  const int g = 2 * warp;
+#pragma unroll 1
+  for (i64 fb = f0; fb < f_end; fb += kBlockFrames) {
+    if (g + 1 < wk.nvoices) {
+      RestState* const two[2] = {cache + g, cache + g + 1};
+      welsh_rest_block<LFO_AMP, ZERO_A, 2, false, false>(two, I, lane, tile_row);
+    } else if (g < wk.nvoices) {
+      RestState* const one[1] = {cache + g};
+      welsh_rest_block<LFO_AMP, ZERO_A, 1, false, false>(one, I, lane, tile_row);
+    }
+    __syncthreads();
+    cta_reduce_store<W>(smem_tiles, s_active, wk.out, fb, f0, f_end);
+    __syncthreads();
+  }
+  for (int t = threadIdx.x; t < wk.nvoices; t += 32 * W) {
+    WelshVoice* vp = voices + wk.voice0 + t;
+    vp->s[0] = cache[t].s[0]; vp->s[1] = cache[t].s[1]; vp->s[2] = cache[t].s[2]; vp->s[3] = cache[t].s[3];
+    vp->knot_frame = kNever;
+  }
+}
+
 // ---- the resting-voice kernel, time-parallel ---------------------------------------------------------
 // welsh_rest_kernel gives every warp its own voices and walks them through the chunk block by block: the
 // chunk's 256 blocks are a serial chain per warp (1.7 us per block), so a shard of a few hundred voices —

@@ -392,6 +392,50 @@ def test_resting_voices_kernel(vpc, monkeypatch):
     check(out, ref)
 
 
+def test_voice_range_resting_chunks(monkeypatch):
+    """Chunks in which EVERY grouped CTA rests run over voice ranges of 14 that ignore instrument boundaries
+    (welsh_rest_vr_kernel: a CTA mixes the tail of one instrument with the head of the next, each warp taking its
+    own instrument record and pan).  12 instruments x 16 voices with different cutoffs, pans and LFO depths
+    = 14 ranges (the last one of 10 voices) against 24 instrument CTAs; GB_REST_VR=0 is the instrument-CTA
+    render of the same scene.  Also covers the overlapped mixdown (12 split instruments, one consumer)."""
+    monkeypatch.setenv("GB_MIN_CUT_VOICES", "1")
+    frames = 10 * 4096 + 300
+
+    def scene(r):
+        uids = []
+        for i in range(12):
+            p = scenes.generic_welsh(voices=16, gain=0.04, pan=-0.9 + 0.16 * i, w1=abi.WAVE_PULSE_WIDTH, pw1=0.1 + 0.02 * i,
+                                     w2=abi.WAVE_SQUARE, mix=0.5, routing=abi.LFO_AMPLITUDE, depth=0.05 + 0.01 * i,
+                                     lfo_hz=7.5, filt=(0.0, 0.01, 0.6, 0.05), amp=(0.02, 0.0, 1.0, 0.0),
+                                     cutoff_start=scenes.hz_to_pct(40.0), cutoff_end=0.5 + 0.03 * i)
+            u = r.add_instrument(abi.INST_WELSH, p)
+            r.patch(u, abi.MAIN_MIXER)
+            uids.append(u)
+        r.finalize()
+        for i, u in enumerate(uids):
+            for v in range(16):
+                r.note_on(5 + 3 * v + i, u, 30 + 2 * v + i % 2)
+                r.note_off(8 * 4096 + 100 + 3 * v, u, 30 + 2 * v + i % 2)
+        return frames
+
+    o = OracleEngine(48000.0)
+    scene(o)
+    ref = o.render(frames)
+    outs, stats = [], []
+    for vr in ("1", "0"):
+        monkeypatch.setenv("GB_REST_VR", vr)
+        g = gpu_engine(48000.0, max_block=4096)
+        scene(g)
+        outs.append(g.render(frames))
+        stats.append(g.stats())
+        g.close()
+    assert stats[0].rest_kernel_launches >= 5 and stats[0].rest_ctas == 14 * stats[0].rest_kernel_launches
+    assert stats[1].rest_ctas == 24 * stats[1].rest_kernel_launches
+    check(outs[0], ref)
+    check(outs[1], ref)
+    assert np.abs(outs[0] - outs[1]).max() < 1e-12
+
+
 @pytest.mark.parametrize("max_block", [0, 100, 64])
 def test_sidechain_link_known_answer_on_gpu(max_block):
     """The oracle's sidechain known answer (tests/test_oracle_known_answers.py) on the CUDA engine: the
