@@ -229,7 +229,8 @@ STAT_SUMS = ("render_ms", "voice_kernel_ms", "fx_kernel_ms", "kernel_launches", 
              "rest_kernel_ms", "rest_kernel_launches", "rest_voice_samples", "rest_ctas",
              "sweep_kernel_ms", "sweep_kernel_launches", "sweep_voice_samples", "sweep_ctas",
              "solo_kernel_ms", "solo_kernel_launches", "solo_voice_samples", "solo_jobs",
-             "fm_kernel_ms", "fm_kernel_launches", "idle_voice_samples", "voice_samples", "h2d_bytes", "d2h_bytes")
+             "fm_kernel_ms", "fm_kernel_launches", "idle_voice_samples", "voice_samples", "h2d_bytes", "d2h_bytes",
+             "rest_tp_launches", "rest_vr_launches")
 
 
 class Acc(dict):
@@ -462,14 +463,21 @@ def run_ours(a) -> None:
             use_rest = dev["rest_kernel_launches"] > 0 and dev["rest_kernel_ms"] > 0.5 * dev["voice_kernel_ms"]
             if use_rest:
                 k_ms, k_l, k_vs, k_ctas = dev["rest_kernel_ms"], dev["rest_kernel_launches"], dev["rest_voice_samples"], dev["rest_ctas"]
-                k_name = "welsh_rest_kernel<8,lfo,flat>"
+                # which resting kernel the launches were: instrument CTAs, voice ranges (all-resting chunks of an
+                # engine whose CTAs then cover every SM evenly) or the time-parallel variant (small shards)
+                n_vr, n_tp = dev["rest_vr_launches"], dev["rest_tp_launches"]
+                k_name = ("welsh_rest_vr_kernel<7,lfo,flat>" if 2 * n_vr > k_l else
+                          "welsh_rest_tp_kernel<8,lfo,flat>" if 2 * n_tp > k_l else "welsh_rest_kernel<8,lfo,flat>")
+                k_name += f" ({int(n_vr // steps)} voice-range, {int(n_tp // steps)} time-parallel of {int(k_l // steps)} resting launches per step)"
             else:
                 k_ms, k_l, k_vs, k_ctas = dev["voice_kernel_ms"], dev["voice_kernel_launches"], per_rank_vs * steps, 0
                 k_name = "welsh_kernel<8,2>"
             # executed-instruction facts of the dominant kernel: from the committed ncu --set full capture
             prof = {}
+            facts = ("r2f_rest_vr_kernel_facts.json" if use_rest and 2 * dev["rest_vr_launches"] > k_l
+                     else "r2_rest_kernel_facts.json")
             try:
-                with open(os.path.join(ROOT, "profiles", "r2_rest_kernel_facts.json")) as f:
+                with open(os.path.join(ROOT, "profiles", facts)) as f:
                     prof = json.load(f)
             except (OSError, ValueError):
                 pass
@@ -481,7 +489,7 @@ def run_ours(a) -> None:
                 "algorithmic_bytes_per_launch": 16.0 * frames_l * ctas_l if ctas_l else None,
                 "traffic": (prof["dram_bytes_per_launch"] * vs_l / prof["voice_samples_per_launch"]
                             if "dram_bytes_per_launch" in prof else None),
-                "traffic_source": "profiles/r2_rest_kernel_facts.json (ncu --set full dram__bytes_read+write of the same "
+                "traffic_source": "profiles/" + facts + " (ncu --set full dram__bytes_read+write of the same "
                                   "kernel, scaled to this run's voice-samples per launch; not measured live)",
                 "peak_source": "FP64 FMA microbenchmark measured live on this GPU (gb_measure_fma_peak); "
                                "MEASURED_PEAKS.json has no FP64 entry",
@@ -539,9 +547,17 @@ def run_ours(a) -> None:
             n_part = dev["rest_ctas"] / max(dev["rest_kernel_launches"], 1) if dev["rest_kernel_launches"] else 0
             mix_bytes = (n_part + 1) * 16.0 * main.frames
             ms = dev["fx_kernel_ms"] / a.steps
+            overlapped = os.environ.get("GB_OVERLAP", "1") != "0"
             out["mixdown"] = {"kernel": "sum_table_kernel (+ pointwise_kernel)", "bound": "hbm", "bytes_per_step": mix_bytes,
-                              "ms_per_step": ms, "achieved": mix_bytes / (ms * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
-                              "frac": mix_bytes / (ms * 1e-3) / 1e9 / hbm_peak, "bus_bytes": 16.0 * main.frames}
+                              "ms_per_step": ms, "achieved": None if overlapped else mix_bytes / (ms * 1e-3) / 1e9,
+                              "peak": hbm_peak, "unit": "GB/s",
+                              "frac": None if overlapped else mix_bytes / (ms * 1e-3) / 1e9 / hbm_peak,
+                              "bus_bytes": 16.0 * main.frames, "overlapped": overlapped,
+                              "note": ("the table sum of chunk i runs on the engine's mix stream WHILE chunk i+1's voice kernels "
+                                       "run on the voice stream (partial buffers alternate by chunk parity): ms_per_step is the "
+                                       "sum kernels' elapsed time on the SM slots the voice kernels leave free, not time added "
+                                       "to the step; alone (GB_OVERLAP=0) the same sums take 2.35 ms at 5.05 TB/s = 0.77 of the "
+                                       "HBM peak (profiles/r2_overlap_ab.txt)") if overlapped else None}
 
     # ---- secondary legs --------------------------------------------------------------------------
     def put(name, d):

@@ -13,7 +13,7 @@ pub use block_render::{BlockRender, Engine, Error, StereoSample};
 pub mod ffi {
     use std::os::raw::{c_char, c_int, c_void};
 
-    pub const GB_ABI_VERSION: u32 = 3;
+    pub const GB_ABI_VERSION: u32 = 4;
     pub const GB_MAIN_MIXER: u32 = 1;
     pub const GB_CONTROL_PERIOD: i64 = 64;
 
@@ -268,6 +268,7 @@ pub mod ffi {
         pub sweep_ctas: u64,
         pub fx_batched_nodes: u64,
         pub rest_tp_launches: u64,
+        pub rest_vr_launches: u64,
     }
 
     extern "C" {

@@ -13,7 +13,7 @@ from typing import Iterable, Optional, Sequence
 
 import numpy as np
 
-ABI_VERSION = 3
+ABI_VERSION = 4
 MAIN_MIXER = 1
 
 # --- error codes -------------------------------------------------------------
@@ -147,7 +147,8 @@ class Stats(C.Structure):
                 ("solo_kernel_launches", C.c_uint64), ("solo_kernel_ms", C.c_double), ("solo_voice_samples", C.c_uint64),
                 ("solo_jobs", C.c_uint64), ("solo_class_items", C.c_uint64 * 4),
                 ("fm_kernel_launches", C.c_uint64), ("fm_kernel_ms", C.c_double), ("idle_voice_samples", C.c_uint64),
-                ("rest_ctas", C.c_uint64), ("sweep_ctas", C.c_uint64), ("fx_batched_nodes", C.c_uint64), ("rest_tp_launches", C.c_uint64)]
+                ("rest_ctas", C.c_uint64), ("sweep_ctas", C.c_uint64), ("fx_batched_nodes", C.c_uint64), ("rest_tp_launches", C.c_uint64),
+                ("rest_vr_launches", C.c_uint64)]
 
 
 # every symbol include/groove_b200.h declares (suffix after the prefix)

@@ -2223,6 +2223,7 @@ int render_chunk(gb_engine* e, int frames, size_t n_ev) {
             default: welsh_rest_vr_kernel<kVrW, true, true><<<e->vr_count, 32 * kVrW, vr_smem, vs>>>(e->d_winst, e->d_wvoice, e->d_vr_work[par], f0, frames); break;
           }
           e->stats.rest_ctas += (uint64_t)e->vr_count;
+          e->stats.rest_vr_launches++;
           e->chunk_vr = true;
           lists[e->vr_class].clear();
           lists[kTp + e->vr_class].clear();

@@ -7,7 +7,7 @@ import math
 
 import numpy as np
 
-from groove_b200 import abi
+from groove_b200 import abi, workloads
 
 LOG800 = math.log(800.0)
 
@@ -321,6 +321,29 @@ def scene_cello_held_chord(r: abi.Renderer) -> int:
     return 200000
 
 
+def scene_cello_ensemble(r: abi.Renderer) -> int:
+    """Config 4's STRUCTURE in miniature: 12 cello instruments of 16 voices with their own pans, all patched to
+    the main mixer (more than kMaxSources inputs: the mixer sums the instruments' CTA partials from a pointer
+    table).  That is the layout the overlapped mixdown needs (voice kernels on their own stream, partial buffers
+    alternating by chunk parity), and with GB_REST_VR=1 the all-resting chunks run over voice ranges of 14
+    across instrument boundaries (welsh_rest_vr_kernel).  Filter decay shortened to 50 ms so that the voices
+    rest from the second 4096-frame chunk on."""
+    uids = []
+    for q in range(12):
+        u = r.add_instrument(abi.INST_WELSH, workloads.cello_params(16, 1.0 / 192.0, -1.0 + 2.0 * q / 11.0, 0.05))
+        r.patch(u, abi.MAIN_MIXER)
+        uids.append(u)
+    r.finalize()
+    ev = []
+    for q, u in enumerate(uids):
+        for j in range(16):
+            ev.append((4 * q + 64 * (j % 4), u, abi.EV_NOTE_ON, 36 + (q + 12 * j) % 49, 127, 0.0))
+            ev.append((36000 + 4 * q, u, abi.EV_NOTE_OFF, 36 + (q + 12 * j) % 49, 0, 0.0))
+    ev.sort(key=lambda t: t[0])
+    r.push_events(ev)
+    return 45000
+
+
 def scene_bare_sources(r: abi.Renderer) -> int:
     """Bare oscillator / envelope devices (the "oscillator" and "envelope" instrument types of the reference's
     filter-*, gain_*, bitcrusher_* and oscillator-* demo projects): free-running oscillators of every
@@ -405,6 +428,7 @@ ALL_SCENES = {
     "fx_chains": scene_fx_chains,
     "cello_chord": scene_cello_chord,
     "cello_held_chord": scene_cello_held_chord,
+    "cello_ensemble": scene_cello_ensemble,
     "welsh_variants": scene_welsh_variants,
     "welsh_sustain": scene_welsh_sustain,
     "fm": scene_fm,
