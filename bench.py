@@ -466,7 +466,7 @@ def run_ours(a) -> None:
                 # which resting kernel the launches were: instrument CTAs, voice ranges (all-resting chunks of an
                 # engine whose CTAs then cover every SM evenly) or the time-parallel variant (small shards)
                 n_vr, n_tp = dev["rest_vr_launches"], dev["rest_tp_launches"]
-                k_name = ("welsh_rest_vr_kernel<7,lfo,flat>" if 2 * n_vr > k_l else
+                k_name = ("welsh_rest_vr_kernel<8,lfo,flat>" if 2 * n_vr > k_l else
                           "welsh_rest_tp_kernel<8,lfo,flat>" if 2 * n_tp > k_l else "welsh_rest_kernel<8,lfo,flat>")
                 k_name += f" ({int(n_vr // steps)} voice-range, {int(n_tp // steps)} time-parallel of {int(k_l // steps)} resting launches per step)"
             else:

@@ -1373,7 +1373,8 @@ int plan_voice_ranges(gb_engine* e) {
         w.inst_a = a->table_index;
         w.inst_b = b->table_index;
         w.split = a == b ? w.nvoices : a->voice0 + a->nvoices - w.voice0;
-        w.pad = 0;
+        // the single-voice warps of the second wave of CTAs sit on the other two sub-partitions
+        w.single0 = r < e->num_sms ? 6 : 4;
         w.out = outs + (size_t)r * mb;
       }
       if ((rc2 = dev_alloc(e, &e->d_vr_work[par2], vw.size(), false))) return rc2;
@@ -2213,8 +2214,8 @@ int render_chunk(gb_engine* e, int frames, size_t n_ev) {
         bool plain = true;
         for (Node* n : e->plan) plain = plain && !n->unit_gain;
         if (plain) {
-          constexpr int kVrW = 7;
-          const size_t vr_smem = (size_t)kVrW * kTileStride * sizeof(double2) + 2 * kVrW * sizeof(RestState);
+          constexpr int kVrW = 8;
+          const size_t vr_smem = (size_t)kVrW * kTileStride * sizeof(double2) + 14 * sizeof(RestState);
           Launch l(e, true, 1, vs);
           switch (e->vr_class) {
             case 0: welsh_rest_vr_kernel<kVrW, false, false><<<e->vr_count, 32 * kVrW, vr_smem, vs>>>(e->d_winst, e->d_wvoice, e->d_vr_work[par], f0, frames); break;

@@ -1644,11 +1644,18 @@ __global__ void __launch_bounds__(32 * W, NVW == 4 ? 1 : 2) welsh_rest_kernel(co
 // every SM).  A warp holds two consecutive voices — of one instrument, since instruments have even voice counts
 // — and takes its instrument record from one of the CTA's two copies; the tile rows are already panned per
 // warp, so the CTA sum mixes both instruments into the range's partial buffer.
+// W = 8 spreads the same 14 voices over 8 warps (6 pairs + 2 single voices, `single0`), four warps of each CTA pair
+// on every sub-partition: measured 0.943 ms per launch against 0.949 ms with 7 warps of two voices
+// (profiles/r2f_vr_warps_ab.txt).
+// Tried and dropped (profiles/r2f_vr_ring_experiment.txt): no CTA barrier at all — every warp writes its block's
+// row into a 4-deep ring, counts itself in, and the LAST warp to arrive for a block reduces it — so that the warps
+// drift out of phase: 1.11 ms per launch against 0.943 ms.  The warps of a CTA in the same phase share the
+// instruction cache (the block is 3400 instructions); out of phase they do not.
 struct alignas(16) VrWork {
   int inst_a, inst_b;  // instrument of the first voices / of the voices from `split` on (== inst_a if the range has one instrument)
   int split;           // voices of inst_a in this range (even)
   int voice0, nvoices; // global voice range
-  int pad;
+  int single0;         // warps single0 and single0 + 1 hold ONE voice each, the others two (>= W: every warp holds two)
   double2* out;
 };
 
@@ -1687,15 +1694,17 @@ __global__ void __launch_bounds__(32 * W, 2) welsh_rest_vr_kernel(const WelshIns
     }
     cache[t] = r;
   }
-  if (lane == 0) s_active[warp] = 2 * warp < wk.nvoices ? 1 : 0;
+  // first voice of this warp: two per warp, except the two single-voice warps
+  const int g = 2 * warp - min(max(warp - wk.single0, 0), 2);
+  const bool pair = !(warp == wk.single0 || warp == wk.single0 + 1);
+  if (lane == 0) s_active[warp] = g < wk.nvoices ? 1 : 0;
   __syncthreads();
-  const WelshInst& I = sI[2 * warp >= wk.split ? 1 : 0];
+  const WelshInst& I = sI[g >= wk.split ? 1 : 0];
   double2* tile_row = smem_tiles + warp * kTileStride;
   const i64 f_end = f0 + nframes;
-  const int g = 2 * warp;
 #pragma unroll 1
   for (i64 fb = f0; fb < f_end; fb += kBlockFrames) {
-    if (g + 1 < wk.nvoices) {
+    if (pair && g + 1 < wk.nvoices) {
       RestState* const two[2] = {cache + g, cache + g + 1};
       welsh_rest_block<LFO_AMP, ZERO_A, 2, false, false>(two, I, lane, tile_row);
     } else if (g < wk.nvoices) {
