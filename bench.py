@@ -272,10 +272,25 @@ def run_ours(a) -> None:
             dist.barrier()
             torch.cuda.synchronize()
 
-    def bus_reduce(eng):
-        """Sum the per-rank stereo buses onto rank 0: one NCCL f64 reduce over NVLink."""
+    # The bus mixdown at N > 1: the root sums the ranks' buses with one kernel whose loads cross NVLink (CUDA IPC
+    # peer buffers, groove_b200.parallel.BusExchange); NCCL's reduce only if the peers cannot be mapped.
+    exchange = None
+    exchange_note = "single GPU"
+    if world > 1:
+        try:
+            if os.environ.get("GB_BUS_NCCL") == "1":
+                raise RuntimeError("GB_BUS_NCCL=1")
+            exchange = parallel.BusExchange(local, max(int(round(a.seconds * SR)), workloads.CFG5_FRAMES))
+            exchange_note = "peer_sum_kernel on rank 0: P2P loads of the ranks' CUDA IPC exchange buffers over NVLink (no NCCL data-path call)"
+        except Exception as ex:   # noqa: BLE001 - any failure to map peers keeps the NCCL path
+            exchange_note = f"ncclReduce(f64 sum) onto rank 0 (peer mapping unavailable: {ex})"
+
+    def bus_reduce(eng, frames):
+        """Sum the per-rank stereo buses onto rank 0."""
         if world == 1:
             return None
+        if exchange is not None:
+            return exchange.reduce(eng, frames)
         return parallel.reduce_bus(parallel.device_bus_tensor(eng, local), dst=0)
 
     class Workload:
@@ -311,7 +326,7 @@ def run_ours(a) -> None:
                 if world > 1 and self.reduce:     # the bus reduce, device-timed on the stream NCCL is enqueued from
                     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
                     ev0.record()
-                    bus_reduce(eng)
+                    bus_reduce(eng, self.frames)
                     ev1.record()
                     torch.cuda.synchronize()
                     reduce_ms = ev0.elapsed_time(ev1)
@@ -328,7 +343,7 @@ def run_ours(a) -> None:
                 eng.render(self.frames, self.host_out)
             else:
                 eng.render_device(self.frames)
-                t = bus_reduce(eng)
+                t = bus_reduce(eng, self.frames)
                 if rank == 0:
                     self.pinned_out.copy_(t)      # D2H of the reduced bus into pinned host memory
                 torch.cuda.synchronize()
@@ -526,7 +541,7 @@ def run_ours(a) -> None:
                 "coefficients": "per-instrument tables while a voice rests; otherwise quadratic through exact knots "
                                 "(every 8 frames in welsh_sweep_kernel, every 4 in welsh_kernel) when the cutoff moves <= "
                                 + os.environ.get("GB_KNOT_MAX_RATE", "1e-5") + "/frame, else exact per frame",
-                "max_block": main.max_block, "parallelism": f"voices sharded over {world} GPU(s); one NCCL f64 bus reduce",
+                "max_block": main.max_block, "parallelism": f"voices sharded over {world} GPU(s); one bus exchange: " + exchange_note,
                 "l2": "256 MiB device memset between steps (L2 flush); fresh engine per step",
             },
             "realtime_factor": value / ((a.variants if headline5 else a.voices) * world * SR),
@@ -601,7 +616,7 @@ def run_ours(a) -> None:
         if rank == 0:
             put("strong", {
                 "what": f"config 4 with its {a.voices} voices split over {world} GPUs ({a.voices // world} per GPU, SURVEY.md 8(e)), "
-                        "one NCCL f64 bus reduce; efficiency against rank 0 rendering all the voices alone in this run",
+                        "one bus exchange (config.parallelism); efficiency against rank 0 rendering all the voices alone in this run",
                 "value": whole.voice_samples / (ms_n * 1e-3), "unit": UNIT, "ms_per_step": ms_n, "scaling": "strong",
                 "ms_per_step_1gpu": ms_1, "efficiency_vs_n1": ms_1 / (world * ms_n),
                 "reduce_ms": acc["reduce_ms"] / 3, "voice_kernel_ms": acc["voice_kernel_ms"] / 3, "mix_ms": acc["fx_kernel_ms"] / 3,

@@ -1,4 +1,4 @@
-//! Raw bindings of `include/groove_b200.h` (ABI version 3) and a safe wrapper.
+//! Raw bindings of `include/groove_b200.h` (ABI version 4) and a safe wrapper.
 //!
 //! Each entry point replaces one interface of the reference (paths relative to sowbug/groove):
 //! `gb_render_block` = `Orchestrator::tick`'s `gather_audio` (orchestration/src/orchestrator.rs:367-470,856-877),
@@ -79,6 +79,13 @@ pub mod ffi {
     pub struct gb_engine {
         _private: [u8; 0],
     }
+
+    /// Opaque: one rank's side of the multi-GPU bus exchange (`GB_IPC_HANDLE_BYTES`-byte handles name the buffers).
+    #[repr(C)]
+    pub struct gb_bus_exchange {
+        _private: [u8; 0],
+    }
+    pub const GB_IPC_HANDLE_BYTES: usize = 64;
 
     #[repr(C)]
     #[derive(Clone, Copy, Debug, Default)]
@@ -296,5 +303,13 @@ pub mod ffi {
         pub fn gb_reset_stats(e: *mut gb_engine) -> c_int;
         pub fn gb_set_timing(e: *mut gb_engine, enabled: i32) -> c_int;
         pub fn gb_measure_fma_peak(e: *mut gb_engine, fp64: i32, tflops: *mut f64) -> c_int;
+        // multi-GPU bus exchange: one process per GPU, the root sums the ranks' CUDA IPC buffers over NVLink
+        pub fn gb_bus_exchange_create(device: i32, frames: usize, out: *mut *mut gb_bus_exchange) -> c_int;
+        pub fn gb_bus_exchange_destroy(x: *mut gb_bus_exchange);
+        pub fn gb_bus_exchange_export(x: *mut gb_bus_exchange, handle: *mut c_void) -> c_int;
+        pub fn gb_bus_exchange_open(x: *mut gb_bus_exchange, handles: *const c_void, n: i32, self_rank: i32) -> c_int;
+        pub fn gb_bus_exchange_publish(x: *mut gb_bus_exchange, e: *mut gb_engine, frames: usize, stream: *mut c_void) -> c_int;
+        pub fn gb_bus_exchange_reduce(x: *mut gb_bus_exchange, frames: usize, stream: *mut c_void) -> c_int;
+        pub fn gb_bus_exchange_result(x: *mut gb_bus_exchange, device_ptr: *mut *mut c_void, frames: *mut usize) -> c_int;
     }
 }

@@ -157,6 +157,8 @@ ABI_SYMBOLS = (
     "push_events", "render_block", "render_pcm16", "render_device", "last_device_buffer", "read_last", "position",
     "save_state",
     "restore_state", "get_stats", "reset_stats", "set_timing", "measure_fma_peak", "link_control", "set_lookahead",
+    "bus_exchange_create", "bus_exchange_destroy", "bus_exchange_export", "bus_exchange_open", "bus_exchange_publish",
+    "bus_exchange_reduce", "bus_exchange_result",
 )
 
 

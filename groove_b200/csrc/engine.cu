@@ -3191,4 +3191,107 @@ int gb_measure_fma_peak(gb_engine* e, int32_t fp64, double* tflops) {
   return 0;
 }
 
+// ---- multi-GPU bus exchange --------------------------------------------------------------------------
+// One process per GPU.  Every rank owns an exchange buffer (its rendered stereo bus, f64 L/R interleaved) whose
+// CUDA IPC handle the host side passes around (16-byte-per-frame buffers, one per rank); the root maps the
+// peers' buffers and sums them with ONE kernel whose loads cross NVLink (peer_sum_kernel) — the transfer and
+// the mix are the same pass, instead of an NCCL reduce that first moves and then adds.  All work is enqueued
+// on the caller's stream (the host side brackets it with its own events / barrier).
+struct gb_bus_exchange {
+  int device = 0;
+  size_t frames = 0;
+  double2* mine = nullptr;
+  double2* sum = nullptr;
+  int n = 0, self = 0;
+  PeerTable tab;
+  std::vector<void*> opened;
+};
+
+int gb_bus_exchange_create(int32_t device, size_t frames, gb_bus_exchange** out) {
+  if (!out || !frames) return fail(nullptr, GB_EINVAL, "gb_bus_exchange_create: bad arguments");
+  if (cudaSetDevice(device) != cudaSuccess) return fail(nullptr, GB_ENODEV, "no CUDA device %d (groove_b200 has no CPU fallback)", device);
+  auto x = std::make_unique<gb_bus_exchange>();
+  x->device = device;
+  x->frames = frames;
+  memset(&x->tab, 0, sizeof x->tab);
+  if (cudaMalloc(&x->mine, frames * sizeof(double2)) != cudaSuccess || cudaMalloc(&x->sum, frames * sizeof(double2)) != cudaSuccess) {
+    if (x->mine) cudaFree(x->mine);
+    return fail(nullptr, GB_ENOMEM, "gb_bus_exchange_create: out of device memory");
+  }
+  cudaMemset(x->mine, 0, frames * sizeof(double2));
+  cudaMemset(x->sum, 0, frames * sizeof(double2));
+  cudaDeviceSynchronize();
+  *out = x.release();
+  return 0;
+}
+void gb_bus_exchange_destroy(gb_bus_exchange* x) {
+  if (!x) return;
+  cudaSetDevice(x->device);
+  for (void* p : x->opened) cudaIpcCloseMemHandle(p);
+  if (x->mine) cudaFree(x->mine);
+  if (x->sum) cudaFree(x->sum);
+  delete x;
+}
+// handle: GB_IPC_HANDLE_BYTES bytes (a cudaIpcMemHandle_t) naming this rank's exchange buffer
+int gb_bus_exchange_export(gb_bus_exchange* x, void* handle) {
+  if (!x || !handle) return GB_EINVAL;
+  static_assert(sizeof(cudaIpcMemHandle_t) == GB_IPC_HANDLE_BYTES, "handle size");
+  cudaIpcMemHandle_t h;
+  cudaSetDevice(x->device);
+  cudaError_t rc = cudaIpcGetMemHandle(&h, x->mine);
+  if (rc != cudaSuccess) return fail(nullptr, GB_ECUDA, "cudaIpcGetMemHandle failed: %s", cudaGetErrorString(rc));
+  memcpy(handle, &h, sizeof h);
+  return 0;
+}
+// handles: n x GB_IPC_HANDLE_BYTES in rank order (entry `self` is ignored: the local buffer is used)
+int gb_bus_exchange_open(gb_bus_exchange* x, const void* handles, int32_t n, int32_t self) {
+  if (!x || !handles || n < 1 || n > kMaxPeers || self < 0 || self >= n) return fail(nullptr, GB_EINVAL, "gb_bus_exchange_open: bad arguments");
+  cudaSetDevice(x->device);
+  for (void* p : x->opened) cudaIpcCloseMemHandle(p);
+  x->opened.clear();
+  memset(&x->tab, 0, sizeof x->tab);
+  for (int r = 0; r < n; ++r) {
+    if (r == self) { x->tab.p[r] = x->mine; continue; }
+    cudaIpcMemHandle_t h;
+    memcpy(&h, (const char*)handles + (size_t)r * GB_IPC_HANDLE_BYTES, sizeof h);
+    void* p = nullptr;
+    cudaError_t rc = cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess);
+    if (rc != cudaSuccess) {
+      cudaGetLastError();
+      return fail(nullptr, GB_ECUDA, "cudaIpcOpenMemHandle (rank %d) failed: %s", r, cudaGetErrorString(rc));
+    }
+    x->opened.push_back(p);
+    x->tab.p[r] = (const double2*)p;
+  }
+  x->n = n;
+  x->self = self;
+  return 0;
+}
+// copy the engine's last device-resident render (gb_render_device) into this rank's exchange buffer
+int gb_bus_exchange_publish(gb_bus_exchange* x, gb_engine* e, size_t frames, void* stream) {
+  if (!x || !e) return GB_EINVAL;
+  if (frames > x->frames || frames > e->full_frames) return fail(e, GB_EINVAL, "gb_bus_exchange_publish: no device-resident render of %zu frames", frames);
+  cudaSetDevice(x->device);
+  CUDA_TRY(e, cudaMemcpyAsync(x->mine, e->d_full, frames * sizeof(double2), cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
+  return 0;
+}
+// root: sum the ranks' buffers (remote ones read over NVLink) into the local result buffer
+int gb_bus_exchange_reduce(gb_bus_exchange* x, size_t frames, void* stream) {
+  if (!x || x->n < 1 || frames > x->frames) return fail(nullptr, GB_EINVAL, "gb_bus_exchange_reduce: exchange not opened");
+  cudaSetDevice(x->device);
+  int sms = 148;
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, x->device);
+  const int grid = (int)std::min<size_t>((frames + 255) / 256, (size_t)sms * 8);
+  peer_sum_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(x->tab, x->n, x->sum, frames);
+  cudaError_t rc = cudaGetLastError();
+  if (rc != cudaSuccess) return fail(nullptr, GB_ECUDA, "peer_sum_kernel launch failed: %s", cudaGetErrorString(rc));
+  return 0;
+}
+int gb_bus_exchange_result(gb_bus_exchange* x, void** device_ptr, size_t* frames) {
+  if (!x || !device_ptr) return GB_EINVAL;
+  *device_ptr = x->sum;
+  if (frames) *frames = x->frames;
+  return 0;
+}
+
 }  // extern "C"

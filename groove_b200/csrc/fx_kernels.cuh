@@ -134,6 +134,26 @@ __global__ void __launch_bounds__(128) sidechain_table_kernel(const double2* __r
 // source per frame.  A block covers 64 frames with 4 thread rows; row r sums sources r, r+4, r+8, ...
 // (4 loads in flight each, so 16 per frame) and row 0 adds the four row sums in row order — a fixed
 // summation order, independent of the launch.
+// The multi-GPU bus mixdown (gb_bus_exchange_reduce): the root GPU sums the ranks' stereo buses straight out of
+// their HBM — ptrs[r] is rank r's exchange buffer, mapped into this process over CUDA IPC, so the loads of the
+// remote rows travel over NVLink (P2P) while the kernel adds; n <= kMaxPeers loads in flight per frame, summed in
+// rank order (a fixed order: the mix does not depend on timing).  16 B per frame per rank in, 16 B out.
+constexpr int kMaxPeers = 16;
+struct PeerTable { const double2* p[kMaxPeers]; };
+__global__ void __launch_bounds__(256) peer_sum_kernel(PeerTable tab, int n, double2* __restrict__ out, size_t frames) {
+  for (size_t t = (size_t)blockIdx.x * 256 + threadIdx.x; t < frames; t += (size_t)gridDim.x * 256) {
+    double2 v[kMaxPeers];
+#pragma unroll
+    for (int r = 0; r < kMaxPeers; ++r)
+      if (r < n) v[r] = __ldcg(tab.p[r] + t);   // L2 only: peer data is read once
+    double l = 0.0, rr = 0.0;
+#pragma unroll
+    for (int r = 0; r < kMaxPeers; ++r)
+      if (r < n) { l += v[r].x; rr += v[r].y; }
+    out[t] = make_double2(l, rr);
+  }
+}
+
 constexpr int kSumRows = 4, kSumFrames = 64;
 __global__ void __launch_bounds__(kSumRows * kSumFrames) sum_table_kernel(const double2* const* __restrict__ ptrs, int n,
                                                                           double2* __restrict__ out, int frames) {

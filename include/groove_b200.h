@@ -332,6 +332,24 @@ int gb_set_timing(gb_engine* e, int32_t enabled); /* per-launch CUDA events on/o
 /* FP64/FP32 FMA microbenchmark on the engine's device: returns TFLOP/s. */
 int gb_measure_fma_peak(gb_engine* e, int32_t fp64, double* tflops);
 
+/* ---- multi-GPU bus exchange ------------------------------------------------
+ * One process per GPU: independent tracks render on their own GPU and meet in ONE exchange step,
+ * the stereo bus.  Every rank owns an exchange buffer; its CUDA IPC handle travels through whatever the host side
+ * uses for rendezvous (torch.distributed in bench.py; a pipe in a Rust host); the root maps the peers' buffers and
+ * sums them with one kernel whose loads cross NVLink (P2P) — transfer and mix in the same pass.  `stream` is a
+ * cudaStream_t (NULL = the legacy default stream); nothing here synchronises: the caller orders publish ->
+ * (its own cross-rank barrier) -> reduce.  Replaces the reference's single-process bus sum
+ * (orchestration/src/orchestrator.rs:401-410 walks every track on one CPU thread). */
+#define GB_IPC_HANDLE_BYTES 64
+typedef struct gb_bus_exchange gb_bus_exchange;
+int gb_bus_exchange_create(int32_t device, size_t frames, gb_bus_exchange** out);
+void gb_bus_exchange_destroy(gb_bus_exchange* x);
+int gb_bus_exchange_export(gb_bus_exchange* x, void* handle /* GB_IPC_HANDLE_BYTES */);
+int gb_bus_exchange_open(gb_bus_exchange* x, const void* handles /* n x GB_IPC_HANDLE_BYTES, rank order */, int32_t n, int32_t self);
+int gb_bus_exchange_publish(gb_bus_exchange* x, gb_engine* e, size_t frames, void* stream); /* after gb_render_device */
+int gb_bus_exchange_reduce(gb_bus_exchange* x, size_t frames, void* stream);                /* root only */
+int gb_bus_exchange_result(gb_bus_exchange* x, void** device_ptr, size_t* frames);
+
 #ifdef __cplusplus
 }
 #endif

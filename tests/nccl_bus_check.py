@@ -25,6 +25,19 @@ def main():
     eng = Engine(48000.0, device=local)
     workloads.build_cfg4(eng, mine)
     eng.render_device(frames)
+    # the product path: the root sums the ranks' exchange buffers over NVLink peer memory (peer_sum_kernel) ...
+    p2p, p2p_err = None, None
+    try:
+        xch = parallel.BusExchange(local, frames)
+        t = xch.reduce(eng, frames)
+        torch.cuda.synchronize()
+        if rank == 0:
+            p2p = t.cpu().numpy().copy()
+        dist.barrier()
+        xch.close()
+    except Exception as ex:   # noqa: BLE001
+        p2p_err = str(ex)
+    # ... and the NCCL reduce of the same buses (the fallback when peers cannot be mapped)
     bus = parallel.device_bus_tensor(eng, local)
     parallel.reduce_bus(bus, dst=0)
     torch.cuda.synchronize()
@@ -43,7 +56,10 @@ def main():
         with open(sys.argv[1], "w") as f:
             json.dump({"world": world, "peak": float(np.abs(alone).max()),
                        "max_abs_vs_single_gpu": float(np.abs(mixed - alone).max()),
-                       "max_abs_vs_oracle": float(np.abs(mixed - ref).max())}, f)
+                       "max_abs_vs_oracle": float(np.abs(mixed - ref).max()),
+                       "p2p_error": p2p_err,
+                       "p2p_max_abs_vs_nccl": None if p2p is None else float(np.abs(p2p - mixed).max()),
+                       "p2p_max_abs_vs_oracle": None if p2p is None else float(np.abs(p2p - ref).max())}, f)
     dist.barrier()
     dist.destroy_process_group()
 

@@ -776,8 +776,9 @@ def test_time_parallel_resting_kernel_hard_sync(monkeypatch):
 
 def test_two_gpu_bus_reduce_matches_single_gpu_render(tmp_path):
     """N > 1 on real GPUs: two ranks (torchrun, NCCL) each render their shard of a config-4 slice, the
-    stereo buses are summed onto rank 0 with one NCCL f64 reduce, and rank 0 compares the result with its
-    own single-GPU render of the union and with the oracle."""
+    stereo buses are summed onto rank 0 — by the product's bus exchange (peer_sum_kernel reading the ranks' CUDA
+    IPC buffers over NVLink) and by one NCCL f64 reduce (the fallback) — and rank 0 compares both results with
+    its own single-GPU render of the union and with the oracle."""
     import subprocess
     import sys
     import torch
@@ -796,3 +797,6 @@ def test_two_gpu_bus_reduce_matches_single_gpu_render(tmp_path):
     assert res["peak"] > 1e-3
     assert res["max_abs_vs_single_gpu"] < 1e-12
     assert res["max_abs_vs_oracle"] < TIGHT
+    # the product's exchange: the root's peer_sum_kernel over the ranks' CUDA IPC buffers (NVLink P2P loads)
+    assert res["p2p_error"] is None, res["p2p_error"]
+    assert res["p2p_max_abs_vs_nccl"] < 1e-15 and res["p2p_max_abs_vs_oracle"] < TIGHT
