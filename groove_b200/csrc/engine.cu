@@ -382,6 +382,7 @@ struct gb_engine {
   int vr_count = 0;                      // ranges (CTAs)
   VrWork* d_vr_work[2] = {nullptr, nullptr};
   bool chunk_vr = false;                 // this chunk's resting voices went through the ranges
+  Rest16Table* d_rest16 = nullptr;       // per Welsh instrument: the tables of welsh_rest_vr16_kernel (16 frames per lane)
   double2* ring = nullptr;                           // pinned: kStageSlots x max_block frames (host-buffer renders)
   uint64_t chunk_seq = 0;
   bool finalized = false;
@@ -402,6 +403,7 @@ struct gb_engine {
     bool rest_kernel = true;      // GB_REST_KERNEL=0
     bool sweep_kernel = true;     // GB_SWEEP_KERNEL=0
     bool sync_kernels = true;     // GB_SYNC_KERNELS=0: hard-sync patches stay on the general kernel
+    bool rest16 = true;           // GB_REST16=0: voice-range chunks keep 8 frames per lane (welsh_rest_vr_kernel)
     int rest_vr = -1;             // GB_REST_VR: 1 = voice-range resting chunks whenever possible, 0 = never, -1 = when they even out the SM load
     int rest_nv = 2;              // GB_REST_NV=4: welsh_rest_kernel with four voices in lockstep per warp (one CTA per SM)
     bool rest_tp = true;          // GB_REST_TP=0: no time-parallel resting kernel (and no CTAs below 8 voices)
@@ -1015,6 +1017,7 @@ int gb_create(const gb_config* cfg, gb_engine** out) {
   if (const char* v = getenv("GB_REST_NV")) e->opt.rest_nv = atoi(v) == 4 ? 4 : 2;
   if (const char* v = getenv("GB_OVERLAP")) e->overlap_enabled = atoi(v) != 0;
   if (const char* v = getenv("GB_REST_VR")) e->opt.rest_vr = atoi(v);
+  if (const char* v = getenv("GB_REST16")) e->opt.rest16 = atoi(v) != 0;
   if (const char* v = getenv("GB_MIN_CUT_VOICES")) e->opt.min_cut_voices = std::max(1, atoi(v));
   if (const char* v = getenv("GB_SOLO_MIN")) e->min_solo_items = atoi(v);
   if (const char* v = getenv("GB_SOLO_WAVES")) e->solo_waves = atoi(v) != 0;
@@ -1388,6 +1391,48 @@ int plan_voice_ranges(gb_engine* e) {
       if ((rc2 = dev_alloc(e, &consumer->d_src_table_vr[par2], tab.size(), false))) return rc2;
       CUDA_TRY(e, cudaMemcpy((void*)consumer->d_src_table_vr[par2], tab.data(), tab.size() * sizeof(double2*), cudaMemcpyHostToDevice));
       consumer->n_src_vr = (int)tab.size();
+    }
+    {  // tables for 16 frames per lane: the same constructions as LtiTable / lane_rot with kT16
+      std::vector<Rest16Table> tabs(e->h_winst.size());
+      memset(tabs.data(), 0, tabs.size() * sizeof(Rest16Table));
+      for (Node* n : e->plan) {
+        if (!n->is_inst) continue;
+        const WelshInst& I = e->h_winst[(size_t)n->table_index];
+        Rest16Table& R = tabs[(size_t)n->table_index];
+        auto table = [](const SecCoef& c, double (*g)[2], double (*mp)[4]) {
+          double h00 = 1.0, h01 = 0.0, h10 = 0.0, h11 = 1.0;  // H = A^j, A = [[a1, 1], [a2, 0]]
+          for (int j = 0; j < kT16; ++j) {
+            g[j][0] = h00; g[j][1] = h01;
+            const double t00 = c.a1 * h00 + h10, t01 = c.a1 * h01 + h11;
+            h10 = c.a2 * h00; h11 = c.a2 * h01;
+            h00 = t00; h01 = t01;
+          }
+          mp[0][0] = h00; mp[0][1] = h01; mp[0][2] = h10; mp[0][3] = h11;
+          for (int k = 1; k < 5; ++k) {
+            const double* m = mp[k - 1];
+            mp[k][0] = m[0] * m[0] + m[1] * m[2]; mp[k][1] = m[0] * m[1] + m[1] * m[3];
+            mp[k][2] = m[2] * m[0] + m[3] * m[2]; mp[k][3] = m[2] * m[1] + m[3] * m[3];
+          }
+          mp[5][0] = mp[5][1] = mp[5][2] = mp[5][3] = 0.0;
+        };
+        table(I.lti.c1, R.g1b, R.mp1);
+        table(I.lti.c2, R.g2, R.mp2);
+        for (int j = 0; j < kT16; ++j) { R.g1b[j][0] *= I.lti.c2.b0; R.g1b[j][1] *= I.lti.c2.b0; }
+        auto rot = [&](uint64_t steps) {
+          const uint64_t q = steps * I.lfo_dq;  // mod 2^64
+          const double ang = 6.283185307179586476925286766559 * ((double)q / 18446744073709551616.0);
+          return make_double2(std::cos(ang), std::sin(ang));
+        };
+        for (int j = 0; j < kT16; ++j) R.lfo_rot[j] = rot((uint64_t)j);
+        for (int l = 0; l < 32; ++l) R.lane_rot[l] = rot((uint64_t)(l * kT16));
+        R.block_rot = rot((uint64_t)kBlock16);
+      }
+      if ((rc2 = dev_alloc(e, &e->d_rest16, tabs.size(), false))) return rc2;
+      CUDA_TRY(e, cudaMemcpy(e->d_rest16, tabs.data(), tabs.size() * sizeof(Rest16Table), cudaMemcpyHostToDevice));
+      CUDA_TRY(e, cudaFuncSetAttribute(welsh_rest_vr16_kernel<8, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kRestSmemMax));
+      CUDA_TRY(e, cudaFuncSetAttribute(welsh_rest_vr16_kernel<8, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kRestSmemMax));
+      CUDA_TRY(e, cudaFuncSetAttribute(welsh_rest_vr16_kernel<8, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kRestSmemMax));
+      CUDA_TRY(e, cudaFuncSetAttribute(welsh_rest_vr16_kernel<8, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kRestSmemMax));
     }
     e->vr_ok = true;
     e->vr_class = cls;
@@ -2215,13 +2260,23 @@ int render_chunk(gb_engine* e, int frames, size_t n_ev) {
         for (Node* n : e->plan) plain = plain && !n->unit_gain;
         if (plain) {
           constexpr int kVrW = 8;
-          const size_t vr_smem = (size_t)kVrW * kTileStride * sizeof(double2) + 14 * sizeof(RestState);
           Launch l(e, true, 1, vs);
-          switch (e->vr_class) {
-            case 0: welsh_rest_vr_kernel<kVrW, false, false><<<e->vr_count, 32 * kVrW, vr_smem, vs>>>(e->d_winst, e->d_wvoice, e->d_vr_work[par], f0, frames); break;
-            case 1: welsh_rest_vr_kernel<kVrW, false, true><<<e->vr_count, 32 * kVrW, vr_smem, vs>>>(e->d_winst, e->d_wvoice, e->d_vr_work[par], f0, frames); break;
-            case 2: welsh_rest_vr_kernel<kVrW, true, false><<<e->vr_count, 32 * kVrW, vr_smem, vs>>>(e->d_winst, e->d_wvoice, e->d_vr_work[par], f0, frames); break;
-            default: welsh_rest_vr_kernel<kVrW, true, true><<<e->vr_count, 32 * kVrW, vr_smem, vs>>>(e->d_winst, e->d_wvoice, e->d_vr_work[par], f0, frames); break;
+          if (e->opt.rest16 && frames % kBlock16 == 0) {  // 16 frames per lane: half the scans and barriers per frame
+            const size_t smem16 = (size_t)kVrW * kTile16Stride * sizeof(double2) + 14 * sizeof(RestState);
+            switch (e->vr_class) {
+              case 0: welsh_rest_vr16_kernel<kVrW, false, false><<<e->vr_count, 32 * kVrW, smem16, vs>>>(e->d_winst, e->d_rest16, e->d_wvoice, e->d_vr_work[par], f0, frames); break;
+              case 1: welsh_rest_vr16_kernel<kVrW, false, true><<<e->vr_count, 32 * kVrW, smem16, vs>>>(e->d_winst, e->d_rest16, e->d_wvoice, e->d_vr_work[par], f0, frames); break;
+              case 2: welsh_rest_vr16_kernel<kVrW, true, false><<<e->vr_count, 32 * kVrW, smem16, vs>>>(e->d_winst, e->d_rest16, e->d_wvoice, e->d_vr_work[par], f0, frames); break;
+              default: welsh_rest_vr16_kernel<kVrW, true, true><<<e->vr_count, 32 * kVrW, smem16, vs>>>(e->d_winst, e->d_rest16, e->d_wvoice, e->d_vr_work[par], f0, frames); break;
+            }
+          } else {
+            const size_t vr_smem = (size_t)kVrW * kTileStride * sizeof(double2) + 14 * sizeof(RestState);
+            switch (e->vr_class) {
+              case 0: welsh_rest_vr_kernel<kVrW, false, false><<<e->vr_count, 32 * kVrW, vr_smem, vs>>>(e->d_winst, e->d_wvoice, e->d_vr_work[par], f0, frames); break;
+              case 1: welsh_rest_vr_kernel<kVrW, false, true><<<e->vr_count, 32 * kVrW, vr_smem, vs>>>(e->d_winst, e->d_wvoice, e->d_vr_work[par], f0, frames); break;
+              case 2: welsh_rest_vr_kernel<kVrW, true, false><<<e->vr_count, 32 * kVrW, vr_smem, vs>>>(e->d_winst, e->d_wvoice, e->d_vr_work[par], f0, frames); break;
+              default: welsh_rest_vr_kernel<kVrW, true, true><<<e->vr_count, 32 * kVrW, vr_smem, vs>>>(e->d_winst, e->d_wvoice, e->d_vr_work[par], f0, frames); break;
+            }
           }
           e->stats.rest_ctas += (uint64_t)e->vr_count;
           e->stats.rest_vr_launches++;

@@ -1722,6 +1722,221 @@ __global__ void __launch_bounds__(32 * W, 2) welsh_rest_vr_kernel(const WelshIns
   }
 }
 
+// ---- voice ranges with 16 frames per lane -------------------------------------------------------------
+// A block of welsh_rest_block costs its warp about 1375 issue cycles per sub-partition plus a share of ~1950 cycles
+// per block in which nobody issues (the two scans' shuffle -> FMA chains, the CTA barriers).  With
+// 16 frames per lane a block is 512 frames: the scans, their matrix loads and the barriers come once per 512 frames
+// instead of once per 256.  The zero-state outputs of the two passes (16 per voice) do not stay in registers: a
+// pair's two values of a frame are exactly one 16-byte word, and that word lives in the warp's tile row — the
+// slot the frame's panned output is written to at the end, when the pair's value is dead.  Tables for 16-frame
+// lanes (rows g, span maps A^(16 2^k), LFO rotations) come from a per-instrument Rest16Table built at gb_finalize.
+constexpr int kT16 = 16;
+constexpr int kBlock16 = 32 * kT16;
+constexpr int kTile16Stride = kBlock16 + kBlock16 / kT16;  // padded (16-byte units): lane stride kT16 + 1
+
+struct alignas(16) Rest16Table {
+  double g1b[kT16][2];     // section 1's entry-state rows, scaled by section 2's b0
+  double g2[kT16][2];      // section 2's entry-state rows
+  double mp1[6][4];        // (A1^16)^(2^k), k = 0..4; [5] = 0
+  double mp2[6][4];
+  double2 lfo_rot[kT16];   // (cos, sin) of j LFO steps
+  double2 lane_rot[32];    // ... of 16 l LFO steps
+  double2 block_rot;       // ... of 512 LFO steps
+};
+
+template <bool LFO_AMP, bool ZERO_A, int NV>
+__device__ __forceinline__ void welsh_rest_block16(RestState* const (&rs)[NV], const WelshInst& I, const Rest16Table& R,
+                                                   int lane, double2* tile_row) {
+  const LtiTable& L = I.lti;
+  double2* row = tile_row + lane * (kT16 + 1);
+  double ps0[NV], ps1[NV];
+  // ---- pass 1: oscillators + section 1 from a zero state (pre-scaled by both sections' b0, as welsh_rest_block) ----
+  {
+    u64 p1[NV], p2[NV], d1[NV], d2[NV];
+#pragma unroll
+    for (int v = 0; v < NV; ++v) {
+      const ulonglong2 pp = *reinterpret_cast<const ulonglong2*>(&rs[v]->p1);
+      const ulonglong2 dd = *reinterpret_cast<const ulonglong2*>(&rs[v]->d1);
+      d1[v] = dd.x; d2[v] = dd.y;
+      p1[v] = pp.x + (u64)(lane * kT16) * dd.x;
+      p2[v] = pp.y + (u64)(lane * kT16) * dd.y;
+      ps0[v] = 0.0; ps1[v] = 0.0;
+    }
+    __syncwarp();  // every lane has read the block's base phases
+    if (lane == 0) {
+#pragma unroll
+      for (int v = 0; v < NV; ++v)
+        *reinterpret_cast<ulonglong2*>(&rs[v]->p1) =
+            make_ulonglong2(p1[v] + (u64)kBlock16 * d1[v], p2[v] + (u64)kBlock16 * d2[v]);
+    }
+    const OscMix o1 = I.m1bb, o2 = I.m2bb;
+    const u64 t1 = I.s1.thresh, t2 = I.s2.thresh;
+    const double a1 = L.c1.a1, a2 = L.c1.a2;
+#pragma unroll
+    for (int j = 0; j < kT16; ++j) {
+      double y[2] = {0.0, 0.0};
+#pragma unroll
+      for (int v = 0; v < NV; ++v) {
+        osc_advance<false>(p1[v], p2[v], d1[v], d2[v]);
+        y[v] = lp_step_bx(osc_mix_eval<ZERO_A>(o1, t1, p1[v], o2, t2, p2[v]), a1, a2, ps0[v], ps1[v]);
+      }
+      row[j] = make_double2(y[0], y[1]);
+    }
+    const double inv = L.inv_b0_2;
+#pragma unroll
+    for (int v = 0; v < NV; ++v) { ps0[v] *= inv; ps1[v] *= inv; }
+  }
+  double e0[NV], e1[NV];
+  lti_scan_entry_t<NV, RestState>(ps0, ps1, R.mp1, lane, rs, 0, e0, e1);
+  // ---- pass 2: section 2 on the fixed-up section-1 output ----
+  {
+    const double a1 = L.c2.a1, a2 = L.c2.a2;
+#pragma unroll
+    for (int v = 0; v < NV; ++v) { ps0[v] = 0.0; ps1[v] = 0.0; }
+#pragma unroll
+    for (int j = 0; j < kT16; ++j) {
+      const double2 g = *reinterpret_cast<const double2*>(R.g1b[j]);
+      const double2 yv = row[j];
+      double y[2] = {yv.x, yv.y};
+#pragma unroll
+      for (int v = 0; v < NV; ++v)
+        y[v] = lp_step_bx(fma(g.y, e1[v], fma(g.x, e0[v], y[v])), a1, a2, ps0[v], ps1[v]);
+      row[j] = make_double2(y[0], y[1]);
+    }
+  }
+  lti_scan_entry_t<NV, RestState>(ps0, ps1, R.mp2, lane, rs, 1, e0, e1);
+  // ---- LFO phasor of this lane; the cached one advances by one block ----
+  double lsd[NV], lcd[NV];
+#pragma unroll
+  for (int v = 0; v < NV; ++v) {
+    lsd[v] = 0.0; lcd[v] = 0.0;
+    if (LFO_AMP) {
+      const double2 ph = *reinterpret_cast<const double2*>(&rs[v]->ls);
+      const double2 r = R.lane_rot[lane];
+      lsd[v] = fma(ph.x, r.x, ph.y * r.y);
+      lcd[v] = fma(ph.y, r.x, -(ph.x * r.y));
+    }
+  }
+  if (LFO_AMP) {
+    __syncwarp();  // every lane has read the block's phasor
+    if (lane == 0) {
+      const double2 r = R.block_rot;
+#pragma unroll
+      for (int v = 0; v < NV; ++v)
+        *reinterpret_cast<double2*>(&rs[v]->ls) =
+            make_double2(fma(lsd[v], r.x, lcd[v] * r.y), fma(lcd[v], r.x, -(lsd[v] * r.y)));
+    }
+  }
+  // ---- amplitude, DCA: the pair's word of each frame becomes the frame's panned output ----
+  const double arest = I.amp_rest;
+  const double gl = I.gl, gr = I.gr;
+#pragma unroll
+  for (int j = 0; j < kT16; ++j) {
+    const double2 g = *reinterpret_cast<const double2*>(R.g2[j]);
+    double2 rot = make_double2(0.0, 0.0);
+    if (LFO_AMP) rot = R.lfo_rot[j];
+    const double2 yv = row[j];
+    const double yy[2] = {yv.x, yv.y};
+    double m = 0.0;
+#pragma unroll
+    for (int v = 0; v < NV; ++v) {
+      const double amp = LFO_AMP ? fma(lsd[v], rot.x, fma(lcd[v], rot.y, arest)) : arest;
+      const double y = fma(g.y, e1[v], fma(g.x, e0[v], yy[v]));
+      m = v == 0 ? y * amp : fma(y, amp, m);
+    }
+    row[j] = make_double2(m * gl, m * gr);
+  }
+  __syncwarp();
+}
+
+template <int W>
+__device__ __forceinline__ void cta_reduce_store16(const double2* tiles, const int* s_active, double2* out, i64 fb, i64 f0) {
+  for (int t = threadIdx.x; t < kBlock16; t += 32 * W) {
+    double l = 0.0, r = 0.0;
+    const int u = t + (t >> 4);
+#pragma unroll
+    for (int w = 0; w < W; ++w) {
+      if (s_active[w]) {
+        const double2 v = tiles[w * kTile16Stride + u];
+        l += v.x; r += v.y;
+      }
+    }
+    out[fb + t - f0] = make_double2(l, r);
+  }
+}
+
+// grid = ranges; block = 32 * W; dynamic smem = W * kTile16Stride double2 + 2 W RestState; nframes a multiple of 512
+template <int W, bool LFO_AMP, bool ZERO_A>
+__global__ void __launch_bounds__(32 * W, 2) welsh_rest_vr16_kernel(const WelshInst* __restrict__ insts,
+                                                                  const Rest16Table* __restrict__ tabs,
+                                                                  WelshVoice* __restrict__ voices,
+                                                                  const VrWork* __restrict__ work, i64 f0, int nframes) {
+  extern __shared__ double2 smem_tiles[];
+  __shared__ int s_active[W];
+  __shared__ WelshInst sI[2];
+  __shared__ Rest16Table sR[2];
+  const VrWork wk = work[blockIdx.x];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  {
+    const int* a = reinterpret_cast<const int*>(insts + wk.inst_a);
+    const int* b = reinterpret_cast<const int*>(insts + wk.inst_b);
+    int* dst = reinterpret_cast<int*>(&sI[0]);
+    constexpr int kWords = (int)(sizeof(WelshInst) / sizeof(int));
+    for (int i = threadIdx.x; i < 2 * kWords; i += 32 * W) dst[i] = i < kWords ? a[i] : b[i - kWords];
+    const int* ra = reinterpret_cast<const int*>(tabs + wk.inst_a);
+    const int* rb = reinterpret_cast<const int*>(tabs + wk.inst_b);
+    int* rdst = reinterpret_cast<int*>(&sR[0]);
+    constexpr int kRWords = (int)(sizeof(Rest16Table) / sizeof(int));
+    for (int i = threadIdx.x; i < 2 * kRWords; i += 32 * W) rdst[i] = i < kRWords ? ra[i] : rb[i - kRWords];
+  }
+  __syncthreads();
+  RestState* cache = reinterpret_cast<RestState*>(smem_tiles + W * kTile16Stride);
+  for (int t = threadIdx.x; t < wk.nvoices; t += 32 * W) {
+    const WelshInst& I = sI[t >= wk.split ? 1 : 0];
+    const WelshVoice* vp = voices + wk.voice0 + t;
+    RestState r;
+    const u64 k = (u64)(f0 - 1 - vp->anchor);
+    r.d1 = vp->d1; r.d2 = vp->d2;
+    r.p1 = vp->p1 + k * r.d1; r.p2 = vp->p2 + k * r.d2;
+    r.s[0] = vp->s[0]; r.s[1] = vp->s[1]; r.s[2] = vp->s[2]; r.s[3] = vp->s[3];
+    r.ls = 0.0; r.lc = 0.0;
+    if (LFO_AMP) {
+      double ls, lc;
+      sincos_phase(vp->pl + (k + 1) * I.lfo_dq, &ls, &lc);
+      const double dl = I.depth * I.amp_rest;
+      r.ls = ls * dl; r.lc = lc * dl;
+    }
+    cache[t] = r;
+  }
+  const int g = 2 * warp - min(max(warp - wk.single0, 0), 2);
+  const bool pair = !(warp == wk.single0 || warp == wk.single0 + 1);
+  if (lane == 0) s_active[warp] = g < wk.nvoices ? 1 : 0;
+  __syncthreads();
+  const int which = g >= wk.split ? 1 : 0;
+  const WelshInst& I = sI[which];
+  const Rest16Table& R = sR[which];
+  double2* tile_row = smem_tiles + warp * kTile16Stride;
+  const i64 f_end = f0 + nframes;
+#pragma unroll 1
+  for (i64 fb = f0; fb < f_end; fb += kBlock16) {
+    if (pair && g + 1 < wk.nvoices) {
+      RestState* const two[2] = {cache + g, cache + g + 1};
+      welsh_rest_block16<LFO_AMP, ZERO_A, 2>(two, I, R, lane, tile_row);
+    } else if (g < wk.nvoices) {
+      RestState* const one[1] = {cache + g};
+      welsh_rest_block16<LFO_AMP, ZERO_A, 1>(one, I, R, lane, tile_row);
+    }
+    __syncthreads();
+    cta_reduce_store16<W>(smem_tiles, s_active, wk.out, fb, f0);
+    __syncthreads();
+  }
+  for (int t = threadIdx.x; t < wk.nvoices; t += 32 * W) {
+    WelshVoice* vp = voices + wk.voice0 + t;
+    vp->s[0] = cache[t].s[0]; vp->s[1] = cache[t].s[1]; vp->s[2] = cache[t].s[2]; vp->s[3] = cache[t].s[3];
+    vp->knot_frame = kNever;
+  }
+}
+
 // ---- the resting-voice kernel, time-parallel ---------------------------------------------------------
 // welsh_rest_kernel gives every warp its own voices and walks them through the chunk block by block: the
 // chunk's 256 blocks are a serial chain per warp (1.7 us per block), so a shard of a few hundred voices —

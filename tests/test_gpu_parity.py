@@ -422,18 +422,23 @@ def test_voice_range_resting_chunks(monkeypatch):
     scene(o)
     ref = o.render(frames)
     outs, stats = [], []
-    for vr in ("1", "0"):
+    # voice ranges with 16 frames per lane (welsh_rest_vr16_kernel: 512-frame blocks, the passes' intermediate values
+    # parked in the tile rows), with 8 frames per lane (welsh_rest_vr_kernel), and the instrument-CTA layout
+    for vr, r16 in (("1", "1"), ("1", "0"), ("0", "1")):
         monkeypatch.setenv("GB_REST_VR", vr)
+        monkeypatch.setenv("GB_REST16", r16)
         g = gpu_engine(48000.0, max_block=4096)
         scene(g)
         outs.append(g.render(frames))
         stats.append(g.stats())
         g.close()
-    assert stats[0].rest_kernel_launches >= 5 and stats[0].rest_ctas == 14 * stats[0].rest_kernel_launches
-    assert stats[1].rest_ctas == 24 * stats[1].rest_kernel_launches
-    check(outs[0], ref)
-    check(outs[1], ref)
-    assert np.abs(outs[0] - outs[1]).max() < 1e-12
+    for k in (0, 1):
+        assert stats[k].rest_kernel_launches >= 5 and stats[k].rest_ctas == 14 * stats[k].rest_kernel_launches
+        assert stats[k].rest_vr_launches == stats[k].rest_kernel_launches
+    assert stats[2].rest_ctas == 24 * stats[2].rest_kernel_launches and stats[2].rest_vr_launches == 0
+    for y in outs:
+        check(y, ref)
+    assert np.abs(outs[0] - outs[2]).max() < 1e-12 and np.abs(outs[1] - outs[2]).max() < 1e-12
 
 
 @pytest.mark.parametrize("max_block", [0, 100, 64])
