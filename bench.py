@@ -230,7 +230,7 @@ STAT_SUMS = ("render_ms", "voice_kernel_ms", "fx_kernel_ms", "kernel_launches", 
              "sweep_kernel_ms", "sweep_kernel_launches", "sweep_voice_samples", "sweep_ctas",
              "solo_kernel_ms", "solo_kernel_launches", "solo_voice_samples", "solo_jobs",
              "fm_kernel_ms", "fm_kernel_launches", "idle_voice_samples", "voice_samples", "h2d_bytes", "d2h_bytes",
-             "rest_tp_launches", "rest_vr_launches")
+             "rest_tp_launches", "rest_vr_launches", "rest_vr16_launches")
 
 
 class Acc(dict):
@@ -480,16 +480,19 @@ def run_ours(a) -> None:
                 k_ms, k_l, k_vs, k_ctas = dev["rest_kernel_ms"], dev["rest_kernel_launches"], dev["rest_voice_samples"], dev["rest_ctas"]
                 # which resting kernel the launches were: instrument CTAs, voice ranges (all-resting chunks of an
                 # engine whose CTAs then cover every SM evenly) or the time-parallel variant (small shards)
-                n_vr, n_tp = dev["rest_vr_launches"], dev["rest_tp_launches"]
-                k_name = ("welsh_rest_vr_kernel<8,lfo,flat>" if 2 * n_vr > k_l else
+                n_vr, n_vr16, n_tp = dev["rest_vr_launches"], dev["rest_vr16_launches"], dev["rest_tp_launches"]
+                k_name = ("welsh_rest_vr16_kernel<8,lfo,flat>" if 2 * n_vr16 > k_l else
+                          "welsh_rest_vr_kernel<8,lfo,flat>" if 2 * n_vr > k_l else
                           "welsh_rest_tp_kernel<8,lfo,flat>" if 2 * n_tp > k_l else "welsh_rest_kernel<8,lfo,flat>")
-                k_name += f" ({int(n_vr // steps)} voice-range, {int(n_tp // steps)} time-parallel of {int(k_l // steps)} resting launches per step)"
+                k_name += (f" ({int(n_vr // steps)} voice-range [{int(n_vr16 // steps)} with 16 frames per lane], "
+                           f"{int(n_tp // steps)} time-parallel of {int(k_l // steps)} resting launches per step)")
             else:
                 k_ms, k_l, k_vs, k_ctas = dev["voice_kernel_ms"], dev["voice_kernel_launches"], per_rank_vs * steps, 0
                 k_name = "welsh_kernel<8,2>"
             # executed-instruction facts of the dominant kernel: from the committed ncu --set full capture
             prof = {}
-            facts = ("r2f_rest_vr_kernel_facts.json" if use_rest and 2 * dev["rest_vr_launches"] > k_l
+            facts = ("r2f_rest_vr16_kernel_facts.json" if use_rest and 2 * dev["rest_vr16_launches"] > k_l
+                     else "r2f_rest_vr_kernel_facts.json" if use_rest and 2 * dev["rest_vr_launches"] > k_l
                      else "r2_rest_kernel_facts.json")
             try:
                 with open(os.path.join(ROOT, "profiles", facts)) as f:

@@ -276,6 +276,7 @@ pub mod ffi {
         pub fx_batched_nodes: u64,
         pub rest_tp_launches: u64,
         pub rest_vr_launches: u64,
+        pub rest_vr16_launches: u64,
     }
 
     extern "C" {

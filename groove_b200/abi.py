@@ -148,7 +148,7 @@ class Stats(C.Structure):
                 ("solo_jobs", C.c_uint64), ("solo_class_items", C.c_uint64 * 4),
                 ("fm_kernel_launches", C.c_uint64), ("fm_kernel_ms", C.c_double), ("idle_voice_samples", C.c_uint64),
                 ("rest_ctas", C.c_uint64), ("sweep_ctas", C.c_uint64), ("fx_batched_nodes", C.c_uint64), ("rest_tp_launches", C.c_uint64),
-                ("rest_vr_launches", C.c_uint64)]
+                ("rest_vr_launches", C.c_uint64), ("rest_vr16_launches", C.c_uint64)]
 
 
 # every symbol include/groove_b200.h declares (suffix after the prefix)

@@ -2262,6 +2262,7 @@ int render_chunk(gb_engine* e, int frames, size_t n_ev) {
           constexpr int kVrW = 8;
           Launch l(e, true, 1, vs);
           if (e->opt.rest16 && frames % kBlock16 == 0) {  // 16 frames per lane: half the scans and barriers per frame
+            e->stats.rest_vr16_launches++;
             const size_t smem16 = (size_t)kVrW * kTile16Stride * sizeof(double2) + 14 * sizeof(RestState);
             switch (e->vr_class) {
               case 0: welsh_rest_vr16_kernel<kVrW, false, false><<<e->vr_count, 32 * kVrW, smem16, vs>>>(e->d_winst, e->d_rest16, e->d_wvoice, e->d_vr_work[par], f0, frames); break;

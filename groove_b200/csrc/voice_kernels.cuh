@@ -1793,10 +1793,15 @@ __device__ __forceinline__ void welsh_rest_block16(RestState* const (&rs)[NV], c
     const double a1 = L.c2.a1, a2 = L.c2.a2;
 #pragma unroll
     for (int v = 0; v < NV; ++v) { ps0[v] = 0.0; ps1[v] = 0.0; }
+    // the row words and table rows of the next two frames are in flight while a frame is computed
+    double2 yq[3], gq[3];
+    yq[0] = row[0]; gq[0] = *reinterpret_cast<const double2*>(R.g1b[0]);
+    yq[1] = row[1]; gq[1] = *reinterpret_cast<const double2*>(R.g1b[1]);
 #pragma unroll
     for (int j = 0; j < kT16; ++j) {
-      const double2 g = *reinterpret_cast<const double2*>(R.g1b[j]);
-      const double2 yv = row[j];
+      if (j + 2 < kT16) { yq[(j + 2) % 3] = row[j + 2]; gq[(j + 2) % 3] = *reinterpret_cast<const double2*>(R.g1b[j + 2]); }
+      const double2 g = gq[j % 3];
+      const double2 yv = yq[j % 3];
       double y[2] = {yv.x, yv.y};
 #pragma unroll
       for (int v = 0; v < NV; ++v)
@@ -1830,12 +1835,21 @@ __device__ __forceinline__ void welsh_rest_block16(RestState* const (&rs)[NV], c
   // ---- amplitude, DCA: the pair's word of each frame becomes the frame's panned output ----
   const double arest = I.amp_rest;
   const double gl = I.gl, gr = I.gr;
+  double2 yq[3], gq[3], rq[3];
+#pragma unroll
+  for (int j = 0; j < 2; ++j) {
+    yq[j] = row[j]; gq[j] = *reinterpret_cast<const double2*>(R.g2[j]);
+    rq[j] = LFO_AMP ? R.lfo_rot[j] : make_double2(0.0, 0.0);
+  }
 #pragma unroll
   for (int j = 0; j < kT16; ++j) {
-    const double2 g = *reinterpret_cast<const double2*>(R.g2[j]);
-    double2 rot = make_double2(0.0, 0.0);
-    if (LFO_AMP) rot = R.lfo_rot[j];
-    const double2 yv = row[j];
+    if (j + 2 < kT16) {
+      yq[(j + 2) % 3] = row[j + 2]; gq[(j + 2) % 3] = *reinterpret_cast<const double2*>(R.g2[j + 2]);
+      rq[(j + 2) % 3] = LFO_AMP ? R.lfo_rot[j + 2] : make_double2(0.0, 0.0);
+    }
+    const double2 g = gq[j % 3];
+    const double2 rot = rq[j % 3];
+    const double2 yv = yq[j % 3];
     const double yy[2] = {yv.x, yv.y};
     double m = 0.0;
 #pragma unroll

@@ -40,7 +40,7 @@ extern "C" {
 #define GB_ABI_VERSION 4 /* 2: gb_link_control, GB_FX_SIGNAL_PASSTHROUGH, gb_stats grew (rest_kernel_*);
                             3: GB_INST_OSCILLATOR / GB_INST_ENVELOPE, gb_stats grew (solo_*, fm_*, idle_*, *_ctas),
                                gb_set_lookahead;
-                            4: gb_stats grew (rest_tp_launches, rest_vr_launches) */
+                            4: gb_stats grew (rest_tp_launches, rest_vr_launches, rest_vr16_launches), gb_bus_exchange_* */
 
 /* ---- error codes --------------------------------------------------------- */
 enum {
@@ -325,6 +325,7 @@ typedef struct {
   uint64_t fx_batched_nodes;      /* effect nodes that shared a launch with others of their kind and graph level */
   uint64_t rest_tp_launches;      /* of rest_kernel_launches: the time-parallel variant (CTAs of <= 8 voices) */
   uint64_t rest_vr_launches;      /* of rest_kernel_launches: all-resting chunks over voice ranges (CTAs across instrument boundaries) */
+  uint64_t rest_vr16_launches;    /* of rest_vr_launches: with 16 frames per lane (chunks of a multiple of 512 frames) */
 } gb_stats;
 int gb_get_stats(gb_engine* e, gb_stats* out);
 int gb_reset_stats(gb_engine* e);
