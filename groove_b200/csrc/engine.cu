@@ -317,6 +317,7 @@ struct Node {
   double2* scratch_alt = nullptr;  // split Welsh instrument: the partial buffers of odd chunks (gb_engine::overlap)
   const double2** d_src_table_vr[2] = {nullptr, nullptr};  // consumer of a voice-range engine: its other sources + the range partials, per chunk parity
   int n_src_vr = 0;
+  bool fused_all_inst = false;  // every live source of this consumer is a split instrument whose partials it sums itself
   int n_src_fused = 0;
   int consumers = 0;           // plan nodes that read this node's buffer
   bool fuse_partials = false;  // split instrument whose only consumer sums its partials itself (no reduce pass)
@@ -382,6 +383,7 @@ struct gb_engine {
   int vr_count = 0;                      // ranges (CTAs)
   VrWork* d_vr_work[2] = {nullptr, nullptr};
   bool chunk_vr = false;                 // this chunk's resting voices went through the ranges
+  bool chunk_all_idle = false;           // this chunk: every grouped Welsh CTA idle (its partial buffer holds zeros)
   Rest16Table* d_rest16 = nullptr;       // per Welsh instrument: the tables of welsh_rest_vr16_kernel (16 frames per lane)
   double2* ring = nullptr;                           // pinned: kStageSlots x max_block frames (host-buffer renders)
   uint64_t chunk_seq = 0;
@@ -819,7 +821,10 @@ int gather_sources(gb_engine* e, Node* n, int frames, SourceList* out, bool* don
     Launch l(e, false);
     const bool plain = done && (n->kind == GB_FX_MIXER || n->kind == GB_FX_SIGNAL_PASSTHROUGH);
     double2* dst = plain ? n->buf : n->scratch;
-    if (e->fused_sums && e->chunk_vr && n->d_src_table_vr[e->parity])
+    if (e->fused_sums && e->overlap && e->chunk_all_idle && n->fused_all_inst)
+      // a silent stretch: every partial buffer holds zeros (idle CTAs are not launched), and so does their sum
+      cudaMemsetAsync(dst, 0, (size_t)frames * sizeof(double2), e->stream);
+    else if (e->fused_sums && e->chunk_vr && n->d_src_table_vr[e->parity])
       sum_table_kernel<<<cdiv(frames, kSumFrames), kSumRows * kSumFrames, 0, e->stream>>>(n->d_src_table_vr[e->parity], n->n_src_vr, dst, frames);
     else if (e->fused_sums && n->d_src_table_fused)
       sum_table_kernel<<<cdiv(frames, kSumFrames), kSumRows * kSumFrames, 0, e->stream>>>(
@@ -1800,6 +1805,11 @@ int gb_finalize(gb_engine* e) {
           else
             fused.push_back(sn->buf);
         }
+        n->fused_all_inst = true;
+        for (uint32_t su : n->sources) {
+          Node* sn = find(e, su);
+          if (sn && sn->order >= 0 && sn->buf && !sn->fuse_partials) n->fused_all_inst = false;
+        }
         if ((rc2 = dev_alloc(e, &n->d_src_table_fused_alt, fused.size(), false))) return rc2;
         CUDA_TRY(e, cudaMemcpy((void*)n->d_src_table_fused_alt, fused.data(), fused.size() * sizeof(double2*), cudaMemcpyHostToDevice));
       }
@@ -2151,6 +2161,7 @@ int render_chunk(gb_engine* e, int frames, size_t n_ev) {
   const int par = e->overlap ? (int)(e->chunk_seq & 1) : 0;
   e->parity = par;
   e->chunk_vr = false;
+  e->chunk_all_idle = false;
   cudaStream_t vs = e->overlap ? e->vstream : e->stream;
   if (e->overlap) {
     CUDA_TRY(e, cudaStreamWaitEvent(vs, e->call_start, 0));
@@ -2238,6 +2249,11 @@ int render_chunk(gb_engine* e, int frames, size_t n_ev) {
           else rest_voices_max = std::max(rest_voices_max, (size_t)w.nvoices);
           rest_voices += (uint64_t)w.nvoices;
         }
+      }
+      {
+        size_t launched = 0;
+        for (auto& l : lists) launched += l.size();
+        e->chunk_all_idle = ng > 0 && launched == 0;
       }
       if (ng) {
         if (e->widx.cap < (size_t)ng) e->widx_on_device.clear();  // a new device buffer holds nothing yet
