@@ -6,16 +6,19 @@
 
 A *step* is one full render of BASELINE config 4 — 4096 Welsh `cello` voices, 60 s at 48 kHz stereo
 = 1.17965e10 voice-samples — through the engine.  At N > 1 every rank renders its own 4096-voice
-shard (weak scaling) and the stereo buses are summed onto rank 0 with one NCCL f64 reduce.
+shard (weak scaling) and the stereo buses are summed onto rank 0 by the engine's bus exchange: one kernel on
+rank 0 whose loads of the other ranks' buses cross NVLink (CUDA IPC peer buffers; NCCL's f64 reduce only if the
+peers cannot be mapped — `config.parallelism` says which).
 
 Printed JSON (one line, rank 0):
   value      whole-job voice-samples/s, device-timed (CUDA events on the engine's stream around
-             each render call; at N > 1 plus CUDA events around the NCCL bus reduce, max over
+             each render call; at N > 1 plus CUDA events around the bus exchange, max over
              ranks), inputs resident in HBM, result left in HBM;
   e2e        the same metric through the C ABI with host buffers: the note events are pushed from
              host memory, rendered, and the f64 stereo result is copied back to a host buffer, all
              inside the timed region (engine construction / plan / allocation stay outside);
-  roofline   dominant kernel (config 4: welsh_rest_kernel, the resting-voice kernel) against the FP64
+  roofline   dominant kernel (config 4: the resting-voice kernel — welsh_rest_vr16_kernel when every voice of
+             a chunk rests, `roofline.kernel` names what ran) against the FP64
              vector pipe, which is what binds this path: achieved = the ALGORITHMIC
              150 FLOP x voice-samples its launches covered / their CUDA-event time; peak = FP64 FMA
              microbenchmark measured live on the same GPU.  `roofline.executed` is the same with the FP64
