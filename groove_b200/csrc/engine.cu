@@ -1061,6 +1061,7 @@ int gb_create(const gb_config* cfg, gb_engine** out) {
 void gb_destroy(gb_engine* e) {
   if (!e) return;
   cudaSetDevice(e->device);
+  if (e->vstream) cudaStreamSynchronize(e->vstream);  // a render that failed half-way may have left voice kernels enqueued
   if (e->stream) cudaStreamSynchronize(e->stream);
   if (e->copy_stream) cudaStreamSynchronize(e->copy_stream);
   for (int i = 0; i < kStageSlots; ++i) {
