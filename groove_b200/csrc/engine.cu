@@ -380,6 +380,7 @@ struct gb_engine {
   // ranges of 14 regardless of instrument boundaries so that all SMs carry the same load.
   bool vr_ok = false;                    // decided by gb_finalize (needs `overlap`)
   int vr_class = -1;                     // the instruments' common rest class
+  int vr_osc = 0;                        // welsh_rest_vr16_kernel's OSC: 1 = every instrument's oscillators are symmetric +-c waveforms, 2 = ... and oscillator 2 a square
   int vr_count = 0;                      // ranges (CTAs)
   VrWork* d_vr_work[2] = {nullptr, nullptr};
   bool chunk_vr = false;                 // this chunk's resting voices went through the ranges
@@ -405,6 +406,7 @@ struct gb_engine {
     bool rest_kernel = true;      // GB_REST_KERNEL=0
     bool sweep_kernel = true;     // GB_SWEEP_KERNEL=0
     bool sync_kernels = true;     // GB_SYNC_KERNELS=0: hard-sync patches stay on the general kernel
+    bool osc_sym = true;          // GB_OSC_SYM=0: no sign-bit oscillator form in welsh_rest_vr16_kernel
     bool rest16 = true;           // GB_REST16=0: voice-range chunks keep 8 frames per lane (welsh_rest_vr_kernel)
     int rest_vr = -1;             // GB_REST_VR: 1 = voice-range resting chunks whenever possible, 0 = never, -1 = when they even out the SM load
     int rest_nv = 2;              // GB_REST_NV=4: welsh_rest_kernel with four voices in lockstep per warp (one CTA per SM)
@@ -1023,6 +1025,7 @@ int gb_create(const gb_config* cfg, gb_engine** out) {
   if (const char* v = getenv("GB_OVERLAP")) e->overlap_enabled = atoi(v) != 0;
   if (const char* v = getenv("GB_REST_VR")) e->opt.rest_vr = atoi(v);
   if (const char* v = getenv("GB_REST16")) e->opt.rest16 = atoi(v) != 0;
+  if (const char* v = getenv("GB_OSC_SYM")) e->opt.osc_sym = atoi(v) != 0;
   if (const char* v = getenv("GB_MIN_CUT_VOICES")) e->opt.min_cut_voices = std::max(1, atoi(v));
   if (const char* v = getenv("GB_SOLO_MIN")) e->min_solo_items = atoi(v);
   if (const char* v = getenv("GB_SOLO_WAVES")) e->solo_waves = atoi(v) != 0;
@@ -1398,12 +1401,18 @@ int plan_voice_ranges(gb_engine* e) {
       CUDA_TRY(e, cudaMemcpy((void*)consumer->d_src_table_vr[par2], tab.data(), tab.size() * sizeof(double2*), cudaMemcpyHostToDevice));
       consumer->n_src_vr = (int)tab.size();
     }
+    int osc = 0;
     {  // tables for 16 frames per lane: the same constructions as LtiTable / lane_rot with kT16
       std::vector<Rest16Table> tabs(e->h_winst.size());
       memset(tabs.data(), 0, tabs.size() * sizeof(Rest16Table));
+      osc = (cls & 1) && e->opt.osc_sym ? 2 : 0;  // piecewise-constant oscillators only
       for (Node* n : e->plan) {
         if (!n->is_inst) continue;
         const WelshInst& I = e->h_winst[(size_t)n->table_index];
+        const bool sym = I.m1bb.b_hi == -I.m1bb.b_lo && I.m2bb.b_hi == -I.m2bb.b_lo && I.m1bb.a_lo == 0.0 && I.m1bb.a_hi == 0.0 &&
+                         I.m2bb.a_lo == 0.0 && I.m2bb.a_hi == 0.0;
+        if (!sym) osc = 0;
+        else if (osc == 2 && I.s2.thresh != (1ull << 63)) osc = 1;
         Rest16Table& R = tabs[(size_t)n->table_index];
         auto table = [](const SecCoef& c, double (*g)[2], double (*mp)[4]) {
           double h00 = 1.0, h01 = 0.0, h10 = 0.0, h11 = 1.0;  // H = A^j, A = [[a1, 1], [a2, 0]]
@@ -1439,8 +1448,13 @@ int plan_voice_ranges(gb_engine* e) {
       CUDA_TRY(e, cudaFuncSetAttribute(welsh_rest_vr16_kernel<8, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kRestSmemMax));
       CUDA_TRY(e, cudaFuncSetAttribute(welsh_rest_vr16_kernel<8, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kRestSmemMax));
       CUDA_TRY(e, cudaFuncSetAttribute(welsh_rest_vr16_kernel<8, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kRestSmemMax));
+      CUDA_TRY(e, cudaFuncSetAttribute(welsh_rest_vr16_kernel<8, false, true, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, kRestSmemMax));
+      CUDA_TRY(e, cudaFuncSetAttribute(welsh_rest_vr16_kernel<8, false, true, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, kRestSmemMax));
+      CUDA_TRY(e, cudaFuncSetAttribute(welsh_rest_vr16_kernel<8, true, true, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, kRestSmemMax));
+      CUDA_TRY(e, cudaFuncSetAttribute(welsh_rest_vr16_kernel<8, true, true, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, kRestSmemMax));
     }
     e->vr_ok = true;
+    e->vr_osc = osc;
     e->vr_class = cls;
     e->vr_count = ranges;
   }
@@ -2283,9 +2297,17 @@ int render_chunk(gb_engine* e, int frames, size_t n_ev) {
             const size_t smem16 = (size_t)kVrW * kTile16Stride * sizeof(double2) + 14 * sizeof(RestState);
             switch (e->vr_class) {
               case 0: welsh_rest_vr16_kernel<kVrW, false, false><<<e->vr_count, 32 * kVrW, smem16, vs>>>(e->d_winst, e->d_rest16, e->d_wvoice, e->d_vr_work[par], f0, frames); break;
-              case 1: welsh_rest_vr16_kernel<kVrW, false, true><<<e->vr_count, 32 * kVrW, smem16, vs>>>(e->d_winst, e->d_rest16, e->d_wvoice, e->d_vr_work[par], f0, frames); break;
+              case 1:
+                if (e->vr_osc == 2) welsh_rest_vr16_kernel<kVrW, false, true, 2><<<e->vr_count, 32 * kVrW, smem16, vs>>>(e->d_winst, e->d_rest16, e->d_wvoice, e->d_vr_work[par], f0, frames);
+                else if (e->vr_osc == 1) welsh_rest_vr16_kernel<kVrW, false, true, 1><<<e->vr_count, 32 * kVrW, smem16, vs>>>(e->d_winst, e->d_rest16, e->d_wvoice, e->d_vr_work[par], f0, frames);
+                else welsh_rest_vr16_kernel<kVrW, false, true><<<e->vr_count, 32 * kVrW, smem16, vs>>>(e->d_winst, e->d_rest16, e->d_wvoice, e->d_vr_work[par], f0, frames);
+                break;
               case 2: welsh_rest_vr16_kernel<kVrW, true, false><<<e->vr_count, 32 * kVrW, smem16, vs>>>(e->d_winst, e->d_rest16, e->d_wvoice, e->d_vr_work[par], f0, frames); break;
-              default: welsh_rest_vr16_kernel<kVrW, true, true><<<e->vr_count, 32 * kVrW, smem16, vs>>>(e->d_winst, e->d_rest16, e->d_wvoice, e->d_vr_work[par], f0, frames); break;
+              default:
+                if (e->vr_osc == 2) welsh_rest_vr16_kernel<kVrW, true, true, 2><<<e->vr_count, 32 * kVrW, smem16, vs>>>(e->d_winst, e->d_rest16, e->d_wvoice, e->d_vr_work[par], f0, frames);
+                else if (e->vr_osc == 1) welsh_rest_vr16_kernel<kVrW, true, true, 1><<<e->vr_count, 32 * kVrW, smem16, vs>>>(e->d_winst, e->d_rest16, e->d_wvoice, e->d_vr_work[par], f0, frames);
+                else welsh_rest_vr16_kernel<kVrW, true, true><<<e->vr_count, 32 * kVrW, smem16, vs>>>(e->d_winst, e->d_rest16, e->d_wvoice, e->d_vr_work[par], f0, frames);
+                break;
             }
           } else {
             const size_t vr_smem = (size_t)kVrW * kTileStride * sizeof(double2) + 14 * sizeof(RestState);

@@ -1744,9 +1744,24 @@ struct alignas(16) Rest16Table {
   double2 block_rot;       // ... of 512 LFO steps
 };
 
-template <bool LFO_AMP, bool ZERO_A, int NV>
+// Symmetric piecewise-constant waveforms (square, pulse: +c below the threshold, -c above): the waveform value is
+// the constant with its SIGN BIT picked by the compare — one 32-bit select instead of a two-word double select —
+// and for a square (threshold = half a turn) the phase's top bit IS that sign: no compare at all.
+//   OSC = 1: both oscillators symmetric;  OSC = 2: ... and oscillator 2 is a square.  Same bits as osc_mix_eval.
+template <int OSC>
+__device__ __forceinline__ double osc_sym_eval(double c1, u64 t1, u64 p1, double c2, u64 t2, u64 p2) {
+  const int c1h = __double2hiint(c1), c2h = __double2hiint(c2);
+  const int h1 = p1 < t1 ? c1h : c1h ^ (int)0x80000000;
+  int h2;
+  if (OSC == 2) h2 = c2h ^ ((int)(p2 >> 32) & (int)0x80000000);
+  else h2 = p2 < t2 ? c2h : c2h ^ (int)0x80000000;
+  return __hiloint2double(h1, __double2loint(c1)) + __hiloint2double(h2, __double2loint(c2));
+}
+
+template <bool LFO_AMP, bool ZERO_A, int NV, int OSC = 0>
 __device__ __forceinline__ void welsh_rest_block16(RestState* const (&rs)[NV], const WelshInst& I, const Rest16Table& R,
                                                    int lane, double2* tile_row) {
+  static_assert(OSC == 0 || ZERO_A, "the sign-bit form is for piecewise-constant waveforms");
   const LtiTable& L = I.lti;
   double2* row = tile_row + lane * (kT16 + 1);
   double ps0[NV], ps1[NV];
@@ -1778,7 +1793,9 @@ __device__ __forceinline__ void welsh_rest_block16(RestState* const (&rs)[NV], c
 #pragma unroll
       for (int v = 0; v < NV; ++v) {
         osc_advance<false>(p1[v], p2[v], d1[v], d2[v]);
-        y[v] = lp_step_bx(osc_mix_eval<ZERO_A>(o1, t1, p1[v], o2, t2, p2[v]), a1, a2, ps0[v], ps1[v]);
+        const double x = OSC ? osc_sym_eval<OSC>(o1.b_lo, t1, p1[v], o2.b_lo, t2, p2[v])
+                             : osc_mix_eval<ZERO_A>(o1, t1, p1[v], o2, t2, p2[v]);
+        y[v] = lp_step_bx(x, a1, a2, ps0[v], ps1[v]);
       }
       row[j] = make_double2(y[0], y[1]);
     }
@@ -1863,24 +1880,25 @@ __device__ __forceinline__ void welsh_rest_block16(RestState* const (&rs)[NV], c
   __syncwarp();
 }
 
+// All W rows are summed unconditionally, in warp order: the rows of warps without voices (the last, partial range)
+// are zeroed once at kernel start, so the loads do not hang on a per-warp flag (in cta_reduce_store that flag load
+// -> compare -> predicated row load chain was 9 % of this kernel's stall samples, r2f_rest_vr16_hot_spots.txt).
 template <int W>
-__device__ __forceinline__ void cta_reduce_store16(const double2* tiles, const int* s_active, double2* out, i64 fb, i64 f0) {
+__device__ __forceinline__ void cta_reduce_store16(const double2* tiles, double2* out, i64 fb, i64 f0) {
   for (int t = threadIdx.x; t < kBlock16; t += 32 * W) {
-    double l = 0.0, r = 0.0;
     const int u = t + (t >> 4);
+    double2 v[W];
 #pragma unroll
-    for (int w = 0; w < W; ++w) {
-      if (s_active[w]) {
-        const double2 v = tiles[w * kTile16Stride + u];
-        l += v.x; r += v.y;
-      }
-    }
+    for (int w = 0; w < W; ++w) v[w] = tiles[w * kTile16Stride + u];
+    double l = 0.0, r = 0.0;
+#pragma unroll
+    for (int w = 0; w < W; ++w) { l += v[w].x; r += v[w].y; }
     out[fb + t - f0] = make_double2(l, r);
   }
 }
 
 // grid = ranges; block = 32 * W; dynamic smem = W * kTile16Stride double2 + 2 W RestState; nframes a multiple of 512
-template <int W, bool LFO_AMP, bool ZERO_A>
+template <int W, bool LFO_AMP, bool ZERO_A, int OSC = 0>
 __global__ void __launch_bounds__(32 * W, 2) welsh_rest_vr16_kernel(const WelshInst* __restrict__ insts,
                                                                   const Rest16Table* __restrict__ tabs,
                                                                   WelshVoice* __restrict__ voices,
@@ -1930,18 +1948,20 @@ __global__ void __launch_bounds__(32 * W, 2) welsh_rest_vr16_kernel(const WelshI
   const WelshInst& I = sI[which];
   const Rest16Table& R = sR[which];
   double2* tile_row = smem_tiles + warp * kTile16Stride;
+  if (g >= wk.nvoices)  // a warp without voices: its row stays zero for the whole launch
+    for (int i = lane; i < kTile16Stride; i += 32) tile_row[i] = make_double2(0.0, 0.0);
   const i64 f_end = f0 + nframes;
 #pragma unroll 1
   for (i64 fb = f0; fb < f_end; fb += kBlock16) {
     if (pair && g + 1 < wk.nvoices) {
       RestState* const two[2] = {cache + g, cache + g + 1};
-      welsh_rest_block16<LFO_AMP, ZERO_A, 2>(two, I, R, lane, tile_row);
+      welsh_rest_block16<LFO_AMP, ZERO_A, 2, OSC>(two, I, R, lane, tile_row);
     } else if (g < wk.nvoices) {
       RestState* const one[1] = {cache + g};
-      welsh_rest_block16<LFO_AMP, ZERO_A, 1>(one, I, R, lane, tile_row);
+      welsh_rest_block16<LFO_AMP, ZERO_A, 1, OSC>(one, I, R, lane, tile_row);
     }
     __syncthreads();
-    cta_reduce_store16<W>(smem_tiles, s_active, wk.out, fb, f0);
+    cta_reduce_store16<W>(smem_tiles, wk.out, fb, f0);
     __syncthreads();
   }
   for (int t = threadIdx.x; t < wk.nvoices; t += 32 * W) {

@@ -424,21 +424,24 @@ def test_voice_range_resting_chunks(monkeypatch):
     outs, stats = [], []
     # voice ranges with 16 frames per lane (welsh_rest_vr16_kernel: 512-frame blocks, the passes' intermediate values
     # parked in the tile rows), with 8 frames per lane (welsh_rest_vr_kernel), and the instrument-CTA layout
-    for vr, r16 in (("1", "1"), ("1", "0"), ("0", "1")):
+    # (the 16-frame kernel twice: with the sign-bit form of the symmetric pulse / square oscillators and without)
+    for vr, r16, sym in (("1", "1", "1"), ("1", "0", "1"), ("0", "1", "1"), ("1", "1", "0")):
         monkeypatch.setenv("GB_REST_VR", vr)
         monkeypatch.setenv("GB_REST16", r16)
+        monkeypatch.setenv("GB_OSC_SYM", sym)
         g = gpu_engine(48000.0, max_block=4096)
         scene(g)
         outs.append(g.render(frames))
         stats.append(g.stats())
         g.close()
-    for k in (0, 1):
+    for k in (0, 1, 3):
         assert stats[k].rest_kernel_launches >= 5 and stats[k].rest_ctas == 14 * stats[k].rest_kernel_launches
         assert stats[k].rest_vr_launches == stats[k].rest_kernel_launches
     assert stats[2].rest_ctas == 24 * stats[2].rest_kernel_launches and stats[2].rest_vr_launches == 0
     for y in outs:
         check(y, ref)
     assert np.abs(outs[0] - outs[2]).max() < 1e-12 and np.abs(outs[1] - outs[2]).max() < 1e-12
+    assert np.array_equal(outs[0], outs[3])      # the sign-bit oscillator form yields the same bits
 
 
 @pytest.mark.parametrize("max_block", [0, 100, 64])
