@@ -825,7 +825,7 @@ int gather_sources(gb_engine* e, Node* n, int frames, SourceList* out, bool* don
     double2* dst = plain ? n->buf : n->scratch;
     if (e->fused_sums && e->overlap && e->chunk_all_idle && n->fused_all_inst)
       // a silent stretch: every partial buffer holds zeros (idle CTAs are not launched), and so does their sum
-      cudaMemsetAsync(dst, 0, (size_t)frames * sizeof(double2), e->stream);
+      CUDA_TRY(e, cudaMemsetAsync(dst, 0, (size_t)frames * sizeof(double2), e->stream));
     else if (e->fused_sums && e->chunk_vr && n->d_src_table_vr[e->parity])
       sum_table_kernel<<<cdiv(frames, kSumFrames), kSumRows * kSumFrames, 0, e->stream>>>(n->d_src_table_vr[e->parity], n->n_src_vr, dst, frames);
     else if (e->fused_sums && n->d_src_table_fused)

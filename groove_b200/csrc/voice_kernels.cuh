@@ -1904,7 +1904,6 @@ __global__ void __launch_bounds__(32 * W, 2) welsh_rest_vr16_kernel(const WelshI
                                                                   WelshVoice* __restrict__ voices,
                                                                   const VrWork* __restrict__ work, i64 f0, int nframes) {
   extern __shared__ double2 smem_tiles[];
-  __shared__ int s_active[W];
   __shared__ WelshInst sI[2];
   __shared__ Rest16Table sR[2];
   const VrWork wk = work[blockIdx.x];
@@ -1942,7 +1941,6 @@ __global__ void __launch_bounds__(32 * W, 2) welsh_rest_vr16_kernel(const WelshI
   }
   const int g = 2 * warp - min(max(warp - wk.single0, 0), 2);
   const bool pair = !(warp == wk.single0 || warp == wk.single0 + 1);
-  if (lane == 0) s_active[warp] = g < wk.nvoices ? 1 : 0;
   __syncthreads();
   const int which = g >= wk.split ? 1 : 0;
   const WelshInst& I = sI[which];
