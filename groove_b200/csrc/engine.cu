@@ -380,6 +380,7 @@ struct gb_engine {
   // ranges of 14 regardless of instrument boundaries so that all SMs carry the same load.
   bool vr_ok = false;                    // decided by gb_finalize (needs `overlap`)
   int vr_class = -1;                     // the instruments' common rest class
+  int vr_sweep_class = -1;               // the instruments' common sweep class (-1: sweeping chunks keep instrument CTAs)
   int vr_osc = 0;                        // welsh_rest_vr16_kernel's OSC: 1 = every instrument's oscillators are symmetric +-c waveforms, 2 = ... and oscillator 2 a square
   int vr_count = 0;                      // ranges (CTAs)
   VrWork* d_vr_work[2] = {nullptr, nullptr};
@@ -1336,7 +1337,7 @@ int plan_voice_ranges(gb_engine* e) {
   int rc2;
   constexpr int kVrVoices = 14;
   Node* consumer = nullptr;
-  int n_cons = 0, n_inst = 0, n_fused_src = 0, next_voice = 0, cls = -2;
+  int n_cons = 0, n_inst = 0, n_fused_src = 0, next_voice = 0, cls = -2, sweep_cls = -1;
   bool vr = e->opt.rest_vr != 0 && e->opt.rest_kernel;
   for (Node* n : e->plan) {
     if (!n->is_inst) {
@@ -1348,6 +1349,8 @@ int plan_voice_ranges(gb_engine* e) {
     vr = vr && n->nvoices % 2 == 0 && n->nvoices >= kVrVoices && n->voice0 == next_voice && I.rest_class >= 0 &&
          I.rest_class < 4 && (cls == -2 || cls == I.rest_class);
     cls = I.rest_class;
+    if (n_inst == 1) sweep_cls = I.sweep_class;
+    else if (sweep_cls != I.sweep_class) sweep_cls = -1;
     next_voice = n->voice0 + n->nvoices;
   }
   if (vr && n_cons == 1) {
@@ -1454,6 +1457,7 @@ int plan_voice_ranges(gb_engine* e) {
       CUDA_TRY(e, cudaFuncSetAttribute(welsh_rest_vr16_kernel<8, true, true, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, kRestSmemMax));
     }
     e->vr_ok = true;
+    e->vr_sweep_class = sweep_cls >= 0 && sweep_cls < 4 && e->opt.sweep_kernel ? sweep_cls : -1;
     e->vr_osc = osc;
     e->vr_class = cls;
     e->vr_count = ranges;
@@ -2362,6 +2366,26 @@ int render_chunk(gb_engine* e, int frames, size_t n_ev) {
       GB_REST_TP_LAUNCH(4, false, false, true)
       GB_REST_TP_LAUNCH(5, true, false, true)
 #undef GB_REST_TP_LAUNCH
+      // every grouped CTA sweeps in this chunk: the voice ranges take it, as they take all-resting chunks
+      if (e->vr_ok && e->vr_sweep_class >= 0 && ng > 0 && lists[kSw + e->vr_sweep_class].size() == (size_t)ng &&
+          e->fused_sums_enabled) {
+        bool plain = true;
+        for (Node* n : e->plan) plain = plain && !n->unit_gain;
+        if (plain) {
+          constexpr int kVrW = 8;
+          const size_t smem = (size_t)kVrW * kTileStride * sizeof(double2) + 14 * sizeof(SweepState);
+          Launch l(e, true, 2, vs);
+          switch (e->vr_sweep_class) {
+            case 0: welsh_sweep_vr_kernel<kVrW, false, false><<<e->vr_count, 32 * kVrW, smem, vs>>>(e->d_winst, e->d_wvoice, e->d_vr_work[par], f0, frames); break;
+            case 1: welsh_sweep_vr_kernel<kVrW, false, true><<<e->vr_count, 32 * kVrW, smem, vs>>>(e->d_winst, e->d_wvoice, e->d_vr_work[par], f0, frames); break;
+            case 2: welsh_sweep_vr_kernel<kVrW, true, false><<<e->vr_count, 32 * kVrW, smem, vs>>>(e->d_winst, e->d_wvoice, e->d_vr_work[par], f0, frames); break;
+            default: welsh_sweep_vr_kernel<kVrW, true, true><<<e->vr_count, 32 * kVrW, smem, vs>>>(e->d_winst, e->d_wvoice, e->d_vr_work[par], f0, frames); break;
+          }
+          e->stats.sweep_ctas += (uint64_t)e->vr_count;
+          e->chunk_vr = true;
+          lists[kSw + e->vr_sweep_class].clear();
+        }
+      }
       e->stats.rest_voice_samples += rest_voices * (uint64_t)frames;
       e->stats.sweep_voice_samples += sweep_voices * (uint64_t)frames;
       const size_t welsh_smem = (size_t)kVoiceWarps * kTileStride * sizeof(double2) + (size_t)kParkWords * 32 * kVoiceWarps * sizeof(double);

@@ -2573,6 +2573,77 @@ __global__ void __launch_bounds__(32 * W, 2) welsh_sweep_kernel(const WelshInst*
   }
 }
 
+// The sweeping kernel over voice ranges (VrWork, as welsh_rest_vr_kernel): chunks in which EVERY grouped CTA sweeps
+// run as ranges of 14 voices regardless of instrument boundaries (28 voices on every SM instead of 32 on 108 SMs
+// and 16 on the rest).  A warp takes voices w and w + W of its range, each with its own instrument record.
+template <int W, bool LFO_AMP, bool ZERO_A>
+__global__ void __launch_bounds__(32 * W, 2) welsh_sweep_vr_kernel(const WelshInst* __restrict__ insts,
+                                                                 WelshVoice* __restrict__ voices,
+                                                                 const VrWork* __restrict__ work, i64 f0, int nframes) {
+  extern __shared__ double2 smem_tiles[];
+  __shared__ int s_active[W];
+  __shared__ WelshInst sI[2];
+  const VrWork wk = work[blockIdx.x];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  {
+    const int* a = reinterpret_cast<const int*>(insts + wk.inst_a);
+    const int* b = reinterpret_cast<const int*>(insts + wk.inst_b);
+    int* dst = reinterpret_cast<int*>(&sI[0]);
+    constexpr int kWords = (int)(sizeof(WelshInst) / sizeof(int));
+    for (int i = threadIdx.x; i < 2 * kWords; i += 32 * W) dst[i] = i < kWords ? a[i] : b[i - kWords];
+  }
+  __syncthreads();
+  SweepState* cache = reinterpret_cast<SweepState*>(smem_tiles + W * kTileStride);
+  for (int t = threadIdx.x; t < wk.nvoices; t += 32 * W) {
+    const WelshInst& I = sI[t >= wk.split ? 1 : 0];
+    const WelshVoice* vp = voices + wk.voice0 + t;
+    SweepState r;
+    const u64 k = (u64)(f0 - 1 - vp->anchor);
+    r.d1 = vp->d1; r.d2 = vp->d2;
+    r.p1 = vp->p1 + k * r.d1; r.p2 = vp->p2 + k * r.d2;
+    r.s[0] = vp->s[0]; r.s[1] = vp->s[1]; r.s[2] = vp->s[2]; r.s[3] = vp->s[3];
+    r.ls = 0.0; r.lc = 0.0;
+    if (LFO_AMP) {
+      double ls, lc;
+      sincos_phase(vp->pl + (k + 1) * I.lfo_dq, &ls, &lc);
+      r.ls = ls * I.depth; r.lc = lc * I.depth;
+    }
+    env_stage_held(I.amp, vp->n_on, vp->la_on, f0, r.aq0, r.aq1, r.aq2, r.aw, r.adw);
+    r.aq0 *= 0.5; r.aq1 *= 0.5; r.aq2 *= 0.5;
+    env_stage_held(I.filt, vp->n_on, vp->lf_on, f0, r.fq0, r.fq1, r.fq2, r.fw, r.fdw);
+#pragma unroll
+    for (int q = 0; q < 2; ++q) {  // knots at f0 - kT and f0: the stage's formula, continued backwards
+      const double w = fma((double)((q - 1) * kT), r.fdw, r.fw);
+      welsh_knot(I, fma(I.cut_b, fma(w, fma(r.fq2, w, r.fq1), r.fq0), I.cut_a), r.kn[q]);
+    }
+    cache[t] = r;
+  }
+  if (lane == 0) s_active[warp] = warp < wk.nvoices ? 1 : 0;
+  __syncthreads();
+  double2* tile_row = smem_tiles + warp * kTileStride;
+  const i64 f_end = f0 + nframes;
+  int t0 = 0;
+#pragma unroll 1
+  for (i64 fb = f0; fb < f_end; fb += kBlockFrames, t0 += kBlockFrames) {
+    bool first = true;
+#pragma unroll 1
+    for (int g = warp; g < wk.nvoices; g += W) {
+      const WelshInst& I = sI[g >= wk.split ? 1 : 0];
+      if (first) welsh_sweep_block<LFO_AMP, ZERO_A, false, false>(cache + g, I, lane, t0, tile_row);
+      else welsh_sweep_block<LFO_AMP, ZERO_A, true, false>(cache + g, I, lane, t0, tile_row);
+      first = false;
+    }
+    __syncthreads();
+    cta_reduce_store<W>(smem_tiles, s_active, wk.out, fb, f0, f_end);
+    __syncthreads();
+  }
+  for (int t = threadIdx.x; t < wk.nvoices; t += 32 * W) {
+    WelshVoice* vp = voices + wk.voice0 + t;
+    vp->s[0] = cache[t].s[0]; vp->s[1] = cache[t].s[1]; vp->s[2] = cache[t].s[2]; vp->s[3] = cache[t].s[3];
+    vp->knot_frame = kNever;
+  }
+}
+
 // ---- the solo-voice kernel -------------------------------------------------------------------------
 // Instruments with fewer voices than a CTA has warps contribute one (instrument, voice, output buffer)
 // item per voice (a batch of one-voice patch variants — BASELINE config 5 — is 4096 such items per GPU).

@@ -444,6 +444,47 @@ def test_voice_range_resting_chunks(monkeypatch):
     assert np.array_equal(outs[0], outs[3])      # the sign-bit oscillator form yields the same bits
 
 
+def test_voice_range_sweeping_chunks(monkeypatch):
+    """Chunks in which EVERY grouped CTA sweeps (all voices inside the filter envelope's decay) also run over voice
+    ranges (welsh_sweep_vr_kernel: a warp's two voices may belong to different instruments).  12 instruments x 16
+    voices with a 1.5 s filter decay: 14 ranges against 24 instrument CTAs per sweeping launch."""
+    monkeypatch.setenv("GB_MIN_CUT_VOICES", "1")
+    frames = 20 * 4096
+
+    def scene(r):
+        uids = []
+        for i in range(12):
+            p = scenes.generic_welsh(voices=16, gain=0.04, pan=-0.9 + 0.16 * i, w1=abi.WAVE_SAWTOOTH, w2=abi.WAVE_PULSE_WIDTH,
+                                     pw2=0.2 + 0.02 * i, mix=0.5, routing=abi.LFO_AMPLITUDE, depth=0.05 + 0.01 * i, lfo_hz=6.0,
+                                     filt=(0.0, 1.5, 0.6, 0.05), amp=(0.01, 0.0, 1.0, 0.0),
+                                     cutoff_start=scenes.hz_to_pct(60.0), cutoff_end=0.45 + 0.02 * i)
+            u = r.add_instrument(abi.INST_WELSH, p)
+            r.patch(u, abi.MAIN_MIXER)
+            uids.append(u)
+        r.finalize()
+        for i, u in enumerate(uids):
+            for v in range(16):
+                r.note_on(5 + 3 * v + i, u, 30 + 2 * v + i % 2)
+        return frames
+
+    o = OracleEngine(48000.0)
+    scene(o)
+    ref = o.render(frames)
+    outs, stats = [], []
+    for vr in ("1", "0"):
+        monkeypatch.setenv("GB_REST_VR", vr)
+        g = gpu_engine(48000.0, max_block=4096)
+        scene(g)
+        outs.append(g.render(frames))
+        stats.append(g.stats())
+        g.close()
+    assert stats[0].sweep_kernel_launches >= 10 and stats[0].sweep_ctas == 14 * stats[0].sweep_kernel_launches
+    assert stats[1].sweep_kernel_launches >= 10 and stats[1].sweep_ctas == 24 * stats[1].sweep_kernel_launches
+    check(outs[0], ref)
+    check(outs[1], ref)
+    assert np.abs(outs[0] - outs[1]).max() < 1e-12
+
+
 @pytest.mark.parametrize("max_block", [0, 100, 64])
 def test_sidechain_link_known_answer_on_gpu(max_block):
     """The oracle's sidechain known answer (tests/test_oracle_known_answers.py) on the CUDA engine: the
