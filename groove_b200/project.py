@@ -379,6 +379,9 @@ class ProjectLoader:
             e.samples = [(k, v, 0.0) for k, v in sorted(KIT_707.items())]
             return e
         if kind_name == "sampler":
+            # older fixtures (projects/tests/load-stereo-wav.json) keep midi-in and the parameters in ONE object
+            if not args and isinstance(body, list) and body and "filename" in body[0]:
+                args = body[0]
             # root: the project's value if positive, else the WAV file's own metadata (README.md:82-84), else the
             # engine default (440 Hz)
             root = float(args.get("root", 0.0))

@@ -76,6 +76,31 @@ def test_loader_reproduces_committed_plans(name, rel):
 
 
 @pytest.mark.skipif(not os.path.isdir(REF), reason="reference tree not present on this box")
+def test_every_reference_project_loads_or_fails_as_the_reference_does():
+    """All 96 project fixtures of the reference (projects/**, test-data/*.json*): 94 compile to plans; the two that
+    do not are Welsh patches the reference itself cannot deserialise (an LFO routing that is not in the enum,
+    settings/src/patches.rs:269-278, and an LFO depth outside its range).  The older sampler schema of
+    projects/tests/load-stereo-wav.json (midi-in and filename in one object) loads and renders a STEREO sample."""
+    import glob
+    files = sorted(glob.glob(os.path.join(REF, "projects", "**", "*.json*"), recursive=True) +
+                   glob.glob(os.path.join(REF, "test-data", "*.json*")))
+    assert len(files) == 96
+    loader = project.ProjectLoader(os.path.join(REF, "assets"))
+    bad = {}
+    for f in files:
+        try:
+            loader.load(f)
+        except Exception as ex:   # noqa: BLE001
+            bad[os.path.relpath(f, REF)] = str(ex)
+    assert sorted(bad) == ["projects/demos/instruments/welsh-harmonica.json", "projects/demos/instruments/welsh-octave-switch.json"], bad
+    plan = loader.load(os.path.join(REF, "projects", "tests", "load-stereo-wav.json"))
+    o = OracleEngine(plan.sample_rate)
+    project.build_plan(o, plan, loader.sample)
+    y = o.render(min(plan.frames, 60000))
+    assert np.abs(y).max() > 0.1 and np.abs(y[:, 0] - y[:, 1]).max() > 1e-3
+
+
+@pytest.mark.skipif(not os.path.isdir(REF), reason="reference tree not present on this box")
 def test_welsh_patch_mapping_quirks():
     """settings/src/patches.rs:87-170: release := decay for both envelopes; mix = m1/(m1+m2);
     cutoff_start from the 12 dB preset, cutoff_hz from the 24 dB preset; every patch file loads
