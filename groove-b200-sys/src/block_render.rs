@@ -305,3 +305,55 @@ impl BlockRender {
         &mut self.engine
     }
 }
+
+/// One rank's side of the multi-GPU bus mixdown (include/groove_b200.h, "multi-GPU bus exchange"): tracks are
+/// independent until the main mixer (orchestration/src/orchestrator.rs:401-410), so a multi-GPU host runs one
+/// `BlockRender` per GPU over a share of the tracks and the stereo buses meet once per render — the root GPU sums
+/// them with one kernel whose loads of the other GPUs' buffers cross NVLink.  The host carries the 64-byte
+/// handles between the processes over whatever channel it has.
+pub struct BusExchange {
+    raw: *mut ffi::gb_bus_exchange,
+}
+unsafe impl Send for BusExchange {}
+
+impl BusExchange {
+    pub fn new(device: i32, max_frames: usize) -> Result<Self> {
+        let mut raw: *mut ffi::gb_bus_exchange = ptr::null_mut();
+        let rc = unsafe { ffi::gb_bus_exchange_create(device, max_frames, &mut raw) };
+        if rc != ffi::GB_OK {
+            return Err(Error { code: rc, message: last_error(ptr::null()) });
+        }
+        Ok(BusExchange { raw })
+    }
+    fn check(&self, rc: i32) -> Result<()> {
+        if rc == ffi::GB_OK { Ok(()) } else { Err(Error { code: rc, message: last_error(ptr::null()) }) }
+    }
+    /// This rank's handle, to be gathered from all ranks in rank order.
+    pub fn export(&self) -> Result<[u8; ffi::GB_IPC_HANDLE_BYTES]> {
+        let mut h = [0u8; ffi::GB_IPC_HANDLE_BYTES];
+        self.check(unsafe { ffi::gb_bus_exchange_export(self.raw, h.as_mut_ptr() as *mut c_void) })?;
+        Ok(h)
+    }
+    /// Root only: map the other ranks' buffers (`handles` = n x 64 bytes in rank order).
+    pub fn open(&mut self, handles: &[u8], self_rank: i32) -> Result<()> {
+        let n = (handles.len() / ffi::GB_IPC_HANDLE_BYTES) as i32;
+        self.check(unsafe { ffi::gb_bus_exchange_open(self.raw, handles.as_ptr() as *const c_void, n, self_rank) })
+    }
+    /// After `Engine::render_device`: copy the rank's bus into its exchange buffer (enqueued on `stream`).
+    pub fn publish(&mut self, engine: &mut Engine, frames: usize, stream: *mut c_void) -> Result<()> {
+        self.check(unsafe { ffi::gb_bus_exchange_publish(self.raw, engine.raw, frames, stream) })
+    }
+    /// Root only, after every rank has published (the host's own barrier): sum the buses; returns the device
+    /// pointer of the mixed `[(f64, f64); frames]`.
+    pub fn reduce(&mut self, frames: usize, stream: *mut c_void) -> Result<*mut c_void> {
+        self.check(unsafe { ffi::gb_bus_exchange_reduce(self.raw, frames, stream) })?;
+        let (mut p, mut n) = (ptr::null_mut(), 0usize);
+        self.check(unsafe { ffi::gb_bus_exchange_result(self.raw, &mut p, &mut n) })?;
+        Ok(p)
+    }
+}
+impl Drop for BusExchange {
+    fn drop(&mut self) {
+        unsafe { ffi::gb_bus_exchange_destroy(self.raw) }
+    }
+}
